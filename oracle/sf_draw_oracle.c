@@ -1,0 +1,439 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/). PARITY AGAINST REAL CAIRO: UNPINNED.
+ *
+ * CPU restatement of the reference frame path
+ *   drawGameStateScaled (draw.cpp:256-270) -> drawJustGameStuff (draw.cpp:227-254)
+ *   -> cv2.cvtColor RGBA2GRAY (ssf_env.py:205) -> cv2.resize INTER_AREA 84x84 (rl/envs.py:29)
+ * libcairo/pixman/freetype (third-party, version unpinned by the reference:
+ * setup.py:8 takes whatever `pkg-config cairo` finds) cannot be built or imported
+ * offline, so this file restates cairo's PUBLISHED image-backend algorithm:
+ *
+ *  M1 geometry  path points are transformed by the CTM in double precision
+ *               (cairo_matrix_multiply / cairo_matrix_transform_point operation
+ *               order) and stored as 24.8 fixed point, round-to-nearest-even
+ *               (_cairo_fixed_from_double).
+ *  M2 stroker   (cairo-path-stroke-polygon.c) every line segment gets two faces
+ *               offset by +-half_width * normal, the offset itself rounded to
+ *               24.8 and ADDED to the fixed end point (compute_face); butt caps;
+ *               miter joins on closed paths (outer_join formula), inner joins
+ *               through the vertex; all sub-paths of one cairo_stroke() form ONE
+ *               polygon filled with the non-zero winding rule.
+ *  M3 coverage  (cairo-tor-scan-converter.c, antialias DEFAULT) GRID_X=256,
+ *               GRID_Y=15: y is rescaled to 15 sub-rows per pixel row
+ *               (round-half-up), an edge is live on sub-rows [ytop,ybot) and its
+ *               x on sub-row s is x1 + floor((s-y1)*dx/dy); per sub-row the
+ *               non-zero-winding spans are box-filtered exactly in x (1/256 px);
+ *               alpha = (c + (c<<4) + 256) >> 9 with c = 2*sum(len) (GRID_XY=7680).
+ *               (cairo's "full row" shortcut for rows without vertices is not
+ *               modelled: every row is sub-sampled.)
+ *  M4 boxes     (cairo-rectangular-scan-converter.c) cairo_rectangle+cairo_fill
+ *               uses exact area coverage: alpha = (A*255 + 32768) >> 16, A in
+ *               1/65536 px^2.
+ *  M5 blend     solid opaque source OVER xrgb32 through an a8 mask
+ *               (cairo-image-compositor.c lerp spans): per channel
+ *               d = mul8(s,a) + mul8(d,255-a), mul8(a,b): t=a*b+128; (t+(t>>8))>>8.
+ *               Colours: 8-bit = (uint16)(v*65535+0.5) >> 8.
+ *  M6 curves    cairo_arc() is a Bezier spline flattened to tolerance 0.1 px;
+ *               the 10-degree explosion arcs (r <= 12.6 px) flatten to one chord
+ *               whose end faces follow the arc's end tangents (radial faces);
+ *               the r=7 circle (1.4 px) flattens to 16 chords. End points are
+ *               taken as centre(fixed) + rounded offset.
+ *  M7 text      drawScore (draw.cpp:160-173) uses the system "monospace" bold
+ *               face: FONT DEPENDENT. No font exists offline; the digits are
+ *               restated as a 7-segment face on the same metrics (advance 0.6 em,
+ *               cap height 0.73 em, centred as centeredText does). Report this
+ *               region separately when comparing with a real cairo build.
+ *  gray         RGBA2GRAY of a grey pixel is the identity.
+ *  resize       cv2 INTER_AREA restated from OpenCV's ResizeArea_ (float weights,
+ *               float accumulation, round-half-even); PINNED against cv2 4.13 in
+ *               tests/test_oracle_frames.py. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sf_oracle.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define W SFO_NATIVE_W
+#define H SFO_NATIVE_H
+#define GRID_Y 15
+#define MAX_EDGES 512
+
+typedef struct { int32_t x, y; } fpt; /* 24.8 device coordinates */
+
+/* ---------------- M1: CTM ---------------- */
+typedef struct { double xx, yx, xy, yy, x0, y0; } mat;
+
+static mat mat_mul(mat a, mat b) { /* cairo_matrix_multiply(r, a, b): a first, then b */
+  mat r;
+  r.xx = a.xx * b.xx + a.yx * b.xy;
+  r.yx = a.xx * b.yx + a.yx * b.yy;
+  r.xy = a.xy * b.xx + a.yy * b.xy;
+  r.yy = a.xy * b.yx + a.yy * b.yy;
+  r.x0 = a.x0 * b.xx + a.y0 * b.xy + b.x0;
+  r.y0 = a.x0 * b.yx + a.y0 * b.yy + b.y0;
+  return r;
+}
+static mat mat_identity(void) { mat m = {1, 0, 0, 1, 0, 0}; return m; }
+static mat mat_scale(mat m, double sx, double sy) { mat t = {sx, 0, 0, sy, 0, 0}; return mat_mul(t, m); }
+static mat mat_translate(mat m, double tx, double ty) { mat t = {1, 0, 0, 1, tx, ty}; return mat_mul(t, m); }
+static mat mat_rotate(mat m, double rad) { double s = sin(rad), c = cos(rad); mat t = {c, s, -s, c, 0, 0}; return mat_mul(t, m); }
+
+static int32_t to_fixed(double v) { return (int32_t)nearbyint(v * 256.0); }
+
+static fpt xform(const mat* m, double x, double y) {
+  double nx = m->xx * x + m->xy * y, ny = m->yx * x + m->yy * y;
+  fpt p; p.x = to_fixed(nx + m->x0); p.y = to_fixed(ny + m->y0);
+  return p;
+}
+
+static mat base_ctm(void) {
+  /* draw.cpp:259-260 with ssf_env.py:50,57-58,164: scale(90/450, 92/460), translate(-130,-80) */
+  mat m = mat_identity();
+  m = mat_scale(m, (double)W / 450.0, (double)H / 460.0);
+  m = mat_translate(m, -130, -80);
+  return m;
+}
+
+/* ---------------- polygon = directed edges (M2/M3) ---------------- */
+typedef struct { int32_t x1, y1, x2, y2; int dir; } pedge; /* y1 < y2 after normalisation */
+typedef struct { pedge e[MAX_EDGES]; int n; } polygon;
+
+static void poly_edge(polygon* p, fpt a, fpt b) {
+  if (a.y == b.y) return; /* horizontal: no winding contribution */
+  pedge* e = &p->e[p->n++];
+  if (a.y < b.y) { e->x1 = a.x; e->y1 = a.y; e->x2 = b.x; e->y2 = b.y; e->dir = 1; }
+  else { e->x1 = b.x; e->y1 = b.y; e->x2 = a.x; e->y2 = a.y; e->dir = -1; }
+}
+
+static void poly_contour(polygon* p, const fpt* pts, int n) {
+  for (int i = 0; i < n; i++) poly_edge(p, pts[i], pts[(i + 1) % n]);
+}
+
+/* ---------------- M5: blend ---------------- */
+static inline unsigned mul8(unsigned a, unsigned b) { unsigned t = a * b + 0x80; return (t + (t >> 8)) >> 8; }
+static inline void blend(uint8_t* d, unsigned colour, unsigned a) {
+  if (a == 0) return;
+  if (a >= 255) { *d = (uint8_t)colour; return; }
+  unsigned v = mul8(colour, a) + mul8(*d, 255 - a);
+  *d = (uint8_t)(v > 255 ? 255 : v);
+}
+static unsigned colour8(double v) { return ((unsigned)(v * 65535.0 + 0.5)) >> 8; }
+
+/* ---------------- M3: 15x256 sub-sampled non-zero fill ---------------- */
+static long floordiv(long a, long b) { long q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
+static int grid_y(int32_t yfixed) { return (int)(((long)yfixed * GRID_Y + 128) >> 8); }
+
+typedef struct { int x, dir; } crossing;
+static int cmp_cross(const void* a, const void* b) {
+  const crossing* p = (const crossing*)a; const crossing* q = (const crossing*)b;
+  return (p->x > q->x) - (p->x < q->x);
+}
+
+static void fill_polygon(uint8_t* img, const polygon* p, unsigned colour) {
+  int gy1[MAX_EDGES], gy2[MAX_EDGES];
+  int smin = 1 << 30, smax = -(1 << 30);
+  for (int i = 0; i < p->n; i++) {
+    gy1[i] = grid_y(p->e[i].y1); gy2[i] = grid_y(p->e[i].y2);
+    if (gy1[i] < gy2[i]) { if (gy1[i] < smin) smin = gy1[i]; if (gy2[i] > smax) smax = gy2[i]; }
+  }
+  if (smin >= smax) return;
+  int row0 = (int)floordiv(smin, GRID_Y), row1 = (int)floordiv(smax - 1, GRID_Y);
+  if (row0 < 0) row0 = 0;
+  if (row1 > H - 1) row1 = H - 1;
+  for (int py = row0; py <= row1; py++) {
+    int len[W];
+    memset(len, 0, sizeof(len));
+    for (int sub = 0; sub < GRID_Y; sub++) {
+      int s = py * GRID_Y + sub;
+      crossing c[MAX_EDGES];
+      int nc = 0;
+      for (int i = 0; i < p->n; i++) {
+        if (gy1[i] <= s && s < gy2[i]) {
+          long dx = (long)p->e[i].x2 - p->e[i].x1, dy = (long)gy2[i] - gy1[i];
+          c[nc].x = p->e[i].x1 + (int)floordiv((long)(s - gy1[i]) * dx, dy);
+          c[nc].dir = p->e[i].dir;
+          nc++;
+        }
+      }
+      if (nc < 2) continue;
+      qsort(c, (size_t)nc, sizeof(crossing), cmp_cross);
+      int wind = 0, xs = 0;
+      for (int k = 0; k < nc; k++) {
+        int before = wind;
+        wind += c[k].dir;
+        if (before == 0 && wind != 0) xs = c[k].x;
+        else if (before != 0 && wind == 0) {
+          int a = xs, b = c[k].x;
+          if (a < 0) a = 0;
+          if (b > W * 256) b = W * 256;
+          for (int px = a >> 8; px < W && px * 256 < b; px++) {
+            int lo = a > px * 256 ? a : px * 256, hi = b < px * 256 + 256 ? b : px * 256 + 256;
+            if (hi > lo) len[px] += hi - lo;
+          }
+        }
+      }
+    }
+    for (int px = 0; px < W; px++) if (len[px]) {
+      unsigned cov = 2u * (unsigned)len[px];
+      blend(&img[py * W + px], colour, (cov + (cov << 4) + 256) >> 9);
+    }
+  }
+}
+
+/* ---------------- M2: stroker ---------------- */
+typedef struct { double ux, uy; fpt off; } face_dir;
+
+static int slope_of(fpt a, fpt b, face_dir* f, double half_width_dev) {
+  double dx = (double)(b.x - a.x) / 256.0, dy = (double)(b.y - a.y) / 256.0;
+  if (dx == 0.0 && dy == 0.0) return 0;
+  if (dx == 0.0) { f->ux = 0.0; f->uy = dy > 0 ? 1.0 : -1.0; }
+  else if (dy == 0.0) { f->uy = 0.0; f->ux = dx > 0 ? 1.0 : -1.0; }
+  else { double mag = sqrt(dx * dx + dy * dy); f->ux = dx / mag; f->uy = dy / mag; }
+  f->off.x = to_fixed(-f->uy * half_width_dev);
+  f->off.y = to_fixed(f->ux * half_width_dev);
+  return 1;
+}
+
+/* half line width in device px: (line_width/2 in user units) pushed through the uniform 0.2 scale */
+static double half_width_dev(double line_width) { return (line_width * 0.5) * ((double)W / 450.0); }
+
+static void stroke_segment(polygon* p, fpt a, fpt b, double hw) {
+  face_dir f;
+  if (!slope_of(a, b, &f, hw)) return; /* degenerate sub-path + butt cap: nothing */
+  fpt q[4] = {{a.x + f.off.x, a.y + f.off.y}, {b.x + f.off.x, b.y + f.off.y},
+              {b.x - f.off.x, b.y - f.off.y}, {a.x - f.off.x, a.y - f.off.y}};
+  poly_contour(p, q, 4);
+}
+
+static void stroke_closed_polygon(polygon* p, const fpt* v, int n, double hw) {
+  /* closed path, miter joins (default join, miter limit 10) */
+  face_dir f[16];
+  for (int i = 0; i < n; i++) slope_of(v[i], v[(i + 1) % n], &f[i], hw);
+  fpt ccw[48], cw[48];
+  int nccw = 0, ncw = 0;
+  for (int i = 0; i < n; i++) {
+    int in = (i + n - 1) % n, out = i; /* join at vertex i between segment in and segment out */
+    fpt P = v[i];
+    fpt in_ccw = {P.x + f[in].off.x, P.y + f[in].off.y}, in_cw = {P.x - f[in].off.x, P.y - f[in].off.y};
+    fpt out_ccw = {P.x + f[out].off.x, P.y + f[out].off.y}, out_cw = {P.x - f[out].off.x, P.y - f[out].off.y};
+    double cross = f[in].ux * f[out].uy - f[in].uy * f[out].ux;
+    /* cross > 0: the path turns towards its ccw side, so ccw is the inner side */
+    int inner_is_ccw = cross > 0;
+    fpt ip = inner_is_ccw ? in_cw : in_ccw, op = inner_is_ccw ? out_cw : out_ccw; /* outer points */
+    double x1 = ip.x / 256.0, y1 = ip.y / 256.0, x2 = op.x / 256.0, y2 = op.y / 256.0;
+    double dx1 = f[in].ux, dy1 = f[in].uy, dx2 = f[out].ux, dy2 = f[out].uy;
+    double my = ((x2 - x1) * dy1 * dy2 - y2 * dx2 * dy1 + y1 * dx1 * dy2) / (dx1 * dy2 - dx2 * dy1);
+    double mx = fabs(dy1) >= fabs(dy2) ? (my - y1) * dx1 / dy1 + x1 : (my - y2) * dx2 / dy2 + x2;
+    fpt tip = {to_fixed(mx), to_fixed(my)};
+    if (inner_is_ccw) {
+      cw[ncw++] = in_cw; cw[ncw++] = tip; cw[ncw++] = out_cw;
+      ccw[nccw++] = in_ccw; ccw[nccw++] = P; ccw[nccw++] = out_ccw;
+    } else {
+      ccw[nccw++] = in_ccw; ccw[nccw++] = tip; ccw[nccw++] = out_ccw;
+      cw[ncw++] = in_cw; cw[ncw++] = P; cw[ncw++] = out_cw;
+    }
+  }
+  /* the two contours wind in opposite senses (cairo walks the cw contour forwards and the
+   * ccw contour backwards) */
+  poly_contour(p, ccw, nccw);
+  fpt rev[48];
+  for (int i = 0; i < ncw; i++) rev[i] = cw[ncw - 1 - i];
+  poly_contour(p, rev, ncw);
+}
+
+/* ---------------- wireframe tables (wireframe.cpp:8-70): from,to as x0,y0,x1,y1 ---------------- */
+static const double WF_MISSILE[3][4] = {{0, 0, -25, 0}, {0, 0, -5, 5}, {0, 0, -5, -5}};
+static const double WF_SHELL[4][4] = {{-8, 0, 0, -6}, {0, -6, 16, 0}, {16, 0, 0, 6}, {0, 6, -8, 0}};
+static const double WF_SHIP[3][4] = {{-18, 0, 18, 0}, {-18, 18, 0, 0}, {0, 0, -18, -18}};
+static const double WF_FORTRESS[4][4] = {{0, 0, 36, 0}, {0, -18, 18, -18}, {18, -18, 18, 18}, {18, 18, 0, 18}};
+
+/* R3: drawWireFrame (draw.cpp:82-100) */
+static void draw_wireframe(uint8_t* img, const double (*lines)[4], int nlines, double x, double y, int angle, double lw) {
+  mat m = base_ctm();
+  m = mat_translate(m, x, y);
+  m = mat_rotate(m, (double)angle * M_PI / 180); /* deg2rad(angle), vector.cpp:34-36 */
+  polygon p; p.n = 0;
+  double hw = half_width_dev(lw);
+  for (int i = 0; i < nlines; i++)
+    stroke_segment(&p, xform(&m, lines[i][0], lines[i][1]), xform(&m, lines[i][2], lines[i][3]), hw);
+  fill_polygon(img, &p, colour8(1.0));
+}
+
+/* R2: drawHexagon (draw.cpp:102-114) with the vertices of hexagon.cpp:13-35 */
+static void draw_hexagon(uint8_t* img, int radius, double lw) {
+  double x1 = floor(355 - radius), x2 = floor(355 - radius * 0.5), x3 = floor(355 + radius * 0.5), x4 = floor(355 + radius);
+  double y1 = 315, y2 = floor(315 - radius * sin(M_PI * 2 / 3)), y3 = floor(315 + radius * sin(M_PI * 2 / 3));
+  double ux[6] = {x1, x2, x3, x4, x3, x2}, uy[6] = {y1, y2, y2, y1, y3, y3};
+  mat m = base_ctm();
+  fpt v[6];
+  for (int i = 0; i < 6; i++) v[i] = xform(&m, ux[i], uy[i]);
+  polygon p; p.n = 0;
+  stroke_closed_polygon(&p, v, 6, half_width_dev(lw));
+  fill_polygon(img, &p, colour8(1.0));
+}
+
+/* R5: drawExplosion (draw.cpp:116-145) under model M6 */
+static fpt polar_off(double r_dev, double deg) {
+  fpt o; o.x = to_fixed(r_dev * cos(deg * M_PI / 180)); o.y = to_fixed(r_dev * sin(deg * M_PI / 180));
+  return o;
+}
+static void draw_explosion(uint8_t* img, double x, double y, double lw) {
+  mat m = base_ctm();
+  fpt c = xform(&m, x, y);
+  double sc = (double)W / 450.0, hw = half_width_dev(lw);
+  int ofs = 0;
+  for (int radius = 15; radius < 70; radius += 8) {
+    ofs += 3;
+    unsigned col = radius < 60 ? colour8(.75) : colour8(.5);
+    for (int angle = 0; angle < 360; angle += 30) {
+      double a0 = angle + ofs, a1 = angle + ofs + 10;
+      fpt s = polar_off(radius * sc, a0), e = polar_off(radius * sc, a1);
+      fpt fs = polar_off(hw, a0), fe = polar_off(hw, a1);
+      fpt q[4] = {{c.x + s.x + fs.x, c.y + s.y + fs.y}, {c.x + e.x + fe.x, c.y + e.y + fe.y},
+                  {c.x + e.x - fe.x, c.y + e.y - fe.y}, {c.x + s.x - fs.x, c.y + s.y - fs.y}};
+      polygon p; p.n = 0;
+      poly_contour(&p, q, 4);
+      fill_polygon(img, &p, col); /* one cairo_stroke per arc (draw.cpp:136-137) */
+    }
+  }
+  polygon p; p.n = 0;
+  for (int k = 0; k < 16; k++) {
+    double a0 = k * 22.5, a1 = (k + 1) * 22.5;
+    fpt s = polar_off(7 * sc, a0), e = polar_off(7 * sc, a1);
+    fpt fs = polar_off(hw, a0), fe = polar_off(hw, a1);
+    fpt q[4] = {{c.x + s.x + fs.x, c.y + s.y + fs.y}, {c.x + e.x + fe.x, c.y + e.y + fe.y},
+                {c.x + e.x - fe.x, c.y + e.y - fe.y}, {c.x + s.x - fs.x, c.y + s.y - fs.y}};
+    poly_contour(&p, q, 4);
+  }
+  fill_polygon(img, &p, colour8(.75));
+}
+
+/* M4: cairo_rectangle + cairo_fill */
+static void fill_box(uint8_t* img, double ux, double uy, double uw, double uh, unsigned colour) {
+  mat m = base_ctm();
+  fpt a = xform(&m, ux, uy), b = xform(&m, ux + uw, uy + uh);
+  if (b.x <= a.x || b.y <= a.y) return;
+  for (int py = a.y >> 8; py < H && py * 256 < b.y; py++) {
+    if (py < 0) continue;
+    int ylo = a.y > py * 256 ? a.y : py * 256, yhi = b.y < py * 256 + 256 ? b.y : py * 256 + 256;
+    for (int px = a.x >> 8; px < W && px * 256 < b.x; px++) {
+      if (px < 0) continue;
+      int xlo = a.x > px * 256 ? a.x : px * 256, xhi = b.x < px * 256 + 256 ? b.x : px * 256 + 256;
+      unsigned area = (unsigned)(xhi - xlo) * (unsigned)(yhi - ylo);
+      blend(&img[py * W + px], colour, (area * 255u + 32768u) >> 16);
+    }
+  }
+}
+
+/* R7 under model M7: "%07d" of (int)mPoints, centred at user (355, 97), grey .5 */
+static void draw_score(uint8_t* img, int pnts) {
+  static const unsigned char SEG[10] = {0x3f, 0x06, 0x5b, 0x4f, 0x66, 0x6d, 0x7d, 0x07, 0x7f, 0x6f}; /* gfedcba */
+  /* segment boxes inside an 18 x 22 user-unit cell (0.6 em advance, 0.73 em cap height at 30 units) */
+  static const double BOX[7][4] = {
+      {3, 0, 12, 4},  /* a top */     {11, 0, 4, 13}, /* b upper right */ {11, 9, 4, 13}, /* c lower right */
+      {3, 18, 12, 4}, /* d bottom */  {3, 9, 4, 13},  /* e lower left */  {3, 0, 4, 13},  /* f upper left */
+      {3, 9, 12, 4}   /* g middle */};
+  if (pnts < 0) pnts = 0;
+  if (pnts > 9999999) pnts = 9999999;
+  char text[16];
+  int v = pnts;
+  for (int i = 6; i >= 0; i--) { text[i] = (char)(v % 10); v /= 10; }
+  double x0 = 355 - 7 * 18 / 2.0, ytop = 97 - 22 / 2.0; /* centeredText, draw.cpp:147-158 */
+  mat m = base_ctm();
+  polygon p; p.n = 0;
+  for (int d = 0; d < 7; d++)
+    for (int sgm = 0; sgm < 7; sgm++) if ((SEG[(int)text[d]] >> sgm) & 1) {
+      double bx = x0 + 18 * d + BOX[sgm][0], by = ytop + BOX[sgm][1];
+      fpt q[4] = {xform(&m, bx, by), xform(&m, bx + BOX[sgm][2], by), xform(&m, bx + BOX[sgm][2], by + BOX[sgm][3]),
+                  xform(&m, bx, by + BOX[sgm][3])};
+      poly_contour(&p, q, 4);
+    }
+  fill_polygon(img, &p, colour8(.5));
+}
+
+/* R8: drawVlner (draw.cpp:207-225) */
+static void draw_vlner(uint8_t* img, int vlner, int kill) {
+  fill_box(img, 355 - 100, 335 + 187, 200, 10, colour8(.33));
+  int k = vlner > 10 ? 10 : vlner;
+  if (k > 0) fill_box(img, 355 - 100, 335 + 187, 20 * k, 10, kill ? colour8(1.0) : colour8(.66));
+}
+
+/* R1: drawGameStateScaled + drawJustGameStuff */
+void sfo_draw_native(const sfr_record* s, uint8_t* img) {
+  const double lw = 3; /* ssf_env.py:50 ls=3 */
+  memset(img, 0, W * H); /* cairo_paint black */
+  draw_hexagon(img, 200, lw);
+  draw_hexagon(img, 40, lw);
+  if (s->ship_alive) draw_wireframe(img, WF_SHIP, 3, s->ship_x, s->ship_y, (int)s->ship_angle, lw);
+  else draw_explosion(img, s->ship_x, s->ship_y, lw);
+  if (s->fortress_alive) draw_wireframe(img, WF_FORTRESS, 4, 355, 315, (int)s->fortress_angle, lw);
+  else draw_explosion(img, 355, 315, lw);
+  for (int i = 0; i < SFR_MAX_MISSILES; i++)
+    if ((s->missile_mask >> i) & 1) draw_wireframe(img, WF_MISSILE, 3, s->missile_x[i], s->missile_y[i], (int)s->missile_angle[i], lw);
+  for (int i = 0; i < SFR_MAX_SHELLS; i++) {
+    if (!((s->shell_mask >> i) & 1)) continue;
+    double dx = s->shell_x[i] - 355, dy = s->shell_y[i] - 315;
+    if (sqrt(dx * dx + dy * dy) > 21) /* quirk Q9, draw.cpp:249-250 */
+      draw_wireframe(img, WF_SHELL, 4, s->shell_x[i], s->shell_y[i], (int)s->shell_angle[i], lw);
+  }
+  draw_score(img, (int)s->points);
+  draw_vlner(img, s->vulnerability, s->vulnerability > 10 && s->fortress_vuln_timer < 250);
+}
+
+/* R10: cv2.resize(..., INTER_AREA) for a non-integer scale, single channel u8.
+ * Restated from OpenCV imgproc/resize.cpp (computeResizeAreaTab + ResizeArea_<uchar,float>):
+ * per-axis tables of (dst index, src index, float weight); rows are accumulated in float in
+ * table order and flushed with round-half-even. */
+typedef struct { int si, di; float alpha; } dtab;
+
+static int area_tab(int ssize, int dsize, double scale, dtab* tab) {
+  int k = 0;
+  for (int dx = 0; dx < dsize; dx++) {
+    double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    double cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    if (sx2 > ssize - 1) sx2 = ssize - 1;
+    if (sx1 > sx2) sx1 = sx2;
+    if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+    for (int sx = sx1; sx < sx2; sx++) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+    if (fsx2 - sx2 > 1e-3) {
+      double a = fsx2 - sx2; if (a > 1.0) a = 1.0; if (a > cell) a = cell;
+      tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(a / cell);
+    }
+  }
+  return k;
+}
+
+void sfo_resize_area(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw) {
+  dtab* xt = (dtab*)malloc(sizeof(dtab) * (size_t)(sw * 2 + 2));
+  dtab* yt = (dtab*)malloc(sizeof(dtab) * (size_t)(sh * 2 + 2));
+  int nx = area_tab(sw, dw, (double)sw / dw, xt), ny = area_tab(sh, dh, (double)sh / dh, yt);
+  float* buf = (float*)malloc(sizeof(float) * (size_t)dw);
+  float* sum = (float*)malloc(sizeof(float) * (size_t)dw);
+  int prev_dy = yt[0].di;
+  for (int x = 0; x < dw; x++) sum[x] = 0;
+  for (int j = 0; j < ny; j++) {
+    float beta = yt[j].alpha;
+    int dy = yt[j].di, sy = yt[j].si;
+    const uint8_t* S = src + sy * sw;
+    for (int x = 0; x < dw; x++) buf[x] = 0;
+    for (int k = 0; k < nx; k++) buf[xt[k].di] += S[xt[k].si] * xt[k].alpha;
+    if (dy != prev_dy) {
+      for (int x = 0; x < dw; x++) { dst[prev_dy * dw + x] = (uint8_t)lrintf(sum[x]); sum[x] = beta * buf[x]; }
+      prev_dy = dy;
+    } else {
+      for (int x = 0; x < dw; x++) sum[x] += beta * buf[x];
+    }
+  }
+  for (int x = 0; x < dw; x++) dst[prev_dy * dw + x] = (uint8_t)lrintf(sum[x]);
+  free(xt); free(yt); free(buf); free(sum);
+}
+
+void sfo_draw_obs(const sfr_record* s, uint8_t* obs84) {
+  uint8_t native[W * H];
+  sfo_draw_native(s, native);
+  sfo_resize_area(native, H, W, obs84, SFO_OBS_H, SFO_OBS_W);
+}
