@@ -1,0 +1,168 @@
+/* sf_b200.h — C-ABI of the B200-native batched Space Fortress simulator.
+ *
+ * Drop-in boundary for ONE path of agakshat/spacefortress: env step + observation render +
+ * auto-reset. Each entry point names the reference interface it replaces (paths are relative
+ * to the reference repository root):
+ *
+ *   reference (CPython type `_spacefortress.Game`, python/spacefortress/src/pymodule.cpp)
+ *   -------------------------------------------------------------------------------------
+ *   Game(config, lw, grayscale, width, height, viewport)   pymodule.cpp:319-354  -> sf_create
+ *   tp_dealloc                                              pymodule.cpp:295-302  -> sf_destroy
+ *   press_key / release_key / step_one_tick(ms) / draw()    pymodule.cpp:199-247  -> sf_step (one call per batch)
+ *   is_game_over()                                          pymodule.cpp:233-240  -> done[] of sf_step
+ *   new Game per episode (ssf_env.py:163-178)               -> sf_reset / auto-reset inside sf_step
+ *   pb_pixels + cv2 gray + cv2.resize (ssf_env.py:205, rl/envs.py:29) -> obs[] of sf_step / sf_render
+ *   37 read-only getters (pymodule.cpp:372-411), dump()     -> sf_get_state (+ host formatting)
+ *   (no setters exist: pymodule.cpp:48-74 commented out)    -> sf_set_state (teacher forcing)
+ *   SubprocVecEnv.step/reset (gym_vecenv 1.0, rl/train.py:32,60,80) -> sf_step / sf_step_host / sf_rollout
+ *   sum(info) / final_rewards bookkeeping (rl/train.py:81-88)       -> sf_episode_stats
+ *
+ * Conventions: plain C types only; every function returns an int status (SF_OK == 0) and never
+ * calls exit() (the reference does on a bad config key, config.cpp:35-38); sf_last_error() gives
+ * the message of the last failure on the calling thread. Pointers named d_* are DEVICE pointers
+ * on the handle's GPU, h_* are HOST pointers. `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream). Device-pointer calls are asynchronous on `stream` and do
+ * not synchronise the host. There is no CPU fallback: without a CUDA device sf_create fails. */
+#ifndef SF_B200_H
+#define SF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SF_OK 0
+#define SF_ERR_INVALID 1  /* bad argument (unknown game type, null pointer, size mismatch) */
+#define SF_ERR_CUDA 2     /* a CUDA runtime call failed; see sf_last_error() */
+#define SF_ERR_UNSUPPORTED 3
+
+#define SF_MAX_MISSILES 20 /* pymodule.cpp:472, game.hh:3 */
+#define SF_MAX_SHELLS 20   /* pymodule.cpp:473, game.hh:4 (the device keeps 4 slots: <= 3 shells can be alive) */
+#define SF_NUM_STATS 13    /* game.hh:29-43 */
+#define SF_OBS_H 84        /* rl/envs.py:29 */
+#define SF_OBS_W 84
+#define SF_NATIVE_H 92     /* int(460*.2), ssf_env.py:58 */
+#define SF_NATIVE_W 90     /* int(450*.2), ssf_env.py:57 */
+#define SF_NUM_EPISODE_STATS 24
+
+/* key mask bits per step: the env sends FIRE, THRUST[, LEFT, RIGHT] every step (ssf_env.py:213-229) */
+enum { SF_KEY_FIRE = 1, SF_KEY_THRUST = 2, SF_KEY_LEFT = 4, SF_KEY_RIGHT = 8 };
+
+/* per-step event bits (replace the event strings of game.cpp:124-127 and Collisions, game.hh:45-47) */
+enum {
+  SF_EV_MISSILE_FIRED = 1 << 0, SF_EV_FORTRESS_FIRED = 1 << 1, SF_EV_HIT_FORTRESS = 1 << 2,
+  SF_EV_VLNER_INCREASED = 1 << 3, SF_EV_VLNER_RESET = 1 << 4, SF_EV_FORTRESS_DESTROYED = 1 << 5,
+  SF_EV_HIT_DEAD_FORTRESS = 1 << 6, SF_EV_EXPLODE_BIGHEX = 1 << 7, SF_EV_EXPLODE_SMALLHEX = 1 << 8,
+  SF_EV_SHELL_HIT_SHIP = 1 << 9, SF_EV_SHIP_RESPAWN = 1 << 10, SF_EV_FORTRESS_RESPAWN = 1 << 11,
+  SF_EV_COL_BIGHEX = 1 << 12, SF_EV_COL_SMALLHEX = 1 << 13, SF_EV_COL_MISSILE_FORTRESS = 1 << 14,
+  SF_EV_COL_SHELL_SHIP = 1 << 15,
+  SF_EV_PRESS_FIRE = 1 << 16, SF_EV_PRESS_THRUST = 1 << 17, SF_EV_PRESS_LEFT = 1 << 18, SF_EV_PRESS_RIGHT = 1 << 19,
+  SF_EV_MISSED_SHOT = 1 << 20,
+  SF_EV_EPISODE_RESET = 1 << 21 /* the env was auto-reset after this step */
+};
+
+/* sf_step / sf_rollout flags */
+enum {
+  SF_FLAG_RENDER = 1,       /* write the 84x84 observation */
+  SF_FLAG_NO_AUTORESET = 2, /* leave finished envs finished (single-env facade: SSF_Env has no auto-reset) */
+  SF_FLAG_ACTIONS_ARE_KEYMASKS = 4, /* actions[] already hold key masks instead of action ids */
+  SF_FLAG_NATIVE_OBS = 8,   /* obs is the native 92x90 frame (SSF_Env.step) instead of 84x84 */
+  SF_FLAG_RAW_REWARD = 16   /* reward = Game.step_one_tick's int (pymodule.cpp:230): no Python-layer shaping, prev_vlner untouched */
+};
+
+/* Per-env state record for get/set (teacher forcing, checkpointing, getters). Same members as the
+ * reference's public Game fields (game.hh:84-107) + prev_vlner (ssf_env.py:92) + rand() position. */
+typedef struct sf_state_record {
+  double ship_x, ship_y, ship_vx, ship_vy, ship_angle;
+  double fortress_angle, fortress_last_angle;
+  double missile_x[SF_MAX_MISSILES], missile_y[SF_MAX_MISSILES];
+  double missile_vx[SF_MAX_MISSILES], missile_vy[SF_MAX_MISSILES], missile_angle[SF_MAX_MISSILES];
+  double shell_x[SF_MAX_SHELLS], shell_y[SF_MAX_SHELLS];
+  double shell_vx[SF_MAX_SHELLS], shell_vy[SF_MAX_SHELLS], shell_angle[SF_MAX_SHELLS];
+  float points, raw_points;
+  uint32_t missile_mask, shell_mask;
+  int32_t ship_alive, fortress_alive;
+  int32_t ship_death_timer, fire_timer, thrust_timer, left_timer, right_timer;
+  int32_t thrust_flag, fire_flag, left_flag, right_flag, turn_flag;
+  int32_t fortress_timer, fortress_death_timer, fortress_vuln_timer;
+  int32_t vulnerability, tick, time;
+  int32_t stats[SF_NUM_STATS];
+  int32_t prev_vlner;
+  uint32_t rng_seed, rng_count;
+  int32_t ep_return; /* running shaped return of the current episode (episode-stat bookkeeping) */
+} sf_state_record;
+
+typedef struct sf_handle sf_handle;
+
+const char* sf_last_error(void);
+int sf_version(void);
+
+/* gametype: "youturn" | "autoturn" | "test-youturn" | "test-autoturn" (pymodule.cpp:331-343; unknown ->
+ * SF_ERR_INVALID, the reference raises RuntimeError). action_set: 1 | 0 | -1 (ssf_env.py:65-90).
+ * Allocates the SoA state slab for n_envs on CUDA device `device`. Envs are not yet reset. */
+int sf_create(const char* gametype, int action_set, int n_envs, int device, sf_handle** out);
+int sf_destroy(sf_handle* h);
+int sf_num_envs(const sf_handle* h);
+int sf_num_actions(const sf_handle* h);
+int sf_action_keymask(const sf_handle* h, int action); /* -1 if out of range */
+long long sf_state_bytes(const sf_handle* h);          /* device bytes held per handle */
+
+/* (Re)seed the per-env libc-rand() streams (glibc TYPE_3, game.cpp:137-148). h_seeds==NULL: every env
+ * gets seed 1 — the reference never calls srand, and forked gym_vecenv workers all replay that stream.
+ * first_global_env offsets nothing in the seeds; it only labels this slab for the synthetic action hash
+ * so that results are shard-invariant across GPUs. */
+int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_global_env, void* stream);
+
+/* SSF_Env.__init__/reset for all envs (d_mask==NULL) or for envs with d_mask[i]!=0: new Game
+ * (game.cpp:18-82); prev_vlner is cleared only when clear_prev_vlner!=0 (= __init__, ssf_env.py:92).
+ * d_obs (may be NULL) receives the first frame, layout per flags. */
+int sf_reset(sf_handle* h, const uint8_t* d_mask, int clear_prev_vlner, uint8_t* d_obs, int flags, void* stream);
+
+/* One SSF_Env.step for every env (ssf_env.py:208-253) + gym_vecenv auto-reset: actions -> key events ->
+ * Game::stepOneTick(34) -> reward shaping -> done -> (reset) -> frame. Outputs may be NULL.
+ *   d_actions int32[n]; d_obs uint8[n][84][84] (or [n][92][90] with SF_FLAG_NATIVE_OBS);
+ *   d_reward int32[n] (the reference returns Python ints); d_done uint8[n]; d_fortkill uint8[n]
+ *   (the reference's `info`, a bool: ssf_env.py:233,250); d_events uint32[n]. */
+int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, int32_t* d_reward, uint8_t* d_done,
+            uint8_t* d_fortkill, uint32_t* d_events, int flags, void* stream);
+
+/* T consecutive steps in ONE launch (state never leaves the SM between steps). d_actions int32[T][n],
+ * or NULL for the synthetic policy: action = hash(action_seed, global_env, t) % num_actions (the same
+ * stream sf_synthetic_action() gives on the host). Outputs are time-major: d_obs[T][n][84][84],
+ * d_reward[T][n], d_done[T][n], d_fortkill[T][n]; any may be NULL. */
+int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_t action_seed, long long t0, uint8_t* d_obs,
+               int32_t* d_reward, uint8_t* d_done, uint8_t* d_fortkill, int flags, void* stream);
+int sf_synthetic_action(uint32_t action_seed, long long global_env, long long t, int num_actions);
+
+/* Render the current state without stepping (Game.draw + gray + resize). */
+int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
+
+/* Host-buffer convenience path (numpy drop-in for rl/train.py:79-80): H2D actions, step, D2H results,
+ * synchronous. Uses pinned staging inside the handle. h_obs may be NULL. */
+int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
+                 uint8_t* h_fortkill, uint32_t* h_events, int flags);
+
+/* State records, host side (synchronous). first..first+count-1. */
+int sf_get_state(sf_handle* h, int first, int count, sf_state_record* h_out);
+int sf_set_state(sf_handle* h, int first, int count, const sf_state_record* h_in);
+
+/* Finished-episode statistics accumulated on the device since the last call with reset!=0:
+ * int64[SF_NUM_EPISODE_STATS] = {episodes, sum_return, sum_return^2, sum_length, sum of the 13 Stats
+ * counters (game.hh:29-43; maxVlner summed), sum (int)points, sum round(raw_points*1000), sum fort_kills,
+ * max maxVlner, steps, 2 reserved}. d_out is a device pointer (feed it to ncclAllReduce / torch.distributed);
+ * integer sums make the reduction bitwise shard-invariant. */
+int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream);
+
+/* Static tables built at sf_create (host copies, for tests/inspection): background frames. */
+int sf_background(const sf_handle* h, uint8_t* h_native /*[92*90]*/, uint8_t* h_obs /*[84*84]*/);
+
+/* Host-only (no GPU needed): compose the static layers of a frame from the same tables the kernels use
+ * (background hexagons, fortress sprite or fortress explosion, score digits, vulnerability bar) into a
+ * native 92x90 frame. Used by the CPU test-suite to check the table builder. */
+int sf_host_static_frame(int fortress_alive, int fortress_angle_deg, int points, int vulnerability, int kill_bar,
+                         uint8_t* h_native /*[92*90]*/, uint8_t* h_bg_obs /*[84*84] or NULL*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SF_B200_H */

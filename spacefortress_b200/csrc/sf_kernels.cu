@@ -1,0 +1,676 @@
+// sf_kernels.cu — kernels and the C-ABI (include/sf_b200.h) of the B200-native batched Space Fortress
+// simulator. sm_100a only; no CPU fallback: every entry point fails with SF_ERR_CUDA without a device.
+//
+// Kernels
+//   sf_rollout_kernel<RENDER>   fused step + render + auto-reset for T consecutive ticks (T=1 == sf_step).
+//                               A warp owns E consecutive envs: lanes < E step one env each (SoA, 128-bit
+//                               loads/stores), then the whole warp rasterises those envs one after another
+//                               out of shared memory and streams the 84x84 frames to HBM.
+//   sf_step_only_kernel         state-only variant (render off), one env per thread.
+//   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sf_b200.h"
+#include "sf_geom.h"
+#include "sf_render.cuh"
+#include "sf_state.cuh"
+#include "sf_step.cuh"
+#include "sf_tables.h"
+
+#define SF_WARPS_PER_BLOCK 8
+#define SF_BLOCK (32 * SF_WARPS_PER_BLOCK)
+
+// ------------------------------------------------------------------------------------------------
+// synthetic policy: stateless counter hash; same function on host and device
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline unsigned sf_hash3(unsigned seed, unsigned long long env, unsigned long long t) {
+  unsigned long long z = (env * 0x9E3779B97F4A7C15ull) ^ (t * 0xC2B2AE3D27D4EB4Full) ^ ((unsigned long long)seed << 32 | 0x5Fu);
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned)(z >> 32);
+}
+__host__ __device__ inline int sf_hash_action(unsigned seed, unsigned long long env, unsigned long long t, int num_actions) {
+  return (int)(((unsigned long long)sf_hash3(seed, env, t) * (unsigned)num_actions) >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finished-episode statistics: warp-reduced, then one atomic per field per warp
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long sf_warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ inline void sf_accumulate_episode(const SfDev& D, const SfEnv& e, bool finished, int lane) {
+  // called by all 32 lanes; `finished` lanes contribute
+  long long f[SF_NUM_EPISODE_STATS];
+  long long ret = e.q3.w;
+  f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = e.q3.z;
+  f[4] = e.st0.x; f[5] = e.st0.y; f[6] = e.st0.z; f[7] = e.st0.w;
+  f[8] = e.st1.x; f[9] = e.st1.y; f[10] = e.st1.z; f[11] = e.st1.w;
+  f[12] = e.st2.x; f[13] = e.st2.y; f[14] = e.st2.z; f[15] = e.st2.w; f[16] = e.st3.x;
+  f[17] = (long long)__float2int_rz(__int_as_float(e.q3.x));
+  f[18] = __double2ll_rn((double)__int_as_float(e.q3.y) * 1000.0);
+  f[19] = e.st1.y;  // fortress kills of the episode (== destroyedFortresses; rl/train.py:81 sums info)
+  f[20] = 0; f[21] = 0; f[22] = 0; f[23] = 0;
+#pragma unroll
+  for (int k = 0; k < 20; k++) {
+    long long v = sf_warp_sum_ll(finished ? f[k] : 0);
+    if (lane == 0 && v) atomicAdd(&D.epi[k], (unsigned long long)v);
+  }
+  int mv = finished ? e.st3.x : 0;
+  mv = sf_warp_max(mv);
+  if (lane == 0 && mv) atomicMax(&D.epi[20], (unsigned long long)mv);
+}
+
+__device__ __forceinline__ void sf_make_render_in(const SfEnv& e, int env, SfRenderIn& r) {
+  r.env = env; r.core = (unsigned)e.q0.x; r.pmask = (unsigned)e.q0.y;
+  r.px = e.pos.x; r.py = e.pos.y;
+  r.points_i = __float2int_rz(__int_as_float(e.q3.x));
+  r.vuln = e.q1.z;
+  r.kill_bar = e.q1.z > 10 && e.q1.y < 250;
+}
+
+__device__ __forceinline__ SfRenderIn sf_bcast_render_in(const SfRenderIn& mine, int src) {
+  SfRenderIn r;
+  r.env = __shfl_sync(0xffffffffu, mine.env, src);
+  r.core = __shfl_sync(0xffffffffu, mine.core, src);
+  r.pmask = __shfl_sync(0xffffffffu, mine.pmask, src);
+  r.px = __shfl_sync(0xffffffffu, mine.px, src);
+  r.py = __shfl_sync(0xffffffffu, mine.py, src);
+  r.points_i = __shfl_sync(0xffffffffu, mine.points_i, src);
+  r.vuln = __shfl_sync(0xffffffffu, mine.vuln, src);
+  r.kill_bar = __shfl_sync(0xffffffffu, (int)mine.kill_bar, src) != 0;
+  return r;
+}
+
+struct SfRollArgs {
+  int T, E, flags;
+  const int* actions;  // [T][n] or NULL
+  unsigned action_seed;
+  long long t0;
+  unsigned char* obs;  // [T][n][obs_bytes]
+  int* reward;         // [T][n]
+  unsigned char* done;
+  unsigned char* fortkill;
+  unsigned* events;
+};
+
+// ------------------------------------------------------------------------------------------------
+// fused step + render
+// ------------------------------------------------------------------------------------------------
+template <bool RENDER>
+__global__ void __launch_bounds__(SF_BLOCK) sf_rollout_kernel(SfDev D, SfRollArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SfWarpSmem& W = reinterpret_cast<SfWarpSmem*>(smem_raw)[RENDER ? warp : 0];
+  const long long wg = (long long)blockIdx.x * SF_WARPS_PER_BLOCK + warp;
+  const long long env0 = wg * A.E;
+  if (env0 >= D.n) return;
+  const int env = (int)env0 + lane;
+  const bool mine = lane < A.E && env < D.n;
+  const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
+  const size_t obs_bytes = (A.flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+
+  for (int t = 0; t < A.T; t++) {
+    SfEnv e;
+    SfRenderIn rin;
+    rin.env = -1; rin.core = 0; rin.pmask = 0; rin.px = 0; rin.py = 0; rin.points_i = 0; rin.vuln = 0; rin.kill_bar = false;
+    bool finished = false;
+    if (mine) {
+      sf_load_env(D, env, e);
+      int a = A.actions ? A.actions[(size_t)t * D.n + env]
+                        : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
+      int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
+      SfStepOut o;
+      sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+      size_t oi = (size_t)t * D.n + env;
+      if (A.reward) A.reward[oi] = o.reward;
+      if (A.done) A.done[oi] = o.done;
+      if (A.fortkill) A.fortkill[oi] = o.fort_kill;
+      if (A.events) A.events[oi] = o.events;
+      finished = o.done && autoreset;
+    }
+    if (__any_sync(0xffffffffu, finished)) {
+      sf_accumulate_episode(D, e, finished, lane);
+      if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
+    }
+    if (mine) {
+      sf_store_env(D, env, e);
+      sf_make_render_in(e, env, rin);
+    }
+    if (RENDER) {
+      __syncwarp();  // projectile arrays written above are read by other lanes below
+      for (int k = 0; k < A.E; k++) {
+        SfRenderIn r = sf_bcast_render_in(rin, k);
+        if (r.env < 0) break;
+        unsigned char* o = A.obs + ((size_t)t * D.n + r.env) * obs_bytes;
+        sf_render_env(D, W, lane, r, (A.flags & SF_FLAG_NATIVE_OBS) ? nullptr : o, (A.flags & SF_FLAG_NATIVE_OBS) ? o : nullptr);
+      }
+    }
+  }
+}
+
+// state-only: one env per thread
+__global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool mine = env < D.n;
+  const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
+  SfEnv e;
+  if (mine) sf_load_env(D, env, e);
+  for (int t = 0; t < A.T; t++) {
+    bool finished = false;
+    if (mine) {
+      int a = A.actions ? A.actions[(size_t)t * D.n + env]
+                        : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
+      int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
+      SfStepOut o;
+      sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+      size_t oi = (size_t)t * D.n + env;
+      if (A.reward) A.reward[oi] = o.reward;
+      if (A.done) A.done[oi] = o.done;
+      if (A.fortkill) A.fortkill[oi] = o.fort_kill;
+      if (A.events) A.events[oi] = o.events;
+      finished = o.done && autoreset;
+    }
+    if (__any_sync(0xffffffffu, finished)) {
+      sf_accumulate_episode(D, e, finished, lane);
+      if (finished) sf_new_game(D, env, e);
+    }
+  }
+  if (mine) sf_store_env(D, env, e);
+}
+
+// render the current state (Game.draw), warp per env
+__global__ void __launch_bounds__(SF_BLOCK) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SfWarpSmem& W = reinterpret_cast<SfWarpSmem*>(smem_raw)[warp];
+  const int env = blockIdx.x * SF_WARPS_PER_BLOCK + warp;
+  if (env >= D.n) return;
+  if (mask && !mask[env]) return;
+  SfEnv e;
+  sf_load_env(D, env, e);  // every lane loads the same env (broadcast)
+  SfRenderIn r;
+  sf_make_render_in(e, env, r);
+  const size_t obs_bytes = (flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+  unsigned char* o = obs + (size_t)env * obs_bytes;
+  sf_render_env(D, W, lane, r, (flags & SF_FLAG_NATIVE_OBS) ? nullptr : o, (flags & SF_FLAG_NATIVE_OBS) ? o : nullptr);
+}
+
+__global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n) return;
+  SfEnv e;
+  sf_load_env(D, env, e);
+  sf_srand(D, env, e, seeds ? seeds[env] : 1u);
+  sf_store_env(D, env, e);
+}
+
+__global__ void sf_reset_kernel(SfDev D, const unsigned char* mask, int clear_prev_vlner) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n) return;
+  if (mask && !mask[env]) return;
+  SfEnv e;
+  sf_load_env(D, env, e);
+  if (clear_prev_vlner) e.q1.w = 0;
+  sf_new_game(D, env, e);
+  sf_store_env(D, env, e);
+}
+
+// ---- state records (AoS <-> SoA), one thread per env ----
+__global__ void sf_get_state_kernel(SfDev D, int first, int count, sf_state_record* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int i = first + k;
+  const SfTables* T = D.tab;
+  SfEnv e;
+  sf_load_env(D, i, e);
+  sf_state_record r;
+  memset(&r, 0, sizeof(r));
+  unsigned core = (unsigned)e.q0.x;
+  r.ship_x = e.pos.x; r.ship_y = e.pos.y; r.ship_vx = e.vel.x; r.ship_vy = e.vel.y;
+  r.ship_angle = (double)(core & SF_CORE_ANGLE_MASK);
+  r.fortress_angle = 10.0 * ((core >> SF_CORE_FANG_SHIFT) & 63u);
+  r.fortress_last_angle = 10.0 * ((core >> SF_CORE_FLAST_SHIFT) & 63u);
+  r.missile_mask = (unsigned)e.q0.y & SF_PMASK_MISSILES;
+  r.shell_mask = ((unsigned)e.q0.y >> SF_PMASK_SHELL_SHIFT) & 0xFu;
+  for (int s = 0; s < SF_MAX_MISSILES; s++) if ((r.missile_mask >> s) & 1) {
+    double2 p = D.mpos[(size_t)s * D.n_pad + i];
+    int a = D.mang[(size_t)s * D.n_pad + i];
+    r.missile_x[s] = p.x; r.missile_y[s] = p.y; r.missile_angle[s] = a;
+    r.missile_vx[s] = SF_DMUL(20.0, T->cos_deg[a]); r.missile_vy[s] = SF_DMUL(20.0, T->sin_deg[a]);
+  }
+  for (int s = 0; s < SF_DEV_SHELLS; s++) if ((r.shell_mask >> s) & 1) {
+    double2 p = D.spos[(size_t)s * D.n_pad + i], v = D.svel[(size_t)s * D.n_pad + i];
+    r.shell_x[s] = p.x; r.shell_y[s] = p.y; r.shell_vx[s] = v.x; r.shell_vy[s] = v.y;
+    r.shell_angle[s] = D.sang[(size_t)s * D.n_pad + i];
+  }
+  r.points = __int_as_float(e.q3.x); r.raw_points = __int_as_float(e.q3.y);
+  r.ship_alive = (core & SF_CORE_SHIP_ALIVE) != 0; r.fortress_alive = (core & SF_CORE_FORT_ALIVE) != 0;
+  r.ship_death_timer = e.q0.z;
+  r.fire_timer = e.q2.x; r.thrust_timer = e.q2.y; r.left_timer = e.q2.z; r.right_timer = e.q2.w;
+  r.thrust_flag = (core & SF_CORE_THRUST) != 0; r.fire_flag = (core & SF_CORE_FIRE) != 0;
+  r.left_flag = (core & SF_CORE_LEFT) != 0; r.right_flag = (core & SF_CORE_RIGHT) != 0;
+  r.turn_flag = (r.left_flag && !r.right_flag) ? 1 : (!r.left_flag && r.right_flag) ? 2 : 0;  // game.cpp:265-270
+  r.fortress_timer = e.q0.w; r.fortress_death_timer = e.q1.x; r.fortress_vuln_timer = e.q1.y;
+  r.vulnerability = e.q1.z; r.tick = e.q3.z; r.time = e.q3.z * SF_TICK_MS;
+  r.stats[0] = e.st0.x; r.stats[1] = e.st0.y; r.stats[2] = e.st0.z; r.stats[3] = e.st0.w;
+  r.stats[4] = e.st1.x; r.stats[5] = e.st1.y; r.stats[6] = e.st1.z; r.stats[7] = e.st1.w;
+  r.stats[8] = e.st2.x; r.stats[9] = e.st2.y; r.stats[10] = e.st2.z; r.stats[11] = e.st2.w;
+  r.stats[12] = e.st3.x;
+  r.prev_vlner = e.q1.w;
+  r.rng_seed = (unsigned)e.st3.w; r.rng_count = (unsigned)e.st3.z;
+  r.ep_return = e.q3.w;
+  out[k] = r;
+}
+
+__global__ void sf_set_state_kernel(SfDev D, int first, int count, const sf_state_record* in) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int i = first + k;
+  const sf_state_record& r = in[k];
+  SfEnv e;
+  sf_load_env(D, i, e);
+  // the rand stream is re-derived from (seed, count)
+  if ((unsigned)e.st3.w != r.rng_seed || (unsigned)e.st3.z > r.rng_count) sf_srand(D, i, e, r.rng_seed);
+  while ((unsigned)e.st3.z < r.rng_count) (void)sf_rand(D, i, e);
+  unsigned core = ((unsigned)(int)r.ship_angle & SF_CORE_ANGLE_MASK) | (((unsigned)(int)(r.fortress_angle / 10.0) & 63u) << SF_CORE_FANG_SHIFT) |
+                  (((unsigned)(int)(r.fortress_last_angle / 10.0) & 63u) << SF_CORE_FLAST_SHIFT);
+  if (r.ship_alive) core |= SF_CORE_SHIP_ALIVE;
+  if (r.fortress_alive) core |= SF_CORE_FORT_ALIVE;
+  if (r.fire_flag) core |= SF_CORE_FIRE;
+  if (r.thrust_flag) core |= SF_CORE_THRUST;
+  if (r.left_flag) core |= SF_CORE_LEFT;
+  if (r.right_flag) core |= SF_CORE_RIGHT;
+  e.pos = make_double2(r.ship_x, r.ship_y); e.vel = make_double2(r.ship_vx, r.ship_vy);
+  e.q0 = make_int4((int)core, (int)((r.missile_mask & SF_PMASK_MISSILES) | ((r.shell_mask & 0xFu) << SF_PMASK_SHELL_SHIFT)), r.ship_death_timer, r.fortress_timer);
+  e.q1 = make_int4(r.fortress_death_timer, r.fortress_vuln_timer, r.vulnerability, r.prev_vlner);
+  e.q2 = make_int4(r.fire_timer, r.thrust_timer, r.left_timer, r.right_timer);
+  e.q3 = make_int4(__float_as_int(r.points), __float_as_int(r.raw_points), r.tick, r.ep_return);
+  e.st0 = make_int4(r.stats[0], r.stats[1], r.stats[2], r.stats[3]);
+  e.st1 = make_int4(r.stats[4], r.stats[5], r.stats[6], r.stats[7]);
+  e.st2 = make_int4(r.stats[8], r.stats[9], r.stats[10], r.stats[11]);
+  e.st3.x = r.stats[12];
+  for (int s = 0; s < SF_MAX_MISSILES; s++) if ((r.missile_mask >> s) & 1) {
+    D.mpos[(size_t)s * D.n_pad + i] = make_double2(r.missile_x[s], r.missile_y[s]);
+    D.mang[(size_t)s * D.n_pad + i] = (short)(int)r.missile_angle[s];
+  }
+  for (int s = 0; s < SF_DEV_SHELLS; s++) if ((r.shell_mask >> s) & 1) {
+    D.spos[(size_t)s * D.n_pad + i] = make_double2(r.shell_x[s], r.shell_y[s]);
+    D.svel[(size_t)s * D.n_pad + i] = make_double2(r.shell_vx[s], r.shell_vy[s]);
+    D.sang[(size_t)s * D.n_pad + i] = r.shell_angle[s];
+  }
+  sf_store_env(D, i, e);
+}
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct sf_handle {
+  SfDev dev;
+  int device;
+  int action_set;
+  int gametype;  // 0 youturn 1 autoturn 2 test-youturn 3 test-autoturn
+  void* slab;
+  size_t slab_bytes;
+  SfTables* h_tab;
+  // pinned staging for sf_step_host
+  int* hp_actions; unsigned char* hp_obs; int* hp_reward; unsigned char* hp_done; unsigned char* hp_kill; unsigned* hp_events;
+  int* d_actions; unsigned char* d_obs; int* d_reward; unsigned char* d_done; unsigned char* d_kill; unsigned* d_events;
+  size_t staging_obs_bytes;
+};
+
+extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
+extern "C" int sf_version(void) { return 100; }
+
+static int gametype_of(const char* s) {
+  if (!s) return -1;
+  if (!strcmp(s, "youturn")) return 0;
+  if (!strcmp(s, "autoturn")) return 1;
+  if (!strcmp(s, "test-youturn")) return 2;
+  if (!strcmp(s, "test-autoturn")) return 3;
+  return -1;
+}
+
+// P2: action tables (ssf_env.py:65-90)
+static int build_actions(int gametype, int action_set, int* km) {
+  bool youturn = gametype == 0 || gametype == 2;
+  if (action_set == 1) {
+    const int tab[5] = {0, SF_KEY_FIRE, SF_KEY_THRUST, SF_KEY_LEFT, SF_KEY_RIGHT};
+    int n = youturn ? 5 : 3;
+    for (int i = 0; i < n; i++) km[i] = tab[i];
+    return n;
+  }
+  if (action_set == 0 && !youturn) {  // np.meshgrid([0,1],[0,1]).T.reshape(-1,2): fire = bit 1, thrust = bit 0
+    for (int a = 0; a < 4; a++) km[a] = ((a >> 1) & 1 ? SF_KEY_FIRE : 0) | ((a & 1) ? SF_KEY_THRUST : 0);
+    return 4;
+  }
+  if (action_set == 0 || action_set == -1) {  // 4-key meshgrid: row = right*8 + left*4 + fire*2 + thrust
+    for (int a = 0; a < 16; a++) {
+      int m = ((a >> 1) & 1 ? SF_KEY_FIRE : 0) | ((a & 1) ? SF_KEY_THRUST : 0) | ((a >> 2) & 1 ? SF_KEY_LEFT : 0) | ((a >> 3) & 1 ? SF_KEY_RIGHT : 0);
+      km[a] = youturn ? m : (m & (SF_KEY_FIRE | SF_KEY_THRUST));
+    }
+    return 16;
+  }
+  return -1;
+}
+
+template <class T>
+static T* carve(char*& p, size_t count) {
+  T* r = reinterpret_cast<T*>(p);
+  size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+  p += bytes;
+  return r;
+}
+
+static size_t layout(SfDev& d, char* base) {
+  char* p = base;
+  size_t np = (size_t)d.n_pad;
+  d.pos = carve<double2>(p, np); d.vel = carve<double2>(p, np);
+  d.q0 = carve<int4>(p, np); d.q1 = carve<int4>(p, np); d.q2 = carve<int4>(p, np); d.q3 = carve<int4>(p, np);
+  d.st0 = carve<int4>(p, np); d.st1 = carve<int4>(p, np); d.st2 = carve<int4>(p, np); d.st3 = carve<int4>(p, np);
+  d.mpos = carve<double2>(p, np * SF_MAX_MISSILES); d.mang = carve<short>(p, np * SF_MAX_MISSILES);
+  d.spos = carve<double2>(p, np * SF_DEV_SHELLS); d.svel = carve<double2>(p, np * SF_DEV_SHELLS); d.sang = carve<double>(p, np * SF_DEV_SHELLS);
+  d.rng = carve<unsigned>(p, np * SF_RNG_WORDS);
+  d.expc = carve<unsigned char>(p, np * SF_EXP_W * SF_EXP_W);
+  d.epi = carve<unsigned long long>(p, SF_NUM_EPISODE_STATS);
+  d.tab = carve<SfTables>(p, 1);
+  return (size_t)(p - base);
+}
+
+extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int device, sf_handle** out) {
+  if (!out) return fail(SF_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int gt = gametype_of(gametype);
+  if (gt < 0) return fail(SF_ERR_INVALID, std::string("cannot initialize Game. Unknown config value: `") + (gametype ? gametype : "(null)") + "'");
+  if (n_envs <= 0) return fail(SF_ERR_INVALID, "n_envs must be positive");
+  int km[16];
+  int na = build_actions(gt, action_set, km);
+  if (na < 0) return fail(SF_ERR_INVALID, "action_set must be 1, 0 or -1");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+
+  sf_handle* h = new sf_handle();
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->action_set = action_set; h->gametype = gt;
+  SfDev& d = h->dev;
+  d.n = n_envs; d.n_pad = (n_envs + 31) & ~31;
+  d.autoturn = (gt == 1 || gt == 3);
+  bool test = gt >= 2;
+  d.shaped = !test;                      // ssf_env.py:235
+  d.destroy_fortress = test ? 100 : 1;   // configs.cpp:8,57,68
+  d.death_penalty = test ? 100 : 1;      // configs.cpp:9,58,69
+  d.missile_penalty = test ? 2.0f : (float)0.05;  // configs.cpp:10,59,70 (double -> float parameter, game.cpp:104)
+  d.num_actions = na;
+  for (int i = 0; i < 16; i++) d.keymask_of_action[i] = i < na ? km[i] : 0;
+  d.first_global_env = 0;
+
+  h->h_tab = new SfTables();
+  char err[256] = {0};
+  if (sf_build_tables(h->h_tab, err, sizeof(err))) { std::string m = err; delete h->h_tab; delete h; return fail(SF_ERR_INVALID, "table build failed: " + m); }
+
+  h->slab_bytes = layout(d, nullptr);
+  cudaError_t ce = cudaMalloc(&h->slab, h->slab_bytes);
+  if (ce != cudaSuccess) { delete h->h_tab; delete h; return fail(SF_ERR_CUDA, std::string("cudaMalloc state slab: ") + cudaGetErrorString(ce)); }
+  layout(d, (char*)h->slab);
+  CUDA_TRY(cudaMemset(h->slab, 0, h->slab_bytes));
+  CUDA_TRY(cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK)));
+  CUDA_TRY(cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK)));
+  // default seeding: every env replays srand(1) — the reference never seeds libc (game.cpp:137-148)
+  sf_seed_kernel<<<(d.n + 127) / 128, 128>>>(d, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return SF_OK;
+}
+
+extern "C" int sf_destroy(sf_handle* h) {
+  if (!h) return SF_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->slab);
+  if (h->hp_actions) cudaFreeHost(h->hp_actions);
+  if (h->hp_obs) cudaFreeHost(h->hp_obs);
+  if (h->hp_reward) cudaFreeHost(h->hp_reward);
+  if (h->hp_done) cudaFreeHost(h->hp_done);
+  if (h->hp_kill) cudaFreeHost(h->hp_kill);
+  if (h->hp_events) cudaFreeHost(h->hp_events);
+  if (h->d_actions) cudaFree(h->d_actions);
+  if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_reward) cudaFree(h->d_reward);
+  if (h->d_done) cudaFree(h->d_done);
+  if (h->d_kill) cudaFree(h->d_kill);
+  if (h->d_events) cudaFree(h->d_events);
+  delete h->h_tab;
+  delete h;
+  return SF_OK;
+}
+
+extern "C" int sf_num_envs(const sf_handle* h) { return h ? h->dev.n : -1; }
+extern "C" int sf_num_actions(const sf_handle* h) { return h ? h->dev.num_actions : -1; }
+extern "C" int sf_action_keymask(const sf_handle* h, int action) {
+  if (!h || action < 0 || action >= h->dev.num_actions) return -1;
+  return h->dev.keymask_of_action[action];
+}
+extern "C" long long sf_state_bytes(const sf_handle* h) { return h ? (long long)h->slab_bytes : -1; }
+
+extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_global_env, void* stream) {
+  if (!h) return fail(SF_ERR_INVALID, "handle is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->dev.first_global_env = first_global_env;
+  unsigned* d_seeds = nullptr;
+  if (h_seeds) {
+    CUDA_TRY(cudaMalloc(&d_seeds, sizeof(unsigned) * h->dev.n));
+    CUDA_TRY(cudaMemcpyAsync(d_seeds, h_seeds, sizeof(unsigned) * h->dev.n, cudaMemcpyHostToDevice, st));
+  }
+  sf_seed_kernel<<<(h->dev.n + 127) / 128, 128, 0, st>>>(h->dev, d_seeds);
+  CUDA_TRY(cudaGetLastError());
+  if (d_seeds) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(d_seeds)); }
+  return SF_OK;
+}
+
+static int envs_per_warp(int n) {
+  // enough warps for ~4 waves of 148 SMs x 8 resident warps; at most 32 envs per warp
+  long long target = 148ll * SF_WARPS_PER_BLOCK * 4;
+  int e = 1;
+  while (e < 32 && (long long)n / e > target) e <<= 1;
+  return e;
+}
+
+static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {
+  int blocks = (h->dev.n + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK;
+  sf_render_kernel<<<blocks, SF_BLOCK, sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK, st>>>(h->dev, d_obs, flags, d_mask);
+  CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_reset(sf_handle* h, const uint8_t* d_mask, int clear_prev_vlner, uint8_t* d_obs, int flags, void* stream) {
+  if (!h) return fail(SF_ERR_INVALID, "handle is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  sf_reset_kernel<<<(h->dev.n + 127) / 128, 128, 0, st>>>(h->dev, d_mask, clear_prev_vlner);
+  CUDA_TRY(cudaGetLastError());
+  if (d_obs) return launch_render(h, d_obs, flags, d_mask, st);
+  return SF_OK;
+}
+
+extern "C" int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream) {
+  if (!h || !d_obs) return fail(SF_ERR_INVALID, "handle or obs is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return launch_render(h, d_obs, flags, nullptr, (cudaStream_t)stream);
+}
+
+static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
+  const SfDev& d = h->dev;
+  bool render = (a.flags & SF_FLAG_RENDER) && a.obs;
+  if (render) {
+    SfRollArgs b = a;
+    b.E = envs_per_warp(d.n);
+    long long warps = ((long long)d.n + b.E - 1) / b.E;
+    int blocks = (int)((warps + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK);
+    sf_rollout_kernel<true><<<blocks, SF_BLOCK, sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK, st>>>(d, b);
+  } else {
+    sf_step_only_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d, a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, int32_t* d_reward, uint8_t* d_done,
+                       uint8_t* d_fortkill, uint32_t* d_events, int flags, void* stream) {
+  if (!h || !d_actions) return fail(SF_ERR_INVALID, "handle or actions is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SfRollArgs a;
+  a.T = 1; a.E = 1; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events;
+  return launch_rollout(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_t action_seed, long long t0, uint8_t* d_obs,
+                          int32_t* d_reward, uint8_t* d_done, uint8_t* d_fortkill, int flags, void* stream) {
+  if (!h || T <= 0) return fail(SF_ERR_INVALID, "handle is NULL or T <= 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  SfRollArgs a;
+  a.T = T; a.E = 1; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr;
+  return launch_rollout(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, long long t, int num_actions) {
+  return sf_hash_action(action_seed, (unsigned long long)global_env, (unsigned long long)t, num_actions);
+}
+
+static int ensure_staging(sf_handle* h, size_t obs_bytes) {
+  size_t n = (size_t)h->dev.n;
+  if (!h->hp_actions) {
+    CUDA_TRY(cudaMallocHost(&h->hp_actions, n * 4)); CUDA_TRY(cudaMallocHost(&h->hp_reward, n * 4));
+    CUDA_TRY(cudaMallocHost(&h->hp_done, n)); CUDA_TRY(cudaMallocHost(&h->hp_kill, n)); CUDA_TRY(cudaMallocHost(&h->hp_events, n * 4));
+    CUDA_TRY(cudaMalloc(&h->d_actions, n * 4)); CUDA_TRY(cudaMalloc(&h->d_reward, n * 4));
+    CUDA_TRY(cudaMalloc(&h->d_done, n)); CUDA_TRY(cudaMalloc(&h->d_kill, n)); CUDA_TRY(cudaMalloc(&h->d_events, n * 4));
+  }
+  if (obs_bytes > h->staging_obs_bytes) {
+    if (h->hp_obs) { cudaFreeHost(h->hp_obs); cudaFree(h->d_obs); h->hp_obs = nullptr; h->d_obs = nullptr; }
+    CUDA_TRY(cudaMallocHost(&h->hp_obs, obs_bytes));
+    CUDA_TRY(cudaMalloc(&h->d_obs, obs_bytes));
+    h->staging_obs_bytes = obs_bytes;
+  }
+  return SF_OK;
+}
+
+extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
+                            uint8_t* h_fortkill, uint32_t* h_events, int flags) {
+  if (!h || !h_actions) return fail(SF_ERR_INVALID, "handle or actions is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  size_t n = (size_t)h->dev.n;
+  size_t per = (flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+  bool render = (flags & SF_FLAG_RENDER) && h_obs;
+  int rc = ensure_staging(h, render ? n * per : 0);
+  if (rc) return rc;
+  cudaStream_t st = 0;  // legacy default stream: ordered with every other call made with stream == NULL
+  memcpy(h->hp_actions, h_actions, n * 4);
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h->hp_actions, n * 4, cudaMemcpyHostToDevice, st));
+  SfRollArgs a;
+  a.T = 1; a.E = 1; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
+  a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events;
+  rc = launch_rollout(h, a, st);
+  if (rc) return rc;
+  if (render) CUDA_TRY(cudaMemcpyAsync(h->hp_obs, h->d_obs, n * per, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->hp_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->hp_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->hp_kill, h->d_kill, n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->hp_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (render) memcpy(h_obs, h->hp_obs, n * per);
+  if (h_reward) memcpy(h_reward, h->hp_reward, n * 4);
+  if (h_done) memcpy(h_done, h->hp_done, n);
+  if (h_fortkill) memcpy(h_fortkill, h->hp_kill, n);
+  if (h_events) memcpy(h_events, h->hp_events, n * 4);
+  return SF_OK;
+}
+
+extern "C" int sf_get_state(sf_handle* h, int first, int count, sf_state_record* h_out) {
+  if (!h || !h_out || first < 0 || count < 0 || first + count > h->dev.n) return fail(SF_ERR_INVALID, "bad range");
+  if (count == 0) return SF_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  sf_state_record* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(sf_state_record) * (size_t)count));
+  CUDA_TRY(cudaDeviceSynchronize());
+  sf_get_state_kernel<<<(count + 63) / 64, 64>>>(h->dev, first, count, d);
+  cudaError_t ce = cudaMemcpy(h_out, d, sizeof(sf_state_record) * (size_t)count, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (ce != cudaSuccess) return fail(SF_ERR_CUDA, std::string("get_state: ") + cudaGetErrorString(ce));
+  return SF_OK;
+}
+
+extern "C" int sf_set_state(sf_handle* h, int first, int count, const sf_state_record* h_in) {
+  if (!h || !h_in || first < 0 || count < 0 || first + count > h->dev.n) return fail(SF_ERR_INVALID, "bad range");
+  for (int k = 0; k < count; k++) {
+    const sf_state_record& r = h_in[k];
+    if (r.ship_angle != (double)(int)r.ship_angle || r.ship_angle < 0 || r.ship_angle >= 360)
+      return fail(SF_ERR_UNSUPPORTED, "ship_angle must be an integer degree in [0,360) (it always is in the reference: game.cpp:148,317-324)");
+    double fa = r.fortress_angle / 10.0, fl = r.fortress_last_angle / 10.0;
+    if (fa != (double)(int)fa || fa < 0 || fa >= 36 || fl != (double)(int)fl || fl < 0 || fl >= 36)
+      return fail(SF_ERR_UNSUPPORTED, "fortress angles must be multiples of 10 in [0,360) (game.cpp:40-41,206)");
+    if (r.shell_mask >> SF_DEV_SHELLS) return fail(SF_ERR_UNSUPPORTED, "shell slots >= 4 can never be alive (at most 3 shells are in flight)");
+    if (r.missile_mask >> SF_MAX_MISSILES) return fail(SF_ERR_INVALID, "missile_mask has more than 20 bits");
+    for (int s = 0; s < SF_MAX_MISSILES; s++) if ((r.missile_mask >> s) & 1) {
+      double a = r.missile_angle[s];
+      if (a != (double)(int)a || a < 0 || a >= 360) return fail(SF_ERR_UNSUPPORTED, "missile angles must be integer degrees in [0,360)");
+    }
+  }
+  if (count == 0) return SF_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  sf_state_record* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(sf_state_record) * (size_t)count));
+  cudaError_t ce = cudaMemcpy(d, h_in, sizeof(sf_state_record) * (size_t)count, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    sf_set_state_kernel<<<(count + 63) / 64, 64>>>(h->dev, first, count, d);
+    ce = cudaDeviceSynchronize();
+  }
+  cudaFree(d);
+  if (ce != cudaSuccess) return fail(SF_ERR_CUDA, std::string("set_state: ") + cudaGetErrorString(ce));
+  return SF_OK;
+}
+
+__global__ void sf_epi_copy_kernel(unsigned long long* epi, long long* out, int reset) {
+  int k = threadIdx.x;
+  if (k < SF_NUM_EPISODE_STATS) {
+    out[k] = (long long)epi[k];
+    if (reset) epi[k] = 0;
+  }
+}
+
+extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream) {
+  if (!h || !d_out) return fail(SF_ERR_INVALID, "handle or out is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  sf_epi_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->dev.epi, d_out, reset);
+  CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_background(const sf_handle* h, uint8_t* h_native, uint8_t* h_obs) {
+  if (!h) return fail(SF_ERR_INVALID, "handle is NULL");
+  if (h_native)
+    for (int r = 0; r < SF_NAT_H; r++) memcpy(h_native + r * SF_NAT_W, h->h_tab->bg_nat + r * SF_NAT_STRIDE, SF_NAT_W);
+  if (h_obs) memcpy(h_obs, h->h_tab->bg_obs, 84 * 84);
+  return SF_OK;
+}

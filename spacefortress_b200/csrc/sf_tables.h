@@ -1,0 +1,65 @@
+// sf_tables.h — static tables built once on the host at sf_create() and uploaded to the GPU.
+// Everything here depends only on constants of the reference (configs.cpp, wireframe.cpp, draw.cpp),
+// never on per-env state: background hexagons, the fortress (fixed position, 36 possible angles),
+// the fortress explosion, score digits, resize weights, trig LUTs for integer degrees.
+#pragma once
+#include <stdint.h>
+
+#define SF_NAT_W 90  // int(450*.2), ssf_env.py:57
+#define SF_NAT_H 92  // int(460*.2), ssf_env.py:58
+
+#define SF_NAT_STRIDE 96           // native tile row stride in bytes (16-byte aligned rows)
+#define SF_FORT_W 17               // fortress sprite box (native px)
+#define SF_FORT_X0 37
+#define SF_FORT_Y0 39
+#define SF_EXP_W 28                // explosion box: centre px - 13 .. centre px + 14
+#define SF_EXP_LAYERS 4
+#define SF_FEXP_X0 (45 - 13)
+#define SF_FEXP_Y0 (47 - 13)
+#define SF_TEXT_X0 32              // score strip (native px)
+#define SF_TEXT_Y0 1
+#define SF_TEXT_W 27
+#define SF_TEXT_H 5
+#define SF_BAR_X0 25
+#define SF_BAR_Y0 88
+#define SF_BAR_W 40
+#define SF_BAR_H 3
+#define SF_EXP_STROKES 85          // 7 rings x 12 arcs + the r=7 circle
+#define SF_EXP_QUADS 100           // 84 arc quads + 16 circle quads
+#define SF_MAX_TAPS 3
+
+struct SfTables {
+  // trig for integer degrees, computed with the host libm exactly as the reference does:
+  // cos(deg2rad(a)) with deg2rad(a) = a*M_PI/180 (vector.cpp:34-36, game.cpp:184-185,328-329)
+  double cos_deg[360], sin_deg[360];
+  // atan2(dy,dx) for the 8 directions where a ceil() downstream could flip on a 1-ulp difference
+  // (index = octant*45 degrees: E, SE(+y), S, SW, W, NW, N, NE in screen coordinates), from the host libm
+  double atan2_oct[8];
+  double ship_start_vx, ship_start_vy;  // cos/sin(deg2rad(-60)), configs.cpp:43-44
+  // hexagons (hexagon.cpp:13-48): vertex i and the edge normal (nx,ny) of edge i->i+1; [0]=big (200), [1]=small (40)
+  double hex_px[2][6], hex_py[2][6], hex_nx[2][6], hex_ny[2][6];
+  // resize tables (cv2 INTER_AREA 92x90 -> 84x84, rl/envs.py:29)
+  int xt_cnt[84], xt_si[84][SF_MAX_TAPS];
+  float xt_a[84][SF_MAX_TAPS];
+  int yt_cnt[84], yt_si[84][SF_MAX_TAPS];
+  float yt_a[84][SF_MAX_TAPS];
+  int col_out0[SF_NAT_W], col_out1[SF_NAT_W];  // first/last output column reading native column c
+  int row_out0[SF_NAT_H], row_out1[SF_NAT_H];
+  // explosion geometry relative to the fixed-point centre: per quad 4 corners (dx,dy)
+  short exp_quad[SF_EXP_QUADS][8];
+  unsigned char exp_colour[SF_EXP_STROKES];
+  // frames
+  unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];      // hexagons on black, native
+  unsigned char bg_obs[84 * 84];                       // resize(bg_nat)
+  unsigned char fort_alpha[36][SF_FORT_W * SF_FORT_W]; // fortress wireframe coverage per sector angle
+  unsigned char fexp_alpha[SF_EXP_LAYERS][SF_EXP_W * SF_EXP_W];  // fortress explosion, ordered layers
+  unsigned char fexp_colour[SF_EXP_LAYERS][SF_EXP_W * SF_EXP_W];
+  int fexp_layers;
+  unsigned char text_alpha[10][SF_TEXT_H * SF_TEXT_W]; // digit d drawn in the slot owning each column
+  unsigned char text_slot[SF_TEXT_W];                  // which of the 7 digit slots owns a strip column (255: none)
+  unsigned char bar_alpha[SF_BAR_H];                   // per-row coverage of the vulnerability bar
+  unsigned char colour_bar_bg, colour_bar_fg, colour_bar_kill, colour_text, colour_white;
+};
+
+// builds the tables on the host; returns 0 on success, else a message in err
+int sf_build_tables(SfTables* t, char* err, int errcap);

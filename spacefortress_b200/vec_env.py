@@ -1,0 +1,284 @@
+"""SFVecEnv — batched drop-in for the reference's vectorised env usage.
+
+The reference trains through ``gym_vecenv.SubprocVecEnv([make_env(...)] * N)`` (rl/train.py:30-34): one OS
+process per env, one pipe round-trip per env per step, numpy in/out. SFVecEnv keeps that interface
+(``reset() -> [N,1,84,84] u8``, ``step(actions) -> (obs, rew, done, infos)``, ``close()``,
+``observation_space``/``action_space``, ``num_envs``, ``step_async/step_wait``; rl/train.py:35-41,60,80-85,179)
+but all N envs live in one SoA slab on one GPU and one kernel launch advances them.
+
+* ``step(np.ndarray)``  -> numpy results through the C-ABI host path (sf_step_host): literal drop-in.
+* ``step(torch.Tensor on cuda)`` -> torch CUDA tensors, no host round trip (sf_step).
+* ``rollout(T, actions=None)`` -> T steps in one launch (sf_rollout), time-major outputs.
+
+Auto-reset follows gym_vecenv's worker loop: when an env is done its returned observation is the first
+frame of the next episode; reward/done/info belong to the terminal step.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .spaces import Box, Discrete
+
+GAMETYPE_OF_ENV_ID = {
+    "SpaceFortress-youturn-image-v0": "youturn",
+    "SpaceFortress-autoturn-image-v0": "autoturn",
+    "SpaceFortress-testyouturn-image-v0": "test-youturn",
+    "SpaceFortress-testautoturn-image-v0": "test-autoturn",
+}
+GAMETYPES = ("youturn", "autoturn", "test-youturn", "test-autoturn")
+
+
+def _gametype(name):
+    if name in GAMETYPE_OF_ENV_ID:
+        return GAMETYPE_OF_ENV_ID[name]
+    return name  # unknown names are rejected by sf_create like pymodule.cpp:341
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class SFVecEnv(object):
+    def __init__(self, env_id="SpaceFortress-youturn-image-v0", num_envs=16, device=0, action_set=1, seeds=None,
+                 render=True, native_obs=False, autoreset=True, first_global_env=0):
+        self.L = _lib.lib()
+        self.gametype = _gametype(env_id)
+        self.num_envs = int(num_envs)
+        self.device_index = int(device) if not isinstance(device, str) else int(device.split(":")[1]) if ":" in device else 0
+        self.render_on = bool(render)
+        self.native_obs = bool(native_obs)
+        self.autoreset = bool(autoreset)
+        h = C.c_void_p()
+        _lib.check(self.L.sf_create(self.gametype.encode(), int(action_set), self.num_envs, self.device_index, C.byref(h)))
+        self.h = h
+        self.num_actions = self.L.sf_num_actions(self.h)
+        self.action_space = Discrete(self.num_actions)
+        self.obs_shape = (1, _lib.NATIVE_H, _lib.NATIVE_W) if native_obs else (1, _lib.OBS_H, _lib.OBS_W)
+        self.observation_space = Box(0, 255, self.obs_shape, dtype=np.uint8)  # rl/envs.py:21-25
+        self.first_global_env = int(first_global_env)
+        if seeds is not None or first_global_env:
+            self.seed_streams(seeds, first_global_env)
+        self._flags = (_lib.FLAG_RENDER if render else 0) | (_lib.FLAG_NATIVE_OBS if native_obs else 0) | \
+                      (0 if autoreset else _lib.FLAG_NO_AUTORESET)
+        self._t = 0
+        self._pending = None
+        self._bufs = None
+        self._np = None
+        self._constructed = False
+        self.closed = False
+
+    # ------------------------------------------------------------------ helpers
+    def _device(self):
+        return _torch().device("cuda", self.device_index)
+
+    def _torch_bufs(self):
+        if self._bufs is None:
+            torch = _torch()
+            dev = self._device()
+            n = self.num_envs
+            self._bufs = dict(
+                obs=torch.empty((n,) + self.obs_shape, dtype=torch.uint8, device=dev),
+                reward=torch.empty(n, dtype=torch.int32, device=dev),
+                done=torch.empty(n, dtype=torch.uint8, device=dev),
+                kill=torch.empty(n, dtype=torch.uint8, device=dev),
+                events=torch.empty(n, dtype=torch.int32, device=dev),
+            )
+        return self._bufs
+
+    def _np_bufs(self):
+        if self._np is None:
+            n = self.num_envs
+            self._np = dict(obs=np.empty((n,) + self.obs_shape, np.uint8), reward=np.empty(n, np.int32),
+                            done=np.empty(n, np.uint8), kill=np.empty(n, np.uint8), events=np.empty(n, np.uint32))
+        return self._np
+
+    @staticmethod
+    def _stream_ptr():
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ API
+    def seed_streams(self, seeds=None, first_global_env=0):
+        """Per-env libc-rand() stream seeds (default: 1 for every env, the reference's behaviour since it
+        never calls srand — game.cpp:137-148). An int s gives seeds s+i (rl/envs.py:13 `seed + rank`)."""
+        if seeds is None:
+            ptr = None
+        else:
+            if np.isscalar(seeds):
+                seeds = int(seeds) + self.first_global_env + np.arange(self.num_envs)
+            arr = np.ascontiguousarray(seeds, dtype=np.uint32)
+            assert arr.shape == (self.num_envs,)
+            ptr = arr.ctypes.data_as(C.c_void_p)
+        _lib.check(self.L.sf_seed(self.h, ptr, int(first_global_env), None))
+        self.first_global_env = int(first_global_env)
+        return [seeds]
+
+    def reset(self, to_numpy=True, clear_prev_vlner=None):
+        """SSF_Env.reset for every env. The first call also plays the role of SSF_Env.__init__ (prev_vlner=0);
+        later calls keep prev_vlner (quirk Q7, ssf_env.py:92)."""
+        if clear_prev_vlner is None:
+            clear_prev_vlner = not self._constructed
+        self._constructed = True
+        torch = _torch()
+        b = self._torch_bufs()
+        obs_ptr = C.c_void_p(b["obs"].data_ptr()) if self.render_on else None
+        _lib.check(self.L.sf_reset(self.h, None, int(bool(clear_prev_vlner)), obs_ptr, self._flags, self._stream_ptr()))
+        self._t = 0
+        if not self.render_on:
+            return None
+        if to_numpy:
+            return b["obs"].cpu().numpy()
+        return b["obs"]
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        a, self._pending = self._pending, None
+        return self.step(a)
+
+    def step(self, actions):
+        if isinstance(actions, np.ndarray) or isinstance(actions, (list, tuple)):
+            return self._step_numpy(np.asarray(actions))
+        return self._step_torch(actions)
+
+    def _step_numpy(self, actions):
+        n = self.num_envs
+        a = np.ascontiguousarray(actions.reshape(n), dtype=np.int32)
+        b = self._np_bufs()
+        _lib.check(self.L.sf_step_host(
+            self.h, a.ctypes.data_as(C.c_void_p), b["obs"].ctypes.data_as(C.c_void_p) if self.render_on else None,
+            b["reward"].ctypes.data_as(C.c_void_p), b["done"].ctypes.data_as(C.c_void_p),
+            b["kill"].ctypes.data_as(C.c_void_p), b["events"].ctypes.data_as(C.c_void_p), self._flags))
+        self._t += 1
+        self.last_events = b["events"].copy()
+        infos = tuple(bool(k) for k in b["kill"])  # the reference's info is a bool per env (ssf_env.py:233,250)
+        return (b["obs"].copy() if self.render_on else None), b["reward"].astype(np.int64), b["done"].astype(bool), infos
+
+    def _step_torch(self, actions):
+        torch = _torch()
+        b = self._torch_bufs()
+        a = actions.to(device=self._device(), dtype=torch.int32).reshape(self.num_envs).contiguous()
+        _lib.check(self.L.sf_step(
+            self.h, C.c_void_p(a.data_ptr()), C.c_void_p(b["obs"].data_ptr()) if self.render_on else None,
+            C.c_void_p(b["reward"].data_ptr()), C.c_void_p(b["done"].data_ptr()), C.c_void_p(b["kill"].data_ptr()),
+            C.c_void_p(b["events"].data_ptr()), self._flags, self._stream_ptr()))
+        self._t += 1
+        return (b["obs"] if self.render_on else None), b["reward"], b["done"].bool(), b["kill"].bool()
+
+    def rollout(self, T, actions=None, action_seed=0, out=None, want=("obs", "reward", "done", "kill")):
+        """T steps in one launch. actions: int32 CUDA tensor [T,N] or None for the synthetic counter-hash
+        policy. Returns a dict of time-major CUDA tensors."""
+        torch = _torch()
+        dev = self._device()
+        n = self.num_envs
+        if out is None:
+            out = {}
+            if "obs" in want and self.render_on:
+                out["obs"] = torch.empty((T, n) + self.obs_shape, dtype=torch.uint8, device=dev)
+            if "reward" in want:
+                out["reward"] = torch.empty((T, n), dtype=torch.int32, device=dev)
+            if "done" in want:
+                out["done"] = torch.empty((T, n), dtype=torch.uint8, device=dev)
+            if "kill" in want:
+                out["kill"] = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        aptr = None
+        if actions is not None:
+            actions = actions.to(device=dev, dtype=torch.int32).reshape(T, n).contiguous()
+            aptr = C.c_void_p(actions.data_ptr())
+
+        def p(k):
+            return C.c_void_p(out[k].data_ptr()) if k in out else None
+        flags = self._flags if "obs" in out else (self._flags & ~_lib.FLAG_RENDER)
+        _lib.check(self.L.sf_rollout(self.h, int(T), aptr, int(action_seed), int(self._t), p("obs"), p("reward"), p("done"),
+                                     p("kill"), flags, self._stream_ptr()))
+        self._t += T
+        return out
+
+    def synthetic_actions(self, T, action_seed=0, t0=None):
+        """Host materialisation of the stream sf_rollout(actions=None) uses (parity runs)."""
+        t0 = self._t if t0 is None else t0
+        a = np.empty((T, self.num_envs), np.int32)
+        for t in range(T):
+            for i in range(self.num_envs):
+                a[t, i] = self.L.sf_synthetic_action(int(action_seed), self.first_global_env + i, t0 + t, self.num_actions)
+        return a
+
+    def render_frames(self, native=False, to_numpy=True):
+        """Game.draw() of the current state without stepping."""
+        torch = _torch()
+        shape = (self.num_envs, _lib.NATIVE_H, _lib.NATIVE_W) if native else (self.num_envs, _lib.OBS_H, _lib.OBS_W)
+        o = torch.empty(shape, dtype=torch.uint8, device=self._device())
+        _lib.check(self.L.sf_render(self.h, C.c_void_p(o.data_ptr()), _lib.FLAG_NATIVE_OBS if native else 0, self._stream_ptr()))
+        return o.cpu().numpy() if to_numpy else o
+
+    def get_state(self, first=0, count=None):
+        count = self.num_envs - first if count is None else count
+        arr = (_lib.StateRecord * count)()
+        _lib.check(self.L.sf_get_state(self.h, first, count, arr))
+        return arr
+
+    def set_state(self, records, first=0):
+        count = len(records)
+        arr = records if isinstance(records, C.Array) else (_lib.StateRecord * count)(*records)
+        _lib.check(self.L.sf_set_state(self.h, first, count, arr))
+
+    def episode_stats(self, reset=True, all_reduce=True):
+        """Finished-episode statistics since the last reset of the accumulators, summed over all ranks when
+        torch.distributed is initialised (one small all-reduce per rollout; replaces rl/train.py:81-88)."""
+        torch = _torch()
+        out = torch.zeros(_lib.NUM_EPISODE_STATS, dtype=torch.int64, device=self._device())
+        _lib.check(self.L.sf_episode_stats(self.h, C.c_void_p(out.data_ptr()), int(bool(reset)), self._stream_ptr()))
+        from .dist import all_reduce_episode_stats
+        if all_reduce:
+            out = all_reduce_episode_stats(out)
+        vals = out.cpu().tolist()
+        return dict(zip(_lib.EPISODE_STAT_NAMES, vals))
+
+    def state_bytes(self):
+        return self.L.sf_state_bytes(self.h)
+
+    def close(self):
+        if not self.closed and getattr(self, "h", None):
+            self.L.sf_destroy(self.h)
+            self.h = None
+            self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EnvThunk(object):
+    """What make_env() returns: rl/envs.py:10-16 builds a closure; here it only carries the parameters."""
+
+    def __init__(self, env_id, seed, rank):
+        self.env_id, self.seed, self.rank = env_id, seed, rank
+
+    def __call__(self):
+        from .gym.envs import SSF_Env
+        from .rl_envs import WrapPyTorch
+        env = SSF_Env(gametype=_gametype(self.env_id))
+        env.seed(self.seed + self.rank)
+        return WrapPyTorch(env)
+
+
+class SubprocVecEnv(SFVecEnv):
+    """gym_vecenv.SubprocVecEnv(list_of_thunks) look-alike (rl/train.py:32): the thunks are not called,
+    one batched GPU env replaces the N worker processes."""
+
+    def __init__(self, env_fns, device=0, **kw):
+        env_fns = list(env_fns)
+        ids = set(getattr(f, "env_id", None) for f in env_fns)
+        if len(ids) != 1 or None in ids:
+            raise ValueError("SubprocVecEnv expects thunks from spacefortress_b200.make_env for ONE env id")
+        SFVecEnv.__init__(self, env_id=ids.pop(), num_envs=len(env_fns), device=device, **kw)
+
+
+class DummyVecEnv(SubprocVecEnv):
+    """gym_vecenv.DummyVecEnv look-alike (rl/train.py:34, rl/evaluate.py:40-47)."""
+    pass
