@@ -7,7 +7,7 @@
  *
  * rand(): the reference calls the process-global libc rand() and never seeds
  * it (game.cpp:137-138,148). This file defines rand() itself and the Makefile
- * links with -Bsymbolic-functions, so every Game instance gets its own glibc random_r() stream
+ * links with -Bsymbolic (and a private static libstdc++), so every Game instance gets its own glibc random_r() stream
  * (real glibc TYPE_3 generator, so this also pins the restatement in
  * sf_oracle.c against the real libc).
  *

@@ -49,8 +49,8 @@ struct SfTables {
   short exp_quad[SF_EXP_QUADS][8];
   unsigned char exp_colour[SF_EXP_STROKES];
   // frames
-  unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];      // hexagons on black, native
-  unsigned char bg_obs[84 * 84];                       // resize(bg_nat)
+  alignas(16) unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];      // hexagons on black, native (read with 128-bit loads)
+  alignas(16) unsigned char bg_obs[84 * 84];                       // resize(bg_nat)
   unsigned char fort_alpha[36][SF_FORT_W * SF_FORT_W]; // fortress wireframe coverage per sector angle
   unsigned char fexp_alpha[SF_EXP_LAYERS][SF_EXP_W * SF_EXP_W];  // fortress explosion, ordered layers
   unsigned char fexp_colour[SF_EXP_LAYERS][SF_EXP_W * SF_EXP_W];
