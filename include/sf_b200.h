@@ -158,7 +158,8 @@ int sf_background(const sf_handle* h, uint8_t* h_native /*[92*90]*/, uint8_t* h_
 
 /* Host-only (no GPU needed): compose the static layers of a frame from the same tables the kernels use
  * (background hexagons, fortress sprite or fortress explosion, score digits, vulnerability bar) into a
- * native 92x90 frame. Used by the CPU test-suite to check the table builder. */
+ * native 92x90 frame. Used by the CPU test-suite to check the table builder. fortress_alive < 0, points < 0
+ * or vulnerability < 0 leave that layer out (all three: the bare background). */
 int sf_host_static_frame(int fortress_alive, int fortress_angle_deg, int points, int vulnerability, int kill_bar,
                          uint8_t* h_native /*[92*90]*/, uint8_t* h_bg_obs /*[84*84] or NULL*/);
 

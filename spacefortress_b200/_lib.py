@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsf_b200.so")
 
-SF_OK = 0
+SF_OK, SF_ERR_INVALID, SF_ERR_CUDA, SF_ERR_UNSUPPORTED = 0, 1, 2, 3
 MAX_MISSILES = 20
 MAX_SHELLS = 20
 NUM_STATS = 13

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(SF_BLOCK) sf_rollout_kernel(SfDev D, SfRollArg
   const bool mine = lane < A.E && env < D.n;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const size_t obs_bytes = (A.flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+  if (RENDER) sf_warp_smem_init(W, lane);
 
   for (int t = 0; t < A.T; t++) {
     SfEnv e;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(SF_BLOCK) sf_render_kernel(SfDev D, unsigned c
   const int env = blockIdx.x * SF_WARPS_PER_BLOCK + warp;
   if (env >= D.n) return;
   if (mask && !mask[env]) return;
+  sf_warp_smem_init(W, lane);
   SfEnv e;
   sf_load_env(D, env, e);  // every lane loads the same env (broadcast)
   SfRenderIn r;

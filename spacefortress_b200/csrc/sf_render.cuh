@@ -214,6 +214,13 @@ __device__ __forceinline__ unsigned char sf_resample(const SfWarpSmem& W, const 
   return (unsigned char)__float2int_rn(sum);
 }
 
+// once per warp at kernel start: the span accumulators must start at zero (every stroke leaves them zeroed)
+__device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
+  for (int k = lane; k < SF_ACC_CELLS; k += 32) W.acc[k] = 0;
+  if (lane == 0) W.nrect = 0;
+  __syncwarp();
+}
+
 struct SfRenderIn {  // warp-uniform view of one env
   int env;
   unsigned core, pmask;

@@ -376,13 +376,13 @@ extern "C" int sf_host_static_frame(int fortress_alive, int fortress_angle_deg, 
   if (!h_native || fortress_angle_deg < 0 || fortress_angle_deg >= 360 || fortress_angle_deg % 10) return SF_ERR_INVALID;
   std::vector<unsigned char> nat(T->bg_nat, T->bg_nat + SF_NAT_H * SF_NAT_STRIDE);
   auto px = [&](int x, int y) -> unsigned char& { return nat[y * SF_NAT_STRIDE + x]; };
-  if (fortress_alive) {
+  if (fortress_alive > 0) {
     const unsigned char* A = T->fort_alpha[fortress_angle_deg / 10];
     for (int i = 0; i < SF_FORT_W * SF_FORT_W; i++) if (A[i]) {
       unsigned char& d = px(SF_FORT_X0 + i % SF_FORT_W, SF_FORT_Y0 + i / SF_FORT_W);
       d = (unsigned char)sf_blend(d, T->colour_white, A[i]);
     }
-  } else {
+  } else if (fortress_alive == 0) {
     for (int i = 0; i < SF_EXP_W * SF_EXP_W; i++)
       for (int l = 0; l < T->fexp_layers && T->fexp_alpha[l][i]; l++) {
         unsigned char& d = px(SF_FEXP_X0 + i % SF_EXP_W, SF_FEXP_Y0 + i / SF_EXP_W);
@@ -390,7 +390,7 @@ extern "C" int sf_host_static_frame(int fortress_alive, int fortress_angle_deg, 
       }
   }
   int pts = std::min(std::max(points, 0), 9999999);
-  for (int i = 0; i < SF_TEXT_H * SF_TEXT_W; i++) {
+  for (int i = 0; i < SF_TEXT_H * SF_TEXT_W && points >= 0; i++) {
     int slot = T->text_slot[i % SF_TEXT_W];
     if (slot >= 7) continue;
     int div = 1;
@@ -399,7 +399,7 @@ extern "C" int sf_host_static_frame(int fortress_alive, int fortress_angle_deg, 
     if (a) { unsigned char& d = px(SF_TEXT_X0 + i % SF_TEXT_W, SF_TEXT_Y0 + i / SF_TEXT_W); d = (unsigned char)sf_blend(d, T->colour_text, a); }
   }
   int filled = 4 * std::min(vulnerability, 10);
-  for (int i = 0; i < SF_BAR_H * SF_BAR_W; i++) {
+  for (int i = 0; i < SF_BAR_H * SF_BAR_W && vulnerability >= 0; i++) {
     int r = i / SF_BAR_W, c = i % SF_BAR_W;
     unsigned char& d = px(SF_BAR_X0 + c, SF_BAR_Y0 + r);
     unsigned v = sf_blend(d, T->colour_bar_bg, T->bar_alpha[r]);

@@ -1,0 +1,341 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C-ABI, against the oracle on the same seeded
+inputs. Bars (BASELINE.json north_star): integer state / events / episode boundaries bit-exact; continuous
+kinematics <= 1e-5 relative per step when teacher-forced (observed: bit-exact except shells, which carry the
+device cos/sin); frames >= 99.9 % identical pixels with max |delta| <= 2 (observed: bit-exact)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import scripted_kill_policy
+from oracle.oracle import OracleEnv, Record, draw_native, draw_obs
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GAMETYPES = ["youturn", "autoturn", "test-youturn", "test-autoturn"]
+FLOAT_REL_TOL = 1e-5  # north_star: continuous kinematics within 1e-5 relative per step
+FRAME_MATCH_FRACTION = 0.999
+FRAME_MAX_DELTA = 2
+
+
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def make(gametype, n, **kw):
+    torch_cuda()
+    from spacefortress_b200 import SFVecEnv
+    return SFVecEnv(gametype, num_envs=n, device=0, **kw)
+
+
+def to_oracle_record(g):
+    r = Record()
+    C.memmove(C.byref(r), C.byref(g), C.sizeof(Record))
+    return r
+
+
+def assert_state_close(o, g, ctx):
+    assert o.int_state() == to_oracle_record(g).int_state(), ctx
+    assert list(o.stats) == list(g.stats), ctx
+    fo, fg = o.float_state(), to_oracle_record(g).float_state()
+    for k in fo:
+        a, b = np.atleast_1d(np.array(fo[k], dtype=np.float64)), np.atleast_1d(np.array(fg[k], dtype=np.float64))
+        if k.startswith("shell_"):
+            assert np.all(np.abs(a - b) <= FLOAT_REL_TOL * np.maximum(1.0, np.abs(a))), (ctx, k, a, b)
+        else:
+            assert np.array_equal(a, b), (ctx, k, a, b)  # everything not touched by device cos/sin is bit-exact
+
+
+def assert_frame_close(expected, got, ctx):
+    d = np.abs(expected.astype(np.int32) - got.astype(np.int32))
+    assert d.max() <= FRAME_MAX_DELTA, (ctx, int(d.max()))
+    assert (d == 0).mean() >= FRAME_MATCH_FRACTION, (ctx, float((d == 0).mean()))
+
+
+@pytest.mark.parametrize("gametype", GAMETYPES)
+def test_free_running_trace_parity(gametype):
+    n, T = 48, 700
+    seeds = np.arange(1, n + 1)
+    env = make(gametype, n, seeds=seeds)
+    obs = env.reset()
+    orc = [OracleEnv(gametype, int(s)) for s in seeds]
+    for i in range(n):
+        assert np.array_equal(orc[i].obs(), obs[i, 0]), "first frame env %d" % i
+    rng = np.random.RandomState(11)
+    for t in range(T):
+        a = rng.randint(0, env.num_actions, size=n)
+        obs, rew, done, info = env.step(a)
+        ev = env.last_events
+        for i in range(n):
+            r, d, k, e = orc[i].step(orc[i].keymask(int(a[i])))
+            assert (r, d, k, e) == (int(rew[i]), bool(done[i]), bool(info[i]), int(ev[i])), (gametype, t, i)
+        if t % 50 == 49:
+            recs = env.get_state()
+            for i in range(n):
+                assert_state_close(orc[i].get_state(), recs[i], (gametype, t, i))
+            for i in range(0, n, 5):
+                assert_frame_close(orc[i].obs(), obs[i, 0], (gametype, t, i))
+    env.close()
+
+
+def test_config1_youturn_single_env_10k_steps_with_frames():
+    """BASELINE.json configs[0]: youturn, 1 env, seeded random-action rollout of 10k steps (crosses the
+    episode boundary at tick 5295), state trace + 84x84 frames, through the on-device rollout path."""
+    torch = torch_cuda()
+    T = 10000
+    env = make("youturn", 1)
+    env.reset()
+    o = OracleEnv("youturn", 1)
+    rng = np.random.RandomState(2)
+    actions = rng.randint(0, 5, size=(T, 1)).astype(np.int32)
+    out = env.rollout(T, actions=torch.from_numpy(actions))
+    obs = out["obs"].cpu().numpy(); rew = out["reward"].cpu().numpy(); done = out["done"].cpu().numpy(); kill = out["kill"].cpu().numpy()
+    ndone = 0
+    for t in range(T):
+        r, d, k, _ = o.step(o.keymask(int(actions[t, 0])))
+        assert (r, d, k) == (int(rew[t, 0]), bool(done[t, 0]), bool(kill[t, 0])), t
+        if d:
+            ndone += 1
+            assert t == 5294
+            o.reset()
+        if t % 7 == 0 or d or 5290 <= t <= 5300:
+            assert_frame_close(o.obs(), obs[t, 0, 0], t)
+    assert ndone == 1
+    assert_state_close(o.get_state(), env.get_state()[0], "final")
+    env.close()
+
+
+def test_golden_fixtures_replayed_on_gpu():
+    torch = torch_cuda()
+    for name in ("youturn", "autoturn", "test-youturn", "test-autoturn", "autoturn_kill"):
+        z = np.load(os.path.join(GOLD, "trace_%s.npz" % name))
+        gametype = "autoturn" if name == "autoturn_kill" else name
+        from spacefortress_b200 import SFVecEnv, _lib
+        env = SFVecEnv(gametype, num_envs=1, device=0, render=False)
+        env._flags |= _lib.FLAG_ACTIONS_ARE_KEYMASKS
+        env.reset()
+        T = len(z["keymask"])
+        km = torch.from_numpy(z["keymask"].astype(np.int32).reshape(T, 1))
+        recs = {int(t): z["records"][k] for k, t in enumerate(z["record_t"])}
+        pos = 0
+        while pos < T:  # replay in chunks of 100 so the stored records can be compared
+            out = env.rollout(100, actions=km[pos:pos + 100])
+            assert np.array_equal(out["reward"].cpu().numpy()[:, 0], z["reward"][pos:pos + 100]), (name, pos)
+            assert np.array_equal(out["done"].cpu().numpy()[:, 0], z["done"][pos:pos + 100]), (name, pos)
+            assert np.array_equal(out["kill"].cpu().numpy()[:, 0], z["fort_kill"][pos:pos + 100]), (name, pos)
+            pos += 100
+            ref = Record(); C.memmove(C.byref(ref), bytes(recs[pos]), C.sizeof(Record))
+            assert_state_close(ref, env.get_state()[0], (name, pos))
+        env.close()
+
+
+def test_kill_path_and_events():
+    env = make("autoturn", 4, render=False)
+    from spacefortress_b200 import _lib
+    env._flags |= _lib.FLAG_ACTIONS_ARE_KEYMASKS
+    env.reset()
+    orc = [OracleEnv("autoturn", 1) for _ in range(4)]
+    kills = 0
+    for t in range(3000):
+        km = np.array([scripted_kill_policy(t + 3 * i, orc[i].get_state().vulnerability) for i in range(4)], np.int32)
+        _, rew, done, info = env.step(km)
+        for i in range(4):
+            r, d, k, e = orc[i].step(int(km[i]))
+            assert (r, d, k, e) == (int(rew[i]), bool(done[i]), bool(info[i]), int(env.last_events[i])), (t, i)
+            kills += k
+    assert kills >= 8
+    for i, g in enumerate(env.get_state()):
+        assert_state_close(orc[i].get_state(), g, i)
+    env.close()
+
+
+def test_teacher_forced_single_steps():
+    """load state -> one step -> compare (kinematics tolerance 1e-5 relative, ints exact)."""
+    n = 64
+    for gametype in ("youturn", "autoturn"):
+        env = make(gametype, n, render=False)
+        from spacefortress_b200 import _lib
+        env._flags |= _lib.FLAG_ACTIONS_ARE_KEYMASKS
+        env.reset()
+        src = [OracleEnv(gametype, 100 + i) for i in range(n)]
+        rng = np.random.RandomState(3)
+        for rnd in range(12):
+            for s in src:
+                for _ in range(int(rng.randint(1, 60))):
+                    s.step(int(rng.randint(16)))
+            recs = [s.get_state() for s in src]
+            env.set_state([to_gpu_record(r) for r in recs])
+            back = env.get_state()
+            for i in range(n):
+                assert_state_close(recs[i], back[i], ("roundtrip", rnd, i))
+            km = rng.randint(0, 16, size=n).astype(np.int32)
+            _, rew, done, info = env.step(km)
+            after = env.get_state()
+            for i in range(n):
+                r, d, k, e = src[i].step(int(km[i]))
+                assert (r, d, k, e) == (int(rew[i]), bool(done[i]), bool(info[i]), int(env.last_events[i])), (gametype, rnd, i)
+                assert_state_close(src[i].get_state(), after[i], (gametype, rnd, i))
+        env.close()
+
+
+def to_gpu_record(r):
+    from spacefortress_b200 import _lib
+    g = _lib.StateRecord()
+    C.memmove(C.byref(g), C.byref(r), C.sizeof(Record))
+    g.ep_return = 0
+    return g
+
+
+def test_frames_from_crafted_states():
+    """Edge cases of the renderer: dead ship (explosion) near the border, dead fortress, objects partly or
+    fully off the 90x92 surface, many missiles, a shell inside/outside the 21-unit hide radius, score digits,
+    all vulnerability bar states."""
+    n = 40
+    env = make("youturn", n)
+    env.reset()
+    rng = np.random.RandomState(4)
+    recs = []
+    for i in range(n):
+        r = OracleEnv("youturn", 1).get_state()
+        r.ship_x = float(rng.uniform(120, 600)); r.ship_y = float(rng.uniform(60, 560)); r.ship_angle = float(rng.randint(360))
+        r.ship_alive = int(i % 3 != 0)
+        r.fortress_alive = int(i % 4 != 1)
+        r.fortress_angle = float(10 * rng.randint(36)); r.fortress_last_angle = r.fortress_angle
+        nm = int(rng.randint(0, 21)) if i % 5 == 0 else int(rng.randint(0, 4))
+        for s in rng.choice(20, nm, replace=False):
+            r.missile_mask |= 1 << int(s)
+            r.missile_x[s] = float(rng.uniform(100, 620)); r.missile_y[s] = float(rng.uniform(50, 580)); r.missile_angle[s] = float(rng.randint(360))
+        for s in range(int(rng.randint(0, 4))):
+            r.shell_mask |= 1 << s
+            rad = 15 + 12 * s if i % 2 else float(rng.uniform(22, 250))
+            ang = float(rng.uniform(0, 360))
+            r.shell_x[s] = 355 + rad * np.cos(np.deg2rad(ang)); r.shell_y[s] = 315 + rad * np.sin(np.deg2rad(ang)); r.shell_angle[s] = ang
+        r.points = float([0, 7, 42, 1234567, 9999999, 30.95][i % 6])
+        r.vulnerability = int(i % 14); r.fortress_vuln_timer = int([0, 249, 250, 1000][i % 4])
+        recs.append(r)
+    env.set_state([to_gpu_record(r) for r in recs])
+    nat = env.render_frames(native=True)
+    obs = env.render_frames(native=False)
+    for i, r in enumerate(recs):
+        assert_frame_close(draw_native(r), nat[i], ("native", i))
+        assert_frame_close(draw_obs(r), obs[i], ("obs", i))
+    # rendering twice (explosion sprite memo path) gives the same frames
+    assert np.array_equal(env.render_frames(native=True), nat)
+    env.close()
+
+
+def test_rollout_equals_stepwise_and_synthetic_stream():
+    torch = torch_cuda()
+    n, T = 96, 64
+    a = make("youturn", n); b = make("youturn", n)
+    a.reset(); b.reset()
+    acts = a.synthetic_actions(T, action_seed=5)
+    out = a.rollout(T, action_seed=5)  # device-side hash policy
+    for t in range(T):
+        obs, rew, done, info = b.step(torch.from_numpy(acts[t]).cuda())
+        assert torch.equal(out["obs"][t], obs) and torch.equal(out["reward"][t], rew)
+        assert torch.equal(out["done"][t].bool(), done) and torch.equal(out["kill"][t].bool(), info)
+    ra, rb = a.get_state(), b.get_state()
+    assert bytes(ra) == bytes(rb)
+    a.close(); b.close()
+
+
+def test_shard_invariance_two_slabs_equal_one():
+    """N envs in one slab == the same envs split over two slabs (what two ranks would own), bitwise;
+    episode statistics add up."""
+    n, T = 64, 150
+    seeds = np.arange(1, n + 1)
+    whole = make("autoturn", n, seeds=seeds)
+    lo = make("autoturn", n // 2, seeds=seeds[:n // 2], first_global_env=0)
+    hi = make("autoturn", n // 2, seeds=seeds[n // 2:], first_global_env=n // 2)
+    for e in (whole, lo, hi):
+        e.reset()
+    ow = whole.rollout(T, action_seed=9); ol = lo.rollout(T, action_seed=9); oh = hi.rollout(T, action_seed=9)
+    import torch
+    assert torch.equal(ow["obs"][:, :n // 2], ol["obs"]) and torch.equal(ow["obs"][:, n // 2:], oh["obs"])
+    assert torch.equal(ow["reward"][:, :n // 2], ol["reward"]) and torch.equal(ow["reward"][:, n // 2:], oh["reward"])
+    assert bytes(whole.get_state(0, n // 2)) == bytes(lo.get_state()) and bytes(whole.get_state(n // 2, n // 2)) == bytes(hi.get_state())
+    for e in (whole, lo, hi):
+        e.close()
+
+
+def test_auto_reset_and_episode_stats():
+    """All envs finish at tick 5295; the returned obs is the first frame of the next episode, prev_vlner
+    survives (quirk Q7), and the device-side episode statistics equal the host sums."""
+    torch = torch_cuda()
+    n = 8
+    env = make("autoturn", n, seeds=np.arange(1, n + 1))
+    env.reset()
+    orc = [OracleEnv("autoturn", s) for s in range(1, n + 1)]
+    T = 5295
+    acts = env.synthetic_actions(T, action_seed=1)
+    out = env.rollout(T, action_seed=1, want=("reward", "done", "kill"))
+    done = out["done"].cpu().numpy(); rew = out["reward"].cpu().numpy()
+    assert done[:-1].sum() == 0 and done[-1].all()
+    exp = dict(episodes=0, sum_return=0, sum_length=0, shipDeaths=0, totalShots=0, fort_kills=0)
+    for i in range(n):
+        ret = 0
+        for t in range(T):
+            r, d, k, _ = orc[i].step(orc[i].keymask(int(acts[t, i])))
+            assert r == int(rew[t, i])
+            ret += r
+        assert d
+        s = orc[i].get_state()
+        exp["episodes"] += 1; exp["sum_return"] += ret; exp["sum_length"] += s.tick
+        exp["shipDeaths"] += s.stats[3]; exp["totalShots"] += s.stats[7]; exp["fort_kills"] += s.stats[5]
+        orc[i].reset()
+    st = env.episode_stats()
+    for k, v in exp.items():
+        assert st[k] == v, (k, st[k], v)
+    frames = env.render_frames()
+    recs = env.get_state()
+    for i in range(n):
+        assert_state_close(orc[i].get_state(), recs[i], ("after auto-reset", i))
+        assert_frame_close(orc[i].obs(), frames[i], ("first frame of next episode", i))
+    assert env.episode_stats()["episodes"] == 0  # accumulators were reset
+    env.close()
+
+
+def test_vecenv_numpy_api_matches_reference_usage():
+    """rl/train.py:30-41,60,80-85 usage pattern with the drop-in classes."""
+    torch_cuda()
+    from spacefortress_b200 import SubprocVecEnv, make_env
+    envs = SubprocVecEnv([make_env("SpaceFortress-autoturn-image-v0", 0, i) for i in range(6)])
+    assert envs.observation_space.shape == (1, 84, 84) and envs.action_space.n == 3 and envs.num_envs == 6
+    obs = envs.reset()
+    assert obs.shape == (6, 1, 84, 84) and obs.dtype == np.uint8
+    obs, rew, done, infos = envs.step(np.array([0, 1, 2, 0, 1, 2]))
+    assert obs.shape == (6, 1, 84, 84) and rew.shape == (6,) and done.dtype == bool and len(infos) == 6 and isinstance(infos[0], bool)
+    assert sum(infos) == 0
+    envs.step_async(np.zeros(6, np.int64)); envs.step_wait()
+    envs.close()
+    with pytest.raises(Exception):
+        SubprocVecEnv([make_env("SpaceFortress-nonsense-v0", 0, 0)])
+
+
+def test_single_env_facade_matches_oracle():
+    """SSF_Env facade: native (92,90) frames, python-int rewards, bool info, no auto-reset, reset keeps prev_vlner."""
+    torch_cuda()
+    from spacefortress_b200.gym import make as gym_make
+    env = gym_make("SpaceFortress-youturn-image-v0")
+    o = OracleEnv("youturn", 1)  # == SSF_Env.__init__ (constructs the first Game)
+    first = env.reset()
+    o.reset()
+    assert first.shape == (92, 90) and np.array_equal(first, o.native_frame())
+    rng = np.random.RandomState(8)
+    for t in range(120):
+        a = int(rng.randint(5))
+        obs, r, d, k = env.step(a)
+        ro, do, ko, _ = o.step(o.keymask(a))
+        assert (r, d, k) == (ro, do, ko) and isinstance(k, bool)
+        if t % 15 == 0:
+            assert np.array_equal(obs, o.native_frame())
+            assert env.g.dump().split(",[")[0] == o.dump().split(",[")[0]
+    assert env.g.stats[:13] == tuple(o.get_state().stats)
+    env.close()
