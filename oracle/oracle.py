@@ -153,6 +153,8 @@ def ref_lib():
         L.sfref_wireframe.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
         L.sfref_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
         L.sfref_run.restype = C.c_long
+        L.sfref_run_render.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        L.sfref_run_render.restype = C.c_long
         _REF = L
     return _REF
 
@@ -304,9 +306,14 @@ class RefEnv:
         self.L.sfref_hexagons(self.h, big, small)
         return np.array(big).reshape(6, 2), np.array(small).reshape(6, 2)
 
-    def run(self, keymasks):
+    def run(self, keymasks, render=False):
+        """Bulk loop in C: reference tick + shaping + auto-reset (+ restated frame when render=True)."""
         km = np.ascontiguousarray(keymasks, dtype=np.uint8)
-        return self.L.sfref_run(self.h, km.ctypes.data, km.size)
+        if not render:
+            return self.L.sfref_run(self.h, km.ctypes.data, km.size)
+        obs = np.zeros((84, 84), np.uint8)
+        draw = C.cast(oracle_lib().sfo_draw_obs, C.c_void_p)
+        return self.L.sfref_run_render(self.h, km.ctypes.data, km.size, draw, obs.ctypes.data)
 
 
 def wireframe(which):

@@ -319,4 +319,23 @@ long sfref_run(RefEnv* e, const unsigned char* keymasks, long steps) {
   return acc;
 }
 
+/* Same loop with a frame per step: the reference draws with cairo (draw.cpp), which cannot be built
+ * offline, so the caller passes the restated renderer (oracle/sf_draw_oracle.c: sfo_draw_obs) as a
+ * function pointer; the game tick, shaping and auto-reset are the reference's own code. */
+typedef void (*sfref_draw_fn)(const sfr_record*, unsigned char*);
+long sfref_run_render(RefEnv* e, const unsigned char* keymasks, long steps, sfref_draw_fn draw, unsigned char* obs84) {
+  long acc = 0;
+  int out[4];
+  sfr_record rec;
+  for (long i = 0; i < steps; i++) {
+    sfref_env_step(e, keymasks[i], out);
+    acc += out[0];
+    if (out[1]) sfref_reset(e);
+    sfref_get_state(e, &rec);
+    draw(&rec, obs84);
+    acc += obs84[(i * 7) % (84 * 84)];
+  }
+  return acc;
+}
+
 } /* extern "C" */

@@ -109,10 +109,9 @@ struct SfRollArgs {
 // fused step + render
 // ------------------------------------------------------------------------------------------------
 template <bool RENDER>
-__global__ void __launch_bounds__(SF_BLOCK) sf_rollout_kernel(SfDev D, SfRollArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(SF_BLOCK, 2) sf_rollout_kernel(SfDev D, SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SfWarpSmem& W = reinterpret_cast<SfWarpSmem*>(smem_raw)[RENDER ? warp : 0];
+  SfWarpSmem& W = sf_my_smem();
   const long long wg = (long long)blockIdx.x * SF_WARPS_PER_BLOCK + warp;
   const long long env0 = wg * A.E;
   if (env0 >= D.n) return;
@@ -120,7 +119,7 @@ __global__ void __launch_bounds__(SF_BLOCK) sf_rollout_kernel(SfDev D, SfRollArg
   const bool mine = lane < A.E && env < D.n;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const size_t obs_bytes = (A.flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  if (RENDER) sf_warp_smem_init(W, lane);
+  if (RENDER) sf_warp_smem_init(W, D.tab, lane);
 
   for (int t = 0; t < A.T; t++) {
     SfEnv e;
@@ -193,14 +192,13 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
 }
 
 // render the current state (Game.draw), warp per env
-__global__ void __launch_bounds__(SF_BLOCK) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(SF_BLOCK, 2) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SfWarpSmem& W = reinterpret_cast<SfWarpSmem*>(smem_raw)[warp];
+  SfWarpSmem& W = sf_my_smem();
   const int env = blockIdx.x * SF_WARPS_PER_BLOCK + warp;
   if (env >= D.n) return;
   if (mask && !mask[env]) return;
-  sf_warp_smem_init(W, lane);
+  sf_warp_smem_init(W, D.tab, lane);
   SfEnv e;
   sf_load_env(D, env, e);  // every lane loads the same env (broadcast)
   SfRenderIn r;

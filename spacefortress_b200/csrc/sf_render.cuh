@@ -1,41 +1,56 @@
-// sf_render.cuh — warp-cooperative rasteriser: one warp draws one env's frame into shared memory
-// (native 92x90 tile), resamples the touched region to 84x84 with cv2's INTER_AREA arithmetic and
-// streams the observation out with 128-bit stores. Replaces drawGameStateScaled (draw.cpp:256-270),
-// the RGBA2GRAY conversion (ssf_env.py:205, identity on grey input) and cv2.resize (rl/envs.py:29).
+// sf_render.cuh — warp-cooperative rasteriser: one warp draws one env's frame.
+// Replaces drawGameStateScaled (draw.cpp:256-270), the RGBA2GRAY conversion (ssf_env.py:205, identity on grey
+// input) and cv2.resize(INTER_AREA, 84x84) (rl/envs.py:29).
 //
 // Draw order and semantics follow draw.cpp:227-269:
-//   black, 2 hexagons [static: bg_nat]  ->  ship wireframe | ship explosion  ->  fortress wireframe |
-//   fortress explosion [static sprites]  ->  missiles  ->  shells further than 21 from the fortress
-//   ->  score digits [static glyph strip]  ->  vulnerability bar.
-// Moving strokes (ship, missiles, shells, ship explosion) are scan-converted on the fly with the
-// model of sf_geom.h: per stroke, lanes own (pixel-row, sub-row) samples, evaluate every quad's span
-// with exact integer edge stepping, merge overlapping spans (non-zero winding == union for equally
-// oriented convex quads) and accumulate 1/256-px span lengths into a shared-memory cell array.
+//   black, 2 hexagons -> ship wireframe | ship explosion -> fortress wireframe | fortress explosion
+//   -> missiles -> shells further than 21 from the fortress -> score digits -> vulnerability bar.
+//
+// Organisation (per env, all in one warp, everything in shared memory until the final stores):
+//  * A persistent native tile (92x90 u8) holds the static background; every env composites its layers into
+//    it, resamples only the touched rectangles, and restores them afterwards.
+//  * Moving strokes (ship, missiles, shells; the ship explosion once per death) are scan-converted in
+//    BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then the (stroke,row,sub-row)
+//    samples of the whole batch are flattened over the lanes; each sample evaluates its stroke's quads with
+//    exact integer edge stepping (one "down" and one "up" edge are live per quad and sub-row), merges
+//    overlapping spans (non-zero winding == union for equally oriented convex quads) and accumulates span
+//    lengths into 16-bit cells. Regions are then blended in draw order.
+//  * The ship explosion is identical for the 30 ticks a ship stays dead: it is rasterised once and kept in
+//    a per-env 28x28 sprite cache (memo, not game state).
+//  * Static layers (fortress sprite per sector angle, fortress explosion, score, vulnerability bar) come
+//    from host-built tables. When no moving rectangle overlaps them their pre-resampled 16-byte OUTPUT
+//    chunks are copied straight into the observation; otherwise they are blended into the tile.
+//  * The observation is assembled from 441 16-byte chunks (background or static-layer tables) written with
+//    coalesced 128-bit stores, then the resampled dirty pixels are patched in.
 #pragma once
 #include "sf_geom.h"
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
-#define SF_ACC_CELLS 1024
-#define SF_MAX_STROKE_QUADS 16
-#define SF_MAX_RECTS 40
+#define SF_ACC_CELLS 1024    // 16-bit span-length cells per batch
+#define SF_BATCH_QUADS 32
+#define SF_BATCH_STROKES 32
+#define SF_MAX_RECTS 32
+#define SF_YBIAS 4096        // grid rows are stored biased so they fit an unsigned 16-bit field
+#define SF_QUAD_IRREGULAR (1 << 20)  // quadrec.y flag: not a 2+2 edge split, test all four edges
 
-// per-warp shared memory
+// per-warp shared memory (14 KB -> 16 warps per SM)
 struct __align__(16) SfWarpSmem {
-  unsigned char nat[SF_NAT_H * SF_NAT_STRIDE];  // 8832 B
-  unsigned char out[84 * 84];                   // 7056 B
-  int acc[SF_ACC_CELLS];                        // span-length accumulators of the current stroke
-  int4 edge[SF_MAX_STROKE_QUADS * 4];           // x_top, y_top(grid), dy(grid), dx
-  unsigned edge_m[SF_MAX_STROKE_QUADS * 4];     // magic reciprocal of dy
-  SfQuad quad[SF_MAX_STROKE_QUADS];
-  int4 rect[SF_MAX_RECTS];                      // dirty rectangles, native px inclusive
-  int nrect;
-  int pad[3];
+  unsigned char nat[SF_NAT_H * SF_TILE_STRIDE];  // 8464 B persistent native tile
+  unsigned short acc[SF_ACC_CELLS];              // 2048 B
+  int4 edge[SF_BATCH_QUADS * 4];                 // 2048 B per quad: down0, down1, up0, up1 = {x_top, (ytop+bias)<<16 | dy, dx, magic}
+  int2 quadrec[SF_BATCH_QUADS];                  //  256 B {ytopQ+bias, ybotQ+bias} (grid rows)
+  int4 region[SF_BATCH_STROKES];                 //  512 B {x0, y0, w | h<<16, acc_off | colour<<16}
+  int2 stroke[SF_BATCH_STROKES];                 //  256 B {region | quad0<<8 | nq<<16, first item}
+  unsigned rect[SF_MAX_RECTS];                   //  128 B dirty rects x0 | y0<<8 | x1<<16 | y1<<24
+  int nrect, nregion, nstroke, nitems;
+  int acc_used, pad0, pad1, pad2;
 };
 
-__constant__ double c_wf_ship[3][4] = {{-18, 0, 18, 0}, {-18, 18, 0, 0}, {0, 0, -18, -18}};       // wireframe.cpp:39-53
-__constant__ double c_wf_missile[3][4] = {{0, 0, -25, 0}, {0, 0, -5, 5}, {0, 0, -5, -5}};          // wireframe.cpp:11-22
-__constant__ double c_wf_shell[4][4] = {{-8, 0, 0, -6}, {0, -6, 16, 0}, {16, 0, 0, 6}, {0, 6, -8, 0}};  // wireframe.cpp:24-37
+// all kernels that render use the same dynamic shared array: one SfWarpSmem per warp. Helpers that are kept
+// out of line re-derive their warp's slot from it, so the compiler still knows the address space.
+extern __shared__ __align__(16) unsigned char sf_smem_raw[];
+__device__ __forceinline__ SfWarpSmem& sf_my_smem() { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw)[threadIdx.x >> 5]; }
 
 __device__ __forceinline__ int sf_warp_min(int v) {
 #pragma unroll
@@ -47,178 +62,346 @@ __device__ __forceinline__ int sf_warp_max(int v) {
   for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a / b for 0 <= a < 2^20, exact
+  return __float2int_rz(((float)a + 0.5f) * inv_b);
+}
+
+// once per warp at kernel start
+__device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, const SfTables* T, int lane) {
+  for (int k = lane; k < SF_ACC_CELLS / 2; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
+  for (int k = lane; k < SF_NAT_H * (SF_TILE_STRIDE / 4); k += 32) {
+    int r = k / (SF_TILE_STRIDE / 4), c = k - r * (SF_TILE_STRIDE / 4);
+    reinterpret_cast<unsigned*>(W.nat)[k] = __ldg(reinterpret_cast<const unsigned*>(T->bg_nat + r * SF_NAT_STRIDE) + c);
+  }
+  if (lane == 0) { W.nrect = 0; W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  __syncwarp();
+}
 
 __device__ __forceinline__ void sf_add_rect(SfWarpSmem& W, int lane, int x0, int y0, int x1, int y1) {
   if (lane == 0) {
     int n = W.nrect;
-    if (n < SF_MAX_RECTS) { W.rect[n] = make_int4(x0, y0, x1, y1); W.nrect = n + 1; }
+    unsigned r = (unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24);
+    if (n < SF_MAX_RECTS) { W.rect[n] = r; W.nrect = n + 1; }
     else {  // overflow: grow the last rectangle to the union (still correct, just more resampling)
-      int4 r = W.rect[SF_MAX_RECTS - 1];
-      W.rect[SF_MAX_RECTS - 1] = make_int4(min(r.x, x0), min(r.y, y0), max(r.z, x1), max(r.w, y1));
+      unsigned q = W.rect[SF_MAX_RECTS - 1];
+      int qx0 = q & 255, qy0 = (q >> 8) & 255, qx1 = (q >> 16) & 255, qy1 = q >> 24;
+      W.rect[SF_MAX_RECTS - 1] = (unsigned)min(qx0, x0) | ((unsigned)min(qy0, y0) << 8) | ((unsigned)max(qx1, x1) << 16) | ((unsigned)max(qy1, y1) << 24);
     }
   }
 }
 
-// exact floor(m*dx/dy) for 0 <= m < dy
-__device__ __forceinline__ int sf_edge_x(int4 E, unsigned M, int m) {
-  int dx = E.w, dy = E.z;
-  unsigned adx = (unsigned)abs(dx);
-  unsigned n = (unsigned)m * adx + (dx < 0 ? (unsigned)(dy - 1) : 0u);
-  unsigned q = M ? __umulhi(n, M) : (dy > 1 ? n / (unsigned)dy : 0u);
-  return E.x + (dx < 0 ? -(int)q : (int)q);
+// ---- edge records --------------------------------------------------------------------------------------
+// x(s) = x_top + floor((s - ytop) * dx / dy), exact, via a magic reciprocal (valid while (dy*|dx|+dy)*dy < 2^32:
+// always true for the strokes drawn here, which are at most ~30 px tall).
+__device__ __forceinline__ int4 sf_make_edge(int xa, int ga, int xb, int gb) {  // ga < gb (grid rows)
+  int dy = gb - ga;
+  unsigned M = dy > 1 ? (unsigned)((1ull << 32) / (unsigned)dy) + 1u : 0u;
+  return make_int4(xa, ((ga + SF_YBIAS) << 16) | dy, xb - xa, (int)M);
+}
+__device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias, ytop <= s < ytop + dy
+  int m = sb - (int)((unsigned)E.y >> 16);
+  int dy = E.y & 0xFFFF;
+  unsigned adx = (unsigned)abs(E.z);
+  unsigned n = (unsigned)m * adx + (E.z < 0 ? (unsigned)(dy - 1) : 0u);
+  unsigned q = __umulhi(n, (unsigned)E.w);
+  return E.z < 0 ? E.x - (int)q : E.x + (int)q;
 }
 
-// Scan-convert the stroke made of quads W.quad[0..nq) (quads in groups of 4 may overlap inside a group;
-// different groups must be disjoint) and blend `colour` into the native tile.
-__device__ __noinline__ void sf_raster_stroke(SfWarpSmem& W, int lane, int nq, unsigned colour) {
-  // ---- edges ----
-  int smin = 1 << 30, smax = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
-  for (int e = lane; e < nq * 4; e += 32) {
-    SfPt a = W.quad[e >> 2].p[e & 3], b = W.quad[e >> 2].p[(e + 1) & 3];
-    int ga = sf_grid_y(a.y), gb = sf_grid_y(b.y);
-    xmin = min(xmin, min(a.x, b.x)); xmax = max(xmax, max(a.x, b.x));
-    int4 E; unsigned M = 0;
-    if (ga == gb) { E = make_int4(0, 0, 0, 0); }
-    else {
-      if (ga < gb) E = make_int4(a.x, ga, gb - ga, b.x - a.x); else E = make_int4(b.x, gb, ga - gb, a.x - b.x);
-      smin = min(smin, E.y); smax = max(smax, E.y + E.z);
-      unsigned dy = (unsigned)E.z, adx = (unsigned)abs(E.w);
-      // magic multiply is exact while (dy*adx + dy) * dy < 2^32; otherwise fall back to a real division
-      if (dy > 1 && (unsigned long long)(dy * (unsigned long long)adx + dy) * dy < (1ull << 32)) M = (unsigned)((1ull << 32) / dy) + 1u;
-    }
-    W.edge[e] = E; W.edge_m[e] = M;
+// Build the 4 edge records of convex quad q (cyclic corners, consistent orientation) into slot `qi`.
+// Edges whose grid rows increase along the traversal lie on one side, the others on the opposite side; a
+// stroked segment is a parallelogram, so each side has at most two non-degenerate edges.
+__device__ __forceinline__ void sf_store_quad_edges(SfWarpSmem& W, int qi, const SfQuad& q, int& ymin_g, int& ymax_g, int& xmin, int& xmax) {
+  int g[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) g[k] = sf_grid_y(q.p[k].y);
+  int4 dn[2], up[2];
+  int nd = 0, nu = 0;
+  int4 none = make_int4(0, 0, 0, 0);  // ytop field 0 with dy 0: never live
+  dn[0] = dn[1] = up[0] = up[1] = none;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int a = k, b = (k + 1) & 3;
+    if (g[a] < g[b]) { int4 E = sf_make_edge(q.p[a].x, g[a], q.p[b].x, g[b]); if (nd == 0) dn[0] = E; else dn[1] = E; nd++; }
+    else if (g[a] > g[b]) { int4 E = sf_make_edge(q.p[b].x, g[b], q.p[a].x, g[a]); if (nu == 0) up[0] = E; else up[1] = E; nu++; }
   }
-  smin = sf_warp_min(smin); smax = sf_warp_max(smax); xmin = sf_warp_min(xmin); xmax = sf_warp_max(xmax);
-  if (smin >= smax) return;
-  // floor division by 15 of possibly negative grid rows
-  int py0 = (smin >= 0) ? smin / SF_GRID_Y : -((-smin + SF_GRID_Y - 1) / SF_GRID_Y);
-  int py1 = (smax - 1 >= 0) ? (smax - 1) / SF_GRID_Y : -((-(smax - 1) + SF_GRID_Y - 1) / SF_GRID_Y);
-  py0 = max(py0, 0); py1 = min(py1, SF_NAT_H - 1);
-  int cx0 = max(xmin >> 8, 0), cx1 = min((xmax - 1) >> 8, SF_NAT_W - 1);
-  if (py0 > py1 || cx0 > cx1) return;  // entirely off the surface
-  const int w = cx1 - cx0 + 1, h = py1 - py0 + 1;
-  const int xlo = cx0 << 8, xhi = (cx1 + 1) << 8;
-  const int hc = min(h, SF_ACC_CELLS / w);
+  int gmin = min(min(g[0], g[1]), min(g[2], g[3])), gmax = max(max(g[0], g[1]), max(g[2], g[3]));
+  bool live = nd > 0 && nu > 0;
+  if (nd > 2 || nu > 2) {
+    // a trapezoid can have three edges on one side (explosion arcs straddling 0/180 degrees): keep all
+    // non-degenerate edges and let the span test every one of them
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int a = k, b = (k + 1) & 3;
+      int4 E = none;
+      if (g[a] < g[b]) E = sf_make_edge(q.p[a].x, g[a], q.p[b].x, g[b]);
+      else if (g[a] > g[b]) E = sf_make_edge(q.p[b].x, g[b], q.p[a].x, g[a]);
+      W.edge[qi * 4 + k] = E;
+      n++;
+    }
+    W.quadrec[qi] = make_int2(gmin + SF_YBIAS, (gmax + SF_YBIAS) | SF_QUAD_IRREGULAR);
+    ymin_g = min(ymin_g, gmin); ymax_g = max(ymax_g, gmax);
+    xmin = min(xmin, min(min(q.p[0].x, q.p[1].x), min(q.p[2].x, q.p[3].x)));
+    xmax = max(xmax, max(max(q.p[0].x, q.p[1].x), max(q.p[2].x, q.p[3].x)));
+    return;
+  }
+  // order each side top to bottom; a side with one edge gets it twice (the second copy is selected by the
+  // split test below and evaluates identically)
+  if (nd == 1) dn[1] = dn[0];
+  else if (nd >= 2 && (unsigned)dn[1].y < (unsigned)dn[0].y) { int4 t = dn[0]; dn[0] = dn[1]; dn[1] = t; }
+  if (nu == 1) up[1] = up[0];
+  else if (nu >= 2 && (unsigned)up[1].y < (unsigned)up[0].y) { int4 t = up[0]; up[0] = up[1]; up[1] = t; }
+  W.edge[qi * 4 + 0] = dn[0]; W.edge[qi * 4 + 1] = dn[1]; W.edge[qi * 4 + 2] = up[0]; W.edge[qi * 4 + 3] = up[1];
+  W.quadrec[qi] = live ? make_int2(gmin + SF_YBIAS, gmax + SF_YBIAS) : make_int2(0, 0);
+  if (live) {
+    ymin_g = min(ymin_g, gmin); ymax_g = max(ymax_g, gmax);
+    xmin = min(xmin, min(min(q.p[0].x, q.p[1].x), min(q.p[2].x, q.p[3].x)));
+    xmax = max(xmax, max(max(q.p[0].x, q.p[1].x), max(q.p[2].x, q.p[3].x)));
+  }
+}
+
+// span of quad slot qi on biased grid row sb; returns false when the quad is not live there
+__device__ __forceinline__ bool sf_quad_span(const SfWarpSmem& W, int qi, int sb, int& lo, int& hi) {
+  int2 qr = W.quadrec[qi];
+  if (qr.y & SF_QUAD_IRREGULAR) {
+    if (sb < qr.x || sb >= (qr.y & ~SF_QUAD_IRREGULAR)) return false;
+    lo = 1 << 30; hi = -(1 << 30);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int4 E = W.edge[qi * 4 + k];
+      int m = sb - (int)((unsigned)E.y >> 16);
+      if ((unsigned)m < (unsigned)(E.y & 0xFFFF)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
+    }
+    return true;
+  }
+  if (sb < qr.x || sb >= qr.y) return false;
+  int4 d1 = W.edge[qi * 4 + 1], u1 = W.edge[qi * 4 + 3];
+  int4 d = (sb < (int)((unsigned)d1.y >> 16)) ? W.edge[qi * 4 + 0] : d1;
+  int4 u = (sb < (int)((unsigned)u1.y >> 16)) ? W.edge[qi * 4 + 2] : u1;
+  int xd = sf_edge_x(d, sb), xu = sf_edge_x(u, sb);
+  lo = min(xd, xu); hi = max(xd, xu);
+  return true;
+}
+
+// ---- batch machinery ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sf_batch_begin(SfWarpSmem& W, int lane) {
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
   __syncwarp();
-  for (int r0 = 0; r0 < h; r0 += hc) {
-    const int hh = min(hc, h - r0);
-    const float inv_hh = 1.0f / (float)hh;
-    const int items = hh * SF_GRID_Y;
-    for (int it0 = 0; it0 < items; it0 += 32) {
-      int it = it0 + lane;
-      if (it < items) {
-        int k = __float2int_rz(((float)it + 0.5f) * inv_hh);  // it / hh (exact: |frac| >= 0.5/hh)
-        int r = it - k * hh;
-        int s = (py0 + r0 + r) * SF_GRID_Y + k;
-        for (int g = 0; g < nq; g += 4) {
-          unsigned key[4];
+}
+
+// floor division of a grid row by 15
+__device__ __forceinline__ int sf_row_of(int g) { return (g >= 0) ? g / SF_GRID_Y : -((-g + SF_GRID_Y - 1) / SF_GRID_Y); }
+
+// Open one region + one stroke per participating lane (`want`), in lane order, with a warp scan: region ids,
+// accumulator offsets and first-item indices are exclusive prefixes. Returns the lane's region id or -1 (stroke
+// off the surface, or the batch is full: cannot happen for the strokes drawn here, see the size notes above).
+__device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax,
+                                               unsigned colour, int quad0, int nq) {
+  int cx0 = 0, py0 = 0, w = 0, h = 0;
+  bool ok = want && ymin_g < ymax_g;
+  if (ok) {
+    py0 = max(sf_row_of(ymin_g), 0); int py1 = min(sf_row_of(ymax_g - 1), SF_NAT_H - 1);
+    cx0 = max(xmin >> 8, 0); int cx1 = min((xmax - 1) >> 8, SF_NAT_W - 1);
+    ok = py0 <= py1 && cx0 <= cx1;
+    w = cx1 - cx0 + 1; h = py1 - py0 + 1;
+  }
+  int cells = ok ? w * h : 0;
+  // inclusive scans of (count, cells) packed in one word: count < 64, cells < 2^20
+  unsigned v = ok ? ((unsigned)cells | (1u << 24)) : 0u;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            key[j] = 0xFFFFFFFFu;
-            if (g + j < nq) {
-              int lo = 1 << 30, hi = -(1 << 30);
+  for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  int incl_cells = v & 0xFFFFFF, incl_cnt = v >> 24;
+  if (ok && incl_cells > SF_ACC_CELLS) ok = false;  // pool full: drop (later strokes are dropped as well)
+  unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  int rid = ok ? __popc(okmask & ((1u << lane) - 1u)) : -1;
+  int items = ok ? h * SF_GRID_Y : 0;
+  int iv = items;
 #pragma unroll
-              for (int c = 0; c < 4; c++) {
-                int4 E = W.edge[(g + j) * 4 + c];
-                int m = s - E.y;
-                if ((unsigned)m < (unsigned)E.z) {
-                  int x = sf_edge_x(E, W.edge_m[(g + j) * 4 + c], m);
-                  lo = min(lo, x); hi = max(hi, x);
-                }
-              }
-              lo = max(lo, xlo); hi = min(hi, xhi);
-              if (lo < hi) key[j] = ((unsigned)(lo - xlo) << 16) | (unsigned)(hi - xlo);
-            }
-          }
-          // sort the 4 spans by start (5-comparator network), then emit each span minus the union of its predecessors
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+  if (ok) {
+    W.region[rid] = make_int4(cx0, py0, w | (h << 16), (incl_cells - cells) | ((int)colour << 16));
+    W.stroke[rid] = make_int2(rid | (quad0 << 8) | (nq << 16), iv - items);
+  }
+  if (lane == 31) { W.nregion = __popc(okmask); W.nstroke = __popc(okmask); W.nitems = iv; W.acc_used = incl_cells; }
+  (void)incl_cnt;
+  return rid;
+}
+
+// Accumulate span lengths of every stroke of the batch. Samples (stroke, row, sub-row) are flattened over lanes.
+__device__ __noinline__ void sf_batch_accumulate() {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  const int nitems = W.nitems, ns = W.nstroke;
+  for (int it0 = 0; it0 < nitems; it0 += 32) {
+    int it = it0 + lane;
+    if (it < nitems) {
+      // binary search: last stroke with first_item <= it
+      int lo_s = 0, hi_s = ns - 1;
+      while (lo_s < hi_s) {
+        int mid = (lo_s + hi_s + 1) >> 1;
+        if (W.stroke[mid].y <= it) lo_s = mid; else hi_s = mid - 1;
+      }
+      int2 S = W.stroke[lo_s];
+      int4 R = W.region[S.x & 255];
+      int quad0 = (S.x >> 8) & 255, nq = (S.x >> 16) & 255;
+      int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+      int li = it - S.y;
+      int sub = sf_div_small(li, h, 1.0f / (float)h);  // rows vary fastest: neighbouring lanes hit different cells
+      int r = li - sub * h;
+      int sb = (R.y + r) * SF_GRID_Y + sub + SF_YBIAS;
+      int xlo = R.x << 8, xhi = (R.x + w) << 8;
+      unsigned short* cells = W.acc + (R.w & 0xFFFF) + r * w;
+      unsigned key[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        key[j] = 0xFFFFFFFFu;
+        int lo, hi;
+        if (j < nq && sf_quad_span(W, quad0 + j, sb, lo, hi)) {
+          lo = max(lo, xlo); hi = min(hi, xhi);
+          if (lo < hi) key[j] = ((unsigned)(lo - xlo) << 16) | (unsigned)(hi - xlo);
+        }
+      }
+      if (nq > 1) {  // sort the spans by start, then emit each span minus the union of its predecessors
 #define SF_CE(a, b) { unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
-          SF_CE(0, 1) SF_CE(2, 3) SF_CE(0, 2) SF_CE(1, 3) SF_CE(1, 2)
+        SF_CE(0, 1) SF_CE(2, 3) SF_CE(0, 2) SF_CE(1, 3) SF_CE(1, 2)
 #undef SF_CE
-          int reach = 0;
+      }
+      int reach = 0;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (key[j] == 0xFFFFFFFFu) break;
-            int a = max((int)(key[j] >> 16), reach), b = (int)(key[j] & 0xFFFFu);
-            reach = max(reach, b);
-            int cell = a >> 8;
-            while (a < b) {
-              int e = min(b, (cell + 1) << 8);
-              atomicAdd(&W.acc[r * w + cell], e - a);
-              a = e; cell++;
-            }
+      for (int j = 0; j < 4; j++) {
+        if (key[j] != 0xFFFFFFFFu) {
+          int a = max((int)(key[j] >> 16), reach), b = (int)(key[j] & 0xFFFFu);
+          reach = max(reach, b);
+          int cell = a >> 8;
+          while (a < b) {
+            int e = min(b, (cell + 1) << 8);
+            // 16-bit cells, 32-bit atomics: a cell never exceeds 15*256 so halves cannot carry into each other
+            unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<size_t>(cells + cell) & ~(size_t)3);
+            unsigned shift = (reinterpret_cast<size_t>(cells + cell) & 2) ? 16u : 0u;
+            atomicAdd(word, (unsigned)(e - a) << shift);
+            a = e; cell++;
           }
         }
       }
     }
-    __syncwarp();
-    const float inv_w = 1.0f / (float)w;
-    for (int idx = lane; idx < hh * w; idx += 32) {
-      int L = W.acc[idx];
-      if (L) {
-        W.acc[idx] = 0;
-        int r = __float2int_rz(((float)idx + 0.5f) * inv_w), c = idx - r * w;
-        unsigned char* px = &W.nat[(py0 + r0 + r) * SF_NAT_STRIDE + cx0 + c];
-        *px = (unsigned char)sf_blend(*px, colour, sf_len_to_alpha((unsigned)L));
-      }
-    }
-    __syncwarp();
-  }
-  sf_add_rect(W, lane, cx0, py0, cx1, py1);
-}
-
-// R3 drawWireFrame (draw.cpp:82-100): lanes < nlines build one stroked quad each
-__device__ __forceinline__ void sf_wireframe(SfWarpSmem& W, int lane, const SfTables* T, const double (*lines)[4], int nlines,
-                                             double px, double py, int angle, unsigned colour) {
-  // quick cull: every model fits in a 37-unit radius (7.4 px) around its origin
-  double dxv = SF_DADD(SF_DMUL(px, SF_CTM_SCALE), SF_CTM_X0), dyv = SF_DADD(SF_DMUL(py, SF_CTM_SCALE), SF_CTM_Y0);
-  if (dxv < -9.0 || dxv > SF_NAT_W + 9.0 || dyv < -9.0 || dyv > SF_NAT_H + 9.0) return;
-  if (lane < nlines) {
-    SfWireXf m = sf_wire_xf(px, py, T->cos_deg[angle], T->sin_deg[angle]);
-    SfQuad q;
-    SfPt a = sf_xform_wire(m, lines[lane][0], lines[lane][1]), b = sf_xform_wire(m, lines[lane][2], lines[lane][3]);
-    if (!sf_stroke_quad(a, b, q)) { q.p[0] = q.p[1] = q.p[2] = q.p[3] = a; }  // degenerate: no area
-    W.quad[lane] = q;
   }
   __syncwarp();
-  sf_raster_stroke(W, lane, nlines, colour);
 }
 
-// R5 drawExplosion (draw.cpp:116-145): 84 arcs, each its own stroke, then the r=7 circle
-__device__ __noinline__ void sf_explosion(SfWarpSmem& W, int lane, const SfTables* T, double px, double py) {
+// Blend one region into the tile (and zero its cells), record its dirty rectangle.
+__device__ __noinline__ void sf_region_blend(int region_id) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  int4 R = W.region[region_id];
+  int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+  unsigned colour = (unsigned)R.w >> 16;
+  unsigned short* cells = W.acc + (R.w & 0xFFFF);
+  float inv_w = 1.0f / (float)w;
+  for (int idx = lane; idx < w * h; idx += 32) {
+    unsigned L = cells[idx];
+    if (L) {
+      cells[idx] = 0;
+      int r = sf_div_small(idx, w, inv_w), c = idx - r * w;
+      unsigned char* px = &W.nat[(R.y + r) * SF_TILE_STRIDE + R.x + c];
+      *px = (unsigned char)sf_blend(*px, colour, sf_len_to_alpha(L));
+    }
+  }
+  sf_add_rect(W, lane, R.x, R.y, R.x + w - 1, R.y + h - 1);
+  __syncwarp();
+}
+
+// ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
+// Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
+// Every lane passes the description of ITS slot's stroke. Returns (by all lanes) the region id of the lane's slot
+// or -1 when that stroke is invisible / did not fit (the caller retries it in the next batch).
+__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
+  const int slot = lane >> 2, line = lane & 3;
+  int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
+  bool has = false;
+  if (kind >= 0) {
+    // quick cull: every model fits in a 37-unit radius (7.4 px) around its origin
+    double dxv = SF_DADD(SF_DMUL(px, SF_CTM_SCALE), SF_CTM_X0), dyv = SF_DADD(SF_DMUL(py, SF_CTM_SCALE), SF_CTM_Y0);
+    bool visible = !(dxv < -9.0 || dxv > SF_NAT_W + 9.0 || dyv < -9.0 || dyv > SF_NAT_H + 9.0);
+    if (visible && line < T->wf_nlines[kind]) {
+      SfWireXf m = sf_wire_xf(px, py, T->cos_deg[angle], T->sin_deg[angle]);
+      const double* L = T->wf_line[kind][line];
+      SfPt a = sf_xform_wire(m, L[0], L[1]), b = sf_xform_wire(m, L[2], L[3]);
+      SfQuad q;
+      if (sf_stroke_quad(a, b, q)) { sf_store_quad_edges(W, slot * 4 + line, q, ymin_g, ymax_g, xmin, xmax); has = true; }
+    }
+  }
+  if (!has) W.quadrec[slot * 4 + line] = make_int2(0, 0);
+  // bounding box of the slot's stroke: reduce over its 4 lanes
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    ymin_g = min(ymin_g, __shfl_xor_sync(0xffffffffu, ymin_g, o)); ymax_g = max(ymax_g, __shfl_xor_sync(0xffffffffu, ymax_g, o));
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+  }
+  // one region + stroke per slot, opened in slot order by the slot's first lane
+  int region_id = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, slot * 4, 4);
+  return __shfl_sync(0xffffffffu, region_id, lane & ~3);
+}
+
+// ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
+__device__ __noinline__ void sf_explosion_raster(const SfTables* T, double px, double py) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
   SfPt c = sf_xform_base(px, py);
-  for (int s = 0; s < SF_EXP_STROKES; s++) {
-    int nq = (s == SF_EXP_STROKES - 1) ? 16 : 1;
-    if (lane < nq) {
-      const short* o = T->exp_quad[s + lane];  // the circle's 16 quads start at index 84 == s
+  // arcs in batches of 32 strokes (one quad each); the last batch is the circle: 16 abutting quads = 4 strokes of
+  // 4 quads sharing one region
+#pragma unroll 1
+  for (int s0 = 0; s0 < SF_EXP_STROKES - 1 + 32; s0 += 32) {
+    const bool circle = s0 >= SF_EXP_STROKES - 1;
+    sf_batch_begin(W, lane);
+    int s = circle ? SF_EXP_STROKES - 1 + lane : s0 + lane;
+    int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
+    bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
+    if (mine) {
+      const short* o = T->exp_quad[s];
       SfQuad q;
 #pragma unroll
       for (int j = 0; j < 4; j++) { q.p[j].x = c.x + o[2 * j]; q.p[j].y = c.y + o[2 * j + 1]; }
-      W.quad[lane] = q;
+      sf_store_quad_edges(W, lane, q, ymin_g, ymax_g, xmin, xmax);
+    } else W.quadrec[lane] = make_int2(0, 0);
+    if (!circle) {
+      sf_open_regions(W, lane, mine, ymin_g, ymax_g, xmin, xmax, mine ? T->exp_colour[s] : 0u, lane, 1);
+    } else {
+      ymin_g = sf_warp_min(ymin_g); ymax_g = sf_warp_max(ymax_g); xmin = sf_warp_min(xmin); xmax = sf_warp_max(xmax);
+      int rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], 0, 4);
+      rid = __shfl_sync(0xffffffffu, rid, 0);
+      __syncwarp();
+      if (rid >= 0 && lane >= 1 && lane < 4) {  // three more strokes over the same region
+        int h = (W.region[0].z >> 16) & 0xFFFF;
+        W.stroke[lane] = make_int2(0 | ((lane * 4) << 8) | (4 << 16), lane * h * SF_GRID_Y);
+      }
+      __syncwarp();
+      if (rid >= 0 && lane == 0) { int h = (W.region[0].z >> 16) & 0xFFFF; W.nstroke = 4; W.nitems = 4 * h * SF_GRID_Y; }
     }
-    __syncwarp();
-    sf_raster_stroke(W, lane, nq, T->exp_colour[s]);
+    sf_batch_accumulate();
+    const int nreg = W.nregion;
+#pragma unroll 1
+    for (int r = 0; r < nreg; r++) sf_region_blend(r);  // regions are in stroke order
   }
 }
 
 // one output pixel of cv2 INTER_AREA (float accumulation in table order, round-half-even)
 __device__ __forceinline__ unsigned char sf_resample(const SfWarpSmem& W, const SfTables* T, int i, int j) {
+  SfTap ty = T->ytap[i], tx = T->xtap[j];
+  const unsigned char* S = &W.nat[ty.si * SF_TILE_STRIDE + tx.si];
   float sum = 0.f;
-  int ny = T->yt_cnt[i], nx = T->xt_cnt[j];
-  for (int ky = 0; ky < ny; ky++) {
-    const unsigned char* S = &W.nat[T->yt_si[i][ky] * SF_NAT_STRIDE];
-    float buf = 0.f;
-    for (int kx = 0; kx < nx; kx++) buf = __fadd_rn(buf, __fmul_rn((float)S[T->xt_si[j][kx]], T->xt_a[j][kx]));
-    float v = __fmul_rn(T->yt_a[i][ky], buf);
-    sum = ky == 0 ? v : __fadd_rn(sum, v);
+#pragma unroll
+  for (int ky = 0; ky < SF_MAX_TAPS; ky++) {
+    if (ky < ty.cnt) {
+      float buf = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 2; kx++)  // the x table never has more than 2 taps (scale 15/14)
+        if (kx < tx.cnt) buf = __fadd_rn(buf, __fmul_rn((float)S[ky * SF_TILE_STRIDE + kx], tx.a[kx]));
+      float v = __fmul_rn(ty.a[ky], buf);
+      sum = ky == 0 ? v : __fadd_rn(sum, v);
+    }
   }
   return (unsigned char)__float2int_rn(sum);
-}
-
-// once per warp at kernel start: the span accumulators must start at zero (every stroke leaves them zeroed)
-__device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
-  for (int k = lane; k < SF_ACC_CELLS; k += 32) W.acc[k] = 0;
-  if (lane == 0) W.nrect = 0;
-  __syncwarp();
 }
 
 struct SfRenderIn {  // warp-uniform view of one env
@@ -229,128 +412,251 @@ struct SfRenderIn {  // warp-uniform view of one env
   bool kill_bar;  // vuln > 10 && vulnerability timer < 250 (draw.cpp:268)
 };
 
+__device__ __forceinline__ bool sf_regions_touch(const SfWarpSmem& W, int nreg, int x0, int y0, int x1, int y1) {
+  bool hit = false;
+  for (int q = 0; q < nreg; q++) {
+    int4 R = W.region[q];
+    int rx1 = R.x + (R.z & 0xFFFF) - 1, ry1 = R.y + ((R.z >> 16) & 0xFFFF) - 1;
+    hit |= !(rx1 < x0 || R.x > x1 || ry1 < y0 || R.y > y1);
+  }
+  return hit;
+}
+__device__ __forceinline__ bool sf_rects_touch(const SfWarpSmem& W, int nr, int x0, int y0, int x1, int y1) {
+  bool hit = false;
+  for (int q = 0; q < nr; q++) {
+    unsigned r = W.rect[q];
+    int rx0 = r & 255, ry0 = (r >> 8) & 255, rx1 = (r >> 16) & 255, ry1 = r >> 24;
+    hit |= !(rx1 < x0 || rx0 > x1 || ry1 < y0 || ry0 > y1);
+  }
+  return hit;
+}
+
 // Draw env `in` and write its observation. obs84: 84*84 bytes (or NULL), nat_out: 92*90 bytes (or NULL).
-__device__ __noinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int lane, const SfRenderIn& in,
-                                           unsigned char* __restrict__ obs84, unsigned char* __restrict__ nat_out) {
+__device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int lane, const SfRenderIn& in,
+                                              unsigned char* __restrict__ obs84, unsigned char* __restrict__ nat_out) {
   const SfTables* T = D.tab;
   const int np = D.n_pad;
-  // ---- background ----
+  const bool ship_alive = in.core & SF_CORE_SHIP_ALIVE, fort_alive = in.core & SF_CORE_FORT_ALIVE;
+  if (lane == 0) W.nrect = 0;
+
+  // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
+  const unsigned mm = in.pmask & SF_PMASK_MISSILES;
+  unsigned sm = 0;
   {
-    const int4* src = reinterpret_cast<const int4*>(T->bg_nat);
-    int4* dst = reinterpret_cast<int4*>(W.nat);
-    for (int k = lane; k < SF_NAT_H * SF_NAT_STRIDE / 16; k += 32) dst[k] = __ldg(&src[k]);
-    if (lane == 0) W.nrect = 0;
+    bool vis = false;
+    if (lane < SF_DEV_SHELLS && ((in.pmask >> (SF_PMASK_SHELL_SHIFT + lane)) & 1u)) {
+      double2 p = D.spos[(size_t)lane * np + in.env];
+      double dx = SF_DSUB(p.x, SF_FORT_X), dy = SF_DSUB(p.y, SF_FORT_Y);
+      vis = SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) > 21.0;  // quirk Q9, draw.cpp:249-250
+    }
+    sm = __ballot_sync(0xffffffffu, vis) & 0xFu;
   }
+  const int n_ship = ship_alive ? 1 : 0, n_mis = __popc(mm), n_strokes = n_ship + n_mis + __popc(sm);
+
+  // ---- ship explosion: memoised sprite (draw.cpp:235-237) ----
   __syncwarp();
-  // ---- ship (draw.cpp:233-237) ----
-  if (in.core & SF_CORE_SHIP_ALIVE) sf_wireframe(W, lane, T, c_wf_ship, 3, in.px, in.py, (int)(in.core & SF_CORE_ANGLE_MASK), T->colour_white);
-  else sf_explosion(W, lane, T, in.px, in.py);
-  // ---- fortress (draw.cpp:238-242): static sprites at (355,315) ----
-  if (in.core & SF_CORE_FORT_ALIVE) {
-    const unsigned char* A = T->fort_alpha[(in.core >> SF_CORE_FANG_SHIFT) & 63u];
-    for (int idx = lane; idx < SF_FORT_W * SF_FORT_W; idx += 32) {
-      unsigned a = A[idx];
-      if (a) {
-        int r = idx / SF_FORT_W, c = idx - r * SF_FORT_W;
-        unsigned char* px = &W.nat[(SF_FORT_Y0 + r) * SF_NAT_STRIDE + SF_FORT_X0 + c];
-        *px = (unsigned char)sf_blend(*px, T->colour_white, a);
+  if (!ship_alive) {
+    SfPt c = sf_xform_base(in.px, in.py);
+    int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
+    unsigned char* cache = D.expc + (size_t)in.env * (SF_EXP_W * SF_EXP_W);
+    if (!(in.core & SF_CORE_EXP_CACHED)) {
+      sf_explosion_raster(T, in.px, in.py);
+      for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+        int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
+        if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) cache[idx] = W.nat[y * SF_TILE_STRIDE + x];
+      }
+      if (lane == 0) D.q0[in.env].x = (int)(in.core | SF_CORE_EXP_CACHED);
+      // the arcs recorded up to 85 small rectangles: replace them by the box
+      if (lane == 0) W.nrect = 0;
+    } else {
+      for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+        int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
+        if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) W.nat[y * SF_TILE_STRIDE + x] = cache[idx];
       }
     }
-    sf_add_rect(W, lane, SF_FORT_X0, SF_FORT_Y0, SF_FORT_X0 + SF_FORT_W - 1, SF_FORT_Y0 + SF_FORT_W - 1);
-  } else {
-    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-      int r = idx / SF_EXP_W, c = idx - r * SF_EXP_W;
-      unsigned char* px = &W.nat[(SF_FEXP_Y0 + r) * SF_NAT_STRIDE + SF_FEXP_X0 + c];
-      unsigned v = *px;
-      for (int l = 0; l < T->fexp_layers; l++) {
-        unsigned a = T->fexp_alpha[l][idx];
-        if (!a) break;
-        v = sf_blend(v, T->fexp_colour[l][idx], a);
-      }
-      *px = (unsigned char)v;
-    }
-    sf_add_rect(W, lane, SF_FEXP_X0, SF_FEXP_Y0, SF_FEXP_X0 + SF_EXP_W - 1, SF_FEXP_Y0 + SF_EXP_W - 1);
+    int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W - 1, SF_NAT_W - 1), y1 = min(by0 + SF_EXP_W - 1, SF_NAT_H - 1);
+    if (x0 <= x1 && y0 <= y1) sf_add_rect(W, lane, x0, y0, x1, y1);
+    __syncwarp();
   }
-  __syncwarp();
-  // ---- missiles (draw.cpp:243-247), slot order ----
-  for (unsigned m = in.pmask & SF_PMASK_MISSILES; m; m &= m - 1) {
-    int s = __ffs(m) - 1;
-    double2 p = D.mpos[(size_t)s * np + in.env];
-    int ang = D.mang[(size_t)s * np + in.env];
-    sf_wireframe(W, lane, T, c_wf_missile, 3, p.x, p.y, ang, T->colour_white);
-  }
-  // ---- shells (draw.cpp:248-253): hidden within 21 units of the fortress (quirk Q9); int angle (Q10) ----
-  for (unsigned m = (in.pmask >> SF_PMASK_SHELL_SHIFT) & 0xFu; m; m &= m - 1) {
-    int s = __ffs(m) - 1;
-    double2 p = D.spos[(size_t)s * np + in.env];
-    double dx = SF_DSUB(p.x, SF_FORT_X), dy = SF_DSUB(p.y, SF_FORT_Y);
-    if (SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) > 21.0) {
-      int ang = __double2int_rz(D.sang[(size_t)s * np + in.env]);
-      if (ang >= 360) ang -= 360;
-      sf_wireframe(W, lane, T, c_wf_shell, 4, p.x, p.y, ang, T->colour_white);
-    }
-  }
-  // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
-  {
-    int pts = min(max(in.points_i, 0), 9999999);
-    for (int idx = lane; idx < SF_TEXT_H * SF_TEXT_W; idx += 32) {
-      int r = idx / SF_TEXT_W, c = idx - r * SF_TEXT_W;
-      int slot = T->text_slot[c];
-      if (slot < 7) {
-        int div = 1;
-        for (int k = slot; k < 6; k++) div *= 10;
-        unsigned a = T->text_alpha[(pts / div) % 10][idx];
-        if (a) {
-          unsigned char* px = &W.nat[(SF_TEXT_Y0 + r) * SF_NAT_STRIDE + SF_TEXT_X0 + c];
-          *px = (unsigned char)sf_blend(*px, T->colour_text, a);
+
+  // ---- moving wireframes in batches of 8 strokes; the fortress layer goes in after the ship ----
+  bool fortress_done = false;
+  // fast path: nothing that moves comes near the sprite -> its pre-resampled output chunks are used and the
+  // tile is left alone. Decided once every moving region is known (explosion box + first batch; with more
+  // than 8 strokes the general path is taken).
+  const int fst_ = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+  bool fortress_general = nat_out != nullptr || n_strokes > 8 ||
+                          sf_rects_touch(W, W.nrect, T->fort_rect[fst_][0] - 2, T->fort_rect[fst_][1] - 2, T->fort_rect[fst_][2] + 2, T->fort_rect[fst_][3] + 2);
+  auto fortress_layer = [&]() {
+    const int st = fst_;
+    const unsigned char* fr = T->fort_rect[st];
+    bool general = fortress_general;
+    if (general) {
+      if (fort_alive) {
+        const int n = T->fort_list_n[st];
+        for (int k = lane; k < n; k += 32) {
+          int idx = T->fort_list_idx[st][k];
+          int r = idx / SF_FORT_W, c = idx - r * SF_FORT_W;
+          unsigned char* px = &W.nat[(SF_FORT_Y0 + r) * SF_TILE_STRIDE + SF_FORT_X0 + c];
+          *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[st][k]);
+        }
+      } else {
+        for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+          unsigned a0 = T->fexp_alpha[0][idx];
+          if (a0) {
+            int r = idx / SF_EXP_W, c = idx - r * SF_EXP_W;
+            unsigned char* px = &W.nat[(SF_FEXP_Y0 + r) * SF_TILE_STRIDE + SF_FEXP_X0 + c];
+            unsigned v = sf_blend(*px, T->fexp_colour[0][idx], a0);
+            for (int l = 1; l < T->fexp_layers; l++) {
+              unsigned a = T->fexp_alpha[l][idx];
+              if (!a) break;
+              v = sf_blend(v, T->fexp_colour[l][idx], a);
+            }
+            *px = (unsigned char)v;
+          }
         }
       }
+      sf_add_rect(W, lane, fr[0], fr[1], fr[2], fr[3]);
+      __syncwarp();
     }
-    sf_add_rect(W, lane, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1);
+    return general;
+  };
+
+  for (int s0 = 0; s0 < n_strokes || !fortress_done; s0 += 8) {
+    int region_id = -1;
+    if (s0 < n_strokes) {
+      sf_batch_begin(W, lane);
+      const int si = s0 + (lane >> 2);
+      int kind = -1, angle = 0;
+      double qx = 0, qy = 0;
+      if (si < n_strokes) {
+        if (si < n_ship) { kind = 0; qx = in.px; qy = in.py; angle = (int)(in.core & SF_CORE_ANGLE_MASK); }
+        else if (si < n_ship + n_mis) {
+          int slot = __fns(mm, 0, si - n_ship + 1);
+          double2 p = D.mpos[(size_t)slot * np + in.env];
+          kind = 1; qx = p.x; qy = p.y; angle = D.mang[(size_t)slot * np + in.env];
+        } else {
+          int slot = __fns(sm, 0, si - n_ship - n_mis + 1);
+          double2 p = D.spos[(size_t)slot * np + in.env];
+          kind = 2; qx = p.x; qy = p.y;
+          angle = __double2int_rz(D.sang[(size_t)slot * np + in.env]);  // `int angle` truncation, quirk Q10
+          if (angle >= 360) angle -= 360;
+        }
+      }
+      region_id = sf_wire_geometry(W, lane, T, kind, qx, qy, angle);
+      if (s0 == 0 && !fortress_general)
+        fortress_general = sf_regions_touch(W, W.nregion, T->fort_rect[fst_][0] - 2, T->fort_rect[fst_][1] - 2, T->fort_rect[fst_][2] + 2, T->fort_rect[fst_][3] + 2);
+      sf_batch_accumulate();
+    }
+    // blend in draw order: ship first, then the fortress layer, then projectiles
+    for (int slot = 0; slot < 8; slot++) {
+      int si = s0 + slot;
+      if (!fortress_done && si >= n_ship) { fortress_layer(); fortress_done = true; }
+      if (si >= n_strokes) break;
+      int rid = __shfl_sync(0xffffffffu, region_id, slot * 4);
+      if (rid >= 0) sf_region_blend(rid);
+    }
   }
-  // ---- vulnerability bar (draw.cpp:207-225,268) ----
+
+  // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
+  const int nmoving = W.nrect;
+  bool text_general, bar_general;
   {
-    int filled = 4 * min(in.vuln, 10);  // 20 user units per step = 4 px
-    unsigned fg = in.kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
-    for (int idx = lane; idx < SF_BAR_H * SF_BAR_W; idx += 32) {
-      int r = idx / SF_BAR_W, c = idx - r * SF_BAR_W;
-      unsigned a = T->bar_alpha[r];
-      unsigned char* px = &W.nat[(SF_BAR_Y0 + r) * SF_NAT_STRIDE + SF_BAR_X0 + c];
-      unsigned v = sf_blend(*px, T->colour_bar_bg, a);
-      if (c < filled) v = sf_blend(v, fg, a);
-      *px = (unsigned char)v;
+    const int pts = min(max(in.points_i, 0), 9999999);
+    bool moving_above = false, moving_below = false;
+    for (int q = 0; q < nmoving; q++) {
+      unsigned r = W.rect[q];
+      moving_above |= (int)((r >> 8) & 255) <= T->text_guard_row;
+      moving_below |= (int)(r >> 24) >= T->bar_guard_row;
     }
-    sf_add_rect(W, lane, SF_BAR_X0, SF_BAR_Y0, SF_BAR_X0 + SF_BAR_W - 1, SF_BAR_Y0 + SF_BAR_H - 1);
+    text_general = nat_out != nullptr || pts != 0 || moving_above;
+    bar_general = nat_out != nullptr || moving_below;
+    if (text_general) {
+      for (int idx = lane; idx < SF_TEXT_H * SF_TEXT_W; idx += 32) {
+        int r = idx / SF_TEXT_W, c = idx - r * SF_TEXT_W;
+        int slot = T->text_slot[c];
+        if (slot < 7) {
+          int div = 1;
+          for (int k = slot; k < 6; k++) div *= 10;
+          unsigned a = T->text_alpha[(pts / div) % 10][idx];
+          if (a) {
+            unsigned char* px = &W.nat[(SF_TEXT_Y0 + r) * SF_TILE_STRIDE + SF_TEXT_X0 + c];
+            *px = (unsigned char)sf_blend(*px, T->colour_text, a);
+          }
+        }
+      }
+      sf_add_rect(W, lane, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1);
+    }
+    // ---- vulnerability bar (draw.cpp:207-225,268) ----
+    if (bar_general) {
+      int filled = 4 * min(in.vuln, 10);  // 20 user units per step = 4 px
+      unsigned fg = in.kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
+      for (int idx = lane; idx < SF_BAR_H * SF_BAR_W; idx += 32) {
+        int r = idx / SF_BAR_W, c = idx - r * SF_BAR_W;
+        unsigned a = T->bar_alpha[r];
+        unsigned char* px = &W.nat[(SF_BAR_Y0 + r) * SF_TILE_STRIDE + SF_BAR_X0 + c];
+        unsigned v = sf_blend(*px, T->colour_bar_bg, a);
+        if (c < filled) v = sf_blend(v, fg, a);
+        *px = (unsigned char)v;
+      }
+      sf_add_rect(W, lane, SF_BAR_X0, SF_BAR_Y0, SF_BAR_X0 + SF_BAR_W - 1, SF_BAR_Y0 + SF_BAR_H - 1);
+    }
   }
   __syncwarp();
-  // ---- native output (SSF_Env.step returns the 92x90 frame) ----
+
+  // ---- native output (SSF_Env.step returns the 92x90 frame): every layer went through the tile ----
   if (nat_out) {
     for (int idx = lane; idx < SF_NAT_H * SF_NAT_W / 2; idx += 32) {
       int r = idx / (SF_NAT_W / 2), c = (idx - r * (SF_NAT_W / 2)) * 2;
-      *reinterpret_cast<uchar2*>(&nat_out[r * SF_NAT_W + c]) = *reinterpret_cast<const uchar2*>(&W.nat[r * SF_NAT_STRIDE + c]);
+      *reinterpret_cast<uchar2*>(&nat_out[r * SF_NAT_W + c]) = *reinterpret_cast<const uchar2*>(&W.nat[r * SF_TILE_STRIDE + c]);
     }
   }
-  // ---- 84x84 observation: static background + resampled dirty rectangles ----
+
+  // ---- 84x84 observation: 441 chunks from the static tables, then the resampled dirty rectangles ----
   if (obs84) {
-    const int4* src = reinterpret_cast<const int4*>(T->bg_obs);
-    int4* dst = reinterpret_cast<int4*>(W.out);
-    for (int k = lane; k < 84 * 84 / 16; k += 32) dst[k] = __ldg(&src[k]);
-    __syncwarp();
+    const int fst = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+    const int bst = in.kill_bar ? 11 : min(in.vuln, 10);
+    const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
+    int4* g = reinterpret_cast<int4*>(obs84);
+    const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
+    const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
+    const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
+#pragma unroll 2
+    for (int k = lane; k < SF_OBS_CHUNKS; k += 32) {
+      const int4* src = &bg[k];
+      if (!fortress_general && k >= fc0 && k < fc1) src = &ft[k - fc0];
+      if (!bar_general && k >= SF_BAR_CHUNK0) src = &bt[k - SF_BAR_CHUNK0];
+      g[k] = __ldg(src);
+    }
+    __syncwarp();  // orders the chunk stores before the byte patches below (same warp)
     const int nr = W.nrect;
     for (int q = 0; q < nr; q++) {
-      int4 R = W.rect[q];
-      int j0 = T->col_out0[R.x], j1 = T->col_out1[R.z], i0 = T->row_out0[R.y], i1 = T->row_out1[R.w];
+      unsigned R = W.rect[q];
+      int x0 = R & 255, y0 = (R >> 8) & 255, x1 = (R >> 16) & 255, y1 = R >> 24;
+      int j0 = T->col_out0[x0], j1 = T->col_out1[x1], i0 = T->row_out0[y0], i1 = T->row_out1[y1];
       int ow = j1 - j0 + 1, cnt = ow * (i1 - i0 + 1);
       float inv_ow = 1.0f / (float)ow;
       for (int idx = lane; idx < cnt; idx += 32) {
-        int r = __float2int_rz(((float)idx + 0.5f) * inv_ow), c = idx - r * ow;
-        W.out[(i0 + r) * 84 + j0 + c] = sf_resample(W, T, i0 + r, j0 + c);
+        int r = sf_div_small(idx, ow, inv_ow), c = idx - r * ow;
+        obs84[(i0 + r) * 84 + j0 + c] = sf_resample(W, T, i0 + r, j0 + c);
       }
     }
-    __syncwarp();
-    int4* g = reinterpret_cast<int4*>(obs84);
-    const int4* o = reinterpret_cast<const int4*>(W.out);
-    for (int k = lane; k < 84 * 84 / 16; k += 32) __stcs(&g[k], o[k]);  // streaming store: obs is write-once
+  }
+  __syncwarp();
+
+  // ---- restore the touched rectangles of the persistent tile ----
+  {
+    const int nr = W.nrect;
+    for (int q = 0; q < nr; q++) {
+      unsigned R = W.rect[q];
+      int x0 = R & 255, y0 = (R >> 8) & 255, x1 = (R >> 16) & 255, y1 = R >> 24;
+      int w = x1 - x0 + 1, cnt = w * (y1 - y0 + 1);
+      float inv_w = 1.0f / (float)w;
+      for (int idx = lane; idx < cnt; idx += 32) {
+        int r = sf_div_small(idx, w, inv_w), c = idx - r * w;
+        W.nat[(y0 + r) * SF_TILE_STRIDE + x0 + c] = T->bg_nat[(y0 + r) * SF_NAT_STRIDE + x0 + c];
+      }
+    }
   }
   __syncwarp();
 }

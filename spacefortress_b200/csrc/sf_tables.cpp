@@ -204,6 +204,26 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     }
   }
 
+  for (int k = 0; k < 84; k++) {
+    t->xtap[k].si = t->xt_si[k][0]; t->xtap[k].cnt = t->xt_cnt[k];
+    t->ytap[k].si = t->yt_si[k][0]; t->ytap[k].cnt = t->yt_cnt[k];
+    for (int j = 0; j < SF_MAX_TAPS; j++) {
+      t->xtap[k].a[j] = j < t->xt_cnt[k] ? t->xt_a[k][j] : 0.f;
+      t->ytap[k].a[j] = j < t->yt_cnt[k] ? t->yt_a[k][j] : 0.f;
+      if (j < t->xt_cnt[k] && t->xt_si[k][j] != t->xt_si[k][0] + j) { snprintf(err, errcap, "x taps not consecutive"); return 1; }
+      if (t->xt_cnt[k] > 2) { snprintf(err, errcap, "x table has more than 2 taps"); return 1; }
+      if (j < t->yt_cnt[k] && t->yt_si[k][j] != t->yt_si[k][0] + j) { snprintf(err, errcap, "y taps not consecutive"); return 1; }
+    }
+  }
+  {
+    static const double WF[3][4][4] = {
+        {{-18, 0, 18, 0}, {-18, 18, 0, 0}, {0, 0, -18, -18}, {0, 0, 0, 0}},      // ship    wireframe.cpp:39-53
+        {{0, 0, -25, 0}, {0, 0, -5, 5}, {0, 0, -5, -5}, {0, 0, 0, 0}},           // missile wireframe.cpp:11-22
+        {{-8, 0, 0, -6}, {0, -6, 16, 0}, {16, 0, 0, 6}, {0, 6, -8, 0}}};         // shell   wireframe.cpp:24-37
+    memcpy(t->wf_line, WF, sizeof(WF));
+    t->wf_nlines[0] = 3; t->wf_nlines[1] = 3; t->wf_nlines[2] = 4;
+  }
+
   std::vector<unsigned char> alpha;
 
   // ---- background: two hexagons on black (draw.cpp:262-263, 230-231) ----
@@ -348,18 +368,101 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     if ((a.y >> 8) != SF_BAR_Y0 || ((b.y - 1) >> 8) != SF_BAR_Y0 + SF_BAR_H - 1) { snprintf(err, errcap, "bar rows"); return 1; }
   }
 
-  // ---- bg_obs = INTER_AREA(bg_nat) with the same float operation order as the device epilogue ----
-  for (int i = 0; i < 84; i++)
-    for (int j = 0; j < 84; j++) {
-      float sum = 0.f;
-      for (int ky = 0; ky < t->yt_cnt[i]; ky++) {
-        float buf = 0.f;
-        const unsigned char* S = &t->bg_nat[t->yt_si[i][ky] * SF_NAT_STRIDE];
-        for (int kx = 0; kx < t->xt_cnt[j]; kx++) buf += (float)S[t->xt_si[j][kx]] * t->xt_a[j][kx];
-        sum = (ky == 0) ? t->yt_a[i][ky] * buf : sum + t->yt_a[i][ky] * buf;
+  // ---- output-space tables: INTER_AREA with the same float operation order as the device epilogue ----
+  auto resample = [&](const std::vector<unsigned char>& nat, unsigned char* obs) {
+    for (int i = 0; i < 84; i++)
+      for (int j = 0; j < 84; j++) {
+        float sum = 0.f;
+        for (int ky = 0; ky < t->yt_cnt[i]; ky++) {
+          float buf = 0.f;
+          const unsigned char* S = &nat[t->yt_si[i][ky] * SF_NAT_STRIDE];
+          for (int kx = 0; kx < t->xt_cnt[j]; kx++) buf += (float)S[t->xt_si[j][kx]] * t->xt_a[j][kx];
+          sum = (ky == 0) ? t->yt_a[i][ky] * buf : sum + t->yt_a[i][ky] * buf;
+        }
+        obs[i * 84 + j] = (unsigned char)lrintf(sum);
       }
-      t->bg_obs[i * 84 + j] = (unsigned char)lrintf(sum);
+  };
+  auto blend_px = [&](std::vector<unsigned char>& nat, int x, int y, unsigned colour, unsigned a) {
+    unsigned char& d = nat[y * SF_NAT_STRIDE + x];
+    d = (unsigned char)sf_blend(d, colour, a);
+  };
+  auto draw_text0 = [&](std::vector<unsigned char>& nat) {
+    for (int i = 0; i < SF_TEXT_H * SF_TEXT_W; i++)
+      if (t->text_slot[i % SF_TEXT_W] < 7 && t->text_alpha[0][i]) blend_px(nat, SF_TEXT_X0 + i % SF_TEXT_W, SF_TEXT_Y0 + i / SF_TEXT_W, t->colour_text, t->text_alpha[0][i]);
+  };
+  auto draw_bar = [&](std::vector<unsigned char>& nat, int state) {
+    int filled = 4 * std::min(state, 10);
+    for (int i = 0; i < SF_BAR_H * SF_BAR_W; i++) {
+      int r = i / SF_BAR_W, c = i % SF_BAR_W;
+      blend_px(nat, SF_BAR_X0 + c, SF_BAR_Y0 + r, t->colour_bar_bg, t->bar_alpha[r]);
+      if (c < filled) blend_px(nat, SF_BAR_X0 + c, SF_BAR_Y0 + r, state == 11 ? t->colour_bar_kill : t->colour_bar_fg, t->bar_alpha[r]);
     }
+  };
+  std::vector<unsigned char> base(t->bg_nat, t->bg_nat + SF_NAT_H * SF_NAT_STRIDE);
+  {
+    std::vector<unsigned char> nat = base;
+    draw_text0(nat);
+    draw_bar(nat, 0);
+    resample(nat, t->bg_obs);  // default observation: hexagons + "0000000" + empty bar
+  }
+  // which native rows do the text / bar output rows read?
+  t->text_guard_row = t->yt_si[t->row_out1[SF_TEXT_Y0 + SF_TEXT_H - 1]][t->yt_cnt[t->row_out1[SF_TEXT_Y0 + SF_TEXT_H - 1]] - 1];
+  t->bar_guard_row = t->yt_si[t->row_out0[SF_BAR_Y0]][0];
+  if (t->row_out0[SF_BAR_Y0] * 84 != SF_BAR_CHUNK0 * 16 || t->row_out1[SF_BAR_Y0 + SF_BAR_H - 1] != 83) { snprintf(err, errcap, "bar output rows are not chunks 420..440"); return 1; }
+  for (int st = 0; st < SF_BAR_STATES; st++) {
+    std::vector<unsigned char> nat = base, obs(84 * 84);
+    draw_text0(nat);
+    draw_bar(nat, st);
+    resample(nat, obs.data());
+    memcpy(t->obs_bar[st], &obs[SF_BAR_CHUNK0 * 16], (SF_OBS_CHUNKS - SF_BAR_CHUNK0) * 16);
+    for (int b = 0; b < SF_BAR_CHUNK0 * 16; b++) if (obs[b] != t->bg_obs[b]) { snprintf(err, errcap, "bar influences rows above chunk 420"); return 1; }
+  }
+  // sparse fortress lists + rects
+  for (int k = 0; k < 36; k++) {
+    int n = 0, x0 = 1 << 20, y0 = 1 << 20, x1 = -1, y1 = -1;
+    for (int i = 0; i < SF_FORT_W * SF_FORT_W; i++) if (t->fort_alpha[k][i]) {
+      if (n >= SF_FORT_LIST) { snprintf(err, errcap, "fortress sprite has more than %d lit pixels", SF_FORT_LIST); return 1; }
+      t->fort_list_idx[k][n] = (unsigned short)i; t->fort_list_a[k][n] = t->fort_alpha[k][i]; n++;
+      int x = SF_FORT_X0 + i % SF_FORT_W, y = SF_FORT_Y0 + i / SF_FORT_W;
+      x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x); y1 = std::max(y1, y);
+    }
+    t->fort_list_n[k] = n;
+    t->fort_rect[k][0] = (unsigned char)x0; t->fort_rect[k][1] = (unsigned char)y0; t->fort_rect[k][2] = (unsigned char)x1; t->fort_rect[k][3] = (unsigned char)y1;
+  }
+  {
+    int x0 = 1 << 20, y0 = 1 << 20, x1 = -1, y1 = -1;
+    for (int i = 0; i < SF_EXP_W * SF_EXP_W; i++) if (t->fexp_alpha[0][i]) {
+      int x = SF_FEXP_X0 + i % SF_EXP_W, y = SF_FEXP_Y0 + i / SF_EXP_W;
+      x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x); y1 = std::max(y1, y);
+    }
+    t->fort_rect[36][0] = (unsigned char)x0; t->fort_rect[36][1] = (unsigned char)y0; t->fort_rect[36][2] = (unsigned char)x1; t->fort_rect[36][3] = (unsigned char)y1;
+  }
+  // pre-resampled fortress states on the default base
+  {
+    std::vector<std::vector<unsigned char>> obs(SF_FORT_STATES, std::vector<unsigned char>(84 * 84));
+    int c0 = SF_OBS_CHUNKS, c1 = -1;
+    for (int st = 0; st < SF_FORT_STATES; st++) {
+      std::vector<unsigned char> nat = base;
+      if (st < 36) {
+        for (int n = 0; n < t->fort_list_n[st]; n++) {
+          int i = t->fort_list_idx[st][n];
+          blend_px(nat, SF_FORT_X0 + i % SF_FORT_W, SF_FORT_Y0 + i / SF_FORT_W, t->colour_white, t->fort_list_a[st][n]);
+        }
+      } else {
+        for (int i = 0; i < SF_EXP_W * SF_EXP_W; i++)
+          for (int l = 0; l < t->fexp_layers && t->fexp_alpha[l][i]; l++)
+            blend_px(nat, SF_FEXP_X0 + i % SF_EXP_W, SF_FEXP_Y0 + i / SF_EXP_W, t->fexp_colour[l][i], t->fexp_alpha[l][i]);
+      }
+      draw_text0(nat);
+      draw_bar(nat, 0);
+      resample(nat, obs[st].data());
+      for (int c = 0; c < SF_OBS_CHUNKS; c++)
+        if (memcmp(&obs[st][c * 16], &t->bg_obs[c * 16], 16)) { c0 = std::min(c0, c); c1 = std::max(c1, c); }
+    }
+    if (c1 < c0 || c1 - c0 + 1 > SF_FORT_CHUNKS || c1 >= SF_BAR_CHUNK0) { snprintf(err, errcap, "fortress chunk range %d..%d", c0, c1); return 1; }
+    t->fort_chunk0 = c0; t->fort_nchunks = c1 - c0 + 1;
+    for (int st = 0; st < SF_FORT_STATES; st++) memcpy(t->obs_fort[st], &obs[st][c0 * 16], (size_t)t->fort_nchunks * 16);
+  }
   return 0;
 }
 

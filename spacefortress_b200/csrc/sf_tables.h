@@ -8,7 +8,8 @@
 #define SF_NAT_W 90  // int(450*.2), ssf_env.py:57
 #define SF_NAT_H 92  // int(460*.2), ssf_env.py:58
 
-#define SF_NAT_STRIDE 96           // native tile row stride in bytes (16-byte aligned rows)
+#define SF_NAT_STRIDE 96           // row stride of the bg_nat table (16-byte aligned rows)
+#define SF_TILE_STRIDE 92          // row stride of the per-warp shared-memory tile (4-byte aligned rows)
 #define SF_FORT_W 17               // fortress sprite box (native px)
 #define SF_FORT_X0 37
 #define SF_FORT_Y0 39
@@ -27,6 +28,14 @@
 #define SF_EXP_STROKES 85          // 7 rings x 12 arcs + the r=7 circle
 #define SF_EXP_QUADS 100           // 84 arc quads + 16 circle quads
 #define SF_MAX_TAPS 3
+#define SF_FORT_LIST 160           // max lit pixels of a fortress sprite
+#define SF_OBS_CHUNKS 441          // 84*84/16
+#define SF_BAR_CHUNK0 420          // output rows 80..83 == chunks 420..440
+#define SF_BAR_STATES 12           // filled 0..10 steps in grey .66, or full white (kill window)
+#define SF_FORT_STATES 37          // 36 sector angles + destroyed (explosion)
+#define SF_FORT_CHUNKS 160         // upper bound of output chunks influenced by the fortress/explosion box
+
+struct SfTap { int si, cnt; float a[SF_MAX_TAPS]; };  // consecutive source indices si..si+cnt-1 and their weights
 
 struct SfTables {
   // trig for integer degrees, computed with the host libm exactly as the reference does:
@@ -43,6 +52,7 @@ struct SfTables {
   float xt_a[84][SF_MAX_TAPS];
   int yt_cnt[84], yt_si[84][SF_MAX_TAPS];
   float yt_a[84][SF_MAX_TAPS];
+  SfTap xtap[84], ytap[84];                    // the same tables, packed for the device epilogue
   int col_out0[SF_NAT_W], col_out1[SF_NAT_W];  // first/last output column reading native column c
   int row_out0[SF_NAT_H], row_out1[SF_NAT_H];
   // explosion geometry relative to the fixed-point centre: per quad 4 corners (dx,dy)
@@ -59,6 +69,22 @@ struct SfTables {
   unsigned char text_slot[SF_TEXT_W];                  // which of the 7 digit slots owns a strip column (255: none)
   unsigned char bar_alpha[SF_BAR_H];                   // per-row coverage of the vulnerability bar
   unsigned char colour_bar_bg, colour_bar_fg, colour_bar_kill, colour_text, colour_white;
+  // wireframe models (wireframe.cpp:8-70): [0]=ship [1]=missile [2]=shell; line = from.x, from.y, to.x, to.y
+  double wf_line[3][4][4];
+  int wf_nlines[3];
+  // sparse fortress sprites: lit pixels only (index into the 17x17 box, coverage), tight bounding rect
+  unsigned short fort_list_idx[36][SF_FORT_LIST];
+  unsigned char fort_list_a[36][SF_FORT_LIST];
+  int fort_list_n[36];
+  unsigned char fort_rect[SF_FORT_STATES][4];  // x0,y0,x1,y1 native px of the lit pixels (state 36 = explosion)
+  // Pre-resampled output for the static layers when no moving object overlaps them. bg_obs above already
+  // contains score "0000000" and the empty vulnerability bar; these tables hold the 16-byte output chunks that
+  // change with the fortress state / bar state (same base frame).
+  int fort_chunk0, fort_nchunks;
+  alignas(16) unsigned char obs_fort[SF_FORT_STATES][SF_FORT_CHUNKS * 16];
+  alignas(16) unsigned char obs_bar[SF_BAR_STATES][(SF_OBS_CHUNKS - SF_BAR_CHUNK0) * 16];
+  int text_guard_row;  // moving rects with y0 <= this native row force the general text path
+  int bar_guard_row;   // moving rects with y1 >= this native row force the general bar path
 };
 
 // builds the tables on the host; returns 0 on success, else a message in err

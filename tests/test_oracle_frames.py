@@ -68,11 +68,11 @@ def test_static_tables_match_oracle(alive):
 
 
 def test_background_observation_table():
-    """bg_obs (the 84x84 frame the kernel starts every observation from) == INTER_AREA(bare background),
-    through the oracle's cv2-pinned resize."""
+    """bg_obs (the 84x84 frame the kernel starts every observation from) == INTER_AREA(hexagons + score
+    "0000000" + empty vulnerability bar), through the oracle's cv2-pinned resize."""
     L = _lib.lib()
     nat = np.zeros((92, 90), np.uint8)
     bgo = np.zeros((84, 84), np.uint8)
-    assert L.sf_host_static_frame(-1, 0, -1, -1, 0, nat.ctypes.data_as(C.c_void_p), bgo.ctypes.data_as(C.c_void_p)) == 0
+    assert L.sf_host_static_frame(-1, 0, 0, 0, 0, nat.ctypes.data_as(C.c_void_p), bgo.ctypes.data_as(C.c_void_p)) == 0
     assert nat.max() > 100 and (nat > 0).sum() > 300  # two hexagons (0.6 px lines never cover a whole pixel)
     assert np.array_equal(resize_area(nat), bgo)
