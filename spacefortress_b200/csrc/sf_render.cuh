@@ -161,17 +161,21 @@ __device__ __forceinline__ void sf_store_quad_edges(SfWarpSmem& W, int qi, const
 }
 
 // span of quad slot qi on biased grid row sb; returns false when the quad is not live there
+__device__ __noinline__ void sf_quad_span_irregular(int qi, int sb, int& lo, int& hi) {
+  const SfWarpSmem& W = sf_my_smem();
+  lo = 1 << 30; hi = -(1 << 30);
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    int4 E = W.edge[qi * 4 + k];
+    int m = sb - (int)((unsigned)E.y >> 16);
+    if ((unsigned)m < (unsigned)(E.y & 0xFFFF)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
+  }
+}
 __device__ __forceinline__ bool sf_quad_span(const SfWarpSmem& W, int qi, int sb, int& lo, int& hi) {
   int2 qr = W.quadrec[qi];
   if (qr.y & SF_QUAD_IRREGULAR) {
     if (sb < qr.x || sb >= (qr.y & ~SF_QUAD_IRREGULAR)) return false;
-    lo = 1 << 30; hi = -(1 << 30);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int4 E = W.edge[qi * 4 + k];
-      int m = sb - (int)((unsigned)E.y >> 16);
-      if ((unsigned)m < (unsigned)(E.y & 0xFFFF)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
-    }
+    sf_quad_span_irregular(qi, sb, lo, hi);
     return true;
   }
   if (sb < qr.x || sb >= qr.y) return false;
@@ -228,62 +232,83 @@ __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool wan
 }
 
 // Accumulate span lengths of every stroke of the batch. Samples (stroke, row, sub-row) are flattened over lanes.
+// Within a stroke, samples are ordered in blocks of 4 pixel rows (row fastest, then sub-row): one pass of 32 lanes
+// then covers ~4 rows x 8 sub-rows, so (a) same-cell atomic conflicts stay low and (b) quads that do not reach
+// those rows are skipped with a warp-uniform test.
 __device__ __noinline__ void sf_batch_accumulate() {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
   __syncwarp();
   const int nitems = W.nitems, ns = W.nstroke;
+  int s_first = 0;  // stroke containing the first sample of the pass (warp uniform)
+#pragma unroll 1
   for (int it0 = 0; it0 < nitems; it0 += 32) {
-    int it = it0 + lane;
-    if (it < nitems) {
-      // binary search: last stroke with first_item <= it
-      int lo_s = 0, hi_s = ns - 1;
-      while (lo_s < hi_s) {
-        int mid = (lo_s + hi_s + 1) >> 1;
-        if (W.stroke[mid].y <= it) lo_s = mid; else hi_s = mid - 1;
+    const int it = it0 + lane;
+    const bool valid = it < nitems;
+    while (s_first + 1 < ns && W.stroke[s_first + 1].y <= it0) s_first++;
+    int si = s_first;
+    while (valid && si + 1 < ns && W.stroke[si + 1].y <= it) si++;
+    const int2 S = W.stroke[si];
+    const int4 R = W.region[S.x & 255];
+    const int quad0 = (S.x >> 8) & 255, nq = (S.x >> 16) & 255;
+    const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+    // sample index -> (row, sub): full blocks of 4 rows, then the remaining 1..3 rows
+    const int li = valid ? it - S.y : 0;
+    const int nfull = h >> 2, rem = h & 3;
+    int r, sub;
+    if (li < nfull * 60) {
+      int blk = sf_div_small(li, 60, 1.0f / 60.0f), t = li - blk * 60;
+      sub = t >> 2; r = blk * 4 + (t & 3);
+    } else {
+      int t = li - nfull * 60;
+      sub = rem == 3 ? sf_div_small(t, 3, 1.0f / 3.0f) : (rem == 2 ? t >> 1 : t);
+      r = nfull * 4 + t - sub * rem;
+    }
+    const int sb = (R.y + r) * SF_GRID_Y + sub + SF_YBIAS;
+    const int xlo = R.x << 8, xhi = (R.x + w) << 8;
+    const int cell0 = (R.w & 0xFFFF) + r * w;
+    // spans of the stroke's quads, kept sorted by start in four registers (insertion keeps the loops rolled so
+    // the whole body stays small enough for the instruction cache)
+    unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+      bool live = false;
+      if (valid && j < nq) {
+        int2 qr = W.quadrec[quad0 + j];
+        live = sb >= qr.x && sb < (qr.y & ~SF_QUAD_IRREGULAR);
       }
-      int2 S = W.stroke[lo_s];
-      int4 R = W.region[S.x & 255];
-      int quad0 = (S.x >> 8) & 255, nq = (S.x >> 16) & 255;
-      int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-      int li = it - S.y;
-      int sub = sf_div_small(li, h, 1.0f / (float)h);  // rows vary fastest: neighbouring lanes hit different cells
-      int r = li - sub * h;
-      int sb = (R.y + r) * SF_GRID_Y + sub + SF_YBIAS;
-      int xlo = R.x << 8, xhi = (R.x + w) << 8;
-      unsigned short* cells = W.acc + (R.w & 0xFFFF) + r * w;
-      unsigned key[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        key[j] = 0xFFFFFFFFu;
+      if (!__any_sync(0xffffffffu, live)) continue;
+      unsigned key = 0xFFFFFFFFu;
+      if (live) {
         int lo, hi;
-        if (j < nq && sf_quad_span(W, quad0 + j, sb, lo, hi)) {
-          lo = max(lo, xlo); hi = min(hi, xhi);
-          if (lo < hi) key[j] = ((unsigned)(lo - xlo) << 16) | (unsigned)(hi - xlo);
+        sf_quad_span(W, quad0 + j, sb, lo, hi);
+        lo = max(lo, xlo); hi = min(hi, xhi);
+        if (lo < hi) key = ((unsigned)(lo - xlo) << 16) | (unsigned)(hi - xlo);
+      }
+      unsigned t = key, m;
+      m = min(k0, t); t = max(k0, t); k0 = m;
+      m = min(k1, t); t = max(k1, t); k1 = m;
+      m = min(k2, t); t = max(k2, t); k2 = m;
+      k3 = min(k3, t);
+    }
+    // emit each span minus the union of its predecessors; 16-bit cells, 32-bit atomics: a cell never exceeds
+    // 15*256, so the two halves of a word cannot carry into each other
+    unsigned* acc32 = reinterpret_cast<unsigned*>(W.acc);
+    int reach = 0;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, k0 != 0xFFFFFFFFu)) {
+      if (k0 != 0xFFFFFFFFu) {
+        int a = max((int)(k0 >> 16), reach), b = (int)(k0 & 0xFFFFu);
+        reach = max(reach, b);
+        int cell = a >> 8;
+        while (a < b) {
+          int e = min(b, (cell + 1) << 8);
+          int ci = cell0 + cell;
+          atomicAdd(&acc32[ci >> 1], (unsigned)(e - a) << ((ci & 1) << 4));
+          a = e; cell++;
         }
       }
-      if (nq > 1) {  // sort the spans by start, then emit each span minus the union of its predecessors
-#define SF_CE(a, b) { unsigned lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
-        SF_CE(0, 1) SF_CE(2, 3) SF_CE(0, 2) SF_CE(1, 3) SF_CE(1, 2)
-#undef SF_CE
-      }
-      int reach = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (key[j] != 0xFFFFFFFFu) {
-          int a = max((int)(key[j] >> 16), reach), b = (int)(key[j] & 0xFFFFu);
-          reach = max(reach, b);
-          int cell = a >> 8;
-          while (a < b) {
-            int e = min(b, (cell + 1) << 8);
-            // 16-bit cells, 32-bit atomics: a cell never exceeds 15*256 so halves cannot carry into each other
-            unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<size_t>(cells + cell) & ~(size_t)3);
-            unsigned shift = (reinterpret_cast<size_t>(cells + cell) & 2) ? 16u : 0u;
-            atomicAdd(word, (unsigned)(e - a) << shift);
-            a = e; cell++;
-          }
-        }
-      }
+      k0 = k1; k1 = k2; k2 = k3; k3 = 0xFFFFFFFFu;
     }
   }
   __syncwarp();
