@@ -50,7 +50,7 @@ __device__ __forceinline__ long long sf_warp_sum_ll(long long v) {
   return v;
 }
 
-__device__ inline void sf_accumulate_episode(const SfDev& D, const SfEnv& e, bool finished, int lane) {
+__device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, const SfEnv& e, bool finished, int lane) {
   // called by all 32 lanes; `finished` lanes contribute
   long long f[SF_NUM_EPISODE_STATS];
   long long ret = e.q3.w;

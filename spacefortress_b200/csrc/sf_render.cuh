@@ -91,11 +91,11 @@ __device__ __forceinline__ void sf_add_rect(SfWarpSmem& W, int lane, int x0, int
 }
 
 // ---- edge records --------------------------------------------------------------------------------------
-// x(s) = x_top + floor((s - ytop) * dx / dy), exact, via a magic reciprocal (valid while (dy*|dx|+dy)*dy < 2^32:
-// always true for the strokes drawn here, which are at most ~30 px tall).
-__device__ __forceinline__ int4 sf_make_edge(int xa, int ga, int xb, int gb) {  // ga < gb (grid rows)
+// x(s) = x_top + floor((s - ytop) * dx / dy), exact, via a magic reciprocal M = floor((2^32-1)/dy) + 1 (valid while
+// (dy*|dx|+dy)*dy < 2^32: always true for the strokes drawn here, which are at most ~30 px tall).
+__device__ __forceinline__ int4 sf_make_edge(const SfTables* T, int xa, int ga, int xb, int gb) {  // ga < gb (grid rows)
   int dy = gb - ga;
-  unsigned M = dy > 1 ? (unsigned)((1ull << 32) / (unsigned)dy) + 1u : 0u;
+  unsigned M = dy < SF_MAGIC_N ? T->magic[dy] : 0xFFFFFFFFu / (unsigned)dy + 1u;
   return make_int4(xa, ((ga + SF_YBIAS) << 16) | dy, xb - xa, (int)M);
 }
 __device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias, ytop <= s < ytop + dy
@@ -107,57 +107,40 @@ __device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias, yt
   return E.z < 0 ? E.x - (int)q : E.x + (int)q;
 }
 
-// Build the 4 edge records of convex quad q (cyclic corners, consistent orientation) into slot `qi`.
-// Edges whose grid rows increase along the traversal lie on one side, the others on the opposite side; a
-// stroked segment is a parallelogram, so each side has at most two non-degenerate edges.
-__device__ __forceinline__ void sf_store_quad_edges(SfWarpSmem& W, int qi, const SfQuad& q, int& ymin_g, int& ymax_g, int& xmin, int& xmax) {
-  int g[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) g[k] = sf_grid_y(q.p[k].y);
-  int4 dn[2], up[2];
-  int nd = 0, nu = 0;
-  int4 none = make_int4(0, 0, 0, 0);  // ytop field 0 with dy 0: never live
-  dn[0] = dn[1] = up[0] = up[1] = none;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    int a = k, b = (k + 1) & 3;
-    if (g[a] < g[b]) { int4 E = sf_make_edge(q.p[a].x, g[a], q.p[b].x, g[b]); if (nd == 0) dn[0] = E; else dn[1] = E; nd++; }
-    else if (g[a] > g[b]) { int4 E = sf_make_edge(q.p[b].x, g[b], q.p[a].x, g[a]); if (nu == 0) up[0] = E; else up[1] = E; nu++; }
-  }
-  int gmin = min(min(g[0], g[1]), min(g[2], g[3])), gmax = max(max(g[0], g[1]), max(g[2], g[3]));
-  bool live = nd > 0 && nu > 0;
+// Build the 4 edge records of convex quad q (cyclic corners, consistent orientation) into slot `qi` and return
+// its bounding box {ymin_g, ymax_g, xmin, xmax} (ymin_g >= ymax_g when the quad covers no sample).
+// Edges whose grid rows increase along the traversal lie on one side, the others on the opposite side; a stroked
+// segment is a parallelogram, so each side has at most two non-degenerate edges. Trapezoids (explosion arcs that
+// straddle 0/180 degrees) can have three on one side: those keep all edges and the span tests every one.
+__device__ __noinline__ int4 sf_store_quad_edges(const SfTables* T, int qi, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3) {
+  SfWarpSmem& W = sf_my_smem();
+  const int g0 = sf_grid_y(y0), g1 = sf_grid_y(y1), g2 = sf_grid_y(y2), g3 = sf_grid_y(y3);
+  const int4 none = make_int4(0, 0, 0, 0);  // dy 0: never live
+  int4 E0 = none, E1 = none, E2 = none, E3 = none;
+  int d0 = 0, d1 = 0, d2 = 0, d3 = 0;  // +1: rows increase along the traversal, -1: decrease, 0: degenerate
+  if (g0 < g1) { E0 = sf_make_edge(T, x0, g0, x1, g1); d0 = 1; } else if (g0 > g1) { E0 = sf_make_edge(T, x1, g1, x0, g0); d0 = -1; }
+  if (g1 < g2) { E1 = sf_make_edge(T, x1, g1, x2, g2); d1 = 1; } else if (g1 > g2) { E1 = sf_make_edge(T, x2, g2, x1, g1); d1 = -1; }
+  if (g2 < g3) { E2 = sf_make_edge(T, x2, g2, x3, g3); d2 = 1; } else if (g2 > g3) { E2 = sf_make_edge(T, x3, g3, x2, g2); d2 = -1; }
+  if (g3 < g0) { E3 = sf_make_edge(T, x3, g3, x0, g0); d3 = 1; } else if (g3 > g0) { E3 = sf_make_edge(T, x0, g0, x3, g3); d3 = -1; }
+  const int nd = (d0 > 0) + (d1 > 0) + (d2 > 0) + (d3 > 0), nu = (d0 < 0) + (d1 < 0) + (d2 < 0) + (d3 < 0);
+  const int gmin = min(min(g0, g1), min(g2, g3)), gmax = max(max(g0, g1), max(g2, g3));
+  if (nd == 0 || nu == 0) { W.quadrec[qi] = make_int2(0, 0); return make_int4(1 << 30, -(1 << 30), 1 << 30, -(1 << 30)); }
   if (nd > 2 || nu > 2) {
-    // a trapezoid can have three edges on one side (explosion arcs straddling 0/180 degrees): keep all
-    // non-degenerate edges and let the span test every one of them
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int a = k, b = (k + 1) & 3;
-      int4 E = none;
-      if (g[a] < g[b]) E = sf_make_edge(q.p[a].x, g[a], q.p[b].x, g[b]);
-      else if (g[a] > g[b]) E = sf_make_edge(q.p[b].x, g[b], q.p[a].x, g[a]);
-      W.edge[qi * 4 + k] = E;
-      n++;
-    }
+    W.edge[qi * 4 + 0] = E0; W.edge[qi * 4 + 1] = E1; W.edge[qi * 4 + 2] = E2; W.edge[qi * 4 + 3] = E3;
     W.quadrec[qi] = make_int2(gmin + SF_YBIAS, (gmax + SF_YBIAS) | SF_QUAD_IRREGULAR);
-    ymin_g = min(ymin_g, gmin); ymax_g = max(ymax_g, gmax);
-    xmin = min(xmin, min(min(q.p[0].x, q.p[1].x), min(q.p[2].x, q.p[3].x)));
-    xmax = max(xmax, max(max(q.p[0].x, q.p[1].x), max(q.p[2].x, q.p[3].x)));
-    return;
+  } else {
+    // first / second edge of each direction in cyclic order
+    int4 dnA = d0 > 0 ? E0 : d1 > 0 ? E1 : d2 > 0 ? E2 : E3;
+    int4 dnB = d3 > 0 ? E3 : d2 > 0 ? E2 : d1 > 0 ? E1 : E0;
+    int4 upA = d0 < 0 ? E0 : d1 < 0 ? E1 : d2 < 0 ? E2 : E3;
+    int4 upB = d3 < 0 ? E3 : d2 < 0 ? E2 : d1 < 0 ? E1 : E0;
+    // order each side top to bottom; a side with one edge has A == B (the split test selects B, same edge)
+    if ((unsigned)dnB.y < (unsigned)dnA.y) { int4 t = dnA; dnA = dnB; dnB = t; }
+    if ((unsigned)upB.y < (unsigned)upA.y) { int4 t = upA; upA = upB; upB = t; }
+    W.edge[qi * 4 + 0] = dnA; W.edge[qi * 4 + 1] = dnB; W.edge[qi * 4 + 2] = upA; W.edge[qi * 4 + 3] = upB;
+    W.quadrec[qi] = make_int2(gmin + SF_YBIAS, gmax + SF_YBIAS);
   }
-  // order each side top to bottom; a side with one edge gets it twice (the second copy is selected by the
-  // split test below and evaluates identically)
-  if (nd == 1) dn[1] = dn[0];
-  else if (nd >= 2 && (unsigned)dn[1].y < (unsigned)dn[0].y) { int4 t = dn[0]; dn[0] = dn[1]; dn[1] = t; }
-  if (nu == 1) up[1] = up[0];
-  else if (nu >= 2 && (unsigned)up[1].y < (unsigned)up[0].y) { int4 t = up[0]; up[0] = up[1]; up[1] = t; }
-  W.edge[qi * 4 + 0] = dn[0]; W.edge[qi * 4 + 1] = dn[1]; W.edge[qi * 4 + 2] = up[0]; W.edge[qi * 4 + 3] = up[1];
-  W.quadrec[qi] = live ? make_int2(gmin + SF_YBIAS, gmax + SF_YBIAS) : make_int2(0, 0);
-  if (live) {
-    ymin_g = min(ymin_g, gmin); ymax_g = max(ymax_g, gmax);
-    xmin = min(xmin, min(min(q.p[0].x, q.p[1].x), min(q.p[2].x, q.p[3].x)));
-    xmax = max(xmax, max(max(q.p[0].x, q.p[1].x), max(q.p[2].x, q.p[3].x)));
-  }
+  return make_int4(gmin, gmax, min(min(x0, x1), min(x2, x3)), max(max(x0, x1), max(x2, x3)));
 }
 
 // span of quad slot qi on biased grid row sb; returns false when the quad is not live there
@@ -353,7 +336,10 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
       const double* L = T->wf_line[kind][line];
       SfPt a = sf_xform_wire(m, L[0], L[1]), b = sf_xform_wire(m, L[2], L[3]);
       SfQuad q;
-      if (sf_stroke_quad(a, b, q)) { sf_store_quad_edges(W, slot * 4 + line, q, ymin_g, ymax_g, xmin, xmax); has = true; }
+      if (sf_stroke_quad(a, b, q)) {
+        int4 bb = sf_store_quad_edges(T, slot * 4 + line, q.p[0].x, q.p[0].y, q.p[1].x, q.p[1].y, q.p[2].x, q.p[2].y, q.p[3].x, q.p[3].y);
+        ymin_g = bb.x; ymax_g = bb.y; xmin = bb.z; xmax = bb.w; has = true;
+      }
     }
   }
   if (!has) W.quadrec[slot * 4 + line] = make_int2(0, 0);
@@ -384,10 +370,8 @@ __device__ __noinline__ void sf_explosion_raster(const SfTables* T, double px, d
     bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
     if (mine) {
       const short* o = T->exp_quad[s];
-      SfQuad q;
-#pragma unroll
-      for (int j = 0; j < 4; j++) { q.p[j].x = c.x + o[2 * j]; q.p[j].y = c.y + o[2 * j + 1]; }
-      sf_store_quad_edges(W, lane, q, ymin_g, ymax_g, xmin, xmax);
+      int4 bb = sf_store_quad_edges(T, lane, c.x + o[0], c.y + o[1], c.x + o[2], c.y + o[3], c.x + o[4], c.y + o[5], c.x + o[6], c.y + o[7]);
+      ymin_g = bb.x; ymax_g = bb.y; xmin = bb.z; xmax = bb.w;
     } else W.quadrec[lane] = make_int2(0, 0);
     if (!circle) {
       sf_open_regions(W, lane, mine, ymin_g, ymax_g, xmin, xmax, mine ? T->exp_colour[s] : 0u, lane, 1);
@@ -427,6 +411,115 @@ __device__ __forceinline__ unsigned char sf_resample(const SfWarpSmem& W, const 
     }
   }
   return (unsigned char)__float2int_rn(sum);
+}
+
+// Ship explosion layer: rasterised once per death, then replayed from the per-env sprite cache.
+__device__ __noinline__ void sf_ship_explosion(const SfTables* T, unsigned char* expc, int4* q0, int env, unsigned core, double px, double py) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  SfPt c = sf_xform_base(px, py);
+  int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
+  unsigned char* cache = expc + (size_t)env * (SF_EXP_W * SF_EXP_W);
+  if (!(core & SF_CORE_EXP_CACHED)) {
+    sf_explosion_raster(T, px, py);
+#pragma unroll 1
+    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+      int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
+      if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) cache[idx] = W.nat[y * SF_TILE_STRIDE + x];
+    }
+    if (lane == 0) q0[env].x = (int)(core | SF_CORE_EXP_CACHED);
+    if (lane == 0) W.nrect = 0;  // the arcs recorded up to 85 small rectangles: replace them by the box
+  } else {
+#pragma unroll 1
+    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+      int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
+      if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) W.nat[y * SF_TILE_STRIDE + x] = cache[idx];
+    }
+  }
+  int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W - 1, SF_NAT_W - 1), y1 = min(by0 + SF_EXP_W - 1, SF_NAT_H - 1);
+  if (x0 <= x1 && y0 <= y1) sf_add_rect(W, lane, x0, y0, x1, y1);
+  __syncwarp();
+}
+
+// Fortress layer blended into the tile (general path: something that moves overlaps it, or native output).
+__device__ __noinline__ void sf_fortress_general(const SfTables* T, int st) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  const unsigned char* fr = T->fort_rect[st];
+  if (st < 36) {
+    const int n = T->fort_list_n[st];
+#pragma unroll 1
+    for (int k = lane; k < n; k += 32) {
+      int idx = T->fort_list_idx[st][k];
+      int r = idx / SF_FORT_W, c = idx - r * SF_FORT_W;
+      unsigned char* px = &W.nat[(SF_FORT_Y0 + r) * SF_TILE_STRIDE + SF_FORT_X0 + c];
+      *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[st][k]);
+    }
+  } else {
+#pragma unroll 1
+    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
+      unsigned a0 = T->fexp_alpha[0][idx];
+      if (a0) {
+        int r = idx / SF_EXP_W, c = idx - r * SF_EXP_W;
+        unsigned char* px = &W.nat[(SF_FEXP_Y0 + r) * SF_TILE_STRIDE + SF_FEXP_X0 + c];
+        unsigned v = sf_blend(*px, T->fexp_colour[0][idx], a0);
+        for (int l = 1; l < T->fexp_layers; l++) {
+          unsigned a = T->fexp_alpha[l][idx];
+          if (!a) break;
+          v = sf_blend(v, T->fexp_colour[l][idx], a);
+        }
+        *px = (unsigned char)v;
+      }
+    }
+  }
+  sf_add_rect(W, lane, fr[0], fr[1], fr[2], fr[3]);
+  __syncwarp();
+}
+
+// Score digits (draw.cpp:160-173,267) and vulnerability bar (draw.cpp:207-225,268) blended into the tile.
+__device__ __noinline__ void sf_text_general(const SfTables* T, int pts) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int idx = lane; idx < SF_TEXT_H * SF_TEXT_W; idx += 32) {
+    int r = idx / SF_TEXT_W, c = idx - r * SF_TEXT_W;
+    int slot = T->text_slot[c];
+    if (slot < 7) {
+      int div = 1;
+      for (int k = slot; k < 6; k++) div *= 10;
+      unsigned a = T->text_alpha[(pts / div) % 10][idx];
+      if (a) {
+        unsigned char* px = &W.nat[(SF_TEXT_Y0 + r) * SF_TILE_STRIDE + SF_TEXT_X0 + c];
+        *px = (unsigned char)sf_blend(*px, T->colour_text, a);
+      }
+    }
+  }
+  sf_add_rect(W, lane, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1);
+}
+__device__ __noinline__ void sf_bar_general(const SfTables* T, int vuln, bool kill_bar) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  int filled = 4 * min(vuln, 10);  // 20 user units per step = 4 px
+  unsigned fg = kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
+#pragma unroll 1
+  for (int idx = lane; idx < SF_BAR_H * SF_BAR_W; idx += 32) {
+    int r = idx / SF_BAR_W, c = idx - r * SF_BAR_W;
+    unsigned a = T->bar_alpha[r];
+    unsigned char* px = &W.nat[(SF_BAR_Y0 + r) * SF_TILE_STRIDE + SF_BAR_X0 + c];
+    unsigned v = sf_blend(*px, T->colour_bar_bg, a);
+    if (c < filled) v = sf_blend(v, fg, a);
+    *px = (unsigned char)v;
+  }
+  sf_add_rect(W, lane, SF_BAR_X0, SF_BAR_Y0, SF_BAR_X0 + SF_BAR_W - 1, SF_BAR_Y0 + SF_BAR_H - 1);
+}
+__device__ __noinline__ void sf_native_out(unsigned char* __restrict__ nat_out) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int idx = lane; idx < SF_NAT_H * SF_NAT_W / 2; idx += 32) {
+    int r = idx / (SF_NAT_W / 2), c = (idx - r * (SF_NAT_W / 2)) * 2;
+    *reinterpret_cast<uchar2*>(&nat_out[r * SF_NAT_W + c]) = *reinterpret_cast<const uchar2*>(&W.nat[r * SF_TILE_STRIDE + c]);
+  }
 }
 
 struct SfRenderIn {  // warp-uniform view of one env
@@ -480,29 +573,7 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
 
   // ---- ship explosion: memoised sprite (draw.cpp:235-237) ----
   __syncwarp();
-  if (!ship_alive) {
-    SfPt c = sf_xform_base(in.px, in.py);
-    int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
-    unsigned char* cache = D.expc + (size_t)in.env * (SF_EXP_W * SF_EXP_W);
-    if (!(in.core & SF_CORE_EXP_CACHED)) {
-      sf_explosion_raster(T, in.px, in.py);
-      for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-        int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
-        if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) cache[idx] = W.nat[y * SF_TILE_STRIDE + x];
-      }
-      if (lane == 0) D.q0[in.env].x = (int)(in.core | SF_CORE_EXP_CACHED);
-      // the arcs recorded up to 85 small rectangles: replace them by the box
-      if (lane == 0) W.nrect = 0;
-    } else {
-      for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-        int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
-        if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) W.nat[y * SF_TILE_STRIDE + x] = cache[idx];
-      }
-    }
-    int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W - 1, SF_NAT_W - 1), y1 = min(by0 + SF_EXP_W - 1, SF_NAT_H - 1);
-    if (x0 <= x1 && y0 <= y1) sf_add_rect(W, lane, x0, y0, x1, y1);
-    __syncwarp();
-  }
+  if (!ship_alive) sf_ship_explosion(T, D.expc, D.q0, in.env, in.core, in.px, in.py);
 
   // ---- moving wireframes in batches of 8 strokes; the fortress layer goes in after the ship ----
   bool fortress_done = false;
@@ -512,40 +583,7 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
   const int fst_ = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
   bool fortress_general = nat_out != nullptr || n_strokes > 8 ||
                           sf_rects_touch(W, W.nrect, T->fort_rect[fst_][0] - 2, T->fort_rect[fst_][1] - 2, T->fort_rect[fst_][2] + 2, T->fort_rect[fst_][3] + 2);
-  auto fortress_layer = [&]() {
-    const int st = fst_;
-    const unsigned char* fr = T->fort_rect[st];
-    bool general = fortress_general;
-    if (general) {
-      if (fort_alive) {
-        const int n = T->fort_list_n[st];
-        for (int k = lane; k < n; k += 32) {
-          int idx = T->fort_list_idx[st][k];
-          int r = idx / SF_FORT_W, c = idx - r * SF_FORT_W;
-          unsigned char* px = &W.nat[(SF_FORT_Y0 + r) * SF_TILE_STRIDE + SF_FORT_X0 + c];
-          *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[st][k]);
-        }
-      } else {
-        for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-          unsigned a0 = T->fexp_alpha[0][idx];
-          if (a0) {
-            int r = idx / SF_EXP_W, c = idx - r * SF_EXP_W;
-            unsigned char* px = &W.nat[(SF_FEXP_Y0 + r) * SF_TILE_STRIDE + SF_FEXP_X0 + c];
-            unsigned v = sf_blend(*px, T->fexp_colour[0][idx], a0);
-            for (int l = 1; l < T->fexp_layers; l++) {
-              unsigned a = T->fexp_alpha[l][idx];
-              if (!a) break;
-              v = sf_blend(v, T->fexp_colour[l][idx], a);
-            }
-            *px = (unsigned char)v;
-          }
-        }
-      }
-      sf_add_rect(W, lane, fr[0], fr[1], fr[2], fr[3]);
-      __syncwarp();
-    }
-    return general;
-  };
+  auto fortress_layer = [&]() { if (fortress_general) sf_fortress_general(T, fst_); };
 
   for (int s0 = 0; s0 < n_strokes || !fortress_done; s0 += 8) {
     int region_id = -1;
@@ -596,46 +634,13 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
     }
     text_general = nat_out != nullptr || pts != 0 || moving_above;
     bar_general = nat_out != nullptr || moving_below;
-    if (text_general) {
-      for (int idx = lane; idx < SF_TEXT_H * SF_TEXT_W; idx += 32) {
-        int r = idx / SF_TEXT_W, c = idx - r * SF_TEXT_W;
-        int slot = T->text_slot[c];
-        if (slot < 7) {
-          int div = 1;
-          for (int k = slot; k < 6; k++) div *= 10;
-          unsigned a = T->text_alpha[(pts / div) % 10][idx];
-          if (a) {
-            unsigned char* px = &W.nat[(SF_TEXT_Y0 + r) * SF_TILE_STRIDE + SF_TEXT_X0 + c];
-            *px = (unsigned char)sf_blend(*px, T->colour_text, a);
-          }
-        }
-      }
-      sf_add_rect(W, lane, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1);
-    }
-    // ---- vulnerability bar (draw.cpp:207-225,268) ----
-    if (bar_general) {
-      int filled = 4 * min(in.vuln, 10);  // 20 user units per step = 4 px
-      unsigned fg = in.kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
-      for (int idx = lane; idx < SF_BAR_H * SF_BAR_W; idx += 32) {
-        int r = idx / SF_BAR_W, c = idx - r * SF_BAR_W;
-        unsigned a = T->bar_alpha[r];
-        unsigned char* px = &W.nat[(SF_BAR_Y0 + r) * SF_TILE_STRIDE + SF_BAR_X0 + c];
-        unsigned v = sf_blend(*px, T->colour_bar_bg, a);
-        if (c < filled) v = sf_blend(v, fg, a);
-        *px = (unsigned char)v;
-      }
-      sf_add_rect(W, lane, SF_BAR_X0, SF_BAR_Y0, SF_BAR_X0 + SF_BAR_W - 1, SF_BAR_Y0 + SF_BAR_H - 1);
-    }
+    if (text_general) sf_text_general(T, pts);
+    if (bar_general) sf_bar_general(T, in.vuln, in.kill_bar);
   }
   __syncwarp();
 
   // ---- native output (SSF_Env.step returns the 92x90 frame): every layer went through the tile ----
-  if (nat_out) {
-    for (int idx = lane; idx < SF_NAT_H * SF_NAT_W / 2; idx += 32) {
-      int r = idx / (SF_NAT_W / 2), c = (idx - r * (SF_NAT_W / 2)) * 2;
-      *reinterpret_cast<uchar2*>(&nat_out[r * SF_NAT_W + c]) = *reinterpret_cast<const uchar2*>(&W.nat[r * SF_TILE_STRIDE + c]);
-    }
-  }
+  if (nat_out) sf_native_out(nat_out);
 
   // ---- 84x84 observation: 441 chunks from the static tables, then the resampled dirty rectangles ----
   if (obs84) {

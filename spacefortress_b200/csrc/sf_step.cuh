@@ -37,14 +37,18 @@ __device__ __forceinline__ void sf_store_env(const SfDev& D, int i, const SfEnv&
 }
 
 // ---- G1: glibc rand() (TYPE_3 lagged sum over a 31-word ring), one stream per env ----
+__device__ __forceinline__ int sf_rand_raw(unsigned* rng, int np, int i, int& idx) {
+  int lag = idx + 28; if (lag >= 31) lag -= 31;  // (k-3) mod 31
+  unsigned v = rng[(size_t)idx * np + i] + rng[(size_t)lag * np + i];
+  rng[(size_t)idx * np + i] = v;
+  idx = (idx + 1 == 31) ? 0 : idx + 1;
+  return (int)(v >> 1);
+}
 __device__ __forceinline__ int sf_rand(const SfDev& D, int i, SfEnv& e) {
   int idx = e.st3.y;
-  int lag = idx + 28; if (lag >= 31) lag -= 31;  // (k-3) mod 31
-  unsigned v = D.rng[(size_t)idx * D.n_pad + i] + D.rng[(size_t)lag * D.n_pad + i];
-  D.rng[(size_t)idx * D.n_pad + i] = v;
-  e.st3.y = (idx + 1 == 31) ? 0 : idx + 1;
-  e.st3.z += 1;
-  return (int)(v >> 1);
+  int r = sf_rand_raw(D.rng, D.n_pad, i, idx);
+  e.st3.y = idx; e.st3.z += 1;
+  return r;
 }
 
 // srand(seed): r[0]=seed, r[k]=16807*r[k-1] mod (2^31-1), 310 outputs dropped
@@ -88,7 +92,7 @@ __device__ __forceinline__ bool sf_outside(double x, double y) {  // game.cpp:12
 // atan2 as the reference's libm gives it where a downstream ceil() could flip (exact octants);
 // elsewhere the CUDA fp64 atan2 (<= 2 ulp) is used — a differing last bit cannot change the
 // quantised angle unless the true angle is within 1e-13 degrees of an integer.
-__device__ __forceinline__ double sf_atan2(const SfTables* T, double dy, double dx) {
+__device__ __noinline__ double sf_atan2(const SfTables* T, double dy, double dx) {
   if (dy == 0.0) return dx >= 0 ? T->atan2_oct[0] : T->atan2_oct[4];
   if (dx == 0.0) return dy > 0 ? T->atan2_oct[2] : T->atan2_oct[6];
   if (fabs(dx) == fabs(dy)) return dx > 0 ? (dy > 0 ? T->atan2_oct[1] : T->atan2_oct[7]) : (dy > 0 ? T->atan2_oct[3] : T->atan2_oct[5]);
@@ -97,6 +101,12 @@ __device__ __forceinline__ double sf_atan2(const SfTables* T, double dy, double 
 #define SF_PI 3.14159265358979323846
 __device__ __forceinline__ double sf_rad2deg(double a) { return SF_DMUL(SF_DDIV(a, SF_PI), 180.0); }  // vector.cpp:38-40
 __device__ __forceinline__ double sf_deg2rad(double a) { return SF_DDIV(SF_DMUL(a, SF_PI), 180.0); }  // vector.cpp:34-36
+
+// S12: shell velocity 6*(cos,sin)(deg2rad(angle)) for a real-valued angle (game.cpp:167-168); out of line: rare
+__device__ __noinline__ double2 sf_shell_velocity(double a) {
+  double rad = sf_deg2rad(a);
+  return make_double2(SF_DMUL(6.0, cos(rad)), SF_DMUL(6.0, sin(rad)));
+}
 
 // S15: reward()/penalize() in float32 (game.cpp:97-106)
 __device__ __forceinline__ void sf_reward(SfEnv& e, float& tick_reward, float amt) {
@@ -115,19 +125,28 @@ __device__ __forceinline__ void sf_kill_ship(SfEnv& e) {  // game.cpp:274-280
   }
 }
 
-// S2: resetShip (game.cpp:133-149)
-__device__ inline void sf_spawn_ship(const SfDev& D, int i, SfEnv& e) {
-  const SfTables* T = D.tab;
-  double x, y;
+// S2: resetShip (game.cpp:133-149): rejection-sample an integer spawn inside the big and outside the small
+// hexagon, then the heading. Out of line (rare); takes and returns plain values so the caller's env stays in
+// registers. Returns {x, y, angle, new ring index}; *calls = number of rand() calls consumed.
+__device__ __noinline__ int4 sf_spawn_draw(unsigned* rng, int np, int i, const SfTables* T, int idx, int* calls) {
+  int x, y, n = 0;
   for (;;) {
-    x = (double)(sf_rand(D, i, e) % 380 + 170);
-    y = (double)(sf_rand(D, i, e) % 330 + 150);
-    if (sf_inside_hex(T, 0, x, y) && !sf_inside_hex(T, 1, x, y)) break;
+    x = sf_rand_raw(rng, np, i, idx) % 380 + 170;
+    y = sf_rand_raw(rng, np, i, idx) % 330 + 150;
+    n += 2;
+    if (sf_inside_hex(T, 0, (double)x, (double)y) && !sf_inside_hex(T, 1, (double)x, (double)y)) break;
   }
-  e.pos = make_double2(x, y);
-  e.vel = make_double2(T->ship_start_vx, T->ship_start_vy);
-  int ang = sf_rand(D, i, e) % 360;
-  e.q0.x = (e.q0.x & ~SF_CORE_ANGLE_MASK) | (unsigned)ang | SF_CORE_SHIP_ALIVE;
+  int ang = sf_rand_raw(rng, np, i, idx) % 360;
+  *calls = n + 1;
+  return make_int4(x, y, ang, idx);
+}
+__device__ __forceinline__ void sf_spawn_ship(const SfDev& D, int i, SfEnv& e) {
+  int calls = 0;
+  int4 sp = sf_spawn_draw(D.rng, D.n_pad, i, D.tab, e.st3.y, &calls);
+  e.st3.y = sp.w; e.st3.z += calls;
+  e.pos = make_double2((double)sp.x, (double)sp.y);
+  e.vel = make_double2(D.tab->ship_start_vx, D.tab->ship_start_vy);
+  e.q0.x = (e.q0.x & ~SF_CORE_ANGLE_MASK) | (unsigned)sp.z | SF_CORE_SHIP_ALIVE;
 }
 
 // S1: Game::Game (game.cpp:18-82) through SSF_Env.reset (ssf_env.py:163-178). prev_vlner (q1.w),
@@ -249,9 +268,8 @@ __device__ inline void sf_env_step(const SfDev& D, int i, SfEnv& e, int keymask,
         int slot = sf_first_free(((unsigned)e.q0.y >> SF_PMASK_SHELL_SHIFT) & 0xFu, SF_DEV_SHELLS);
         if (slot >= 0) {
           e.q0.y |= 1 << (SF_PMASK_SHELL_SHIFT + slot);
-          double rad = sf_deg2rad(a);
           D.spos[(size_t)slot * np + i] = make_double2(SF_FORT_X, SF_FORT_Y);
-          D.svel[(size_t)slot * np + i] = make_double2(SF_DMUL(6.0, cos(rad)), SF_DMUL(6.0, sin(rad)));
+          D.svel[(size_t)slot * np + i] = sf_shell_velocity(a);
           D.sang[(size_t)slot * np + i] = a;
           ev |= SF_EV_FORTRESS_FIRED;
         }

@@ -177,6 +177,8 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
       t->hex_nx[h][i] = -(uy[j] - uy[i]); t->hex_ny[h][i] = ux[j] - ux[i];
     }
   }
+  t->magic[0] = 0; t->magic[1] = 0;  // dy == 1: the only sample has m == 0
+  for (unsigned d = 2; d < SF_MAGIC_N; d++) t->magic[d] = 0xFFFFFFFFu / d + 1u;
   t->ship_start_vx = cos(-60.0 * M_PI / 180);
   t->ship_start_vy = sin(-60.0 * M_PI / 180);
   t->colour_bar_bg = (unsigned char)colour8(.33);

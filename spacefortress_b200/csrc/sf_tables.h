@@ -28,6 +28,7 @@
 #define SF_EXP_STROKES 85          // 7 rings x 12 arcs + the r=7 circle
 #define SF_EXP_QUADS 100           // 84 arc quads + 16 circle quads
 #define SF_MAX_TAPS 3
+#define SF_MAGIC_N 512              // magic reciprocals floor((2^32-1)/d)+1 for edge heights d < 512 sub-rows
 #define SF_FORT_LIST 160           // max lit pixels of a fortress sprite
 #define SF_OBS_CHUNKS 441          // 84*84/16
 #define SF_BAR_CHUNK0 420          // output rows 80..83 == chunks 420..440
@@ -45,6 +46,7 @@ struct SfTables {
   // (index = octant*45 degrees: E, SE(+y), S, SW, W, NW, N, NE in screen coordinates), from the host libm
   double atan2_oct[8];
   double ship_start_vx, ship_start_vy;  // cos/sin(deg2rad(-60)), configs.cpp:43-44
+  unsigned magic[SF_MAGIC_N];            // exact-division reciprocals used by the scan converter
   // hexagons (hexagon.cpp:13-48): vertex i and the edge normal (nx,ny) of edge i->i+1; [0]=big (200), [1]=small (40)
   double hex_px[2][6], hex_py[2][6], hex_nx[2][6], hex_ny[2][6];
   // resize tables (cv2 INTER_AREA 92x90 -> 84x84, rl/envs.py:29)
