@@ -10,6 +10,7 @@
 //   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -488,6 +489,7 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 }
 
 static int envs_per_warp(int n) {
+  if (const char* ov = getenv("SF_ENVS_PER_WARP")) { int e = atoi(ov); if (e >= 1 && e <= 32) return e; }  // tuning knob
   // enough warps for ~4 waves of 148 SMs x 8 resident warps; at most 32 envs per warp
   long long target = 148ll * SF_WARPS_PER_BLOCK * 4;
   int e = 1;

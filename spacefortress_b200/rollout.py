@@ -1,0 +1,104 @@
+"""On-device rollout collection (BASELINE.json configs[2]): the env, the frame
+history and the policy all stay on the GPU; nothing crosses PCIe inside the loop.
+
+Replaces the host ping-pong of rl/train.py:73-98 (GPU->CPU actions :79, pipe per env :80, CPU->GPU obs :53-56,97).
+Observations are kept as SINGLE frames in a time-major buffer [T+3+1, N, 84, 84] u8 — the reference stores the
+whole 4-stack per step as float (rl/storage.py:11,37: 238 GB at 65 536 envs x 128 steps; single u8 frames are
+59 GB). The 4-stack is a window over that buffer; frames older than the last `done` are zeroed exactly like
+`current_obs *= mask` does (rl/train.py:92-95).
+
+The policy is a consumer, kept in plain PyTorch (dense conv/GEMM work -> cuDNN/cuBLAS, not a hand-written
+kernel): SFGRUPolicy has the layer shapes of the reference's ACNet (rl/networks.py:20-76).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class SFGRUPolicy(nn.Module):
+    """conv(4->16,k8,s4) -> conv(16->32,k4,s2) -> fc 2592->256 -> GRUCell(256) -> action / value heads
+    (rl/networks.py:23-33); orthogonal weights, zero biases (rl/networks.py:6-18)."""
+
+    def __init__(self, num_actions, feedforward=False):
+        super().__init__()
+        self.feedforward = feedforward
+        self.conv1 = nn.Conv2d(4, 16, kernel_size=8, stride=4)
+        self.conv2 = nn.Conv2d(16, 32, kernel_size=4, stride=2)
+        self.fc1 = nn.Linear(2592, 256)
+        self.core = nn.Linear(256, 256) if feedforward else nn.GRUCell(256, 256)
+        self.action = nn.Linear(256, num_actions)
+        self.value = nn.Linear(256, 1)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.orthogonal_(m.weight); nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.GRUCell):
+                nn.init.orthogonal_(m.weight_ih); nn.init.orthogonal_(m.weight_hh)
+                nn.init.zeros_(m.bias_ih); nn.init.zeros_(m.bias_hh)
+
+    def features(self, obs_u8, state, mask):
+        dt = self.conv1.weight.dtype  # fp32 like the reference, or bf16 via policy.bfloat16()
+        x = F.relu(self.conv1(obs_u8.to(dt) / 255.0))
+        x = F.relu(self.conv2(x)).flatten(1)
+        x = F.relu(self.fc1(x))
+        if self.feedforward:
+            return F.relu(self.core(x)), state
+        h = self.core(x, (state * mask).to(x.dtype))
+        return h, h
+
+    @torch.no_grad()
+    def act(self, obs_u8, state, mask, deterministic=False):
+        x, state = self.features(obs_u8, state, mask)
+        logits = self.action(x)
+        logp = F.log_softmax(logits, dim=1)
+        action = logits.argmax(1, keepdim=True) if deterministic else torch.multinomial(logp.float().exp(), 1)
+        return self.value(x), action, logp.gather(1, action), state
+
+
+class OnDeviceRollout(object):
+    """Collects T-step rollouts of `env` (SFVecEnv) under `policy` entirely on the device."""
+
+    def __init__(self, env, policy, num_steps=128, num_stack=4):
+        self.env, self.policy, self.T, self.S = env, policy, int(num_steps), int(num_stack)
+        n, dev = env.num_envs, env._device()
+        self.frames = torch.zeros((self.T + self.S, n, 84, 84), dtype=torch.uint8, device=dev)  # [S-1 history | T+1]
+        self.valid = torch.zeros(n, dtype=torch.int32, device=dev)   # frames since the last reset, capped at S
+        self.state = torch.zeros(n, 256, device=dev, dtype=next(policy.parameters()).dtype)
+        self.mask = torch.ones(n, 1, device=dev, dtype=next(policy.parameters()).dtype)
+        self.actions = torch.zeros((self.T, n), dtype=torch.int32, device=dev)
+        self.rewards = torch.zeros((self.T, n), dtype=torch.int32, device=dev)
+        self.dones = torch.zeros((self.T, n), dtype=torch.bool, device=dev)
+        self.values = torch.zeros((self.T, n), device=dev)
+        self.logps = torch.zeros((self.T, n), device=dev)
+        self.episode_return = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.final_return = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.num_destruction = torch.zeros((), dtype=torch.int64, device=dev)
+        self._age_idx = torch.arange(self.S, device=dev, dtype=torch.int32).view(1, self.S, 1, 1)
+        first = env.reset(to_numpy=False)
+        self.frames[self.S - 1].copy_(first[:, 0])
+        self.valid.fill_(1)
+
+    def stack(self, t):
+        """[N,S,84,84] u8 window ending at frame t (buffer index t+S-1); frames from before the last reset read 0."""
+        w = self.frames[t:t + self.S].permute(1, 0, 2, 3)
+        keep = self._age_idx >= (self.S - self.valid).view(-1, 1, 1, 1)
+        return w * keep.to(torch.uint8)
+
+    def collect(self):
+        env, S = self.env, self.S
+        for t in range(self.T):
+            value, action, logp, self.state = self.policy.act(self.stack(t), self.state, self.mask)
+            a = action.squeeze(1).to(torch.int32)
+            _, reward, done, kill = env.step(a, out_obs=self.frames[t + S].unsqueeze(1))
+            self.actions[t] = a; self.rewards[t] = reward; self.dones[t] = done
+            self.values[t] = value.squeeze(1).float(); self.logps[t] = logp.squeeze(1).float()
+            self.num_destruction += kill.sum()
+            self.episode_return += reward
+            self.final_return = torch.where(done, self.episode_return, self.final_return)
+            self.episode_return = torch.where(done, torch.zeros_like(self.episode_return), self.episode_return)
+            self.mask = (~done).to(self.state.dtype).unsqueeze(1)
+            self.valid = torch.where(done, torch.ones_like(self.valid), torch.clamp(self.valid + 1, max=S))
+        # carry the last S-1 frames over as history of the next rollout
+        self.frames[:S - 1].copy_(self.frames[self.T:self.T + S - 1].clone())
+        self.frames[S - 1].copy_(self.frames[self.T + S - 1].clone())
+        return dict(frames=self.frames, actions=self.actions, rewards=self.rewards, dones=self.dones,
+                    values=self.values, logps=self.logps)

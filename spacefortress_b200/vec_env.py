@@ -139,10 +139,10 @@ class SFVecEnv(object):
         a, self._pending = self._pending, None
         return self.step(a)
 
-    def step(self, actions):
+    def step(self, actions, out_obs=None):
         if isinstance(actions, np.ndarray) or isinstance(actions, (list, tuple)):
             return self._step_numpy(np.asarray(actions))
-        return self._step_torch(actions)
+        return self._step_torch(actions, out_obs)
 
     def _step_numpy(self, actions):
         n = self.num_envs
@@ -157,10 +157,15 @@ class SFVecEnv(object):
         infos = tuple(bool(k) for k in b["kill"])  # the reference's info is a bool per env (ssf_env.py:233,250)
         return (b["obs"].copy() if self.render_on else None), b["reward"].astype(np.int64), b["done"].astype(bool), infos
 
-    def _step_torch(self, actions):
+    def _step_torch(self, actions, out_obs=None):
+        """Device path. out_obs: optional contiguous uint8 CUDA tensor [N,1,84,84] to receive the frames (e.g.
+        a slice of a time-major rollout buffer) instead of the env's own buffer."""
         torch = _torch()
         b = self._torch_bufs()
         a = actions.to(device=self._device(), dtype=torch.int32).reshape(self.num_envs).contiguous()
+        if out_obs is not None:
+            assert out_obs.is_contiguous() and out_obs.dtype == torch.uint8 and out_obs.numel() == b["obs"].numel()
+            b = dict(b, obs=out_obs)
         _lib.check(self.L.sf_step(
             self.h, C.c_void_p(a.data_ptr()), C.c_void_p(b["obs"].data_ptr()) if self.render_on else None,
             C.c_void_p(b["reward"].data_ptr()), C.c_void_p(b["done"].data_ptr()), C.c_void_p(b["kill"].data_ptr()),

@@ -339,3 +339,41 @@ def test_single_env_facade_matches_oracle():
             assert env.g.dump().split(",[")[0] == o.dump().split(",[")[0]
     assert env.g.stats[:13] == tuple(o.get_state().stats)
     env.close()
+
+
+def test_on_device_rollout_frame_stack_matches_reference_loop():
+    """OnDeviceRollout (config 3 plumbing): the 4-frame window over the single-frame buffer equals the
+    reference's running `current_obs` (rl/train.py:51-56,92-97: zero the stack on done, shift, append)."""
+    torch = torch_cuda()
+    from spacefortress_b200 import SFVecEnv
+    from spacefortress_b200.rollout import OnDeviceRollout, SFGRUPolicy
+    n, T = 6, 24
+    env = SFVecEnv("youturn", num_envs=n, device=0)
+    env.reset()
+    recs = env.get_state()
+    for i in range(n):  # stagger the episode ends so that dones fall inside the rollout
+        recs[i].tick = 5295 - 3 - 2 * i
+        recs[i].time = recs[i].tick * 34
+    env.set_state(recs)
+    torch.manual_seed(0)
+    ro = OnDeviceRollout(env, SFGRUPolicy(env.num_actions).cuda().eval(), num_steps=T)
+    env.set_state(recs)  # OnDeviceRollout reset the envs: restore the staggered clocks (frames stay valid: same ship spawn? no -> re-render)
+    ro.frames[ro.S - 1].copy_(torch.from_numpy(env.render_frames()).cuda())
+    first = ro.frames[ro.S - 1].clone()
+    cur = torch.zeros((n, 4, 84, 84), device="cuda")
+    cur[:, -1] = first.float()
+    stacks = []
+    for t in range(T):  # drive collect() step by step through its own pieces to snapshot stack(t)
+        stacks.append(ro.stack(t).clone())
+        assert torch.equal(stacks[-1].float(), cur), t
+        value, action, logp, ro.state = ro.policy.act(stacks[-1], ro.state, ro.mask)
+        a = action.squeeze(1).to(torch.int32)
+        obs, reward, done, kill = env.step(a, out_obs=ro.frames[t + ro.S].unsqueeze(1))
+        mask = (~done).float()
+        cur *= mask.view(-1, 1, 1, 1)
+        cur[:, :-1] = cur[:, 1:].clone()
+        cur[:, -1] = ro.frames[t + ro.S].float()
+        ro.mask = mask.unsqueeze(1)
+        ro.valid = torch.where(done, torch.ones_like(ro.valid), torch.clamp(ro.valid + 1, max=ro.S))
+    assert sum(int(s.sum() == 0) for s in stacks) == 0
+    env.close()
