@@ -80,7 +80,7 @@ SF_HD SfPt sf_xform_wire(const SfWireXf& m, double mx, double my) {
 
 // unit direction of a fixed-point segment (cairo normalize_slope) ; returns false if degenerate
 SF_HD bool sf_unit_dir(SfPt a, SfPt b, double& ux, double& uy) {
-  double dx = SF_DDIV((double)(b.x - a.x), 256.0), dy = SF_DDIV((double)(b.y - a.y), 256.0);
+  double dx = SF_DMUL((double)(b.x - a.x), 0.00390625), dy = SF_DMUL((double)(b.y - a.y), 0.00390625);  // exact: /256
   if (dx == 0.0 && dy == 0.0) return false;
   if (dx == 0.0) { ux = 0.0; uy = dy > 0 ? 1.0 : -1.0; }
   else if (dy == 0.0) { uy = 0.0; ux = dx > 0 ? 1.0 : -1.0; }

@@ -95,7 +95,7 @@ __device__ __forceinline__ void sf_add_rect(SfWarpSmem& W, int lane, int x0, int
 // (dy*|dx|+dy)*dy < 2^32: always true for the strokes drawn here, which are at most ~30 px tall).
 __device__ __forceinline__ int4 sf_make_edge(const SfTables* T, int xa, int ga, int xb, int gb) {  // ga < gb (grid rows)
   int dy = gb - ga;
-  unsigned M = dy < SF_MAGIC_N ? T->magic[dy] : 0xFFFFFFFFu / (unsigned)dy + 1u;
+  unsigned M = T->magic[min(dy, SF_MAGIC_N - 1)];  // device strokes are far shorter than 512 sub-rows (34 px)
   return make_int4(xa, ((ga + SF_YBIAS) << 16) | dy, xb - xa, (int)M);
 }
 __device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias, ytop <= s < ytop + dy
@@ -283,12 +283,17 @@ __device__ __noinline__ void sf_batch_accumulate() {
       if (k0 != 0xFFFFFFFFu) {
         int a = max((int)(k0 >> 16), reach), b = (int)(k0 & 0xFFFFu);
         reach = max(reach, b);
-        int cell = a >> 8;
-        while (a < b) {
-          int e = min(b, (cell + 1) << 8);
-          int ci = cell0 + cell;
-          atomicAdd(&acc32[ci >> 1], (unsigned)(e - a) << ((ci & 1) << 4));
-          a = e; cell++;
+        if (a < b) {
+          // first cell (partial), last cell (partial), full cells in between (only for near-horizontal spans)
+          int c1 = a >> 8, c2 = (b - 1) >> 8;
+          int ci = cell0 + c1;
+          int len1 = min(b, (c1 + 1) << 8) - a;
+          atomicAdd(&acc32[ci >> 1], (unsigned)len1 << ((ci & 1) << 4));
+          if (c2 > c1) {
+            int cj = cell0 + c2;
+            atomicAdd(&acc32[cj >> 1], (unsigned)(b - (c2 << 8)) << ((cj & 1) << 4));
+            for (int c = c1 + 1; c < c2; c++) { int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
+          }
         }
       }
       k0 = k1; k1 = k2; k2 = k3; k3 = 0xFFFFFFFFu;
@@ -651,13 +656,17 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
     const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
     const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
     const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
-#pragma unroll 2
-    for (int k = lane; k < SF_OBS_CHUNKS; k += 32) {
-      const int4* src = &bg[k];
-      if (!fortress_general && k >= fc0 && k < fc1) src = &ft[k - fc0];
-      if (!bar_general && k >= SF_BAR_CHUNK0) src = &bt[k - SF_BAR_CHUNK0];
-      g[k] = __ldg(src);
-    }
+    // three ranges with a fixed source each: [0, fc0) background, [fc0, fc1) fortress table (fast path),
+    // [fc1, 420) background, [420, 441) bar table (fast path)
+    const int4* fsrc = fortress_general ? bg + fc0 : ft;
+    const int4* bsrc = bar_general ? bg + SF_BAR_CHUNK0 : bt;
+#pragma unroll 1
+    for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
+#pragma unroll 1
+    for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&fsrc[k - fc0]);
+#pragma unroll 1
+    for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
+    if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bsrc[lane]);
     __syncwarp();  // orders the chunk stores before the byte patches below (same warp)
     const int nr = W.nrect;
     for (int q = 0; q < nr; q++) {
