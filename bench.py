@@ -243,7 +243,7 @@ def ours(args):
                    "timing": "best of %d launches, CUDA events on the launching stream, max over ranks" % args.repeats},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": n * (7056 + 4 + 1 + 1 + 4),
-                "api": "SFVecEnv.step(np.ndarray) -> sf_step_host (pinned staging), %d steps" % args.e2e_steps},
+                "api": "SFVecEnv.step(np.ndarray) -> sf_step_host, actions from and results into page-locked numpy buffers, %d steps" % args.e2e_steps},
         "gpu_launches": 1,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "bytes_per_env_step": B_RENDER, "env_steps_per_launch": n * K, "launch_ms": ms},

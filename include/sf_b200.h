@@ -138,9 +138,14 @@ int sf_synthetic_action(uint32_t action_seed, long long global_env, long long t,
 int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
 
 /* Host-buffer convenience path (numpy drop-in for rl/train.py:79-80): H2D actions, step, D2H results,
- * synchronous. Uses pinned staging inside the handle. h_obs may be NULL. */
+ * synchronous. Copies go straight from/to the caller's buffers (use sf_host_alloc for them). h_obs may be NULL. */
 int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
                  uint8_t* h_fortkill, uint32_t* h_events, int flags);
+
+/* Page-locked host memory for the buffers handed to sf_step_host: the device<->host copies then run as
+ * direct DMA into the caller's arrays (pageable memory also works, but is staged by the driver). */
+int sf_host_alloc(void** out, long long bytes);
+int sf_host_free(void* p);
 
 /* State records, host side (synchronous). first..first+count-1. */
 int sf_get_state(sf_handle* h, int first, int count, sf_state_record* h_out);

@@ -81,6 +81,8 @@ _PROTOTYPES = {
     "sf_synthetic_action": (C.c_int, [C.c_uint32, C.c_longlong, C.c_longlong, C.c_int]),
     "sf_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sf_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "sf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_longlong]),
+    "sf_host_free": (C.c_int, [C.c_void_p]),
     "sf_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_set_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -110,3 +112,15 @@ def check(rc):
     if rc != SF_OK:
         msg = lib().sf_last_error()
         raise SFError("sf_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory (sf_host_alloc): device<->host copies DMA straight into it."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    check(lib().sf_host_alloc(C.byref(p), max(nbytes, 1)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    return arr, p

@@ -331,7 +331,6 @@ struct sf_handle {
   size_t slab_bytes;
   SfTables* h_tab;
   // pinned staging for sf_step_host
-  int* hp_actions; unsigned char* hp_obs; int* hp_reward; unsigned char* hp_done; unsigned char* hp_kill; unsigned* hp_events;
   int* d_actions; unsigned char* d_obs; int* d_reward; unsigned char* d_done; unsigned char* d_kill; unsigned* d_events;
   size_t staging_obs_bytes;
 };
@@ -447,12 +446,6 @@ extern "C" int sf_destroy(sf_handle* h) {
   if (!h) return SF_OK;
   cudaSetDevice(h->device);
   cudaFree(h->slab);
-  if (h->hp_actions) cudaFreeHost(h->hp_actions);
-  if (h->hp_obs) cudaFreeHost(h->hp_obs);
-  if (h->hp_reward) cudaFreeHost(h->hp_reward);
-  if (h->hp_done) cudaFreeHost(h->hp_done);
-  if (h->hp_kill) cudaFreeHost(h->hp_kill);
-  if (h->hp_events) cudaFreeHost(h->hp_events);
   if (h->d_actions) cudaFree(h->d_actions);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
@@ -562,18 +555,25 @@ extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, l
 
 static int ensure_staging(sf_handle* h, size_t obs_bytes) {
   size_t n = (size_t)h->dev.n;
-  if (!h->hp_actions) {
-    CUDA_TRY(cudaMallocHost(&h->hp_actions, n * 4)); CUDA_TRY(cudaMallocHost(&h->hp_reward, n * 4));
-    CUDA_TRY(cudaMallocHost(&h->hp_done, n)); CUDA_TRY(cudaMallocHost(&h->hp_kill, n)); CUDA_TRY(cudaMallocHost(&h->hp_events, n * 4));
+  if (!h->d_actions) {
     CUDA_TRY(cudaMalloc(&h->d_actions, n * 4)); CUDA_TRY(cudaMalloc(&h->d_reward, n * 4));
     CUDA_TRY(cudaMalloc(&h->d_done, n)); CUDA_TRY(cudaMalloc(&h->d_kill, n)); CUDA_TRY(cudaMalloc(&h->d_events, n * 4));
   }
   if (obs_bytes > h->staging_obs_bytes) {
-    if (h->hp_obs) { cudaFreeHost(h->hp_obs); cudaFree(h->d_obs); h->hp_obs = nullptr; h->d_obs = nullptr; }
-    CUDA_TRY(cudaMallocHost(&h->hp_obs, obs_bytes));
+    if (h->d_obs) { cudaFree(h->d_obs); h->d_obs = nullptr; }
     CUDA_TRY(cudaMalloc(&h->d_obs, obs_bytes));
     h->staging_obs_bytes = obs_bytes;
   }
+  return SF_OK;
+}
+
+extern "C" int sf_host_alloc(void** out, long long bytes) {
+  if (!out || bytes <= 0) return fail(SF_ERR_INVALID, "sf_host_alloc: bad arguments");
+  CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+  return SF_OK;
+}
+extern "C" int sf_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
   return SF_OK;
 }
 
@@ -587,24 +587,18 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   int rc = ensure_staging(h, render ? n * per : 0);
   if (rc) return rc;
   cudaStream_t st = 0;  // legacy default stream: ordered with every other call made with stream == NULL
-  memcpy(h->hp_actions, h_actions, n * 4);
-  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h->hp_actions, n * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, st));
   SfRollArgs a;
   a.T = 1; a.E = 1; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
   a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events;
   rc = launch_rollout(h, a, st);
   if (rc) return rc;
-  if (render) CUDA_TRY(cudaMemcpyAsync(h->hp_obs, h->d_obs, n * per, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h->hp_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h->hp_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h->hp_kill, h->d_kill, n, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(h->hp_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, st));
+  if (render) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * per, cudaMemcpyDeviceToHost, st));
+  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
+  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+  if (h_fortkill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, st));
+  if (h_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (render) memcpy(h_obs, h->hp_obs, n * per);
-  if (h_reward) memcpy(h_reward, h->hp_reward, n * 4);
-  if (h_done) memcpy(h_done, h->hp_done, n);
-  if (h_fortkill) memcpy(h_fortkill, h->hp_kill, n);
-  if (h_events) memcpy(h_events, h->hp_events, n * 4);
   return SF_OK;
 }
 

@@ -42,7 +42,7 @@ def _torch():
 
 class SFVecEnv(object):
     def __init__(self, env_id="SpaceFortress-youturn-image-v0", num_envs=16, device=0, action_set=1, seeds=None,
-                 render=True, native_obs=False, autoreset=True, first_global_env=0):
+                 render=True, native_obs=False, autoreset=True, first_global_env=0, copy_outputs=False):
         self.L = _lib.lib()
         self.gametype = _gametype(env_id)
         self.num_envs = int(num_envs)
@@ -50,6 +50,7 @@ class SFVecEnv(object):
         self.render_on = bool(render)
         self.native_obs = bool(native_obs)
         self.autoreset = bool(autoreset)
+        self.copy_outputs = bool(copy_outputs)
         h = C.c_void_p()
         _lib.check(self.L.sf_create(self.gametype.encode(), int(action_set), self.num_envs, self.device_index, C.byref(h)))
         self.h = h
@@ -90,8 +91,13 @@ class SFVecEnv(object):
     def _np_bufs(self):
         if self._np is None:
             n = self.num_envs
-            self._np = dict(obs=np.empty((n,) + self.obs_shape, np.uint8), reward=np.empty(n, np.int32),
-                            done=np.empty(n, np.uint8), kill=np.empty(n, np.uint8), events=np.empty(n, np.uint32))
+            self._pinned = []
+            self._np = {}
+            for k, shape, dt in (("obs", (n,) + self.obs_shape, np.uint8), ("reward", (n,), np.int32), ("done", (n,), np.uint8),
+                                 ("kill", (n,), np.uint8), ("events", (n,), np.uint32), ("actions", (n,), np.int32)):
+                arr, ptr = _lib.pinned_array(shape, dt)  # page-locked: D2H lands directly in what step() returns
+                self._np[k] = arr
+                self._pinned.append(ptr)
         return self._np
 
     @staticmethod
@@ -146,16 +152,20 @@ class SFVecEnv(object):
 
     def _step_numpy(self, actions):
         n = self.num_envs
-        a = np.ascontiguousarray(actions.reshape(n), dtype=np.int32)
         b = self._np_bufs()
+        a = b["actions"]
+        a[:] = actions.reshape(n)
         _lib.check(self.L.sf_step_host(
             self.h, a.ctypes.data_as(C.c_void_p), b["obs"].ctypes.data_as(C.c_void_p) if self.render_on else None,
             b["reward"].ctypes.data_as(C.c_void_p), b["done"].ctypes.data_as(C.c_void_p),
             b["kill"].ctypes.data_as(C.c_void_p), b["events"].ctypes.data_as(C.c_void_p), self._flags))
         self._t += 1
         self.last_events = b["events"].copy()
-        infos = tuple(bool(k) for k in b["kill"])  # the reference's info is a bool per env (ssf_env.py:233,250)
-        return (b["obs"].copy() if self.render_on else None), b["reward"].astype(np.int64), b["done"].astype(bool), infos
+        infos = tuple(b["kill"].astype(bool).tolist())  # the reference's info is a bool per env (ssf_env.py:233,250)
+        # obs is the env's page-locked output buffer, overwritten by the next step() (pass copy_outputs=True to
+        # the constructor for fresh arrays like gym_vecenv's np.stack)
+        obs = None if not self.render_on else (b["obs"].copy() if self.copy_outputs else b["obs"])
+        return obs, b["reward"].astype(np.int64), b["done"].astype(bool), infos
 
     def _step_torch(self, actions, out_obs=None):
         """Device path. out_obs: optional contiguous uint8 CUDA tensor [N,1,84,84] to receive the frames (e.g.
@@ -247,6 +257,10 @@ class SFVecEnv(object):
 
     def close(self):
         if not self.closed and getattr(self, "h", None):
+            self._np = None
+            for ptr in getattr(self, "_pinned", []):
+                self.L.sf_host_free(ptr)
+            self._pinned = []
             self.L.sf_destroy(self.h)
             self.h = None
             self.closed = True
