@@ -25,8 +25,11 @@
 #include "sf_step.cuh"
 #include "sf_tables.h"
 
-#define SF_WARPS_PER_BLOCK 8
+#define SF_WARPS_PER_BLOCK 4
 #define SF_BLOCK (32 * SF_WARPS_PER_BLOCK)
+// resident blocks per SM the render kernels are compiled for: 7 x 4 warps = 28 warps (<= 72 registers per thread),
+// which is what 4096 envs on 148 SMs need to be co-resident with one warp per env
+#define SF_RENDER_MIN_BLOCKS 7
 
 // ------------------------------------------------------------------------------------------------
 // synthetic policy: stateless counter hash; same function on host and device
@@ -110,9 +113,10 @@ struct SfRollArgs {
 // fused step + render
 // ------------------------------------------------------------------------------------------------
 template <bool RENDER>
-__global__ void __launch_bounds__(SF_BLOCK, 2) sf_rollout_kernel(SfDev D, SfRollArgs A) {
+__global__ void __launch_bounds__(SF_BLOCK, SF_RENDER_MIN_BLOCKS) sf_rollout_kernel(SfDev D, SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SfWarpSmem& W = sf_my_smem();
+  if (RENDER) sf_block_smem_init(D.tab);
   const long long wg = (long long)blockIdx.x * SF_WARPS_PER_BLOCK + warp;
   const long long env0 = wg * A.E;
   if (env0 >= D.n) return;
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(SF_BLOCK, 2) sf_rollout_kernel(SfDev D, SfRoll
   const bool mine = lane < A.E && env < D.n;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const size_t obs_bytes = (A.flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  if (RENDER) sf_warp_smem_init(W, D.tab, lane);
+  if (RENDER) sf_warp_smem_init(W, lane);
 
   for (int t = 0; t < A.T; t++) {
     SfEnv e;
@@ -193,13 +197,14 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
 }
 
 // render the current state (Game.draw), warp per env
-__global__ void __launch_bounds__(SF_BLOCK, 2) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
+__global__ void __launch_bounds__(SF_BLOCK, SF_RENDER_MIN_BLOCKS) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SfWarpSmem& W = sf_my_smem();
+  sf_block_smem_init(D.tab);
   const int env = blockIdx.x * SF_WARPS_PER_BLOCK + warp;
   if (env >= D.n) return;
   if (mask && !mask[env]) return;
-  sf_warp_smem_init(W, D.tab, lane);
+  sf_warp_smem_init(W, lane);
   SfEnv e;
   sf_load_env(D, env, e);  // every lane loads the same env (broadcast)
   SfRenderIn r;
@@ -432,8 +437,8 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   layout(d, (char*)h->slab);
   CUDA_TRY(cudaMemset(h->slab, 0, h->slab_bytes));
   CUDA_TRY(cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK)));
-  CUDA_TRY(cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK)));
+  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
+  CUDA_TRY(cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
   // default seeding: every env replays srand(1) — the reference never seeds libc (game.cpp:137-148)
   sf_seed_kernel<<<(d.n + 127) / 128, 128>>>(d, nullptr);
   CUDA_TRY(cudaGetLastError());
@@ -483,8 +488,8 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 
 static int envs_per_warp(int n) {
   if (const char* ov = getenv("SF_ENVS_PER_WARP")) { int e = atoi(ov); if (e >= 1 && e <= 32) return e; }  // tuning knob
-  // enough warps for ~4 waves of 148 SMs x 8 resident warps; at most 32 envs per warp
-  long long target = 148ll * SF_WARPS_PER_BLOCK * 4;
+  // one warp per env while all warps are co-resident (148 SMs x 28 warps), then ~4 envs-per-warp-waves; <= 32
+  long long target = 148ll * SF_WARPS_PER_BLOCK * SF_RENDER_MIN_BLOCKS;
   int e = 1;
   while (e < 32 && (long long)n / e > target) e <<= 1;
   return e;
@@ -492,7 +497,7 @@ static int envs_per_warp(int n) {
 
 static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {
   int blocks = (h->dev.n + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK;
-  sf_render_kernel<<<blocks, SF_BLOCK, sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK, st>>>(h->dev, d_obs, flags, d_mask);
+  sf_render_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(h->dev, d_obs, flags, d_mask);
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
@@ -521,7 +526,7 @@ static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
     b.E = envs_per_warp(d.n);
     long long warps = ((long long)d.n + b.E - 1) / b.E;
     int blocks = (int)((warps + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK);
-    sf_rollout_kernel<true><<<blocks, SF_BLOCK, sizeof(SfWarpSmem) * SF_WARPS_PER_BLOCK, st>>>(d, b);
+    sf_rollout_kernel<true><<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
   } else {
     sf_step_only_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d, a);
   }

@@ -6,51 +6,68 @@
 //   black, 2 hexagons -> ship wireframe | ship explosion -> fortress wireframe | fortress explosion
 //   -> missiles -> shells further than 21 from the fortress -> score digits -> vulnerability bar.
 //
-// Organisation (per env, all in one warp, everything in shared memory until the final stores):
-//  * A persistent native tile (92x90 u8) holds the static background; every env composites its layers into
-//    it, resamples only the touched rectangles, and restores them afterwards.
-//  * Moving strokes (ship, missiles, shells; the ship explosion once per death) are scan-converted in
-//    BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then the (stroke,row,sub-row)
-//    samples of the whole batch are flattened over the lanes; each sample evaluates its stroke's quads with
-//    exact integer edge stepping (one "down" and one "up" edge are live per quad and sub-row), merges
-//    overlapping spans (non-zero winding == union for equally oriented convex quads) and accumulates span
-//    lengths into 16-bit cells. Regions are then blended in draw order.
+// Organisation (per env, all in one warp; 6.7 KB of shared memory per warp, so 28+ warps fit on an SM):
+//  * The observation is first written from STATIC, pre-resampled 16-byte chunk tables (background with the
+//    "0000000" score and the empty bar, the fortress sprite of the current sector angle, the bar state):
+//    441 coalesced 128-bit stores.
+//  * Everything that moves (ship, missiles, shells, the ship explosion, a non-zero score) is a small box. Its
+//    strokes are scan-converted in BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then the
+//    (stroke,row,sub-row) samples of the whole batch are flattened over the lanes; each sample evaluates its
+//    stroke's quads with exact integer edge stepping, merges overlapping spans (non-zero winding == union for
+//    equally oriented convex quads) and accumulates span lengths into 16-bit coverage cells that stay in shared
+//    memory until the frame is done.
+//  * For every moving box a WINDOW is composited: the native pixels that the box's output pixels read
+//    (INTER_AREA footprint closure, at most 30x32) are initialised from the background and EVERY layer that
+//    intersects the window is blended in draw order, clipped to it. The window is resampled and its output
+//    pixels overwrite the static ones. Windows are independent of each other (overlapping windows recompute
+//    the same pixels), so no full-frame tile exists anywhere.
 //  * The ship explosion is identical for the 30 ticks a ship stays dead: it is rasterised once and kept in
 //    a per-env 28x28 sprite cache (memo, not game state).
-//  * Static layers (fortress sprite per sector angle, fortress explosion, score, vulnerability bar) come
-//    from host-built tables. When no moving rectangle overlaps them their pre-resampled 16-byte OUTPUT
-//    chunks are copied straight into the observation; otherwise they are blended into the tile.
-//  * The observation is assembled from 441 16-byte chunks (background or static-layer tables) written with
-//    coalesced 128-bit stores, then the resampled dirty pixels are patched in.
 #pragma once
 #include "sf_geom.h"
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
-#define SF_ACC_CELLS 1024    // 16-bit span-length cells per batch
+#define SF_ACC_CELLS 1280    // 16-bit coverage cells: ship <= 100, 20 missiles <= 40 each, 3 shells <= 36 each
 #define SF_BATCH_QUADS 32
-#define SF_BATCH_STROKES 32
-#define SF_MAX_RECTS 32
+#define SF_MAX_REGIONS 32
+// A window is the INTER_AREA footprint closure of a box of at most 28x28 native pixels (the explosion sprite):
+// +1 column each side (<= 2 taps in x), +2 rows each side (<= 3 taps in y) -> at most 30 x 32. Rows are 32 bytes
+// apart; the resampler always reads 2 x 3 taps (missing ones have weight 0), i.e. up to row h+1 and column w.
+#define SF_PATCH_STRIDE 32
+#define SF_PATCH_BYTES (36 * 32)
+#define SF_WIN_MAX_W 31
+#define SF_WIN_MAX_H 34
 #define SF_YBIAS 4096        // grid rows are stored biased so they fit an unsigned 16-bit field
 #define SF_QUAD_IRREGULAR (1 << 20)  // quadrec.y flag: not a 2+2 edge split, test all four edges
+#define SF_TAG_SHIP 0
+#define SF_TAG_PROJECTILE 1
 
-// per-warp shared memory (14 KB -> 16 warps per SM)
+// per-warp shared memory
 struct __align__(16) SfWarpSmem {
-  unsigned char nat[SF_NAT_H * SF_TILE_STRIDE];  // 8464 B persistent native tile
-  unsigned short acc[SF_ACC_CELLS];              // 2048 B
-  int4 edge[SF_BATCH_QUADS * 4];                 // 2048 B per quad: down0, down1, up0, up1 = {x_top, (ytop+bias)<<16 | dy, dx, magic}
-  int2 quadrec[SF_BATCH_QUADS];                  //  256 B {ytopQ+bias, ybotQ+bias} (grid rows)
-  int4 region[SF_BATCH_STROKES];                 //  512 B {x0, y0, w | h<<16, acc_off | colour<<16}
-  int2 stroke[SF_BATCH_STROKES];                 //  256 B {region | quad0<<8 | nq<<16, first item}
-  unsigned rect[SF_MAX_RECTS];                   //  128 B dirty rects x0 | y0<<8 | x1<<16 | y1<<24
-  int nrect, nregion, nstroke, nitems;
-  int acc_used, pad0, pad1, pad2;
+  int4 edge[SF_BATCH_QUADS * 4];            // 2048 B per quad: down0, down1, up0, up1 = {x_top, (ytop+bias)<<16 | dy, dx, magic}
+  unsigned short acc[SF_ACC_CELLS];         // 2560 B coverage cells of every region of the frame
+  unsigned char patch[SF_PATCH_BYTES];      // 1152 B the window being composited (native pixels)
+  int4 region[SF_MAX_REGIONS];              //  512 B {x0, y0, w | h<<16, acc_off | tag<<12 | colour<<16}, draw order
+  int2 quadrec[SF_BATCH_QUADS];             //  256 B {ytopQ+bias, ybotQ+bias} (grid rows), per batch
+  int2 stroke[SF_MAX_REGIONS];              //  256 B per batch: {region | quad0<<8 | nq<<16, first item}
+  int nregion, nstroke, nitems, acc_used;
 };
 
-// all kernels that render use the same dynamic shared array: one SfWarpSmem per warp. Helpers that are kept
-// out of line re-derive their warp's slot from it, so the compiler still knows the address space.
+// per-block shared memory: INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
+struct __align__(16) SfBlockSmem {
+  int4 xtap[84];
+  int4 ytap[84];
+};
+
+// all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
+// Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
-__device__ __forceinline__ SfWarpSmem& sf_my_smem() { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw)[threadIdx.x >> 5]; }
+__device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
+__device__ __forceinline__ SfWarpSmem& sf_my_smem() {
+  return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[threadIdx.x >> 5];
+}
+#define SF_RENDER_SMEM_BYTES(warps) (sizeof(SfBlockSmem) + sizeof(SfWarpSmem) * (warps))
 
 __device__ __forceinline__ int sf_warp_min(int v) {
 #pragma unroll
@@ -66,28 +83,30 @@ __device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a /
   return __float2int_rz(((float)a + 0.5f) * inv_b);
 }
 
-// once per warp at kernel start
-__device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, const SfTables* T, int lane) {
-  for (int k = lane; k < SF_ACC_CELLS / 2; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
-  for (int k = lane; k < SF_NAT_H * (SF_TILE_STRIDE / 4); k += 32) {
-    int r = k / (SF_TILE_STRIDE / 4), c = k - r * (SF_TILE_STRIDE / 4);
-    reinterpret_cast<unsigned*>(W.nat)[k] = __ldg(reinterpret_cast<const unsigned*>(T->bg_nat + r * SF_NAT_STRIDE) + c);
+// once per block at kernel start (every thread of the block calls it, before any early exit)
+__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
+  SfBlockSmem& B = sf_block_smem();
+  for (int k = threadIdx.x; k < 168; k += blockDim.x) {
+    const SfTap t = k < 84 ? T->xtap[k] : T->ytap[k - 84];
+    int4 v = make_int4(t.si | (t.cnt << 8), __float_as_int(t.a[0]), __float_as_int(t.a[1]), __float_as_int(t.a[2]));
+    if (k < 84) B.xtap[k] = v; else B.ytap[k - 84] = v;
   }
-  if (lane == 0) { W.nrect = 0; W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  __syncthreads();
+}
+// once per warp at kernel start
+__device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
+  for (int k = lane; k < SF_ACC_CELLS / 2; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
   __syncwarp();
 }
 
-__device__ __forceinline__ void sf_add_rect(SfWarpSmem& W, int lane, int x0, int y0, int x1, int y1) {
-  if (lane == 0) {
-    int n = W.nrect;
-    unsigned r = (unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24);
-    if (n < SF_MAX_RECTS) { W.rect[n] = r; W.nrect = n + 1; }
-    else {  // overflow: grow the last rectangle to the union (still correct, just more resampling)
-      unsigned q = W.rect[SF_MAX_RECTS - 1];
-      int qx0 = q & 255, qy0 = (q >> 8) & 255, qx1 = (q >> 16) & 255, qy1 = q >> 24;
-      W.rect[SF_MAX_RECTS - 1] = (unsigned)min(qx0, x0) | ((unsigned)min(qy0, y0) << 8) | ((unsigned)max(qx1, x1) << 16) | ((unsigned)max(qy1, y1) << 24);
-    }
-  }
+// body(c, r) for every 0 <= c < w, 0 <= r < h (w <= 32): narrow rectangles put several rows on one pass
+template <class F>
+__device__ __forceinline__ void sf_for_rect(int lane, int w, int h, F body) {
+  const int s = w <= 8 ? 3 : (w <= 16 ? 4 : 5);
+  const int c = lane & ((1 << s) - 1), rstep = 32 >> s;
+  if (c < w)
+    for (int r = lane >> s; r < h; r += rstep) body(c, r);
 }
 
 // ---- edge records --------------------------------------------------------------------------------------
@@ -171,7 +190,17 @@ __device__ __forceinline__ bool sf_quad_span(const SfWarpSmem& W, int qi, int sb
 }
 
 // ---- batch machinery ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void sf_batch_begin(SfWarpSmem& W, int lane) {
+// A frame owns the region list and the coverage cells; a batch owns the edge / quad / stroke records.
+__device__ __forceinline__ void sf_frame_begin(SfWarpSmem& W, int lane) {
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  __syncwarp();
+}
+// zero the coverage cells handed out since sf_frame_begin and forget the regions
+__device__ __forceinline__ void sf_frame_end(SfWarpSmem& W, int lane) {
+  __syncwarp();
+  const int nw = (W.acc_used + 1) >> 1;
+  for (int k = lane; k < nw; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
+  __syncwarp();
   if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
   __syncwarp();
 }
@@ -179,11 +208,14 @@ __device__ __forceinline__ void sf_batch_begin(SfWarpSmem& W, int lane) {
 // floor division of a grid row by 15
 __device__ __forceinline__ int sf_row_of(int g) { return (g >= 0) ? g / SF_GRID_Y : -((-g + SF_GRID_Y - 1) / SF_GRID_Y); }
 
-// Open one region + one stroke per participating lane (`want`), in lane order, with a warp scan: region ids,
-// accumulator offsets and first-item indices are exclusive prefixes. Returns the lane's region id or -1 (stroke
-// off the surface, or the batch is full: cannot happen for the strokes drawn here, see the size notes above).
+// Append one region + open one stroke per participating lane (`want`), in lane order, with a warp scan: region
+// ids continue the frame's list, accumulator offsets continue its pool, first-item indices are exclusive prefixes
+// of this batch. Returns the lane's region id or -1 (stroke off the surface, or a pool is full: cannot happen
+// for the strokes drawn here, see the size notes above; such a stroke and every later one is not drawn).
 __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax,
-                                               unsigned colour, int quad0, int nq) {
+                                               unsigned colour, int tag, int quad0, int nq) {
+  __syncwarp();
+  const int base_r = W.nregion, base_c = W.acc_used;
   int cx0 = 0, py0 = 0, w = 0, h = 0;
   bool ok = want && ymin_g < ymax_g;
   if (ok) {
@@ -192,25 +224,28 @@ __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool wan
     ok = py0 <= py1 && cx0 <= cx1;
     w = cx1 - cx0 + 1; h = py1 - py0 + 1;
   }
-  int cells = ok ? w * h : 0;
-  // inclusive scans of (count, cells) packed in one word: count < 64, cells < 2^20
-  unsigned v = ok ? ((unsigned)cells | (1u << 24)) : 0u;
+  const int cells = ok ? w * h : 0;
+  int incl_cells = cells;  // inclusive scan
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-  int incl_cells = v & 0xFFFFFF, incl_cnt = v >> 24;
-  if (ok && incl_cells > SF_ACC_CELLS) ok = false;  // pool full: drop (later strokes are dropped as well)
-  unsigned okmask = __ballot_sync(0xffffffffu, ok);
-  int rid = ok ? __popc(okmask & ((1u << lane) - 1u)) : -1;
-  int items = ok ? h * SF_GRID_Y : 0;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl_cells, o); if (lane >= o) incl_cells += t; }
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned m1 = __ballot_sync(0xffffffffu, ok);
+  if (ok && (base_c + incl_cells > SF_ACC_CELLS || base_r + __popc(m1 & lt) >= SF_MAX_REGIONS)) ok = false;
+  const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+  const int sid = __popc(okmask & lt);
+  const int rid = ok ? base_r + sid : -1;
+  const int items = ok ? h * SF_GRID_Y : 0;
   int iv = items;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
   if (ok) {
-    W.region[rid] = make_int4(cx0, py0, w | (h << 16), (incl_cells - cells) | ((int)colour << 16));
-    W.stroke[rid] = make_int2(rid | (quad0 << 8) | (nq << 16), iv - items);
+    W.region[rid] = make_int4(cx0, py0, w | (h << 16), (base_c + incl_cells - cells) | (tag << 12) | ((int)colour << 16));
+    W.stroke[sid] = make_int2(rid | (quad0 << 8) | (nq << 16), iv - items);
   }
-  if (lane == 31) { W.nregion = __popc(okmask); W.nstroke = __popc(okmask); W.nitems = iv; W.acc_used = incl_cells; }
-  (void)incl_cnt;
+  const int last = 31 - __clz((int)(okmask | 1u));  // highest participating lane (lane 0 when none: its cells count 0 then)
+  const int used = __shfl_sync(0xffffffffu, ok ? incl_cells : 0, last);
+  if (lane == 31) { W.nregion = base_r + __popc(okmask); W.nstroke = __popc(okmask); W.nitems = iv; W.acc_used = base_c + used; }
+  __syncwarp();
   return rid;
 }
 
@@ -249,7 +284,7 @@ __device__ __noinline__ void sf_batch_accumulate() {
     }
     const int sb = (R.y + r) * SF_GRID_Y + sub + SF_YBIAS;
     const int xlo = R.x << 8, xhi = (R.x + w) << 8;
-    const int cell0 = (R.w & 0xFFFF) + r * w;
+    const int cell0 = (R.w & 0xFFF) + r * w;
     // spans of the stroke's quads, kept sorted by start in four registers (insertion keeps the loops rolled so
     // the whole body stays small enough for the instruction cache)
     unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
@@ -302,33 +337,204 @@ __device__ __noinline__ void sf_batch_accumulate() {
   __syncwarp();
 }
 
-// Blend one region into the tile (and zero its cells), record its dirty rectangle.
-__device__ __noinline__ void sf_region_blend(int region_id) {
+// ---- windows ---------------------------------------------------------------------------------------------
+// win = nx0 | ny0<<8 | pw<<16 | ph<<24 : native rectangle held in W.patch (row stride 32)
+#define SF_WIN_X0(win) ((win) & 255)
+#define SF_WIN_Y0(win) (((win) >> 8) & 255)
+#define SF_WIN_W(win) (((win) >> 16) & 255)
+#define SF_WIN_H(win) (((unsigned)(win)) >> 24)
+
+__device__ __forceinline__ void sf_patch_init(SfWarpSmem& W, const SfTables* T, int lane, int win) {
+  const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
+  const unsigned char* bg = T->bg_nat + ny0 * SF_NAT_STRIDE + nx0;
+  sf_for_rect(lane, SF_WIN_W(win), SF_WIN_H(win), [&](int c, int r) { W.patch[r * SF_PATCH_STRIDE + c] = bg[r * SF_NAT_STRIDE + c]; });
+  __syncwarp();
+}
+
+// Blend region `rid` into the window (clipped to it).
+__device__ __noinline__ void sf_blend_region(int rid, int win) {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
-  int4 R = W.region[region_id];
-  int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-  unsigned colour = (unsigned)R.w >> 16;
-  unsigned short* cells = W.acc + (R.w & 0xFFFF);
-  float inv_w = 1.0f / (float)w;
-  for (int idx = lane; idx < w * h; idx += 32) {
-    unsigned L = cells[idx];
+  const int4 R = W.region[rid];
+  const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+  const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
+  const int ix0 = max(R.x, nx0), ix1 = min(R.x + w, nx0 + SF_WIN_W(win));
+  const int iy0 = max(R.y, ny0), iy1 = min(R.y + h, ny0 + (int)SF_WIN_H(win));
+  if (ix0 >= ix1 || iy0 >= iy1) return;
+  const unsigned colour = ((unsigned)R.w >> 16) & 255u;
+  const unsigned short* cells = W.acc + (R.w & 0xFFF) + (iy0 - R.y) * w + (ix0 - R.x);
+  unsigned char* p0 = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
+  sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
+    unsigned L = cells[r * w + c];
     if (L) {
-      cells[idx] = 0;
-      int r = sf_div_small(idx, w, inv_w), c = idx - r * w;
-      unsigned char* px = &W.nat[(R.y + r) * SF_TILE_STRIDE + R.x + c];
+      unsigned char* px = p0 + r * SF_PATCH_STRIDE + c;
       *px = (unsigned char)sf_blend(*px, colour, sf_len_to_alpha(L));
     }
+  });
+  __syncwarp();
+}
+
+// Composite every layer that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
+// ebox: explosion sprite box origin (bx0+64) | (by0+64)<<8 of a dead ship.
+__device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char* expcache, unsigned core, int points_i, int vuln,
+                                          int kill_bar, int ebox, int win) {
+  SfWarpSmem& W = sf_my_smem();
+  const int lane = threadIdx.x & 31;
+  const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
+  const int nx1 = nx0 + SF_WIN_W(win), ny1 = ny0 + (int)SF_WIN_H(win);  // exclusive
+  sf_patch_init(W, T, lane, win);
+  // regions of this frame that reach into the window
+  const int nreg = W.nregion;
+  bool hit = false;
+  if (lane < nreg) {
+    int4 R = W.region[lane];
+    hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
   }
-  sf_add_rect(W, lane, R.x, R.y, R.x + w - 1, R.y + h - 1);
+  unsigned rmask = __ballot_sync(0xffffffffu, hit);
+  // ---- ship wireframe | ship explosion (draw.cpp:233-237) ----
+  if (core & SF_CORE_SHIP_ALIVE) {
+    if ((rmask & 1u) && ((W.region[0].w >> 12) & 1) == SF_TAG_SHIP) { sf_blend_region(0, win); rmask &= ~1u; }
+  } else {
+    const int bx0 = (ebox & 255) - 64, by0 = ((ebox >> 8) & 255) - 64;
+    const int ix0 = max(max(bx0, 0), nx0), ix1 = min(min(bx0 + SF_EXP_W, SF_NAT_W), nx1);
+    const int iy0 = max(max(by0, 0), ny0), iy1 = min(min(by0 + SF_EXP_W, SF_NAT_H), ny1);
+    if (ix0 < ix1 && iy0 < iy1) {
+      const unsigned char* src = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
+      unsigned char* dst = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
+      sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_PATCH_STRIDE + c] = src[r * SF_EXP_W + c]; });
+      __syncwarp();
+    }
+  }
+  // ---- fortress wireframe | fortress explosion (draw.cpp:238-242) ----
+  {
+    const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+    const unsigned char* fr = T->fort_rect[fst];
+    if ((int)fr[0] < nx1 && (int)fr[2] >= nx0 && (int)fr[1] < ny1 && (int)fr[3] >= ny0) {
+      if (fst < 36) {
+        const int n = T->fort_list_n[fst];
+#pragma unroll 1
+        for (int k = lane; k < n; k += 32) {
+          const int xy = T->fort_list_xy[fst][k];
+          const int x = xy & 255, y = xy >> 8;
+          if (x >= nx0 && x < nx1 && y >= ny0 && y < ny1) {
+            unsigned char* px = &W.patch[(y - ny0) * SF_PATCH_STRIDE + (x - nx0)];
+            *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[fst][k]);
+          }
+        }
+      } else {
+        const int ix0 = max(SF_FEXP_X0, nx0), ix1 = min(SF_FEXP_X0 + SF_EXP_W, nx1);
+        const int iy0 = max(SF_FEXP_Y0, ny0), iy1 = min(SF_FEXP_Y0 + SF_EXP_W, ny1);
+        if (ix0 < ix1 && iy0 < iy1) {
+          sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
+            const int idx = (iy0 + r - SF_FEXP_Y0) * SF_EXP_W + (ix0 + c - SF_FEXP_X0);
+            unsigned a0 = T->fexp_alpha[0][idx];
+            if (a0) {
+              unsigned char* px = &W.patch[(iy0 + r - ny0) * SF_PATCH_STRIDE + (ix0 + c - nx0)];
+              unsigned v = sf_blend(*px, T->fexp_colour[0][idx], a0);
+              for (int l = 1; l < T->fexp_layers; l++) {
+                unsigned a = T->fexp_alpha[l][idx];
+                if (!a) break;
+                v = sf_blend(v, T->fexp_colour[l][idx], a);
+              }
+              *px = (unsigned char)v;
+            }
+          });
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- missiles, then shells (draw.cpp:243-253): regions are stored in draw order ----
+#pragma unroll 1
+  while (rmask) {
+    const int q = __ffs(rmask) - 1;
+    rmask &= rmask - 1;
+    sf_blend_region(q, win);
+  }
+  // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
+  {
+    const int ix0 = max(SF_TEXT_X0, nx0), ix1 = min(SF_TEXT_X0 + SF_TEXT_W, nx1);
+    const int iy0 = max(SF_TEXT_Y0, ny0), iy1 = min(SF_TEXT_Y0 + SF_TEXT_H, ny1);
+    if (ix0 < ix1 && iy0 < iy1) {
+      const int pts = min(max(points_i, 0), 9999999);
+      sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
+        const int tc = ix0 + c - SF_TEXT_X0, tr = iy0 + r - SF_TEXT_Y0;
+        const int slot = T->text_slot[tc];
+        if (slot < 7) {
+          int div = 1;
+          for (int k = slot; k < 6; k++) div *= 10;
+          unsigned a = T->text_alpha[(pts / div) % 10][tr * SF_TEXT_W + tc];
+          if (a) {
+            unsigned char* px = &W.patch[(iy0 + r - ny0) * SF_PATCH_STRIDE + (ix0 + c - nx0)];
+            *px = (unsigned char)sf_blend(*px, T->colour_text, a);
+          }
+        }
+      });
+      __syncwarp();
+    }
+  }
+  // ---- vulnerability bar (draw.cpp:207-225,268) ----
+  {
+    const int ix0 = max(SF_BAR_X0, nx0), ix1 = min(SF_BAR_X0 + SF_BAR_W, nx1);
+    const int iy0 = max(SF_BAR_Y0, ny0), iy1 = min(SF_BAR_Y0 + SF_BAR_H, ny1);
+    if (ix0 < ix1 && iy0 < iy1) {
+      const int filled = 4 * min(vuln, 10);  // 20 user units per step = 4 px
+      const unsigned fg = kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
+      sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
+        const unsigned a = T->bar_alpha[iy0 + r - SF_BAR_Y0];
+        unsigned char* px = &W.patch[(iy0 + r - ny0) * SF_PATCH_STRIDE + (ix0 + c - nx0)];
+        unsigned v = sf_blend(*px, T->colour_bar_bg, a);
+        if (ix0 + c - SF_BAR_X0 < filled) v = sf_blend(v, fg, a);
+        *px = (unsigned char)v;
+      });
+      __syncwarp();
+    }
+  }
+}
+
+// Resample the window (cv2 INTER_AREA: float accumulation in table order, round-half-even; a missing tap has
+// weight +0 and reads a byte of the patch that is never used) and overwrite the output rectangle
+// orect = j0 | i0<<8 | ow<<16 | oh<<24.
+__device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __restrict__ obs84) {
+  const SfWarpSmem& W = sf_my_smem();
+  const SfBlockSmem& B = sf_block_smem();
+  const int lane = threadIdx.x & 31;
+  const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
+  const int j0 = orect & 255, i0 = (orect >> 8) & 255;
+  sf_for_rect(lane, (orect >> 16) & 255, (int)((unsigned)orect >> 24), [&](int c, int r) {
+    const int i = i0 + r, j = j0 + c;
+    const int4 tx = B.xtap[j], ty = B.ytap[i];
+    const unsigned char* S = &W.patch[((ty.x & 255) - ny0) * SF_PATCH_STRIDE + ((tx.x & 255) - nx0)];
+    const float ax0 = __int_as_float(tx.y), ax1 = __int_as_float(tx.z);
+    const float b0 = __fadd_rn(__fmul_rn((float)S[0], ax0), __fmul_rn((float)S[1], ax1));
+    const float b1 = __fadd_rn(__fmul_rn((float)S[SF_PATCH_STRIDE], ax0), __fmul_rn((float)S[SF_PATCH_STRIDE + 1], ax1));
+    const float b2 = __fadd_rn(__fmul_rn((float)S[2 * SF_PATCH_STRIDE], ax0), __fmul_rn((float)S[2 * SF_PATCH_STRIDE + 1], ax1));
+    float sum = __fmul_rn(__int_as_float(ty.y), b0);
+    sum = __fadd_rn(sum, __fmul_rn(__int_as_float(ty.z), b1));
+    sum = __fadd_rn(sum, __fmul_rn(__int_as_float(ty.w), b2));
+    obs84[i * 84 + j] = (unsigned char)__float2int_rn(sum);
+  });
+}
+
+// Window of the native box [x0..x1] x [y0..y1] (inclusive, inside the frame): composite + resample.
+__device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char* expcache, unsigned core, int points_i, int vuln,
+                                          int kill_bar, int ebox, int x0, int y0, int x1, int y1, unsigned char* obs84) {
+  const SfBlockSmem& B = sf_block_smem();
+  const int j0 = T->col_out0[x0], j1 = T->col_out1[x1], i0 = T->row_out0[y0], i1 = T->row_out1[y1];
+  const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
+  const int nx0 = tx0 & 255, nx1 = (tx1 & 255) + (tx1 >> 8) - 1, ny0 = ty0 & 255, ny1 = (ty1 & 255) + (ty1 >> 8) - 1;
+  if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
+  const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
+  const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
+  sf_composite(T, expcache, core, points_i, vuln, kill_bar, ebox, win);
+  sf_window_out(win, orect, obs84);
   __syncwarp();
 }
 
 // ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
 // Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
-// Every lane passes the description of ITS slot's stroke. Returns (by all lanes) the region id of the lane's slot
-// or -1 when that stroke is invisible / did not fit (the caller retries it in the next batch).
-__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
+// Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke.
+__device__ __forceinline__ void sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
   const int slot = lane >> 2, line = lane & 3;
   int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
   bool has = false;
@@ -355,21 +561,27 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
     xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
   }
   // one region + stroke per slot, opened in slot order by the slot's first lane
-  int region_id = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, slot * 4, 4);
-  return __shfl_sync(0xffffffffu, region_id, lane & ~3);
+  sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE, slot * 4, 4);
 }
 
 // ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
-__device__ __noinline__ void sf_explosion_raster(const SfTables* T, double px, double py) {
+// Rasterised once per death into the window of its 28x28 box (clipped to the frame) and stored in the env's sprite
+// cache as final native pixels (it is the first layer on the background).
+__device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char* cache, double px, double py) {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
   SfPt c = sf_xform_base(px, py);
+  const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
+  const int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W, SF_NAT_W), y1 = min(by0 + SF_EXP_W, SF_NAT_H);
+  if (x0 >= x1 || y0 >= y1) return;
+  const int win = x0 | (y0 << 8) | ((x1 - x0) << 16) | ((y1 - y0) << 24);
+  sf_patch_init(W, T, lane, win);
   // arcs in batches of 32 strokes (one quad each); the last batch is the circle: 16 abutting quads = 4 strokes of
   // 4 quads sharing one region
 #pragma unroll 1
   for (int s0 = 0; s0 < SF_EXP_STROKES - 1 + 32; s0 += 32) {
     const bool circle = s0 >= SF_EXP_STROKES - 1;
-    sf_batch_begin(W, lane);
+    sf_frame_begin(W, lane);
     int s = circle ? SF_EXP_STROKES - 1 + lane : s0 + lane;
     int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
     bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
@@ -379,12 +591,11 @@ __device__ __noinline__ void sf_explosion_raster(const SfTables* T, double px, d
       ymin_g = bb.x; ymax_g = bb.y; xmin = bb.z; xmax = bb.w;
     } else W.quadrec[lane] = make_int2(0, 0);
     if (!circle) {
-      sf_open_regions(W, lane, mine, ymin_g, ymax_g, xmin, xmax, mine ? T->exp_colour[s] : 0u, lane, 1);
+      sf_open_regions(W, lane, mine, ymin_g, ymax_g, xmin, xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1);
     } else {
       ymin_g = sf_warp_min(ymin_g); ymax_g = sf_warp_max(ymax_g); xmin = sf_warp_min(xmin); xmax = sf_warp_max(xmax);
-      int rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], 0, 4);
+      int rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 4);
       rid = __shfl_sync(0xffffffffu, rid, 0);
-      __syncwarp();
       if (rid >= 0 && lane >= 1 && lane < 4) {  // three more strokes over the same region
         int h = (W.region[0].z >> 16) & 0xFFFF;
         W.stroke[lane] = make_int2(0 | ((lane * 4) << 8) | (4 << 16), lane * h * SF_GRID_Y);
@@ -395,136 +606,12 @@ __device__ __noinline__ void sf_explosion_raster(const SfTables* T, double px, d
     sf_batch_accumulate();
     const int nreg = W.nregion;
 #pragma unroll 1
-    for (int r = 0; r < nreg; r++) sf_region_blend(r);  // regions are in stroke order
+    for (int r = 0; r < nreg; r++) sf_blend_region(r, win);  // regions are in stroke order
+    sf_frame_end(W, lane);
   }
-}
-
-// one output pixel of cv2 INTER_AREA (float accumulation in table order, round-half-even)
-__device__ __forceinline__ unsigned char sf_resample(const SfWarpSmem& W, const SfTables* T, int i, int j) {
-  SfTap ty = T->ytap[i], tx = T->xtap[j];
-  const unsigned char* S = &W.nat[ty.si * SF_TILE_STRIDE + tx.si];
-  float sum = 0.f;
-#pragma unroll
-  for (int ky = 0; ky < SF_MAX_TAPS; ky++) {
-    if (ky < ty.cnt) {
-      float buf = 0.f;
-#pragma unroll
-      for (int kx = 0; kx < 2; kx++)  // the x table never has more than 2 taps (scale 15/14)
-        if (kx < tx.cnt) buf = __fadd_rn(buf, __fmul_rn((float)S[ky * SF_TILE_STRIDE + kx], tx.a[kx]));
-      float v = __fmul_rn(ty.a[ky], buf);
-      sum = ky == 0 ? v : __fadd_rn(sum, v);
-    }
-  }
-  return (unsigned char)__float2int_rn(sum);
-}
-
-// Ship explosion layer: rasterised once per death, then replayed from the per-env sprite cache.
-__device__ __noinline__ void sf_ship_explosion(const SfTables* T, unsigned char* expc, int4* q0, int env, unsigned core, double px, double py) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
-  SfPt c = sf_xform_base(px, py);
-  int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
-  unsigned char* cache = expc + (size_t)env * (SF_EXP_W * SF_EXP_W);
-  if (!(core & SF_CORE_EXP_CACHED)) {
-    sf_explosion_raster(T, px, py);
-#pragma unroll 1
-    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-      int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
-      if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) cache[idx] = W.nat[y * SF_TILE_STRIDE + x];
-    }
-    if (lane == 0) q0[env].x = (int)(core | SF_CORE_EXP_CACHED);
-    if (lane == 0) W.nrect = 0;  // the arcs recorded up to 85 small rectangles: replace them by the box
-  } else {
-#pragma unroll 1
-    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-      int r = idx / SF_EXP_W, cc = idx - r * SF_EXP_W, x = bx0 + cc, y = by0 + r;
-      if (x >= 0 && x < SF_NAT_W && y >= 0 && y < SF_NAT_H) W.nat[y * SF_TILE_STRIDE + x] = cache[idx];
-    }
-  }
-  int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W - 1, SF_NAT_W - 1), y1 = min(by0 + SF_EXP_W - 1, SF_NAT_H - 1);
-  if (x0 <= x1 && y0 <= y1) sf_add_rect(W, lane, x0, y0, x1, y1);
+  unsigned char* dst = cache + (y0 - by0) * SF_EXP_W + (x0 - bx0);
+  sf_for_rect(lane, x1 - x0, y1 - y0, [&](int cc, int r) { dst[r * SF_EXP_W + cc] = W.patch[r * SF_PATCH_STRIDE + cc]; });
   __syncwarp();
-}
-
-// Fortress layer blended into the tile (general path: something that moves overlaps it, or native output).
-__device__ __noinline__ void sf_fortress_general(const SfTables* T, int st) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
-  const unsigned char* fr = T->fort_rect[st];
-  if (st < 36) {
-    const int n = T->fort_list_n[st];
-#pragma unroll 1
-    for (int k = lane; k < n; k += 32) {
-      int idx = T->fort_list_idx[st][k];
-      int r = idx / SF_FORT_W, c = idx - r * SF_FORT_W;
-      unsigned char* px = &W.nat[(SF_FORT_Y0 + r) * SF_TILE_STRIDE + SF_FORT_X0 + c];
-      *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[st][k]);
-    }
-  } else {
-#pragma unroll 1
-    for (int idx = lane; idx < SF_EXP_W * SF_EXP_W; idx += 32) {
-      unsigned a0 = T->fexp_alpha[0][idx];
-      if (a0) {
-        int r = idx / SF_EXP_W, c = idx - r * SF_EXP_W;
-        unsigned char* px = &W.nat[(SF_FEXP_Y0 + r) * SF_TILE_STRIDE + SF_FEXP_X0 + c];
-        unsigned v = sf_blend(*px, T->fexp_colour[0][idx], a0);
-        for (int l = 1; l < T->fexp_layers; l++) {
-          unsigned a = T->fexp_alpha[l][idx];
-          if (!a) break;
-          v = sf_blend(v, T->fexp_colour[l][idx], a);
-        }
-        *px = (unsigned char)v;
-      }
-    }
-  }
-  sf_add_rect(W, lane, fr[0], fr[1], fr[2], fr[3]);
-  __syncwarp();
-}
-
-// Score digits (draw.cpp:160-173,267) and vulnerability bar (draw.cpp:207-225,268) blended into the tile.
-__device__ __noinline__ void sf_text_general(const SfTables* T, int pts) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int idx = lane; idx < SF_TEXT_H * SF_TEXT_W; idx += 32) {
-    int r = idx / SF_TEXT_W, c = idx - r * SF_TEXT_W;
-    int slot = T->text_slot[c];
-    if (slot < 7) {
-      int div = 1;
-      for (int k = slot; k < 6; k++) div *= 10;
-      unsigned a = T->text_alpha[(pts / div) % 10][idx];
-      if (a) {
-        unsigned char* px = &W.nat[(SF_TEXT_Y0 + r) * SF_TILE_STRIDE + SF_TEXT_X0 + c];
-        *px = (unsigned char)sf_blend(*px, T->colour_text, a);
-      }
-    }
-  }
-  sf_add_rect(W, lane, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1);
-}
-__device__ __noinline__ void sf_bar_general(const SfTables* T, int vuln, bool kill_bar) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
-  int filled = 4 * min(vuln, 10);  // 20 user units per step = 4 px
-  unsigned fg = kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
-#pragma unroll 1
-  for (int idx = lane; idx < SF_BAR_H * SF_BAR_W; idx += 32) {
-    int r = idx / SF_BAR_W, c = idx - r * SF_BAR_W;
-    unsigned a = T->bar_alpha[r];
-    unsigned char* px = &W.nat[(SF_BAR_Y0 + r) * SF_TILE_STRIDE + SF_BAR_X0 + c];
-    unsigned v = sf_blend(*px, T->colour_bar_bg, a);
-    if (c < filled) v = sf_blend(v, fg, a);
-    *px = (unsigned char)v;
-  }
-  sf_add_rect(W, lane, SF_BAR_X0, SF_BAR_Y0, SF_BAR_X0 + SF_BAR_W - 1, SF_BAR_Y0 + SF_BAR_H - 1);
-}
-__device__ __noinline__ void sf_native_out(unsigned char* __restrict__ nat_out) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int idx = lane; idx < SF_NAT_H * SF_NAT_W / 2; idx += 32) {
-    int r = idx / (SF_NAT_W / 2), c = (idx - r * (SF_NAT_W / 2)) * 2;
-    *reinterpret_cast<uchar2*>(&nat_out[r * SF_NAT_W + c]) = *reinterpret_cast<const uchar2*>(&W.nat[r * SF_TILE_STRIDE + c]);
-  }
 }
 
 struct SfRenderIn {  // warp-uniform view of one env
@@ -535,32 +622,27 @@ struct SfRenderIn {  // warp-uniform view of one env
   bool kill_bar;  // vuln > 10 && vulnerability timer < 250 (draw.cpp:268)
 };
 
-__device__ __forceinline__ bool sf_regions_touch(const SfWarpSmem& W, int nreg, int x0, int y0, int x1, int y1) {
-  bool hit = false;
-  for (int q = 0; q < nreg; q++) {
-    int4 R = W.region[q];
-    int rx1 = R.x + (R.z & 0xFFFF) - 1, ry1 = R.y + ((R.z >> 16) & 0xFFFF) - 1;
-    hit |= !(rx1 < x0 || R.x > x1 || ry1 < y0 || R.y > y1);
-  }
-  return hit;
-}
-__device__ __forceinline__ bool sf_rects_touch(const SfWarpSmem& W, int nr, int x0, int y0, int x1, int y1) {
-  bool hit = false;
-  for (int q = 0; q < nr; q++) {
-    unsigned r = W.rect[q];
-    int rx0 = r & 255, ry0 = (r >> 8) & 255, rx1 = (r >> 16) & 255, ry1 = r >> 24;
-    hit |= !(rx1 < x0 || rx0 > x1 || ry1 < y0 || ry0 > y1);
-  }
-  return hit;
-}
-
 // Draw env `in` and write its observation. obs84: 84*84 bytes (or NULL), nat_out: 92*90 bytes (or NULL).
 __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int lane, const SfRenderIn& in,
                                               unsigned char* __restrict__ obs84, unsigned char* __restrict__ nat_out) {
   const SfTables* T = D.tab;
   const int np = D.n_pad;
   const bool ship_alive = in.core & SF_CORE_SHIP_ALIVE, fort_alive = in.core & SF_CORE_FORT_ALIVE;
-  if (lane == 0) W.nrect = 0;
+  unsigned char* expcache = D.expc + (size_t)in.env * (SF_EXP_W * SF_EXP_W);
+  const int kill_bar = in.kill_bar ? 1 : 0;
+
+  // ---- ship explosion: sprite rasterised once per death (draw.cpp:235-237) ----
+  int ebox = 0, ex0 = 0, ey0 = 0, ex1 = -1, ey1 = -1;
+  if (!ship_alive) {
+    if (!(in.core & SF_CORE_EXP_CACHED)) {
+      sf_explosion_build(T, expcache, in.px, in.py);
+      if (lane == 0) D.q0[in.env].x = (int)(in.core | SF_CORE_EXP_CACHED);
+    }
+    SfPt c = sf_xform_base(in.px, in.py);
+    const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
+    ebox = (bx0 + 64) | ((by0 + 64) << 8);
+    ex0 = max(bx0, 0); ey0 = max(by0, 0); ex1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1; ey1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
+  }
 
   // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
   const unsigned mm = in.pmask & SF_PMASK_MISSILES;
@@ -576,126 +658,76 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
   }
   const int n_ship = ship_alive ? 1 : 0, n_mis = __popc(mm), n_strokes = n_ship + n_mis + __popc(sm);
 
-  // ---- ship explosion: memoised sprite (draw.cpp:235-237) ----
-  __syncwarp();
-  if (!ship_alive) sf_ship_explosion(T, D.expc, D.q0, in.env, in.core, in.px, in.py);
-
-  // ---- moving wireframes in batches of 8 strokes; the fortress layer goes in after the ship ----
-  bool fortress_done = false;
-  // fast path: nothing that moves comes near the sprite -> its pre-resampled output chunks are used and the
-  // tile is left alone. Decided once every moving region is known (explosion box + first batch; with more
-  // than 8 strokes the general path is taken).
-  const int fst_ = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-  bool fortress_general = nat_out != nullptr || n_strokes > 8 ||
-                          sf_rects_touch(W, W.nrect, T->fort_rect[fst_][0] - 2, T->fort_rect[fst_][1] - 2, T->fort_rect[fst_][2] + 2, T->fort_rect[fst_][3] + 2);
-  auto fortress_layer = [&]() { if (fortress_general) sf_fortress_general(T, fst_); };
-
-  for (int s0 = 0; s0 < n_strokes || !fortress_done; s0 += 8) {
-    int region_id = -1;
-    if (s0 < n_strokes) {
-      sf_batch_begin(W, lane);
-      const int si = s0 + (lane >> 2);
-      int kind = -1, angle = 0;
-      double qx = 0, qy = 0;
-      if (si < n_strokes) {
-        if (si < n_ship) { kind = 0; qx = in.px; qy = in.py; angle = (int)(in.core & SF_CORE_ANGLE_MASK); }
-        else if (si < n_ship + n_mis) {
-          int slot = __fns(mm, 0, si - n_ship + 1);
-          double2 p = D.mpos[(size_t)slot * np + in.env];
-          kind = 1; qx = p.x; qy = p.y; angle = D.mang[(size_t)slot * np + in.env];
-        } else {
-          int slot = __fns(sm, 0, si - n_ship - n_mis + 1);
-          double2 p = D.spos[(size_t)slot * np + in.env];
-          kind = 2; qx = p.x; qy = p.y;
-          angle = __double2int_rz(D.sang[(size_t)slot * np + in.env]);  // `int angle` truncation, quirk Q10
-          if (angle >= 360) angle -= 360;
-        }
+  // ---- scan-convert the moving wireframes in batches of 8 strokes; their regions stay until sf_frame_end ----
+  sf_frame_begin(W, lane);
+#pragma unroll 1
+  for (int s0 = 0; s0 < n_strokes; s0 += 8) {
+    const int si = s0 + (lane >> 2);
+    int kind = -1, angle = 0;
+    double qx = 0, qy = 0;
+    if (si < n_strokes) {
+      if (si < n_ship) { kind = 0; qx = in.px; qy = in.py; angle = (int)(in.core & SF_CORE_ANGLE_MASK); }
+      else if (si < n_ship + n_mis) {
+        int slot = __fns(mm, 0, si - n_ship + 1);
+        double2 p = D.mpos[(size_t)slot * np + in.env];
+        kind = 1; qx = p.x; qy = p.y; angle = D.mang[(size_t)slot * np + in.env];
+      } else {
+        int slot = __fns(sm, 0, si - n_ship - n_mis + 1);
+        double2 p = D.spos[(size_t)slot * np + in.env];
+        kind = 2; qx = p.x; qy = p.y;
+        angle = __double2int_rz(D.sang[(size_t)slot * np + in.env]);  // `int angle` truncation, quirk Q10
+        if (angle >= 360) angle -= 360;
       }
-      region_id = sf_wire_geometry(W, lane, T, kind, qx, qy, angle);
-      if (s0 == 0 && !fortress_general)
-        fortress_general = sf_regions_touch(W, W.nregion, T->fort_rect[fst_][0] - 2, T->fort_rect[fst_][1] - 2, T->fort_rect[fst_][2] + 2, T->fort_rect[fst_][3] + 2);
-      sf_batch_accumulate();
     }
-    // blend in draw order: ship first, then the fortress layer, then projectiles
-    for (int slot = 0; slot < 8; slot++) {
-      int si = s0 + slot;
-      if (!fortress_done && si >= n_ship) { fortress_layer(); fortress_done = true; }
-      if (si >= n_strokes) break;
-      int rid = __shfl_sync(0xffffffffu, region_id, slot * 4);
-      if (rid >= 0) sf_region_blend(rid);
-    }
+    sf_wire_geometry(W, lane, T, kind, qx, qy, angle);
+    sf_batch_accumulate();
   }
+  const int nreg = W.nregion;
 
-  // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
-  const int nmoving = W.nrect;
-  bool text_general, bar_general;
-  {
-    const int pts = min(max(in.points_i, 0), 9999999);
-    bool moving_above = false, moving_below = false;
-    for (int q = 0; q < nmoving; q++) {
-      unsigned r = W.rect[q];
-      moving_above |= (int)((r >> 8) & 255) <= T->text_guard_row;
-      moving_below |= (int)(r >> 24) >= T->bar_guard_row;
-    }
-    text_general = nat_out != nullptr || pts != 0 || moving_above;
-    bar_general = nat_out != nullptr || moving_below;
-    if (text_general) sf_text_general(T, pts);
-    if (bar_general) sf_bar_general(T, in.vuln, in.kill_bar);
-  }
-  __syncwarp();
-
-  // ---- native output (SSF_Env.step returns the 92x90 frame): every layer went through the tile ----
-  if (nat_out) sf_native_out(nat_out);
-
-  // ---- 84x84 observation: 441 chunks from the static tables, then the resampled dirty rectangles ----
   if (obs84) {
-    const int fst = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-    const int bst = in.kill_bar ? 11 : min(in.vuln, 10);
-    const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
-    int4* g = reinterpret_cast<int4*>(obs84);
-    const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
-    const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
-    const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
-    // three ranges with a fixed source each: [0, fc0) background, [fc0, fc1) fortress table (fast path),
-    // [fc1, 420) background, [420, 441) bar table (fast path)
-    const int4* fsrc = fortress_general ? bg + fc0 : ft;
-    const int4* bsrc = bar_general ? bg + SF_BAR_CHUNK0 : bt;
+    // ---- static base: 441 chunks from the pre-resampled tables ----
+    {
+      const int fst = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+      const int bst = in.kill_bar ? 11 : min(in.vuln, 10);
+      const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
+      int4* g = reinterpret_cast<int4*>(obs84);
+      const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
+      const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
+      const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
 #pragma unroll 1
-    for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
+      for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
 #pragma unroll 1
-    for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&fsrc[k - fc0]);
+      for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&ft[k - fc0]);
 #pragma unroll 1
-    for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
-    if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bsrc[lane]);
-    __syncwarp();  // orders the chunk stores before the byte patches below (same warp)
-    const int nr = W.nrect;
-    for (int q = 0; q < nr; q++) {
-      unsigned R = W.rect[q];
-      int x0 = R & 255, y0 = (R >> 8) & 255, x1 = (R >> 16) & 255, y1 = R >> 24;
-      int j0 = T->col_out0[x0], j1 = T->col_out1[x1], i0 = T->row_out0[y0], i1 = T->row_out1[y1];
-      int ow = j1 - j0 + 1, cnt = ow * (i1 - i0 + 1);
-      float inv_ow = 1.0f / (float)ow;
-      for (int idx = lane; idx < cnt; idx += 32) {
-        int r = sf_div_small(idx, ow, inv_ow), c = idx - r * ow;
-        obs84[(i0 + r) * 84 + j0 + c] = sf_resample(W, T, i0 + r, j0 + c);
-      }
+      for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
+      if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bt[lane]);
+      __syncwarp();  // orders the chunk stores before the window bytes below (same warp)
     }
+    // ---- one window per moving box ----
+#pragma unroll 1
+    for (int q = 0; q < nreg; q++) {
+      const int4 R = W.region[q];
+      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, R.x, R.y, R.x + (R.z & 0xFFFF) - 1, R.y + ((R.z >> 16) & 0xFFFF) - 1, obs84);
+    }
+    if (!ship_alive && ex0 <= ex1 && ey0 <= ey1)
+      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, ex0, ey0, ex1, ey1, obs84);
+    if (in.points_i > 0)  // the static base shows "0000000"
+      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1, obs84);
   }
-  __syncwarp();
 
-  // ---- restore the touched rectangles of the persistent tile ----
-  {
-    const int nr = W.nrect;
-    for (int q = 0; q < nr; q++) {
-      unsigned R = W.rect[q];
-      int x0 = R & 255, y0 = (R >> 8) & 255, x1 = (R >> 16) & 255, y1 = R >> 24;
-      int w = x1 - x0 + 1, cnt = w * (y1 - y0 + 1);
-      float inv_w = 1.0f / (float)w;
-      for (int idx = lane; idx < cnt; idx += 32) {
-        int r = sf_div_small(idx, w, inv_w), c = idx - r * w;
-        W.nat[(y0 + r) * SF_TILE_STRIDE + x0 + c] = T->bg_nat[(y0 + r) * SF_NAT_STRIDE + x0 + c];
+  // ---- native output (SSF_Env.step returns the 92x90 frame): the whole frame as 30x30 windows ----
+  if (nat_out) {
+#pragma unroll 1
+    for (int ty = 0; ty < SF_NAT_H; ty += 30)
+#pragma unroll 1
+      for (int tx = 0; tx < SF_NAT_W; tx += 30) {
+        const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
+        const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
+        sf_composite(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, win);
+        unsigned char* dst = nat_out + ty * SF_NAT_W + tx;
+        sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
+        __syncwarp();
       }
-    }
   }
-  __syncwarp();
+  sf_frame_end(W, lane);
 }

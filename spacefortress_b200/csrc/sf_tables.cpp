@@ -424,8 +424,8 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     int n = 0, x0 = 1 << 20, y0 = 1 << 20, x1 = -1, y1 = -1;
     for (int i = 0; i < SF_FORT_W * SF_FORT_W; i++) if (t->fort_alpha[k][i]) {
       if (n >= SF_FORT_LIST) { snprintf(err, errcap, "fortress sprite has more than %d lit pixels", SF_FORT_LIST); return 1; }
-      t->fort_list_idx[k][n] = (unsigned short)i; t->fort_list_a[k][n] = t->fort_alpha[k][i]; n++;
       int x = SF_FORT_X0 + i % SF_FORT_W, y = SF_FORT_Y0 + i / SF_FORT_W;
+      t->fort_list_idx[k][n] = (unsigned short)i; t->fort_list_xy[k][n] = (unsigned short)(x | (y << 8)); t->fort_list_a[k][n] = t->fort_alpha[k][i]; n++;
       x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x); y1 = std::max(y1, y);
     }
     t->fort_list_n[k] = n;

@@ -76,6 +76,7 @@ struct SfTables {
   int wf_nlines[3];
   // sparse fortress sprites: lit pixels only (index into the 17x17 box, coverage), tight bounding rect
   unsigned short fort_list_idx[36][SF_FORT_LIST];
+  unsigned short fort_list_xy[36][SF_FORT_LIST];  // the same pixels as native x | y<<8
   unsigned char fort_list_a[36][SF_FORT_LIST];
   int fort_list_n[36];
   unsigned char fort_rect[SF_FORT_STATES][4];  // x0,y0,x1,y1 native px of the lit pixels (state 36 = explosion)
