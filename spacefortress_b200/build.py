@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         "--fmad=false",
         "-Xptxas", "-v" if verbose else "-O3",
         "-I", os.path.join(HERE, "..", "include"),
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    ] + os.environ.get("SF_NVCC_DEFS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))

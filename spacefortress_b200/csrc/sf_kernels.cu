@@ -25,11 +25,14 @@
 #include "sf_step.cuh"
 #include "sf_tables.h"
 
+#ifndef SF_WARPS_PER_BLOCK
 #define SF_WARPS_PER_BLOCK 4
+#endif
 #define SF_BLOCK (32 * SF_WARPS_PER_BLOCK)
-// resident blocks per SM the render kernels are compiled for: 7 x 4 warps = 28 warps (<= 72 registers per thread),
-// which is what 4096 envs on 148 SMs need to be co-resident with one warp per env
-#define SF_RENDER_MIN_BLOCKS 7
+// resident blocks per SM the render kernels are compiled for (shared memory: 4 x (4 x 11.8 KB + 2.7 KB) = 200 KB)
+#ifndef SF_RENDER_MIN_BLOCKS
+#define SF_RENDER_MIN_BLOCKS 4
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // synthetic policy: stateless counter hash; same function on host and device
@@ -488,7 +491,7 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 
 static int envs_per_warp(int n) {
   if (const char* ov = getenv("SF_ENVS_PER_WARP")) { int e = atoi(ov); if (e >= 1 && e <= 32) return e; }  // tuning knob
-  // one warp per env while all warps are co-resident (148 SMs x 28 warps), then ~4 envs-per-warp-waves; <= 32
+  // one warp per env while all warps are co-resident, then more envs per warp (<= 32)
   long long target = 148ll * SF_WARPS_PER_BLOCK * SF_RENDER_MIN_BLOCKS;
   int e = 1;
   while (e < 32 && (long long)n / e > target) e <<= 1;

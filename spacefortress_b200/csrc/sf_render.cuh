@@ -6,16 +6,16 @@
 //   black, 2 hexagons -> ship wireframe | ship explosion -> fortress wireframe | fortress explosion
 //   -> missiles -> shells further than 21 from the fortress -> score digits -> vulnerability bar.
 //
-// Organisation (per env, all in one warp; 6.7 KB of shared memory per warp, so 28+ warps fit on an SM):
+// Organisation (per env, all in one warp; 11.8 KB of shared memory per warp):
 //  * The observation is first written from STATIC, pre-resampled 16-byte chunk tables (background with the
 //    "0000000" score and the empty bar, the fortress sprite of the current sector angle, the bar state):
 //    441 coalesced 128-bit stores.
 //  * Everything that moves (ship, missiles, shells, the ship explosion, a non-zero score) is a small box. Its
-//    strokes are scan-converted in BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then the
-//    (stroke,row,sub-row) samples of the whole batch are flattened over the lanes; each sample evaluates its
-//    stroke's quads with exact integer edge stepping, merges overlapping spans (non-zero winding == union for
-//    equally oriented convex quads) and accumulates span lengths into 16-bit coverage cells that stay in shared
-//    memory until the frame is done.
+//    strokes are scan-converted in BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then
+//    (1) every live (quad, sub-row) pair of the batch gets a lane that computes the exact span (integer edge
+//    stepping) into a per-(stroke, sub-row) scratch, (2) every (stroke, sub-row) gets a lane that merges the
+//    <= 4 spans (non-zero winding == union for equally oriented convex quads) and adds the lengths to 16-bit
+//    coverage cells that stay in shared memory until the frame is done.
 //  * For every moving box a WINDOW is composited: the native pixels that the box's output pixels read
 //    (INTER_AREA footprint closure, at most 30x32) are initialised from the background and EVERY layer that
 //    intersects the window is blended in draw order, clipped to it. The window is resampled and its output
@@ -28,9 +28,17 @@
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
+// experiment knob: align the warps of a block on the phases of a frame (instruction-cache locality)
+#ifdef SF_PHASE_SYNC
+#define SF_PHASE_BARRIER() __syncthreads()
+#else
+#define SF_PHASE_BARRIER() ((void)0)
+#endif
 #define SF_ACC_CELLS 1280    // 16-bit coverage cells: ship <= 100, 20 missiles <= 40 each, 3 shells <= 36 each
 #define SF_BATCH_QUADS 32
 #define SF_MAX_REGIONS 32
+#define SF_SPAN_ITEMS 256    // (stroke, sub-row) items of one batch whose quads must be unioned
+#define SF_MAX_GROUPS 352    // (quad, 8 sub-rows) work groups of one batch: 32 quads x <= 8 groups, or <= 4*256/8 + 32
 // A window is the INTER_AREA footprint closure of a box of at most 28x28 native pixels (the explosion sprite):
 // +1 column each side (<= 2 taps in x), +2 rows each side (<= 3 taps in y) -> at most 30 x 32. Rows are 32 bytes
 // apart; the resampler always reads 2 x 3 taps (missing ones have weight 0), i.e. up to row h+1 and column w.
@@ -39,19 +47,27 @@
 #define SF_WIN_MAX_W 31
 #define SF_WIN_MAX_H 34
 #define SF_YBIAS 4096        // grid rows are stored biased so they fit an unsigned 16-bit field
-#define SF_QUAD_IRREGULAR (1 << 20)  // quadrec.y flag: not a 2+2 edge split, test all four edges
 #define SF_TAG_SHIP 0
 #define SF_TAG_PROJECTILE 1
+#define SF_SPAN_NONE 0xFFFFFFFFu
+#define SF_QF_DIRECT 1       // quad flag: its stroke has no other quad -> spans go straight to the coverage cells
+#define SF_QF_IRREGULAR 2    // quad flag: not a 2+2 edge split, test all four edges
 
-// per-warp shared memory
+// per-warp shared memory (11.6 KB)
 struct __align__(16) SfWarpSmem {
-  int4 edge[SF_BATCH_QUADS * 4];            // 2048 B per quad: down0, down1, up0, up1 = {x_top, (ytop+bias)<<16 | dy, dx, magic}
+  // union scratch of a batch; the window patch aliases it (compositing starts after the last batch)
+  union {
+    uint4 span[SF_SPAN_ITEMS];              // 4096 B per item: <= 4 spans (lo<<16 | hi, relative to the region), sorted later
+    unsigned char patch[SF_PATCH_BYTES];    // 1152 B the window being composited (native pixels)
+  };
+  int4 edge[SF_BATCH_QUADS * 4];            // 2048 B per quad: down A,B, up A,B = {x0, yref | yother<<16 (biased), dx, magic}
+  int4 qinfo[SF_BATCH_QUADS * 2];           // 1024 B per quad: {g0 | g1<<16, splitD | splitU<<16, xlo, xhi}, {sink, top, w, flags}
   unsigned short acc[SF_ACC_CELLS];         // 2560 B coverage cells of every region of the frame
-  unsigned char patch[SF_PATCH_BYTES];      // 1152 B the window being composited (native pixels)
   int4 region[SF_MAX_REGIONS];              //  512 B {x0, y0, w | h<<16, acc_off | tag<<12 | colour<<16}, draw order
-  int2 quadrec[SF_BATCH_QUADS];             //  256 B {ytopQ+bias, ybotQ+bias} (grid rows), per batch
   int2 stroke[SF_MAX_REGIONS];              //  256 B per batch: {region | quad0<<8 | nq<<16, first item}
+  unsigned short glist[SF_MAX_GROUPS];      //  704 B per batch: quad | k<<5 : sub-rows g0 + 8k .. g0 + 8k + 7 of a quad
   int nregion, nstroke, nitems, acc_used;
+  int ngroups, pad0, pad1, pad2;
 };
 
 // per-block shared memory: INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
@@ -82,6 +98,7 @@ __device__ __forceinline__ int sf_warp_max(int v) {
 __device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a / b for 0 <= a < 2^20, exact
   return __float2int_rz(((float)a + 0.5f) * inv_b);
 }
+__device__ __forceinline__ int sf_div15(int d) { return (d * 2185) >> 15; }  // exact for 0 <= d < 4694
 
 // once per block at kernel start (every thread of the block calls it, before any early exit)
 __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
@@ -96,7 +113,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
   for (int k = lane; k < SF_ACC_CELLS / 2; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
   __syncwarp();
 }
 
@@ -110,31 +127,38 @@ __device__ __forceinline__ void sf_for_rect(int lane, int w, int h, F body) {
 }
 
 // ---- edge records --------------------------------------------------------------------------------------
-// x(s) = x_top + floor((s - ytop) * dx / dy), exact, via a magic reciprocal M = floor((2^32-1)/dy) + 1 (valid while
-// (dy*|dx|+dy)*dy < 2^32: always true for the strokes drawn here, which are at most ~30 px tall).
-__device__ __forceinline__ int4 sf_make_edge(const SfTables* T, int xa, int ga, int xb, int gb) {  // ga < gb (grid rows)
-  int dy = gb - ga;
-  unsigned M = T->magic[min(dy, SF_MAGIC_N - 1)];  // device strokes are far shorter than 512 sub-rows (34 px)
-  return make_int4(xa, ((ga + SF_YBIAS) << 16) | dy, xb - xa, (int)M);
+// An edge from (xa, ga) to (xb, gb), ga < gb grid rows, crosses sub-row s at x(s) = xa + floor((s - ga) * dx / dy).
+// The record is referenced to the end where the product is non-negative: dx >= 0: x0 = xa, yref = ga; dx < 0:
+// x0 = xb, yref = gb (floor((s-ga)*dx/dy) == dx + floor((gb-s)*|dx|/dy)). Then n = (s - yref) * dx >= 0 always and
+// x(s) = x0 + floor(n / dy) = x0 + umulhi(n, M) with the magic reciprocal M = floor((2^32-1)/dy) + 1 (exact while
+// n * dy < 2^32: always true for the strokes drawn here, at most ~30 px tall and ~10 px wide).
+__device__ __forceinline__ int4 sf_make_edge(const SfTables* T, int xa, int ga, int xb, int gb) {  // ga < gb
+  const int dy = gb - ga, dx = xb - xa;
+  const unsigned M = T->magic[min(dy, SF_MAGIC_N - 1)];  // device strokes are far shorter than 512 sub-rows (34 px)
+  const int a = ga + SF_YBIAS, b = gb + SF_YBIAS;
+  if (dy == 1) return make_int4(xa, a | (b << 16), 0, 0);  // one sample, at the top row: x = xa (2^32/1 has no 32-bit magic)
+  return dx >= 0 ? make_int4(xa, a | (b << 16), dx, (int)M) : make_int4(xb, b | (a << 16), dx, (int)M);
 }
-__device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias, ytop <= s < ytop + dy
-  int m = sb - (int)((unsigned)E.y >> 16);
-  int dy = E.y & 0xFFFF;
-  unsigned adx = (unsigned)abs(E.z);
-  unsigned n = (unsigned)m * adx + (E.z < 0 ? (unsigned)(dy - 1) : 0u);
-  unsigned q = __umulhi(n, (unsigned)E.w);
-  return E.z < 0 ? E.x - (int)q : E.x + (int)q;
+__device__ __forceinline__ int sf_edge_x(int4 E, int sb) {  // sb = s + bias inside the edge's rows
+  return E.x + (int)__umulhi((unsigned)((sb - (E.y & 0xFFFF)) * E.z), (unsigned)E.w);
 }
 
-// Build the 4 edge records of convex quad q (cyclic corners, consistent orientation) into slot `qi` and return
-// its bounding box {ymin_g, ymax_g, xmin, xmax} (ymin_g >= ymax_g when the quad covers no sample).
+// what the lane that built a quad knows about it
+struct SfQuadGeom {
+  int ymin_g, ymax_g, xmin, xmax;  // bounding box (grid rows / 24.8 x); ymin_g >= ymax_g: covers no sample
+  int split;                       // first (biased) sub-row of the second down edge | second up edge << 16
+  int flags;                       // SF_QF_IRREGULAR
+};
+
+// Build the 4 edge records of convex quad q (cyclic corners, consistent orientation) into slot `qi`.
 // Edges whose grid rows increase along the traversal lie on one side, the others on the opposite side; a stroked
 // segment is a parallelogram, so each side has at most two non-degenerate edges. Trapezoids (explosion arcs that
 // straddle 0/180 degrees) can have three on one side: those keep all edges and the span tests every one.
-__device__ __noinline__ int4 sf_store_quad_edges(const SfTables* T, int qi, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3) {
+__device__ __noinline__ void sf_store_quad_edges(const SfTables* T, int qi, int x0, int y0, int x1, int y1, int x2, int y2, int x3, int y3,
+                                                  SfQuadGeom& G) {
   SfWarpSmem& W = sf_my_smem();
   const int g0 = sf_grid_y(y0), g1 = sf_grid_y(y1), g2 = sf_grid_y(y2), g3 = sf_grid_y(y3);
-  const int4 none = make_int4(0, 0, 0, 0);  // dy 0: never live
+  const int4 none = make_int4(0, 0, 0, 0);  // yref == yother: never live
   int4 E0 = none, E1 = none, E2 = none, E3 = none;
   int d0 = 0, d1 = 0, d2 = 0, d3 = 0;  // +1: rows increase along the traversal, -1: decrease, 0: degenerate
   if (g0 < g1) { E0 = sf_make_edge(T, x0, g0, x1, g1); d0 = 1; } else if (g0 > g1) { E0 = sf_make_edge(T, x1, g1, x0, g0); d0 = -1; }
@@ -143,56 +167,32 @@ __device__ __noinline__ int4 sf_store_quad_edges(const SfTables* T, int qi, int 
   if (g3 < g0) { E3 = sf_make_edge(T, x3, g3, x0, g0); d3 = 1; } else if (g3 > g0) { E3 = sf_make_edge(T, x0, g0, x3, g3); d3 = -1; }
   const int nd = (d0 > 0) + (d1 > 0) + (d2 > 0) + (d3 > 0), nu = (d0 < 0) + (d1 < 0) + (d2 < 0) + (d3 < 0);
   const int gmin = min(min(g0, g1), min(g2, g3)), gmax = max(max(g0, g1), max(g2, g3));
-  if (nd == 0 || nu == 0) { W.quadrec[qi] = make_int2(0, 0); return make_int4(1 << 30, -(1 << 30), 1 << 30, -(1 << 30)); }
+  G.flags = 0; G.split = 0;
+  if (nd == 0 || nu == 0) { G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); return; }
   if (nd > 2 || nu > 2) {
     W.edge[qi * 4 + 0] = E0; W.edge[qi * 4 + 1] = E1; W.edge[qi * 4 + 2] = E2; W.edge[qi * 4 + 3] = E3;
-    W.quadrec[qi] = make_int2(gmin + SF_YBIAS, (gmax + SF_YBIAS) | SF_QUAD_IRREGULAR);
+    G.flags = SF_QF_IRREGULAR;
   } else {
-    // first / second edge of each direction in cyclic order
+    // first / second edge of each direction in cyclic order, with the (biased) top row of each
+    auto top = [](int4 E) { return min(E.y & 0xFFFF, (int)((unsigned)E.y >> 16)); };
     int4 dnA = d0 > 0 ? E0 : d1 > 0 ? E1 : d2 > 0 ? E2 : E3;
     int4 dnB = d3 > 0 ? E3 : d2 > 0 ? E2 : d1 > 0 ? E1 : E0;
     int4 upA = d0 < 0 ? E0 : d1 < 0 ? E1 : d2 < 0 ? E2 : E3;
     int4 upB = d3 < 0 ? E3 : d2 < 0 ? E2 : d1 < 0 ? E1 : E0;
     // order each side top to bottom; a side with one edge has A == B (the split test selects B, same edge)
-    if ((unsigned)dnB.y < (unsigned)dnA.y) { int4 t = dnA; dnA = dnB; dnB = t; }
-    if ((unsigned)upB.y < (unsigned)upA.y) { int4 t = upA; upA = upB; upB = t; }
+    if (top(dnB) < top(dnA)) { int4 t = dnA; dnA = dnB; dnB = t; }
+    if (top(upB) < top(upA)) { int4 t = upA; upA = upB; upB = t; }
     W.edge[qi * 4 + 0] = dnA; W.edge[qi * 4 + 1] = dnB; W.edge[qi * 4 + 2] = upA; W.edge[qi * 4 + 3] = upB;
-    W.quadrec[qi] = make_int2(gmin + SF_YBIAS, gmax + SF_YBIAS);
+    G.split = top(dnB) | (top(upB) << 16);
   }
-  return make_int4(gmin, gmax, min(min(x0, x1), min(x2, x3)), max(max(x0, x1), max(x2, x3)));
-}
-
-// span of quad slot qi on biased grid row sb; returns false when the quad is not live there
-__device__ __noinline__ void sf_quad_span_irregular(int qi, int sb, int& lo, int& hi) {
-  const SfWarpSmem& W = sf_my_smem();
-  lo = 1 << 30; hi = -(1 << 30);
-#pragma unroll 1
-  for (int k = 0; k < 4; k++) {
-    int4 E = W.edge[qi * 4 + k];
-    int m = sb - (int)((unsigned)E.y >> 16);
-    if ((unsigned)m < (unsigned)(E.y & 0xFFFF)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
-  }
-}
-__device__ __forceinline__ bool sf_quad_span(const SfWarpSmem& W, int qi, int sb, int& lo, int& hi) {
-  int2 qr = W.quadrec[qi];
-  if (qr.y & SF_QUAD_IRREGULAR) {
-    if (sb < qr.x || sb >= (qr.y & ~SF_QUAD_IRREGULAR)) return false;
-    sf_quad_span_irregular(qi, sb, lo, hi);
-    return true;
-  }
-  if (sb < qr.x || sb >= qr.y) return false;
-  int4 d1 = W.edge[qi * 4 + 1], u1 = W.edge[qi * 4 + 3];
-  int4 d = (sb < (int)((unsigned)d1.y >> 16)) ? W.edge[qi * 4 + 0] : d1;
-  int4 u = (sb < (int)((unsigned)u1.y >> 16)) ? W.edge[qi * 4 + 2] : u1;
-  int xd = sf_edge_x(d, sb), xu = sf_edge_x(u, sb);
-  lo = min(xd, xu); hi = max(xd, xu);
-  return true;
+  G.ymin_g = gmin; G.ymax_g = gmax;
+  G.xmin = min(min(x0, x1), min(x2, x3)); G.xmax = max(max(x0, x1), max(x2, x3));
 }
 
 // ---- batch machinery ---------------------------------------------------------------------------------------
-// A frame owns the region list and the coverage cells; a batch owns the edge / quad / stroke records.
+// A frame owns the region list and the coverage cells; a batch owns the edge / quad / stroke / span records.
 __device__ __forceinline__ void sf_frame_begin(SfWarpSmem& W, int lane) {
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
   __syncwarp();
 }
 // zero the coverage cells handed out since sf_frame_begin and forget the regions
@@ -201,19 +201,21 @@ __device__ __forceinline__ void sf_frame_end(SfWarpSmem& W, int lane) {
   const int nw = (W.acc_used + 1) >> 1;
   for (int k = lane; k < nw; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
   __syncwarp();
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; }
+  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
   __syncwarp();
 }
 
 // floor division of a grid row by 15
 __device__ __forceinline__ int sf_row_of(int g) { return (g >= 0) ? g / SF_GRID_Y : -((-g + SF_GRID_Y - 1) / SF_GRID_Y); }
 
-// Append one region + open one stroke per participating lane (`want`), in lane order, with a warp scan: region
-// ids continue the frame's list, accumulator offsets continue its pool, first-item indices are exclusive prefixes
-// of this batch. Returns the lane's region id or -1 (stroke off the surface, or a pool is full: cannot happen
-// for the strokes drawn here, see the size notes above; such a stroke and every later one is not drawn).
+// Append one region + open one stroke per participating lane (`want`), in lane order, with warp scans: region ids
+// continue the frame's list, accumulator offsets continue its pool, first-item indices are exclusive prefixes of
+// this batch (strokes with nq == 1 need no union and take no items). Returns the lane's region id, -1 when the
+// stroke is off the surface (or a pool is full: cannot happen for the strokes drawn here, see the size notes
+// above), or -2 when the union scratch of this batch is full: the stroke and every later one is DEFERRED to the
+// next batch (*first_deferred = lane of the first such stroke, 32 if none).
 __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax,
-                                               unsigned colour, int tag, int quad0, int nq) {
+                                               unsigned colour, int tag, int quad0, int nq, int* first_deferred, int* item0_out) {
   __syncwarp();
   const int base_r = W.nregion, base_c = W.acc_used;
   int cx0 = 0, py0 = 0, w = 0, h = 0;
@@ -224,8 +226,19 @@ __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool wan
     ok = py0 <= py1 && cx0 <= cx1;
     w = cx1 - cx0 + 1; h = py1 - py0 + 1;
   }
+  int items = (ok && nq > 1) ? h * SF_GRID_Y : 0;
+  if (items > SF_SPAN_ITEMS) { ok = false; items = 0; }  // no stroke drawn here is 17 rows tall
+  // inclusive scans of items (deferral) and cells (pool)
+  int iv = items;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+  const unsigned defer_mask = __ballot_sync(0xffffffffu, ok && iv > SF_SPAN_ITEMS);
+  const int fd = defer_mask ? __ffs(defer_mask) - 1 : 32;
+  *first_deferred = fd;
+  const bool deferred = lane >= fd;
+  if (deferred) { ok = false; }
   const int cells = ok ? w * h : 0;
-  int incl_cells = cells;  // inclusive scan
+  int incl_cells = cells;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl_cells, o); if (lane >= o) incl_cells += t; }
   const unsigned lt = (1u << lane) - 1u;
@@ -233,32 +246,119 @@ __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool wan
   if (ok && (base_c + incl_cells > SF_ACC_CELLS || base_r + __popc(m1 & lt) >= SF_MAX_REGIONS)) ok = false;
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
   const int sid = __popc(okmask & lt);
-  const int rid = ok ? base_r + sid : -1;
-  const int items = ok ? h * SF_GRID_Y : 0;
-  int iv = items;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+  const int rid = ok ? base_r + sid : (deferred && want ? -2 : -1);
   if (ok) {
     W.region[rid] = make_int4(cx0, py0, w | (h << 16), (base_c + incl_cells - cells) | (tag << 12) | ((int)colour << 16));
     W.stroke[sid] = make_int2(rid | (quad0 << 8) | (nq << 16), iv - items);
   }
-  const int last = 31 - __clz((int)(okmask | 1u));  // highest participating lane (lane 0 when none: its cells count 0 then)
+  *item0_out = iv - items;
+  const int last = 31 - __clz((int)(okmask | 1u));  // highest participating lane (lane 0 when none: it counts 0 then)
   const int used = __shfl_sync(0xffffffffu, ok ? incl_cells : 0, last);
-  if (lane == 31) { W.nregion = base_r + __popc(okmask); W.nstroke = __popc(okmask); W.nitems = iv; W.acc_used = base_c + used; }
+  const int nit = __shfl_sync(0xffffffffu, ok ? iv : 0, last);
+  if (lane == 31) { W.nregion = base_r + __popc(okmask); W.nstroke = __popc(okmask); W.nitems = nit; W.acc_used = base_c + used; }
   __syncwarp();
   return rid;
 }
 
-// Accumulate span lengths of every stroke of the batch. Samples (stroke, row, sub-row) are flattened over lanes.
-// Within a stroke, samples are ordered in blocks of 4 pixel rows (row fastest, then sub-row): one pass of 32 lanes
-// then covers ~4 rows x 8 sub-rows, so (a) same-cell atomic conflicts stay low and (b) quads that do not reach
-// those rows are skipped with a warp-uniform test.
+// Every lane that built a quad publishes it for the scan converter: live sub-rows clipped to the region, edge
+// splits, clip range in x and where its spans go (the union scratch, or straight to the cells when the stroke
+// has no other quad). j = index of the quad in its stroke, item0 = first item of the stroke.
+__device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const SfQuadGeom& G, bool has, int rid, int j, int item0, bool direct) {
+  int len = 0;
+  if (has && rid >= 0) {
+    const int4 R = W.region[rid];
+    const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+    const int top = R.y * SF_GRID_Y + SF_YBIAS;
+    const int g0 = max(G.ymin_g + SF_YBIAS, top), g1 = min(G.ymax_g + SF_YBIAS, top + h * SF_GRID_Y);
+    len = max(g1 - g0, 0);
+    W.qinfo[lane * 2 + 0] = make_int4(g0 | (g1 << 16), G.split, R.x << 8, (R.x + w) << 8);
+    W.qinfo[lane * 2 + 1] = make_int4(direct ? (R.w & 0xFFF) : (item0 * 4 + j), top, w, G.flags | (direct ? SF_QF_DIRECT : 0));
+  }
+  // work groups of 8 consecutive sub-rows
+  const int n8 = (len + 7) >> 3;
+  int gs = n8;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, gs, o); if (lane >= o) gs += t; }
+  const int total = __shfl_sync(0xffffffffu, gs, 31);
+  gs -= n8;
+  for (int k = 0; k < n8; k++)
+    if (gs + k < SF_MAX_GROUPS) W.glist[gs + k] = (unsigned short)(lane | (k << 5));
+  if (lane == 0) W.ngroups = min(total, SF_MAX_GROUPS);
+  __syncwarp();
+}
+
+// add the span [a, b) (24.8, relative to the region's left edge) of one sub-row to the cells of its pixel row.
+// 16-bit cells, 32-bit atomics: a cell never exceeds 15*256, so the two halves of a word cannot carry into each other
+__device__ __forceinline__ void sf_emit_span(unsigned* acc32, int cell0, int a, int b) {
+  // first cell (partial), last cell (partial), full cells in between (only for near-horizontal spans)
+  const int c1 = a >> 8, c2 = (b - 1) >> 8;
+  const int ci = cell0 + c1;
+  const int len1 = min(b, (c1 + 1) << 8) - a;
+  atomicAdd(&acc32[ci >> 1], (unsigned)len1 << ((ci & 1) << 4));
+  if (c2 > c1) {
+    const int cj = cell0 + c2;
+    atomicAdd(&acc32[cj >> 1], (unsigned)(b - (c2 << 8)) << ((cj & 1) << 4));
+    for (int c = c1 + 1; c < c2; c++) { const int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
+  }
+}
+
+// span of an irregular quad: min / max over the edges that are live on sub-row sb
+__device__ __noinline__ void sf_quad_span_irregular(int qi, int sb, int& lo, int& hi) {
+  const SfWarpSmem& W = sf_my_smem();
+  lo = 1 << 30; hi = -(1 << 30);
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const int4 E = W.edge[qi * 4 + k];
+    const int ya = E.y & 0xFFFF, yb = (int)((unsigned)E.y >> 16);
+    if (sb >= min(ya, yb) && sb < max(ya, yb)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
+  }
+}
+
+// Scan-convert the batch.
+//  Phase 1: one lane per live (quad, sub-row): exact edge crossings -> span, clipped to the region. A quad that is
+//           alone in its stroke adds the span to the coverage cells; otherwise it goes to slot j of the stroke's
+//           (row, sub-row) item in the union scratch.
+//  Phase 2: one lane per item: sort the <= 4 spans, add each one minus the union of its predecessors (non-zero
+//           winding of equally oriented convex quads == union). Items are visited in blocks of 4 pixel rows
+//           (row fastest, then sub-row) so that a pass spreads its same-cell atomics over 4 rows.
 __device__ __noinline__ void sf_batch_accumulate() {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  const int nitems = W.nitems, ns = W.nstroke;
-  int s_first = 0;  // stroke containing the first sample of the pass (warp uniform)
+  const int nitems = W.nitems, ns = W.nstroke, ngroups = W.ngroups;
+  unsigned* acc32 = reinterpret_cast<unsigned*>(W.acc);
+  for (int k = lane; k < nitems; k += 32) W.span[k] = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
+  __syncwarp();
+  // ---- phase 1 ----
+#pragma unroll 1
+  for (int g0 = 0; g0 < ngroups; g0 += 4) {
+    const int gi = g0 + (lane >> 3);
+    if (gi < ngroups) {
+      const int ent = W.glist[gi];
+      const int q = ent & 31;
+      const int4 Q0 = W.qinfo[q * 2], Q1 = W.qinfo[q * 2 + 1];
+      const int sb = (Q0.x & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
+      if (sb < (int)((unsigned)Q0.x >> 16)) {
+        int lo, hi;
+        if (Q1.w & SF_QF_IRREGULAR) sf_quad_span_irregular(q, sb, lo, hi);
+        else {
+          const int4 Ed = W.edge[q * 4 + (sb >= (Q0.y & 0xFFFF) ? 1 : 0)];
+          const int4 Eu = W.edge[q * 4 + 2 + (sb >= (int)((unsigned)Q0.y >> 16) ? 1 : 0)];
+          const int xd = sf_edge_x(Ed, sb), xu = sf_edge_x(Eu, sb);
+          lo = min(xd, xu); hi = max(xd, xu);
+        }
+        lo = max(lo, Q0.z) - Q0.z; hi = min(hi, Q0.w) - Q0.z;
+        if (lo < hi) {
+          const int d = sb - Q1.y;  // sub-row index inside the region
+          if (Q1.w & SF_QF_DIRECT) sf_emit_span(acc32, Q1.x + sf_div15(d) * Q1.z, lo, hi);
+          else reinterpret_cast<unsigned*>(W.span)[Q1.x + d * 4] = ((unsigned)lo << 16) | (unsigned)hi;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ---- phase 2 ----
+  int s_first = 0;  // stroke containing the first item of the pass (warp uniform)
 #pragma unroll 1
   for (int it0 = 0; it0 < nitems; it0 += 32) {
     const int it = it0 + lane;
@@ -268,9 +368,8 @@ __device__ __noinline__ void sf_batch_accumulate() {
     while (valid && si + 1 < ns && W.stroke[si + 1].y <= it) si++;
     const int2 S = W.stroke[si];
     const int4 R = W.region[S.x & 255];
-    const int quad0 = (S.x >> 8) & 255, nq = (S.x >> 16) & 255;
     const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-    // sample index -> (row, sub): full blocks of 4 rows, then the remaining 1..3 rows
+    // item index -> (row, sub): full blocks of 4 rows, then the remaining 1..3 rows
     const int li = valid ? it - S.y : 0;
     const int nfull = h >> 2, rem = h & 3;
     int r, sub;
@@ -282,56 +381,23 @@ __device__ __noinline__ void sf_batch_accumulate() {
       sub = rem == 3 ? sf_div_small(t, 3, 1.0f / 3.0f) : (rem == 2 ? t >> 1 : t);
       r = nfull * 4 + t - sub * rem;
     }
-    const int sb = (R.y + r) * SF_GRID_Y + sub + SF_YBIAS;
-    const int xlo = R.x << 8, xhi = (R.x + w) << 8;
+    uint4 K = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
+    if (valid && ((S.x >> 16) & 255) > 1) K = W.span[S.y + r * SF_GRID_Y + sub];
+    if (!__any_sync(0xffffffffu, K.x != SF_SPAN_NONE || K.y != SF_SPAN_NONE || K.z != SF_SPAN_NONE || K.w != SF_SPAN_NONE)) continue;
+    // sort by start (none == 0xFFFFFFFF sinks to the end)
+    unsigned k0 = min(K.x, K.y), k1 = max(K.x, K.y), k2 = min(K.z, K.w), k3 = max(K.z, K.w), t0;
+    t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
+    t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
+    t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
     const int cell0 = (R.w & 0xFFF) + r * w;
-    // spans of the stroke's quads, kept sorted by start in four registers (insertion keeps the loops rolled so
-    // the whole body stays small enough for the instruction cache)
-    unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
-#pragma unroll 1
-    for (int j = 0; j < 4; j++) {
-      bool live = false;
-      if (valid && j < nq) {
-        int2 qr = W.quadrec[quad0 + j];
-        live = sb >= qr.x && sb < (qr.y & ~SF_QUAD_IRREGULAR);
-      }
-      if (!__any_sync(0xffffffffu, live)) continue;
-      unsigned key = 0xFFFFFFFFu;
-      if (live) {
-        int lo, hi;
-        sf_quad_span(W, quad0 + j, sb, lo, hi);
-        lo = max(lo, xlo); hi = min(hi, xhi);
-        if (lo < hi) key = ((unsigned)(lo - xlo) << 16) | (unsigned)(hi - xlo);
-      }
-      unsigned t = key, m;
-      m = min(k0, t); t = max(k0, t); k0 = m;
-      m = min(k1, t); t = max(k1, t); k1 = m;
-      m = min(k2, t); t = max(k2, t); k2 = m;
-      k3 = min(k3, t);
-    }
-    // emit each span minus the union of its predecessors; 16-bit cells, 32-bit atomics: a cell never exceeds
-    // 15*256, so the two halves of a word cannot carry into each other
-    unsigned* acc32 = reinterpret_cast<unsigned*>(W.acc);
     int reach = 0;
-#pragma unroll 1
-    while (__any_sync(0xffffffffu, k0 != 0xFFFFFFFFu)) {
-      if (k0 != 0xFFFFFFFFu) {
-        int a = max((int)(k0 >> 16), reach), b = (int)(k0 & 0xFFFFu);
-        reach = max(reach, b);
-        if (a < b) {
-          // first cell (partial), last cell (partial), full cells in between (only for near-horizontal spans)
-          int c1 = a >> 8, c2 = (b - 1) >> 8;
-          int ci = cell0 + c1;
-          int len1 = min(b, (c1 + 1) << 8) - a;
-          atomicAdd(&acc32[ci >> 1], (unsigned)len1 << ((ci & 1) << 4));
-          if (c2 > c1) {
-            int cj = cell0 + c2;
-            atomicAdd(&acc32[cj >> 1], (unsigned)(b - (c2 << 8)) << ((cj & 1) << 4));
-            for (int c = c1 + 1; c < c2; c++) { int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
-          }
-        }
+    if (k0 != SF_SPAN_NONE) { int a = (int)(k0 >> 16), b = (int)(k0 & 0xFFFFu); reach = b; sf_emit_span(acc32, cell0, a, b); }
+    if (__any_sync(0xffffffffu, k1 != SF_SPAN_NONE)) {
+      if (k1 != SF_SPAN_NONE) { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+      if (__any_sync(0xffffffffu, k2 != SF_SPAN_NONE)) {
+        if (k2 != SF_SPAN_NONE) { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+        if (k3 != SF_SPAN_NONE) { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
       }
-      k0 = k1; k1 = k2; k2 = k3; k3 = 0xFFFFFFFFu;
     }
   }
   __syncwarp();
@@ -531,12 +597,15 @@ __device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char
   __syncwarp();
 }
 
+
 // ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
 // Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
-// Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke.
-__device__ __forceinline__ void sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
+// Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke and publishes the
+// quads. Returns the number of slots consumed (8, or the first slot deferred to the next batch).
+__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
   const int slot = lane >> 2, line = lane & 3;
-  int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
+  SfQuadGeom G;
+  G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
   bool has = false;
   if (kind >= 0) {
     // quick cull: every model fits in a 37-unit radius (7.4 px) around its origin
@@ -548,25 +617,33 @@ __device__ __forceinline__ void sf_wire_geometry(SfWarpSmem& W, int lane, const 
       SfPt a = sf_xform_wire(m, L[0], L[1]), b = sf_xform_wire(m, L[2], L[3]);
       SfQuad q;
       if (sf_stroke_quad(a, b, q)) {
-        int4 bb = sf_store_quad_edges(T, slot * 4 + line, q.p[0].x, q.p[0].y, q.p[1].x, q.p[1].y, q.p[2].x, q.p[2].y, q.p[3].x, q.p[3].y);
-        ymin_g = bb.x; ymax_g = bb.y; xmin = bb.z; xmax = bb.w; has = true;
+        sf_store_quad_edges(T, lane, q.p[0].x, q.p[0].y, q.p[1].x, q.p[1].y, q.p[2].x, q.p[2].y, q.p[3].x, q.p[3].y, G);
+        has = G.ymin_g < G.ymax_g;
       }
     }
   }
-  if (!has) W.quadrec[slot * 4 + line] = make_int2(0, 0);
   // bounding box of the slot's stroke: reduce over its 4 lanes
+  int ymin_g = G.ymin_g, ymax_g = G.ymax_g, xmin = G.xmin, xmax = G.xmax;
 #pragma unroll
   for (int o = 1; o <= 2; o <<= 1) {
     ymin_g = min(ymin_g, __shfl_xor_sync(0xffffffffu, ymin_g, o)); ymax_g = max(ymax_g, __shfl_xor_sync(0xffffffffu, ymax_g, o));
     xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
   }
   // one region + stroke per slot, opened in slot order by the slot's first lane
-  sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE, slot * 4, 4);
+  int fd = 32, item0 = 0;
+  int rid = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE,
+                            slot * 4, 4, &fd, &item0);
+  rid = __shfl_sync(0xffffffffu, rid, lane & ~3);
+  item0 = __shfl_sync(0xffffffffu, item0, lane & ~3);
+  sf_publish_quads(W, lane, G, has, rid, line, item0, false);
+  return fd >> 2;
 }
 
 // ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
 // Rasterised once per death into the window of its 28x28 box (clipped to the frame) and stored in the env's sprite
-// cache as final native pixels (it is the first layer on the background).
+// cache as final native pixels (it is the first layer on the background). Every arc is ONE quad and the 16 quads
+// of the circle abut along shared radial edges (identical edge records give identical crossings), so no stroke
+// needs a union: all spans go straight to the coverage cells.
 __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char* cache, double px, double py) {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
@@ -576,33 +653,29 @@ __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char
   if (x0 >= x1 || y0 >= y1) return;
   const int win = x0 | (y0 << 8) | ((x1 - x0) << 16) | ((y1 - y0) << 24);
   sf_patch_init(W, T, lane, win);
-  // arcs in batches of 32 strokes (one quad each); the last batch is the circle: 16 abutting quads = 4 strokes of
-  // 4 quads sharing one region
+  // arcs in batches of 32 strokes; the last batch is the circle: 16 quads sharing one region
 #pragma unroll 1
   for (int s0 = 0; s0 < SF_EXP_STROKES - 1 + 32; s0 += 32) {
     const bool circle = s0 >= SF_EXP_STROKES - 1;
     sf_frame_begin(W, lane);
-    int s = circle ? SF_EXP_STROKES - 1 + lane : s0 + lane;
-    int ymin_g = 1 << 30, ymax_g = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
-    bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
+    const int s = circle ? SF_EXP_STROKES - 1 + lane : s0 + lane;
+    const bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
+    SfQuadGeom G;
+    G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
     if (mine) {
       const short* o = T->exp_quad[s];
-      int4 bb = sf_store_quad_edges(T, lane, c.x + o[0], c.y + o[1], c.x + o[2], c.y + o[3], c.x + o[4], c.y + o[5], c.x + o[6], c.y + o[7]);
-      ymin_g = bb.x; ymax_g = bb.y; xmin = bb.z; xmax = bb.w;
-    } else W.quadrec[lane] = make_int2(0, 0);
-    if (!circle) {
-      sf_open_regions(W, lane, mine, ymin_g, ymax_g, xmin, xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1);
-    } else {
-      ymin_g = sf_warp_min(ymin_g); ymax_g = sf_warp_max(ymax_g); xmin = sf_warp_min(xmin); xmax = sf_warp_max(xmax);
-      int rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 4);
-      rid = __shfl_sync(0xffffffffu, rid, 0);
-      if (rid >= 0 && lane >= 1 && lane < 4) {  // three more strokes over the same region
-        int h = (W.region[0].z >> 16) & 0xFFFF;
-        W.stroke[lane] = make_int2(0 | ((lane * 4) << 8) | (4 << 16), lane * h * SF_GRID_Y);
-      }
-      __syncwarp();
-      if (rid >= 0 && lane == 0) { int h = (W.region[0].z >> 16) & 0xFFFF; W.nstroke = 4; W.nitems = 4 * h * SF_GRID_Y; }
+      sf_store_quad_edges(T, lane, c.x + o[0], c.y + o[1], c.x + o[2], c.y + o[3], c.x + o[4], c.y + o[5], c.x + o[6], c.y + o[7], G);
     }
+    const bool has = mine && G.ymin_g < G.ymax_g;
+    int fd, item0, rid;
+    if (!circle) {
+      rid = sf_open_regions(W, lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1, &fd, &item0);
+    } else {
+      const int ymin_g = sf_warp_min(G.ymin_g), ymax_g = sf_warp_max(G.ymax_g), xmin = sf_warp_min(G.xmin), xmax = sf_warp_max(G.xmax);
+      rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 1, &fd, &item0);
+      rid = __shfl_sync(0xffffffffu, rid, 0);
+    }
+    sf_publish_quads(W, lane, G, has, rid, 0, 0, true);
     sf_batch_accumulate();
     const int nreg = W.nregion;
 #pragma unroll 1
@@ -659,9 +732,10 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
   const int n_ship = ship_alive ? 1 : 0, n_mis = __popc(mm), n_strokes = n_ship + n_mis + __popc(sm);
 
   // ---- scan-convert the moving wireframes in batches of 8 strokes; their regions stay until sf_frame_end ----
+  SF_PHASE_BARRIER();
   sf_frame_begin(W, lane);
 #pragma unroll 1
-  for (int s0 = 0; s0 < n_strokes; s0 += 8) {
+  for (int s0 = 0; s0 < n_strokes;) {
     const int si = s0 + (lane >> 2);
     int kind = -1, angle = 0;
     double qx = 0, qy = 0;
@@ -679,10 +753,11 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
         if (angle >= 360) angle -= 360;
       }
     }
-    sf_wire_geometry(W, lane, T, kind, qx, qy, angle);
+    s0 += sf_wire_geometry(W, lane, T, kind, qx, qy, angle);  // fewer than 8 when the union scratch was full
     sf_batch_accumulate();
   }
   const int nreg = W.nregion;
+  SF_PHASE_BARRIER();
 
   if (obs84) {
     // ---- static base: 441 chunks from the pre-resampled tables ----
@@ -730,4 +805,5 @@ __device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int
       }
   }
   sf_frame_end(W, lane);
+  SF_PHASE_BARRIER();
 }

@@ -34,7 +34,7 @@ def getsrc(f, ln):
         p = os.path.join(ROOT, d, f)
         if os.path.exists(p):
             if p not in src: src[p] = open(p).read().split("\n")
-            return src[p][ln - 1].strip()[:100]
+            return src[p][ln - 1].strip()[:100] if ln - 1 < len(src[p]) else ""
     return ""
 for k, (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("TOP", "40"))]:
     if k: print("%5.1f%% inst %5.1f%% smp  %-14s:%-4d %s" % (n / tot * 100, s / stot * 100, k[0], k[1], getsrc(*k)))
