@@ -25,14 +25,8 @@
 #include "sf_step.cuh"
 #include "sf_tables.h"
 
-#ifndef SF_WARPS_PER_BLOCK
-#define SF_WARPS_PER_BLOCK 4
-#endif
+#define SF_WARPS_PER_BLOCK SF_RENDER_WARPS  // sf_render.cuh: one block per SM
 #define SF_BLOCK (32 * SF_WARPS_PER_BLOCK)
-// resident blocks per SM the render kernels are compiled for (shared memory: 4 x (4 x 11.8 KB + 2.7 KB) = 200 KB)
-#ifndef SF_RENDER_MIN_BLOCKS
-#define SF_RENDER_MIN_BLOCKS 4
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // synthetic policy: stateless counter hash; same function on host and device
@@ -79,29 +73,22 @@ __device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, const SfEn
   if (lane == 0 && mv) atomicMax(&D.epi[20], (unsigned long long)mv);
 }
 
-__device__ __forceinline__ void sf_make_render_in(const SfEnv& e, int env, SfRenderIn& r) {
-  r.env = env; r.core = (unsigned)e.q0.x; r.pmask = (unsigned)e.q0.y;
+// the renderer's view of one stepped env (written by the env's lane into the block's record array)
+__device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, int env, SfEnvRec& r) {
   r.px = e.pos.x; r.py = e.pos.y;
+  r.core = (unsigned)e.q0.x; r.pmask = (unsigned)e.q0.y;
   r.points_i = __float2int_rz(__int_as_float(e.q3.x));
   r.vuln = e.q1.z;
-  r.kill_bar = e.q1.z > 10 && e.q1.y < 250;
-}
-
-__device__ __forceinline__ SfRenderIn sf_bcast_render_in(const SfRenderIn& mine, int src) {
-  SfRenderIn r;
-  r.env = __shfl_sync(0xffffffffu, mine.env, src);
-  r.core = __shfl_sync(0xffffffffu, mine.core, src);
-  r.pmask = __shfl_sync(0xffffffffu, mine.pmask, src);
-  r.px = __shfl_sync(0xffffffffu, mine.px, src);
-  r.py = __shfl_sync(0xffffffffu, mine.py, src);
-  r.points_i = __shfl_sync(0xffffffffu, mine.points_i, src);
-  r.vuln = __shfl_sync(0xffffffffu, mine.vuln, src);
-  r.kill_bar = __shfl_sync(0xffffffffu, (int)mine.kill_bar, src) != 0;
-  return r;
+  r.kill_bar = (e.q1.z > 10 && e.q1.y < 250) ? 1 : 0;
+  r.env = env;
+  r.s0 = 0; r.ebox = 0;
+  int vis;
+  r.ns = sf_count_strokes(D, env, r.core, r.pmask, &vis);
+  r.shell_vis = vis;
 }
 
 struct SfRollArgs {
-  int T, E, flags;
+  int T, EB, ngroups, flags;  // EB = envs per group (<= 32), ngroups = ceil(n / EB)
   const int* actions;  // [T][n] or NULL
   unsigned action_seed;
   long long t0;
@@ -115,55 +102,55 @@ struct SfRollArgs {
 // ------------------------------------------------------------------------------------------------
 // fused step + render
 // ------------------------------------------------------------------------------------------------
-template <bool RENDER>
-__global__ void __launch_bounds__(SF_BLOCK, SF_RENDER_MIN_BLOCKS) sf_rollout_kernel(SfDev D, SfRollArgs A) {
+// One block renders groups of EB envs (persistent over the groups it owns, group-major, T ticks each). Per tick:
+// warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
+// warps run the block-cooperative frame pipeline (sf_render.cuh).
+__global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(SfDev D, SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
-  if (RENDER) sf_block_smem_init(D.tab);
-  const long long wg = (long long)blockIdx.x * SF_WARPS_PER_BLOCK + warp;
-  const long long env0 = wg * A.E;
-  if (env0 >= D.n) return;
-  const int env = (int)env0 + lane;
-  const bool mine = lane < A.E && env < D.n;
+  sf_block_smem_init(D.tab);
+  sf_warp_smem_init(W, lane);
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
-  const size_t obs_bytes = (A.flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  if (RENDER) sf_warp_smem_init(W, lane);
-
-  for (int t = 0; t < A.T; t++) {
-    SfEnv e;
-    SfRenderIn rin;
-    rin.env = -1; rin.core = 0; rin.pmask = 0; rin.px = 0; rin.py = 0; rin.points_i = 0; rin.vuln = 0; rin.kill_bar = false;
-    bool finished = false;
-    if (mine) {
-      sf_load_env(D, env, e);
-      int a = A.actions ? A.actions[(size_t)t * D.n + env]
-                        : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
-      int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
-      SfStepOut o;
-      sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
-      size_t oi = (size_t)t * D.n + env;
-      if (A.reward) A.reward[oi] = o.reward;
-      if (A.done) A.done[oi] = o.done;
-      if (A.fortkill) A.fortkill[oi] = o.fort_kill;
-      if (A.events) A.events[oi] = o.events;
-      finished = o.done && autoreset;
-    }
-    if (__any_sync(0xffffffffu, finished)) {
-      sf_accumulate_episode(D, e, finished, lane);
-      if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
-    }
-    if (mine) {
-      sf_store_env(D, env, e);
-      sf_make_render_in(e, env, rin);
-    }
-    if (RENDER) {
-      __syncwarp();  // projectile arrays written above are read by other lanes below
-      for (int k = 0; k < A.E; k++) {
-        SfRenderIn r = sf_bcast_render_in(rin, k);
-        if (r.env < 0) break;
-        unsigned char* o = A.obs + ((size_t)t * D.n + r.env) * obs_bytes;
-        sf_render_env(D, W, lane, r, (A.flags & SF_FLAG_NATIVE_OBS) ? nullptr : o, (A.flags & SF_FLAG_NATIVE_OBS) ? o : nullptr);
+  SfFrameOut out;
+  out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
+  out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+#pragma unroll 1
+  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
+#pragma unroll 1
+    for (int t = 0; t < A.T; t++) {
+      if (warp == 0) {
+        const int env = group * A.EB + lane;
+        const bool mine = lane < A.EB && env < D.n;
+        SfEnv e;
+        bool finished = false;
+        if (mine) {
+          sf_load_env(D, env, e);
+          int a = A.actions ? A.actions[(size_t)t * D.n + env]
+                            : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
+          int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
+          SfStepOut o;
+          sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+          size_t oi = (size_t)t * D.n + env;
+          if (A.reward) A.reward[oi] = o.reward;
+          if (A.done) A.done[oi] = o.done;
+          if (A.fortkill) A.fortkill[oi] = o.fort_kill;
+          if (A.events) A.events[oi] = o.events;
+          finished = o.done && autoreset;
+        }
+        if (__any_sync(0xffffffffu, finished)) {
+          sf_accumulate_episode(D, e, finished, lane);
+          if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
+        }
+        if (mine) {
+          sf_store_env(D, env, e);
+          sf_make_env_rec(D, e, env, B.env[lane]);
+        } else B.env[lane].env = -1;
+        __syncwarp();
+        sf_round_scan(B, lane, 0);
       }
+      out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
+      sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out);
     }
   }
 }
@@ -199,22 +186,32 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
   if (mine) sf_store_env(D, env, e);
 }
 
-// render the current state (Game.draw), warp per env
-__global__ void __launch_bounds__(SF_BLOCK, SF_RENDER_MIN_BLOCKS) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask) {
+// render the current state (Game.draw): the same block-cooperative pipeline without the step
+__global__ void __launch_bounds__(SF_BLOCK, 1) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask, int EB, int ngroups) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
-  const int env = blockIdx.x * SF_WARPS_PER_BLOCK + warp;
-  if (env >= D.n) return;
-  if (mask && !mask[env]) return;
   sf_warp_smem_init(W, lane);
-  SfEnv e;
-  sf_load_env(D, env, e);  // every lane loads the same env (broadcast)
-  SfRenderIn r;
-  sf_make_render_in(e, env, r);
-  const size_t obs_bytes = (flags & SF_FLAG_NATIVE_OBS) ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  unsigned char* o = obs + (size_t)env * obs_bytes;
-  sf_render_env(D, W, lane, r, (flags & SF_FLAG_NATIVE_OBS) ? nullptr : o, (flags & SF_FLAG_NATIVE_OBS) ? o : nullptr);
+  SfFrameOut out;
+  out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
+  out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+  out.obs = obs;
+#pragma unroll 1
+  for (int group = blockIdx.x; group < ngroups; group += gridDim.x) {
+    if (warp == 0) {
+      const int env = group * EB + lane;
+      const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
+      if (mine) {
+        SfEnv e;
+        sf_load_env(D, env, e);
+        sf_make_env_rec(D, e, env, B.env[lane]);
+      } else B.env[lane].env = -1;
+      __syncwarp();
+      sf_round_scan(B, lane, 0);
+    }
+    sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out);
+  }
 }
 
 __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
@@ -335,6 +332,7 @@ struct sf_handle {
   int device;
   int action_set;
   int gametype;  // 0 youturn 1 autoturn 2 test-youturn 3 test-autoturn
+  int num_sms;
   void* slab;
   size_t slab_bytes;
   SfTables* h_tab;
@@ -414,10 +412,12 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(SF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
   CUDA_TRY(cudaSetDevice(device));
+  int num_sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 
   sf_handle* h = new sf_handle();
   memset(h, 0, sizeof(*h));
-  h->device = device; h->action_set = action_set; h->gametype = gt;
+  h->device = device; h->num_sms = num_sms > 0 ? num_sms : 148; h->action_set = action_set; h->gametype = gt;
   SfDev& d = h->dev;
   d.n = n_envs; d.n_pad = (n_envs + 31) & ~31;
   d.autoturn = (gt == 1 || gt == 3);
@@ -440,7 +440,7 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   layout(d, (char*)h->slab);
   CUDA_TRY(cudaMemset(h->slab, 0, h->slab_bytes));
   CUDA_TRY(cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
+  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
   CUDA_TRY(cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
   // default seeding: every env replays srand(1) — the reference never seeds libc (game.cpp:137-148)
   sf_seed_kernel<<<(d.n + 127) / 128, 128>>>(d, nullptr);
@@ -489,18 +489,22 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
   return SF_OK;
 }
 
-static int envs_per_warp(int n) {
-  if (const char* ov = getenv("SF_ENVS_PER_WARP")) { int e = atoi(ov); if (e >= 1 && e <= 32) return e; }  // tuning knob
-  // one warp per env while all warps are co-resident, then more envs per warp (<= 32)
-  long long target = 148ll * SF_WARPS_PER_BLOCK * SF_RENDER_MIN_BLOCKS;
-  int e = 1;
-  while (e < 32 && (long long)n / e > target) e <<= 1;
-  return e;
+// Envs per group (= per block and tick). While every group can have its own SM the envs are spread evenly over
+// the SMs (4096 envs -> 28 per block, 147 blocks); beyond that a group is a full warp of 32 stepping lanes and
+// the blocks are persistent over their groups.
+static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) {
+  const int n = h->dev.n, sms = h->num_sms;
+  int eb = n <= sms * SF_GROUP_ENVS ? (n + sms - 1) / sms : SF_GROUP_ENVS;
+  if (const char* ov = getenv("SF_ENVS_PER_BLOCK")) { int e = atoi(ov); if (e >= 1 && e <= SF_GROUP_ENVS) eb = e; }  // tuning knob
+  *EB = eb;
+  *ngroups = (n + eb - 1) / eb;
+  *blocks = std::min(*ngroups, sms);
 }
 
 static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {
-  int blocks = (h->dev.n + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK;
-  sf_render_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(h->dev, d_obs, flags, d_mask);
+  int EB, ngroups, blocks;
+  group_shape(h, &EB, &ngroups, &blocks);
+  sf_render_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(h->dev, d_obs, flags, d_mask, EB, ngroups);
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
@@ -526,10 +530,9 @@ static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
   bool render = (a.flags & SF_FLAG_RENDER) && a.obs;
   if (render) {
     SfRollArgs b = a;
-    b.E = envs_per_warp(d.n);
-    long long warps = ((long long)d.n + b.E - 1) / b.E;
-    int blocks = (int)((warps + SF_WARPS_PER_BLOCK - 1) / SF_WARPS_PER_BLOCK);
-    sf_rollout_kernel<true><<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
+    int blocks;
+    group_shape(h, &b.EB, &b.ngroups, &blocks);
+    sf_rollout_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
   } else {
     sf_step_only_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d, a);
   }
@@ -542,7 +545,7 @@ extern "C" int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, i
   if (!h || !d_actions) return fail(SF_ERR_INVALID, "handle or actions is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
-  a.T = 1; a.E = 1; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
+  a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
   a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
@@ -552,7 +555,7 @@ extern "C" int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_
   if (!h || T <= 0) return fail(SF_ERR_INVALID, "handle is NULL or T <= 0");
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
-  a.T = T; a.E = 1; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
+  a.T = T; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
   a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
@@ -597,7 +600,7 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   cudaStream_t st = 0;  // legacy default stream: ordered with every other call made with stream == NULL
   CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, st));
   SfRollArgs a;
-  a.T = 1; a.E = 1; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
+  a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
   a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events;
   rc = launch_rollout(h, a, st);
   if (rc) return rc;

@@ -6,7 +6,8 @@
 //   black, 2 hexagons -> ship wireframe | ship explosion -> fortress wireframe | fortress explosion
 //   -> missiles -> shells further than 21 from the fortress -> score digits -> vulnerability bar.
 //
-// Organisation (per env, all in one warp; 11.8 KB of shared memory per warp):
+// Organisation (one block per SM renders a group of <= 32 envs per tick; 11.8 KB of scratch per warp; see the
+// block-cooperative pipeline at the end of this file):
 //  * The observation is first written from STATIC, pre-resampled 16-byte chunk tables (background with the
 //    "0000000" score and the empty bar, the fortress sprite of the current sector angle, the bar state):
 //    441 coalesced 128-bit stores.
@@ -28,12 +29,6 @@
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
-// experiment knob: align the warps of a block on the phases of a frame (instruction-cache locality)
-#ifdef SF_PHASE_SYNC
-#define SF_PHASE_BARRIER() __syncthreads()
-#else
-#define SF_PHASE_BARRIER() ((void)0)
-#endif
 #define SF_ACC_CELLS 1280    // 16-bit coverage cells: ship <= 100, 20 missiles <= 40 each, 3 shells <= 36 each
 #define SF_BATCH_QUADS 32
 #define SF_MAX_REGIONS 32
@@ -70,19 +65,41 @@ struct __align__(16) SfWarpSmem {
   int ngroups, pad0, pad1, pad2;
 };
 
-// per-block shared memory: INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
+// what the renderer needs to know about one env of the block's group (written by the lane that stepped it)
+struct __align__(16) SfEnvRec {
+  double px, py;              // ship position (wireframe / explosion centre)
+  unsigned core, pmask;       // sf_state.cuh: q0.x, q0.y
+  int points_i, vuln, kill_bar;  // (int)mPoints, mVulnerability, vuln > 10 && vulnerability timer < 250 (draw.cpp:268)
+  int env;                    // index into the slab; -1: slot unused / masked out
+  int s0, ns;                 // this env's strokes in the round's list (draw order)
+  int ebox;                   // dead ship: explosion sprite box origin (bx0+64) | (by0+64)<<8
+  int shell_vis;              // shells further than 21 from the fortress (quirk Q9), bit per slot
+  int pad0, pad1;
+};
+// one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = warp<<8 | region id, -1: none
+struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
+
+#ifndef SF_RENDER_WARPS
+#define SF_RENDER_WARPS 16   // warps per block (one block per SM): 16 x 11.8 KB of scratch
+#endif
+#define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
+#define SF_ROUND_STROKES (8 * SF_RENDER_WARPS)   // strokes pooled per round: at most one batch of 8 per warp
+
+// per-block shared memory
 struct __align__(16) SfBlockSmem {
-  int4 xtap[84];
+  int4 xtap[84];   // INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
   int4 ytap[84];
+  SfEnvRec env[SF_GROUP_ENVS];
+  SfStrokeRec stroke[SF_ROUND_STROKES];
+  int r0, r1, nstrokes, pad;   // the current round: env slots [r0, r1), strokes in the list
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
-__device__ __forceinline__ SfWarpSmem& sf_my_smem() {
-  return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[threadIdx.x >> 5];
-}
+__device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
+__device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
 #define SF_RENDER_SMEM_BYTES(warps) (sizeof(SfBlockSmem) + sizeof(SfWarpSmem) * (warps))
 
 __device__ __forceinline__ int sf_warp_min(int v) {
@@ -417,18 +434,19 @@ __device__ __forceinline__ void sf_patch_init(SfWarpSmem& W, const SfTables* T, 
   __syncwarp();
 }
 
-// Blend region `rid` into the window (clipped to it).
-__device__ __noinline__ void sf_blend_region(int rid, int win) {
+// Blend region `rid` of warp `owner` (its coverage cells) into this warp's window (clipped to it).
+__device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
   SfWarpSmem& W = sf_my_smem();
+  const SfWarpSmem& O = sf_warp_smem(owner);
   const int lane = threadIdx.x & 31;
-  const int4 R = W.region[rid];
+  const int4 R = O.region[rid];
   const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
   const int ix0 = max(R.x, nx0), ix1 = min(R.x + w, nx0 + SF_WIN_W(win));
   const int iy0 = max(R.y, ny0), iy1 = min(R.y + h, ny0 + (int)SF_WIN_H(win));
   if (ix0 >= ix1 || iy0 >= iy1) return;
   const unsigned colour = ((unsigned)R.w >> 16) & 255u;
-  const unsigned short* cells = W.acc + (R.w & 0xFFF) + (iy0 - R.y) * w + (ix0 - R.x);
+  const unsigned short* cells = O.acc + (R.w & 0xFFF) + (iy0 - R.y) * w + (ix0 - R.x);
   unsigned char* p0 = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
   sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
     unsigned L = cells[r * w + c];
@@ -440,27 +458,34 @@ __device__ __noinline__ void sf_blend_region(int rid, int win) {
   __syncwarp();
 }
 
-// Composite every layer that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
-// ebox: explosion sprite box origin (bx0+64) | (by0+64)<<8 of a dead ship.
-__device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char* expcache, unsigned core, int points_i, int vuln,
-                                          int kill_bar, int ebox, int win) {
+// Composite every layer of env slot `e` that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
+__device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char* expcache, int e, int win) {
   SfWarpSmem& W = sf_my_smem();
+  const SfBlockSmem& B = sf_block_smem();
+  const SfEnvRec& rec = B.env[e];
   const int lane = threadIdx.x & 31;
+  const unsigned core = rec.core;
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
   const int nx1 = nx0 + SF_WIN_W(win), ny1 = ny0 + (int)SF_WIN_H(win);  // exclusive
   sf_patch_init(W, T, lane, win);
-  // regions of this frame that reach into the window
-  const int nreg = W.nregion;
+  // regions of this env (one per visible stroke, in draw order) that reach into the window
+  int sr = -1, tag = SF_TAG_PROJECTILE;
   bool hit = false;
-  if (lane < nreg) {
-    int4 R = W.region[lane];
-    hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
+  if (lane < rec.ns) {
+    sr = B.stroke[rec.s0 + lane].region;
+    if (sr >= 0) {
+      const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
+      hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
+      tag = (R.w >> 12) & 1;
+    }
   }
   unsigned rmask = __ballot_sync(0xffffffffu, hit);
+  const bool first_is_ship = __shfl_sync(0xffffffffu, tag, 0) == SF_TAG_SHIP;
   // ---- ship wireframe | ship explosion (draw.cpp:233-237) ----
   if (core & SF_CORE_SHIP_ALIVE) {
-    if ((rmask & 1u) && ((W.region[0].w >> 12) & 1) == SF_TAG_SHIP) { sf_blend_region(0, win); rmask &= ~1u; }
+    if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r >> 8, s0r & 255, win); rmask &= ~1u; }
   } else {
+    const int ebox = rec.ebox;
     const int bx0 = (ebox & 255) - 64, by0 = ((ebox >> 8) & 255) - 64;
     const int ix0 = max(max(bx0, 0), nx0), ix1 = min(min(bx0 + SF_EXP_W, SF_NAT_W), nx1);
     const int iy0 = max(max(by0, 0), ny0), iy1 = min(min(by0 + SF_EXP_W, SF_NAT_H), ny1);
@@ -510,19 +535,20 @@ __device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char
       __syncwarp();
     }
   }
-  // ---- missiles, then shells (draw.cpp:243-253): regions are stored in draw order ----
+  // ---- missiles, then shells (draw.cpp:243-253): the env's strokes are stored in draw order ----
 #pragma unroll 1
   while (rmask) {
     const int q = __ffs(rmask) - 1;
     rmask &= rmask - 1;
-    sf_blend_region(q, win);
+    const int sq = __shfl_sync(0xffffffffu, sr, q);
+    sf_blend_region(sq >> 8, sq & 255, win);
   }
   // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
   {
     const int ix0 = max(SF_TEXT_X0, nx0), ix1 = min(SF_TEXT_X0 + SF_TEXT_W, nx1);
     const int iy0 = max(SF_TEXT_Y0, ny0), iy1 = min(SF_TEXT_Y0 + SF_TEXT_H, ny1);
     if (ix0 < ix1 && iy0 < iy1) {
-      const int pts = min(max(points_i, 0), 9999999);
+      const int pts = min(max(rec.points_i, 0), 9999999);
       sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
         const int tc = ix0 + c - SF_TEXT_X0, tr = iy0 + r - SF_TEXT_Y0;
         const int slot = T->text_slot[tc];
@@ -544,8 +570,8 @@ __device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char
     const int ix0 = max(SF_BAR_X0, nx0), ix1 = min(SF_BAR_X0 + SF_BAR_W, nx1);
     const int iy0 = max(SF_BAR_Y0, ny0), iy1 = min(SF_BAR_Y0 + SF_BAR_H, ny1);
     if (ix0 < ix1 && iy0 < iy1) {
-      const int filled = 4 * min(vuln, 10);  // 20 user units per step = 4 px
-      const unsigned fg = kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
+      const int filled = 4 * min(rec.vuln, 10);  // 20 user units per step = 4 px
+      const unsigned fg = rec.kill_bar ? T->colour_bar_kill : T->colour_bar_fg;
       sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
         const unsigned a = T->bar_alpha[iy0 + r - SF_BAR_Y0];
         unsigned char* px = &W.patch[(iy0 + r - ny0) * SF_PATCH_STRIDE + (ix0 + c - nx0)];
@@ -582,9 +608,8 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
   });
 }
 
-// Window of the native box [x0..x1] x [y0..y1] (inclusive, inside the frame): composite + resample.
-__device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char* expcache, unsigned core, int points_i, int vuln,
-                                          int kill_bar, int ebox, int x0, int y0, int x1, int y1, unsigned char* obs84) {
+// Window of the native box [x0..x1] x [y0..y1] (inclusive, inside the frame) of env slot e: composite + resample.
+__device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char* expcache, int e, int x0, int y0, int x1, int y1, unsigned char* obs84) {
   const SfBlockSmem& B = sf_block_smem();
   const int j0 = T->col_out0[x0], j1 = T->col_out1[x1], i0 = T->row_out0[y0], i1 = T->row_out1[y1];
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
@@ -592,17 +617,17 @@ __device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
-  sf_composite(T, expcache, core, points_i, vuln, kill_bar, ebox, win);
+  sf_composite(T, expcache, e, win);
   sf_window_out(win, orect, obs84);
   __syncwarp();
 }
 
-
 // ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
 // Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
 // Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke and publishes the
-// quads. Returns the number of slots consumed (8, or the first slot deferred to the next batch).
-__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
+// quads. *rid_out = region of the lane's slot (-1 invisible, -2 deferred). Returns the number of slots consumed
+// (8, or the first slot deferred to the next batch).
+__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle, int* rid_out) {
   const int slot = lane >> 2, line = lane & 3;
   SfQuadGeom G;
   G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
@@ -636,6 +661,7 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
   rid = __shfl_sync(0xffffffffu, rid, lane & ~3);
   item0 = __shfl_sync(0xffffffffu, item0, lane & ~3);
   sf_publish_quads(W, lane, G, has, rid, line, item0, false);
+  *rid_out = rid;
   return fd >> 2;
 }
 
@@ -646,7 +672,7 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 // needs a union: all spans go straight to the coverage cells.
 __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char* cache, double px, double py) {
   SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, me = threadIdx.x >> 5;
   SfPt c = sf_xform_base(px, py);
   const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
   const int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W, SF_NAT_W), y1 = min(by0 + SF_EXP_W, SF_NAT_H);
@@ -679,7 +705,7 @@ __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char
     sf_batch_accumulate();
     const int nreg = W.nregion;
 #pragma unroll 1
-    for (int r = 0; r < nreg; r++) sf_blend_region(r, win);  // regions are in stroke order
+    for (int r = 0; r < nreg; r++) sf_blend_region(me, r, win);  // regions are in stroke order
     sf_frame_end(W, lane);
   }
   unsigned char* dst = cache + (y0 - by0) * SF_EXP_W + (x0 - bx0);
@@ -687,123 +713,217 @@ __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char
   __syncwarp();
 }
 
-struct SfRenderIn {  // warp-uniform view of one env
-  int env;
-  unsigned core, pmask;
-  double px, py;
-  int points_i, vuln;
-  bool kill_bar;  // vuln > 10 && vulnerability timer < 250 (draw.cpp:268)
+// ================================================================================================================
+// Block-cooperative frame pipeline. One block renders a GROUP of up to 32 envs per tick; the env records were
+// written by the lanes of warp 0 (one env per lane). The strokes of all envs of the group are pooled and spread
+// evenly over the warps, so that every warp of the SM runs the same phase at the same time:
+//   scan   (warp 0)  strokes per env -> offsets into the round's stroke list (a round takes as many envs as fit)
+//   A  env tasks     explosion sprite (first dead frame), static 16-byte output chunks, stroke list entries
+//   B  stroke tasks  geometry + scan conversion of <= 8 strokes per warp into the warp's coverage cells
+//   C  window tasks  one window per visible stroke / dead ship / non-zero score: composite ALL layers of the env
+//                    (reading the cells of whichever warp scan-converted them) + resample + overwrite the pixels
+// ================================================================================================================
+struct SfFrameOut {
+  unsigned char* obs;   // frames of this tick, env-major
+  size_t obs_bytes;     // 84*84 or 92*90
+  int native;           // 92x90 output (SSF_Env.step)
 };
 
-// Draw env `in` and write its observation. obs84: 84*84 bytes (or NULL), nat_out: 92*90 bytes (or NULL).
-__device__ __forceinline__ void sf_render_env(const SfDev& D, SfWarpSmem& W, int lane, const SfRenderIn& in,
-                                              unsigned char* __restrict__ obs84, unsigned char* __restrict__ nat_out) {
+// per-env stroke count (written by the env's lane before the scan)
+__device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigned core, unsigned pmask, int* shell_vis) {
+  unsigned vis = 0;
+  for (unsigned m = (pmask >> SF_PMASK_SHELL_SHIFT) & 0xFu; m; m &= m - 1) {
+    const int s = __ffs(m) - 1;
+    const double2 p = D.spos[(size_t)s * D.n_pad + env];
+    const double dx = SF_DSUB(p.x, SF_FORT_X), dy = SF_DSUB(p.y, SF_FORT_Y);
+    if (SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) > 21.0) vis |= 1u << s;  // quirk Q9, draw.cpp:249-250
+  }
+  *shell_vis = (int)vis;
+  return ((core & SF_CORE_SHIP_ALIVE) ? 1 : 0) + __popc(pmask & SF_PMASK_MISSILES) + __popc(vis);
+}
+
+// warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
+__device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_begin) {
+  const bool cand = lane >= r_begin && B.env[lane].env >= 0;
+  const int cnt = cand ? B.env[lane].ns : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES);
+  const int r1 = over ? __ffs(over) - 1 : 32;
+  if (lane < r1) B.env[lane].s0 = incl - cnt;
+  const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
+  if (lane == 0) { B.r0 = r_begin; B.r1 = r1; B.nstrokes = r1 > 0 ? total : 0; }
+}
+
+// phase A for env slot e (whole warp)
+__device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, const SfFrameOut& out) {
   const SfTables* T = D.tab;
+  SfEnvRec& rec = B.env[e];
+  const int env = rec.env;
+  if (env < 0) return;
+  unsigned core = rec.core;
   const int np = D.n_pad;
-  const bool ship_alive = in.core & SF_CORE_SHIP_ALIVE, fort_alive = in.core & SF_CORE_FORT_ALIVE;
-  unsigned char* expcache = D.expc + (size_t)in.env * (SF_EXP_W * SF_EXP_W);
-  const int kill_bar = in.kill_bar ? 1 : 0;
-
+  unsigned char* expcache = D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W);
   // ---- ship explosion: sprite rasterised once per death (draw.cpp:235-237) ----
-  int ebox = 0, ex0 = 0, ey0 = 0, ex1 = -1, ey1 = -1;
-  if (!ship_alive) {
-    if (!(in.core & SF_CORE_EXP_CACHED)) {
-      sf_explosion_build(T, expcache, in.px, in.py);
-      if (lane == 0) D.q0[in.env].x = (int)(in.core | SF_CORE_EXP_CACHED);
+  if (!(core & SF_CORE_SHIP_ALIVE)) {
+    if (!(core & SF_CORE_EXP_CACHED)) {
+      sf_explosion_build(T, expcache, rec.px, rec.py);
+      core |= SF_CORE_EXP_CACHED;
+      if (lane == 0) { D.q0[env].x = (int)core; rec.core = core; }
     }
-    SfPt c = sf_xform_base(in.px, in.py);
-    const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
-    ebox = (bx0 + 64) | ((by0 + 64) << 8);
-    ex0 = max(bx0, 0); ey0 = max(by0, 0); ex1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1; ey1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
-  }
-
-  // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
-  const unsigned mm = in.pmask & SF_PMASK_MISSILES;
-  unsigned sm = 0;
-  {
-    bool vis = false;
-    if (lane < SF_DEV_SHELLS && ((in.pmask >> (SF_PMASK_SHELL_SHIFT + lane)) & 1u)) {
-      double2 p = D.spos[(size_t)lane * np + in.env];
-      double dx = SF_DSUB(p.x, SF_FORT_X), dy = SF_DSUB(p.y, SF_FORT_Y);
-      vis = SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) > 21.0;  // quirk Q9, draw.cpp:249-250
+    if (lane == 0) {
+      SfPt c = sf_xform_base(rec.px, rec.py);
+      rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
     }
-    sm = __ballot_sync(0xffffffffu, vis) & 0xFu;
   }
-  const int n_ship = ship_alive ? 1 : 0, n_mis = __popc(mm), n_strokes = n_ship + n_mis + __popc(sm);
-
-  // ---- scan-convert the moving wireframes in batches of 8 strokes; their regions stay until sf_frame_end ----
-  SF_PHASE_BARRIER();
-  sf_frame_begin(W, lane);
+  // ---- static base of the observation: 441 chunks from the pre-resampled tables ----
+  if (!out.native) {
+    const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+    const int bst = rec.kill_bar ? 11 : min(rec.vuln, 10);
+    const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
+    int4* g = reinterpret_cast<int4*>(out.obs + (size_t)env * out.obs_bytes);
+    const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
+    const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
+    const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
 #pragma unroll 1
-  for (int s0 = 0; s0 < n_strokes;) {
-    const int si = s0 + (lane >> 2);
-    int kind = -1, angle = 0;
-    double qx = 0, qy = 0;
-    if (si < n_strokes) {
-      if (si < n_ship) { kind = 0; qx = in.px; qy = in.py; angle = (int)(in.core & SF_CORE_ANGLE_MASK); }
-      else if (si < n_ship + n_mis) {
-        int slot = __fns(mm, 0, si - n_ship + 1);
-        double2 p = D.mpos[(size_t)slot * np + in.env];
-        kind = 1; qx = p.x; qy = p.y; angle = D.mang[(size_t)slot * np + in.env];
-      } else {
-        int slot = __fns(sm, 0, si - n_ship - n_mis + 1);
-        double2 p = D.spos[(size_t)slot * np + in.env];
-        kind = 2; qx = p.x; qy = p.y;
-        angle = __double2int_rz(D.sang[(size_t)slot * np + in.env]);  // `int angle` truncation, quirk Q10
+    for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
+#pragma unroll 1
+    for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&ft[k - fc0]);
+#pragma unroll 1
+    for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
+    if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bt[lane]);
+  }
+  // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
+  {
+    bool want = false;
+    int kind = 0, angle = 0;
+    double x = 0, y = 0;
+    if (lane == 0) {
+      if (core & SF_CORE_SHIP_ALIVE) { want = true; kind = 0; x = rec.px; y = rec.py; angle = (int)(core & SF_CORE_ANGLE_MASK); }
+    } else if (lane <= SF_MAX_MISSILES) {
+      const int s = lane - 1;
+      if ((rec.pmask >> s) & 1u) {
+        const double2 p = D.mpos[(size_t)s * np + env];
+        want = true; kind = 1; x = p.x; y = p.y; angle = D.mang[(size_t)s * np + env];
+      }
+    } else if (lane <= SF_MAX_MISSILES + SF_DEV_SHELLS) {
+      const int s = lane - 1 - SF_MAX_MISSILES;
+      if ((rec.shell_vis >> s) & 1) {
+        const double2 p = D.spos[(size_t)s * np + env];
+        want = true; kind = 2; x = p.x; y = p.y;
+        angle = __double2int_rz(D.sang[(size_t)s * np + env]);  // `int angle` truncation, quirk Q10
         if (angle >= 360) angle -= 360;
       }
     }
-    s0 += sf_wire_geometry(W, lane, T, kind, qx, qy, angle);  // fewer than 8 when the union scratch was full
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (want) {
+      SfStrokeRec& S = B.stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
+      S.x = x; S.y = y; S.desc = kind | (angle << 2) | (e << 12); S.region = -1;
+    }
+  }
+  (void)W;
+}
+
+// phase B for this warp: scan-convert strokes [first, first + cnt) of the round's list
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int first, int cnt) {
+  const SfTables* T = D.tab;
+  sf_frame_begin(W, lane);
+#pragma unroll 1
+  for (int s = 0; s < cnt;) {
+    const int slot = lane >> 2;
+    const bool valid = s + slot < cnt;
+    int kind = -1, angle = 0;
+    double x = 0, y = 0;
+    if (valid) {
+      const SfStrokeRec& S = B.stroke[first + s + slot];
+      x = S.x; y = S.y; kind = S.desc & 3; angle = (S.desc >> 2) & 1023;
+    }
+    int rid;
+    const int used = sf_wire_geometry(W, lane, T, kind, x, y, angle, &rid);
+    if (valid && slot < used && (lane & 3) == 0) B.stroke[first + s + slot].region = rid >= 0 ? ((warp << 8) | rid) : -1;
     sf_batch_accumulate();
+    s += used;
   }
-  const int nreg = W.nregion;
-  SF_PHASE_BARRIER();
+}
 
-  if (obs84) {
-    // ---- static base: 441 chunks from the pre-resampled tables ----
+// phase C task t of this round
+__device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int r0, int r1, const SfFrameOut& out) {
+  const SfTables* T = D.tab;
+  int e, x0, y0, x1, y1;
+  if (t < 64) {
+    e = t >> 1;
+    if (e < r0 || e >= r1) return;
+    const SfEnvRec& rec = B.env[e];
+    if (rec.env < 0) return;
+    if ((t & 1) == 0) {  // dead ship: the explosion box
+      if (rec.core & SF_CORE_SHIP_ALIVE) return;
+      const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
+      x0 = max(bx0, 0); y0 = max(by0, 0); x1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1; y1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
+      if (x0 > x1 || y0 > y1) return;
+    } else {             // non-zero score: the static base shows "0000000"
+      if (rec.points_i <= 0) return;
+      x0 = SF_TEXT_X0; y0 = SF_TEXT_Y0; x1 = SF_TEXT_X0 + SF_TEXT_W - 1; y1 = SF_TEXT_Y0 + SF_TEXT_H - 1;
+    }
+  } else {
+    const SfStrokeRec& S = B.stroke[t - 64];
+    const int sr = S.region;
+    if (sr < 0) return;
+    e = S.desc >> 12;
+    const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
+    x0 = R.x; y0 = R.y; x1 = R.x + (R.z & 0xFFFF) - 1; y1 = R.y + ((R.z >> 16) & 0xFFFF) - 1;
+  }
+  const int env = B.env[e].env;
+  sf_window(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, x0, y0, x1, y1, out.obs + (size_t)env * out.obs_bytes);
+  (void)W; (void)lane;
+}
+
+// native output (SSF_Env.step returns the 92x90 frame): tile `tile` (30x30 windows, 3 x 4 of them) of env slot e
+__device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, int tile, const SfFrameOut& out) {
+  const int env = B.env[e].env;
+  if (env < 0) return;
+  const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
+  const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
+  const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
+  sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win);
+  unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + ty * SF_NAT_W + tx;
+  sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
+  __syncwarp();
+}
+
+// All frames of the group. Every thread of the block calls this after warp 0 has written the env records and
+// run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed.
+__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, const SfFrameOut& out) {
+#pragma unroll 1
+  for (;;) {
+    __syncthreads();  // records + scan visible
+    const int r0 = B.r0, r1 = B.r1, nst = B.nstrokes;
+    // ---- A: env tasks ----
+#pragma unroll 1
+    for (int e = r0 + warp; e < r1; e += nwarps) sf_phase_env(D, B, W, lane, e, out);
+    __syncthreads();
+    // ---- B: stroke tasks, spread evenly (<= 8 per warp: nst <= 8 * nwarps) ----
     {
-      const int fst = fort_alive ? (int)((in.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-      const int bst = in.kill_bar ? 11 : min(in.vuln, 10);
-      const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
-      int4* g = reinterpret_cast<int4*>(obs84);
-      const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
-      const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
-      const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
-#pragma unroll 1
-      for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
-#pragma unroll 1
-      for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&ft[k - fc0]);
-#pragma unroll 1
-      for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
-      if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bt[lane]);
-      __syncwarp();  // orders the chunk stores before the window bytes below (same warp)
+      const int spw = min(8, max(1, (nst + nwarps - 1) / nwarps));
+      const int first = warp * spw;
+      sf_phase_strokes(D, B, W, lane, warp, first, max(0, min(spw, nst - first)));
     }
-    // ---- one window per moving box ----
+    __syncthreads();
+    // ---- C: window tasks ----
+    if (!out.native) {
 #pragma unroll 1
-    for (int q = 0; q < nreg; q++) {
-      const int4 R = W.region[q];
-      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, R.x, R.y, R.x + (R.z & 0xFFFF) - 1, R.y + ((R.z >> 16) & 0xFFFF) - 1, obs84);
+      for (int t = warp; t < 64 + nst; t += nwarps) sf_phase_window(D, B, W, lane, t, r0, r1, out);
+    } else {
+#pragma unroll 1
+      for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
     }
-    if (!ship_alive && ex0 <= ex1 && ey0 <= ey1)
-      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, ex0, ey0, ex1, ey1, obs84);
-    if (in.points_i > 0)  // the static base shows "0000000"
-      sf_window(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, SF_TEXT_X0, SF_TEXT_Y0, SF_TEXT_X0 + SF_TEXT_W - 1, SF_TEXT_Y0 + SF_TEXT_H - 1, obs84);
+    __syncthreads();  // every warp is done reading the others' cells
+    sf_frame_end(W, lane);
+    // more envs than one round could take?
+    bool more = false;
+    for (int e = r1; e < SF_GROUP_ENVS; e++) more |= B.env[e].env >= 0;
+    if (!more) break;
+    __syncthreads();  // everybody has read r1 / the records
+    if (warp == 0) sf_round_scan(B, lane, r1);
   }
-
-  // ---- native output (SSF_Env.step returns the 92x90 frame): the whole frame as 30x30 windows ----
-  if (nat_out) {
-#pragma unroll 1
-    for (int ty = 0; ty < SF_NAT_H; ty += 30)
-#pragma unroll 1
-      for (int tx = 0; tx < SF_NAT_W; tx += 30) {
-        const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
-        const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
-        sf_composite(T, expcache, in.core, in.points_i, in.vuln, kill_bar, ebox, win);
-        unsigned char* dst = nat_out + ty * SF_NAT_W + tx;
-        sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
-        __syncwarp();
-      }
-  }
-  sf_frame_end(W, lane);
-  SF_PHASE_BARRIER();
 }
