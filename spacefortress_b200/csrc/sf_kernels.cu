@@ -82,6 +82,7 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
   r.kill_bar = (e.q1.z > 10 && e.q1.y < 250) ? 1 : 0;
   r.env = env;
   r.s0 = 0; r.ebox = 0;
+  r.building = (!(r.core & SF_CORE_SHIP_ALIVE) && !(r.core & SF_CORE_EXP_CACHED)) ? 1 : 0;
   int vis;
   r.ns = sf_count_strokes(D, env, r.core, r.pmask, &vis);
   r.shell_vis = vis;
@@ -673,6 +674,15 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
+
+#ifdef SF_PHASE_TIMING
+extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
+  return SF_OK;
+}
+#endif
 
 extern "C" int sf_background(const sf_handle* h, uint8_t* h_native, uint8_t* h_obs) {
   if (!h) return fail(SF_ERR_INVALID, "handle is NULL");

@@ -74,7 +74,8 @@ struct __align__(16) SfEnvRec {
   int s0, ns;                 // this env's strokes in the round's list (draw order)
   int ebox;                   // dead ship: explosion sprite box origin (bx0+64) | (by0+64)<<8
   int shell_vis;              // shells further than 21 from the fortress (quirk Q9), bit per slot
-  int pad0, pad1;
+  int building;               // dead ship whose explosion sprite is not cached yet: its arcs are scan-converted this round
+  int pad1;
 };
 // one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = warp<<8 | region id, -1: none
 struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
@@ -91,7 +92,13 @@ struct __align__(16) SfBlockSmem {
   int4 ytap[84];
   SfEnvRec env[SF_GROUP_ENVS];
   SfStrokeRec stroke[SF_ROUND_STROKES];
-  int r0, r1, nstrokes, pad;   // the current round: env slots [r0, r1), strokes in the list
+  int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
+  int next_task, pad0, pad1, pad2;   // phase C work queue
+  int arc_region[SF_EXP_STROKES + 3];  // build: region (warp<<8 | id, -1 none) of the 84 arcs and of the circle, stroke order
+  // copies of the static tables that every window touches
+  alignas(16) unsigned char bg_obs[84 * 84];                 // default observation: source of the bulk chunk stores
+  alignas(16) unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];  // hexagons on black, native
+  unsigned char col_out0[SF_NAT_W + 2], col_out1[SF_NAT_W + 2], row_out0[SF_NAT_H], row_out1[SF_NAT_H];  // native -> output footprint
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
@@ -125,6 +132,13 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
     int4 v = make_int4(t.si | (t.cnt << 8), __float_as_int(t.a[0]), __float_as_int(t.a[1]), __float_as_int(t.a[2]));
     if (k < 84) B.xtap[k] = v; else B.ytap[k - 84] = v;
   }
+  for (int k = threadIdx.x; k < 84 * 84 / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_obs)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_obs) + k);
+  for (int k = threadIdx.x; k < SF_NAT_H * SF_NAT_STRIDE / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_nat)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_nat) + k);
+  for (int k = threadIdx.x; k < SF_NAT_W; k += blockDim.x) { B.col_out0[k] = (unsigned char)T->col_out0[k]; B.col_out1[k] = (unsigned char)T->col_out1[k]; }
+  for (int k = threadIdx.x; k < SF_NAT_H; k += blockDim.x) { B.row_out0[k] = (unsigned char)T->row_out0[k]; B.row_out1[k] = (unsigned char)T->row_out1[k]; }
+  if (threadIdx.x == 0) B.next_task = 0;
+  // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 }
 // once per warp at kernel start
@@ -429,7 +443,7 @@ __device__ __noinline__ void sf_batch_accumulate() {
 
 __device__ __forceinline__ void sf_patch_init(SfWarpSmem& W, const SfTables* T, int lane, int win) {
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
-  const unsigned char* bg = T->bg_nat + ny0 * SF_NAT_STRIDE + nx0;
+  const unsigned char* bg = sf_block_smem().bg_nat + ny0 * SF_NAT_STRIDE + nx0;
   sf_for_rect(lane, SF_WIN_W(win), SF_WIN_H(win), [&](int c, int r) { W.patch[r * SF_PATCH_STRIDE + c] = bg[r * SF_NAT_STRIDE + c]; });
   __syncwarp();
 }
@@ -459,7 +473,7 @@ __device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
 }
 
 // Composite every layer of env slot `e` that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
-__device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char* expcache, int e, int win) {
+__device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, bool store_sprite) {
   SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
   const SfEnvRec& rec = B.env[e];
@@ -490,9 +504,23 @@ __device__ __noinline__ void sf_composite(const SfTables* T, const unsigned char
     const int ix0 = max(max(bx0, 0), nx0), ix1 = min(min(bx0 + SF_EXP_W, SF_NAT_W), nx1);
     const int iy0 = max(max(by0, 0), ny0), iy1 = min(min(by0 + SF_EXP_W, SF_NAT_H), ny1);
     if (ix0 < ix1 && iy0 < iy1) {
-      const unsigned char* src = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
-      unsigned char* dst = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
-      sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_PATCH_STRIDE + c] = src[r * SF_EXP_W + c]; });
+      if (rec.building) {
+        // first dead frame: the arcs were scan-converted this round (sf_phase_arcs); blend them in stroke order
+#pragma unroll 1
+        for (int k = 0; k < SF_EXP_STROKES; k++) {
+          const int ar = B.arc_region[k];
+          if (ar >= 0) sf_blend_region(ar >> 8, ar & 255, win);
+        }
+        if (store_sprite) {  // this window covers the whole box: keep the sprite (first layer on the background)
+          unsigned char* dst = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
+          const unsigned char* src = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
+          sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_EXP_W + c] = src[r * SF_PATCH_STRIDE + c]; });
+        }
+      } else {
+        const unsigned char* src = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
+        unsigned char* dst = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
+        sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_PATCH_STRIDE + c] = src[r * SF_EXP_W + c]; });
+      }
       __syncwarp();
     }
   }
@@ -609,15 +637,15 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
 }
 
 // Window of the native box [x0..x1] x [y0..y1] (inclusive, inside the frame) of env slot e: composite + resample.
-__device__ __forceinline__ void sf_window(const SfTables* T, const unsigned char* expcache, int e, int x0, int y0, int x1, int y1, unsigned char* obs84) {
+__device__ __forceinline__ void sf_window(const SfTables* T, unsigned char* expcache, int e, int x0, int y0, int x1, int y1, unsigned char* obs84, bool store_sprite) {
   const SfBlockSmem& B = sf_block_smem();
-  const int j0 = T->col_out0[x0], j1 = T->col_out1[x1], i0 = T->row_out0[y0], i1 = T->row_out1[y1];
+  const int j0 = B.col_out0[x0], j1 = B.col_out1[x1], i0 = B.row_out0[y0], i1 = B.row_out1[y1];
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
   const int nx0 = tx0 & 255, nx1 = (tx1 & 255) + (tx1 >> 8) - 1, ny0 = ty0 & 255, ny1 = (ty1 & 255) + (ty1 >> 8) - 1;
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
-  sf_composite(T, expcache, e, win);
+  sf_composite(T, expcache, e, win, store_sprite);
   sf_window_out(win, orect, obs84);
   __syncwarp();
 }
@@ -666,26 +694,22 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 }
 
 // ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
-// Rasterised once per death into the window of its 28x28 box (clipped to the frame) and stored in the env's sprite
-// cache as final native pixels (it is the first layer on the background). Every arc is ONE quad and the 16 quads
-// of the circle abut along shared radial edges (identical edge records give identical crossings), so no stroke
-// needs a union: all spans go straight to the coverage cells.
-__device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char* cache, double px, double py) {
-  SfWarpSmem& W = sf_my_smem();
-  const int lane = threadIdx.x & 31, me = threadIdx.x >> 5;
-  SfPt c = sf_xform_base(px, py);
-  const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;
-  const int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W, SF_NAT_W), y1 = min(by0 + SF_EXP_W, SF_NAT_H);
-  if (x0 >= x1 || y0 >= y1) return;
-  const int win = x0 | (y0 << 8) | ((x1 - x0) << 16) | ((y1 - y0) << 24);
-  sf_patch_init(W, T, lane, win);
-  // arcs in batches of 32 strokes; the last batch is the circle: 16 quads sharing one region
+// The explosion is identical for the 30 ticks a ship stays dead. On the first dead frame its 85 strokes are
+// scan-converted by ALL warps of the block (this warp: arcs [a0, a1), the last warp: the circle) into coverage
+// cells like any other stroke; the window of the explosion box blends them in stroke order and keeps the result in
+// the env's 28x28 sprite cache (final native pixels: it is the first layer on the background). Every arc is ONE
+// quad and the 16 quads of the circle abut along shared radial edges (identical edge records give identical
+// crossings), so no stroke needs a union: all spans go straight to the coverage cells.
+__device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, double px, double py) {
+  const SfPt c = sf_xform_base(px, py);
+  const int apw = (SF_EXP_STROKES - 1 + nwarps - 1) / nwarps;
+  const int a0 = warp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);
 #pragma unroll 1
-  for (int s0 = 0; s0 < SF_EXP_STROKES - 1 + 32; s0 += 32) {
-    const bool circle = s0 >= SF_EXP_STROKES - 1;
-    sf_frame_begin(W, lane);
-    const int s = circle ? SF_EXP_STROKES - 1 + lane : s0 + lane;
-    const bool mine = circle ? lane < 16 : s < SF_EXP_STROKES - 1;
+  for (int pass = 0; pass < 2; pass++) {
+    const bool circle = pass == 1;
+    if (circle ? warp != nwarps - 1 : a0 >= a1) continue;
+    const int s = circle ? SF_EXP_STROKES - 1 + lane : a0 + lane;
+    const bool mine = circle ? lane < 16 : s < a1;
     SfQuadGeom G;
     G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
     if (mine) {
@@ -696,21 +720,16 @@ __device__ __noinline__ void sf_explosion_build(const SfTables* T, unsigned char
     int fd, item0, rid;
     if (!circle) {
       rid = sf_open_regions(W, lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1, &fd, &item0);
+      if (mine) B.arc_region[s] = rid >= 0 ? ((warp << 8) | rid) : -1;
     } else {
       const int ymin_g = sf_warp_min(G.ymin_g), ymax_g = sf_warp_max(G.ymax_g), xmin = sf_warp_min(G.xmin), xmax = sf_warp_max(G.xmax);
       rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 1, &fd, &item0);
       rid = __shfl_sync(0xffffffffu, rid, 0);
+      if (lane == 0) B.arc_region[SF_EXP_STROKES - 1] = rid >= 0 ? ((warp << 8) | rid) : -1;
     }
     sf_publish_quads(W, lane, G, has, rid, 0, 0, true);
     sf_batch_accumulate();
-    const int nreg = W.nregion;
-#pragma unroll 1
-    for (int r = 0; r < nreg; r++) sf_blend_region(me, r, win);  // regions are in stroke order
-    sf_frame_end(W, lane);
   }
-  unsigned char* dst = cache + (y0 - by0) * SF_EXP_W + (x0 - bx0);
-  sf_for_rect(lane, x1 - x0, y1 - y0, [&](int cc, int r) { dst[r * SF_EXP_W + cc] = W.patch[r * SF_PATCH_STRIDE + cc]; });
-  __syncwarp();
 }
 
 // ================================================================================================================
@@ -749,11 +768,13 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES);
+  const unsigned builders = __ballot_sync(0xffffffffu, cand && B.env[lane].building);
+  const unsigned second = builders & (builders - 1);  // a round scan-converts the explosion of at most one env
+  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES) | (second ? ~((second & (0u - second)) - 1u) : 0u);
   const int r1 = over ? __ffs(over) - 1 : 32;
   if (lane < r1) B.env[lane].s0 = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
-  if (lane == 0) { B.r0 = r_begin; B.r1 = r1; B.nstrokes = r1 > 0 ? total : 0; }
+  if (lane == 0) { B.r0 = r_begin; B.r1 = r1; B.nstrokes = r1 > 0 ? total : 0; B.build_env = builders ? __ffs(builders) - 1 : -1; }
 }
 
 // phase A for env slot e (whole warp)
@@ -764,34 +785,35 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
   if (env < 0) return;
   unsigned core = rec.core;
   const int np = D.n_pad;
-  unsigned char* expcache = D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W);
-  // ---- ship explosion: sprite rasterised once per death (draw.cpp:235-237) ----
-  if (!(core & SF_CORE_SHIP_ALIVE)) {
-    if (!(core & SF_CORE_EXP_CACHED)) {
-      sf_explosion_build(T, expcache, rec.px, rec.py);
-      core |= SF_CORE_EXP_CACHED;
-      if (lane == 0) { D.q0[env].x = (int)core; rec.core = core; }
-    }
-    if (lane == 0) {
-      SfPt c = sf_xform_base(rec.px, rec.py);
-      rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
-    }
+  // ---- ship explosion box (draw.cpp:235-237) ----
+  if (!(core & SF_CORE_SHIP_ALIVE) && lane == 0) {
+    SfPt c = sf_xform_base(rec.px, rec.py);
+    rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
   }
-  // ---- static base of the observation: 441 chunks from the pre-resampled tables ----
+  // ---- static base of the observation: 441 16-byte chunks. Background chunks go out as two bulk copies from the
+  //      block's copy of the default observation (TMA engine, asynchronous; sf_block_frames waits for them before
+  //      the windows overwrite pixels); the fortress and bar chunks come from the pre-resampled state tables ----
   if (!out.native) {
     const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
     const int bst = rec.kill_bar ? 11 : min(rec.vuln, 10);
-    const int fc0 = T->fort_chunk0, fc1 = fc0 + T->fort_nchunks;
-    int4* g = reinterpret_cast<int4*>(out.obs + (size_t)env * out.obs_bytes);
-    const int4* bg = reinterpret_cast<const int4*>(T->bg_obs);
+    const int fc0 = T->fort_chunk0, nfc = T->fort_nchunks, fc1 = fc0 + nfc;
+    unsigned char* gb = out.obs + (size_t)env * out.obs_bytes;
+    if (lane == 0) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(fc0 * 16) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb + fc1 * 16), "r"(src + fc1 * 16), "r"((SF_BAR_CHUNK0 - fc1) * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    int4* g = reinterpret_cast<int4*>(gb);
     const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
     const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
-#pragma unroll 1
-    for (int k = lane; k < fc0; k += 32) g[k] = __ldg(&bg[k]);
-#pragma unroll 1
-    for (int k = fc0 + lane; k < fc1; k += 32) g[k] = __ldg(&ft[k - fc0]);
-#pragma unroll 1
-    for (int k = fc1 + lane; k < SF_BAR_CHUNK0; k += 32) g[k] = __ldg(&bg[k]);
+    {  // up to 160 fortress chunks: 5 loads in flight per lane
+      int4 v[5];
+#pragma unroll
+      for (int u = 0; u < 5; u++) if (lane + 32 * u < nfc) v[u] = __ldg(&ft[lane + 32 * u]);
+#pragma unroll
+      for (int u = 0; u < 5; u++) if (lane + 32 * u < nfc) g[fc0 + lane + 32 * u] = v[u];
+    }
     if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bt[lane]);
   }
   // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
@@ -845,6 +867,8 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
     sf_batch_accumulate();
     s += used;
   }
+  const int be = B.build_env;
+  if (be >= 0 && be < B.r1) sf_phase_arcs(T, B, W, lane, warp, SF_RENDER_WARPS, B.env[be].px, B.env[be].py);
 }
 
 // phase C task t of this round
@@ -874,8 +898,10 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
     x0 = R.x; y0 = R.y; x1 = R.x + (R.z & 0xFFFF) - 1; y1 = R.y + ((R.z >> 16) & 0xFFFF) - 1;
   }
   const int env = B.env[e].env;
-  sf_window(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, x0, y0, x1, y1, out.obs + (size_t)env * out.obs_bytes);
-  (void)W; (void)lane;
+  const bool store_sprite = t < 64 && (t & 1) == 0 && B.env[e].building;
+  sf_window(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, x0, y0, x1, y1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
+  if (store_sprite && lane == 0) D.q0[env].x = (int)(B.env[e].core | SF_CORE_EXP_CACHED);
+  (void)W;
 }
 
 // native output (SSF_Env.step returns the 92x90 frame): tile `tile` (30x30 windows, 3 x 4 of them) of env slot e
@@ -885,7 +911,7 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
   const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
   const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
-  sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win);
+  sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win, false);  // native frames never fill the sprite cache
   unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + ty * SF_NAT_W + tx;
   sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
   __syncwarp();
@@ -893,31 +919,58 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 
 // All frames of the group. Every thread of the block calls this after warp 0 has written the env records and
 // run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed.
+#ifdef SF_PHASE_TIMING
+__device__ unsigned long long sf_dbg_cycles[16];
+#define SF_TICK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
+#define SF_WTICK(k) do { if (lane == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - w_last_)); w_last_ = now_; } } while (0)
+#else
+#define SF_TICK(k) ((void)0)
+#define SF_WTICK(k) ((void)0)
+#endif
+
 __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, const SfFrameOut& out) {
+#ifdef SF_PHASE_TIMING
+  long long t_last_ = clock64(), w_last_ = t_last_;
+#endif
 #pragma unroll 1
   for (;;) {
     __syncthreads();  // records + scan visible
+    SF_TICK(0); SF_WTICK(8);
     const int r0 = B.r0, r1 = B.r1, nst = B.nstrokes;
     // ---- A: env tasks ----
 #pragma unroll 1
     for (int e = r0 + warp; e < r1; e += nwarps) sf_phase_env(D, B, W, lane, e, out);
+    SF_WTICK(9);
     __syncthreads();
+    SF_TICK(1); SF_WTICK(8);
     // ---- B: stroke tasks, spread evenly (<= 8 per warp: nst <= 8 * nwarps) ----
     {
       const int spw = min(8, max(1, (nst + nwarps - 1) / nwarps));
       const int first = warp * spw;
       sf_phase_strokes(D, B, W, lane, warp, first, max(0, min(spw, nst - first)));
     }
+    SF_WTICK(10);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's chunk copies have landed
     __syncthreads();
-    // ---- C: window tasks ----
+    SF_TICK(2); SF_WTICK(8);
+    // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
     if (!out.native) {
 #pragma unroll 1
-      for (int t = warp; t < 64 + nst; t += nwarps) sf_phase_window(D, B, W, lane, t, r0, r1, out);
+      for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&B.next_task, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= 64 + nst) break;
+        sf_phase_window(D, B, W, lane, t, r0, r1, out);
+      }
     } else {
 #pragma unroll 1
       for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
     }
+    SF_WTICK(11);
     __syncthreads();  // every warp is done reading the others' cells
+    SF_TICK(3); SF_WTICK(8);
+    if (threadIdx.x == 0) B.next_task = 0;
     sf_frame_end(W, lane);
     // more envs than one round could take?
     bool more = false;

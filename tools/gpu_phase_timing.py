@@ -1,0 +1,27 @@
+"""Debug build with -DSF_PHASE_TIMING: cycles block 0 spends per phase (thread 0: barrier to barrier; all warps: busy vs waiting)."""
+import os, subprocess, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS="-DSF_PHASE_TIMING"), check=True)
+import torch
+from spacefortress_b200 import SFVecEnv, _lib
+n, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 64
+env = SFVecEnv("autoturn", num_envs=n, device=0); env.reset(to_numpy=False)
+env.rollout(300, want=("reward",))
+out = {"obs": torch.empty((T, n, 1, 84, 84), dtype=torch.uint8, device="cuda")}
+env.rollout(T, out=out); torch.cuda.synchronize()
+L = _lib.lib()
+buf = (C.c_ulonglong * 16)()
+L.sf_debug_cycles.restype = C.c_int; L.sf_debug_cycles.argtypes = [C.c_void_p, C.c_int]
+L.sf_debug_cycles(buf, 1)
+s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+s.record(); env.rollout(T, out=out); e.record(); torch.cuda.synchronize()
+L.sf_debug_cycles(buf, 1)
+v = list(buf)
+print("launch %.3f ms, %d ticks; block 0, cycles per tick:" % (s.elapsed_time(e), T))
+names = ["step+scan (wait for warp 0)", "A env tasks", "B strokes", "C windows"]
+for k in range(4): print("  thread0 phase %-28s %8.0f" % (names[k], v[k] / T))
+print("  sum %8.0f cycles per tick = %.1f us" % (sum(v[:4]) / T, sum(v[:4]) / T / 1.965e3))
+W = 16
+print("  all warps: waiting at barriers (+frame_end/step) %8.0f per warp-tick; busy A %6.0f  B %6.0f  C %6.0f" % (v[8] / T / W, v[9] / T / W, v[10] / T / W, v[11] / T / W))
+subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
