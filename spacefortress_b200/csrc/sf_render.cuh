@@ -93,7 +93,8 @@ struct __align__(16) SfBlockSmem {
   SfEnvRec env[SF_GROUP_ENVS];
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
-  int next_task, pad0, pad1, pad2;   // phase C work queue
+  int next_task, netask, pad1, pad2;  // phase C work queue; env tasks of the round
+  unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   int arc_region[SF_EXP_STROKES + 3];  // build: region (warp<<8 | id, -1 none) of the 84 arcs and of the circle, stroke order
   // copies of the static tables that every window touches
   alignas(16) unsigned char bg_obs[84 * 84];                 // default observation: source of the bulk chunk stores
@@ -136,7 +137,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < SF_NAT_H * SF_NAT_STRIDE / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_nat)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_nat) + k);
   for (int k = threadIdx.x; k < SF_NAT_W; k += blockDim.x) { B.col_out0[k] = (unsigned char)T->col_out0[k]; B.col_out1[k] = (unsigned char)T->col_out1[k]; }
   for (int k = threadIdx.x; k < SF_NAT_H; k += blockDim.x) { B.row_out0[k] = (unsigned char)T->row_out0[k]; B.row_out1[k] = (unsigned char)T->row_out1[k]; }
-  if (threadIdx.x == 0) B.next_task = 0;
+  if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; }
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -507,9 +508,24 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
       if (rec.building) {
         // first dead frame: the arcs were scan-converted this round (sf_phase_arcs); blend them in stroke order
 #pragma unroll 1
-        for (int k = 0; k < SF_EXP_STROKES; k++) {
-          const int ar = B.arc_region[k];
-          if (ar >= 0) sf_blend_region(ar >> 8, ar & 255, win);
+        for (int k0 = 0; k0 < SF_EXP_STROKES; k0 += 32) {
+          int ar = -1;
+          bool ahit = false;
+          if (k0 + lane < SF_EXP_STROKES) {
+            ar = B.arc_region[k0 + lane];
+            if (ar >= 0) {
+              const int4 R = sf_warp_smem(ar >> 8).region[ar & 255];
+              ahit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
+            }
+          }
+          unsigned am = __ballot_sync(0xffffffffu, ahit);
+#pragma unroll 1
+          while (am) {
+            const int q = __ffs(am) - 1;
+            am &= am - 1;
+            const int aq = __shfl_sync(0xffffffffu, ar, q);
+            sf_blend_region(aq >> 8, aq & 255, win);
+          }
         }
         if (store_sprite) {  // this window covers the whole box: keep the sprite (first layer on the background)
           unsigned char* dst = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
@@ -636,10 +652,9 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
   });
 }
 
-// Window of the native box [x0..x1] x [y0..y1] (inclusive, inside the frame) of env slot e: composite + resample.
-__device__ __forceinline__ void sf_window(const SfTables* T, unsigned char* expcache, int e, int x0, int y0, int x1, int y1, unsigned char* obs84, bool store_sprite) {
+// Window of the output rectangle [j0..j1] x [i0..i1] of env slot e: composite its native footprint + resample.
+__device__ __forceinline__ void sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84, bool store_sprite) {
   const SfBlockSmem& B = sf_block_smem();
-  const int j0 = B.col_out0[x0], j1 = B.col_out1[x1], i0 = B.row_out0[y0], i1 = B.row_out1[y1];
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
   const int nx0 = tx0 & 255, nx1 = (tx1 & 255) + (tx1 >> 8) - 1, ny0 = ty0 & 255, ny1 = (ty1 & 255) + (ty1 >> 8) - 1;
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
@@ -786,9 +801,17 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
   unsigned core = rec.core;
   const int np = D.n_pad;
   // ---- ship explosion box (draw.cpp:235-237) ----
-  if (!(core & SF_CORE_SHIP_ALIVE) && lane == 0) {
-    SfPt c = sf_xform_base(rec.px, rec.py);
-    rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
+  if (lane == 0) {
+    const bool dead = !(core & SF_CORE_SHIP_ALIVE), score = rec.points_i > 0;
+    if (dead) {
+      SfPt c = sf_xform_base(rec.px, rec.py);
+      rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
+    }
+    if ((dead || score) && !out.native) {  // window tasks of this env that do not belong to a stroke
+      int k = atomicAdd(&B.netask, (dead ? 4 : 0) + (score ? 1 : 0));
+      if (dead) for (int q = 0; q < 4; q++) B.etask[k++] = (unsigned short)(e | (q << 5));
+      if (score) B.etask[k] = (unsigned short)(e | (4 << 5));
+    }
   }
   // ---- static base of the observation: 441 16-byte chunks. Background chunks go out as two bulk copies from the
   //      block's copy of the default observation (TMA engine, asynchronous; sf_block_frames waits for them before
@@ -871,35 +894,40 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   if (be >= 0 && be < B.r1) sf_phase_arcs(T, B, W, lane, warp, SF_RENDER_WARPS, B.env[be].px, B.env[be].py);
 }
 
-// phase C task t of this round
-__device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int r0, int r1, const SfFrameOut& out) {
+// phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
+__device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int netask, const SfFrameOut& out) {
   const SfTables* T = D.tab;
-  int e, x0, y0, x1, y1;
-  if (t < 64) {
-    e = t >> 1;
-    if (e < r0 || e >= r1) return;
+  int e, j0, i0, j1, i1;
+  bool store_sprite = false;
+  if (t < netask) {
+    const int et = B.etask[t], kind = et >> 5;
+    e = et & 31;
     const SfEnvRec& rec = B.env[e];
-    if (rec.env < 0) return;
-    if ((t & 1) == 0) {  // dead ship: the explosion box
-      if (rec.core & SF_CORE_SHIP_ALIVE) return;
+    int x0, y0, x1, y1;
+    if (kind < 4) {  // dead ship: a quarter (in output rows) of the explosion box
       const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
       x0 = max(bx0, 0); y0 = max(by0, 0); x1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1; y1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
       if (x0 > x1 || y0 > y1) return;
-    } else {             // non-zero score: the static base shows "0000000"
-      if (rec.points_i <= 0) return;
+    } else {         // non-zero score: the static base shows "0000000"
       x0 = SF_TEXT_X0; y0 = SF_TEXT_Y0; x1 = SF_TEXT_X0 + SF_TEXT_W - 1; y1 = SF_TEXT_Y0 + SF_TEXT_H - 1;
     }
+    j0 = B.col_out0[x0]; j1 = B.col_out1[x1]; i0 = B.row_out0[y0]; i1 = B.row_out1[y1];
+    if (kind < 4) {
+      const int hb = (i1 - i0 + 4) >> 2;
+      i0 += kind * hb; i1 = min(i1, i0 + hb - 1);
+      if (i0 > i1) return;
+      store_sprite = rec.building != 0;
+    }
   } else {
-    const SfStrokeRec& S = B.stroke[t - 64];
+    const SfStrokeRec& S = B.stroke[t - netask];
     const int sr = S.region;
     if (sr < 0) return;
     e = S.desc >> 12;
     const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
-    x0 = R.x; y0 = R.y; x1 = R.x + (R.z & 0xFFFF) - 1; y1 = R.y + ((R.z >> 16) & 0xFFFF) - 1;
+    j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
   const int env = B.env[e].env;
-  const bool store_sprite = t < 64 && (t & 1) == 0 && B.env[e].building;
-  sf_window(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, x0, y0, x1, y1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
+  sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
   if (store_sprite && lane == 0) D.q0[env].x = (int)(B.env[e].core | SF_CORE_EXP_CACHED);
   (void)W;
 }
@@ -955,13 +983,14 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     SF_TICK(2); SF_WTICK(8);
     // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
     if (!out.native) {
+      const int netask = B.netask;
 #pragma unroll 1
       for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&B.next_task, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= 64 + nst) break;
-        sf_phase_window(D, B, W, lane, t, r0, r1, out);
+        if (t >= netask + nst) break;
+        sf_phase_window(D, B, W, lane, t, netask, out);
       }
     } else {
 #pragma unroll 1
@@ -970,7 +999,7 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     SF_WTICK(11);
     __syncthreads();  // every warp is done reading the others' cells
     SF_TICK(3); SF_WTICK(8);
-    if (threadIdx.x == 0) B.next_task = 0;
+    if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; }
     sf_frame_end(W, lane);
     // more envs than one round could take?
     bool more = false;
