@@ -82,10 +82,21 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
   r.kill_bar = (e.q1.z > 10 && e.q1.y < 250) ? 1 : 0;
   r.env = env;
   r.s0 = 0; r.ebox = 0;
-  r.building = (!(r.core & SF_CORE_SHIP_ALIVE) && !(r.core & SF_CORE_EXP_CACHED)) ? 1 : 0;
+  r.life = (unsigned)e.st3.z + 1u;
+  r.building = 0;  // decided by sf_publish_recs, when the frames of the previous tick are done
   int vis;
   r.ns = sf_count_strokes(D, env, r.core, r.pmask, &vis);
   r.shell_vis = vis;
+}
+
+// warp 0, after the frames of the previous tick: the staged records become current; a dead ship whose explosion
+// is not the cached one gets it scan-converted this tick
+__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, int lane) {
+  SfEnvRec r = B.env_next[lane];
+  if (r.env >= 0) r.building = (!(r.core & SF_CORE_SHIP_ALIVE) && D.expstamp[r.env] != r.life) ? 1 : 0;
+  B.env[lane] = r;
+  __syncwarp();
+  sf_round_scan(B, lane, 0);
 }
 
 struct SfRollArgs {
@@ -106,52 +117,59 @@ struct SfRollArgs {
 // One block renders groups of EB envs (persistent over the groups it owns, group-major, T ticks each). Per tick:
 // warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
 // warps run the block-cooperative frame pipeline (sf_render.cuh).
-__global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(SfDev D, SfRollArgs A) {
+// one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
+__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t) {
+  SfBlockSmem& B = sf_block_smem();
+  const int lane = threadIdx.x & 31;
+  const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
+  const int env = group * A.EB + lane;
+  const bool mine = lane < A.EB && env < D.n;
+  SfEnv e;
+  bool finished = false;
+  if (mine) {
+    sf_load_env(D, env, e);
+    int a = A.actions ? A.actions[(size_t)t * D.n + env]
+                      : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
+    int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
+    SfStepOut o;
+    sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+    size_t oi = (size_t)t * D.n + env;
+    if (A.reward) A.reward[oi] = o.reward;
+    if (A.done) A.done[oi] = o.done;
+    if (A.fortkill) A.fortkill[oi] = o.fort_kill;
+    if (A.events) A.events[oi] = o.events;
+    finished = o.done && autoreset;
+  }
+  if (__any_sync(0xffffffffu, finished)) {
+    sf_accumulate_episode(D, e, finished, lane);
+    if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
+  }
+  if (mine) {
+    sf_store_env(D, env, e);
+    sf_make_env_rec(D, e, env, B.env_next[lane]);
+  } else B.env_next[lane].env = -1;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
   sf_warp_smem_init(W, lane);
-  const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
 #pragma unroll 1
   for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
+    if (warp == 0) sf_step_group(D, A, group, 0);
 #pragma unroll 1
     for (int t = 0; t < A.T; t++) {
-      if (warp == 0) {
-        const int env = group * A.EB + lane;
-        const bool mine = lane < A.EB && env < D.n;
-        SfEnv e;
-        bool finished = false;
-        if (mine) {
-          sf_load_env(D, env, e);
-          int a = A.actions ? A.actions[(size_t)t * D.n + env]
-                            : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
-          int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
-          SfStepOut o;
-          sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
-          size_t oi = (size_t)t * D.n + env;
-          if (A.reward) A.reward[oi] = o.reward;
-          if (A.done) A.done[oi] = o.done;
-          if (A.fortkill) A.fortkill[oi] = o.fort_kill;
-          if (A.events) A.events[oi] = o.events;
-          finished = o.done && autoreset;
-        }
-        if (__any_sync(0xffffffffu, finished)) {
-          sf_accumulate_episode(D, e, finished, lane);
-          if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
-        }
-        if (mine) {
-          sf_store_env(D, env, e);
-          sf_make_env_rec(D, e, env, B.env[lane]);
-        } else B.env[lane].env = -1;
-        __syncwarp();
-        sf_round_scan(B, lane, 0);
-      }
+      if (warp == 0) sf_publish_recs(D, B, lane);
       out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
-      sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out);
+      // the step of tick t+1 runs while the other warps composite the windows of tick t: it writes the SoA state
+      // and the staged records, which the frames of tick t no longer read
+      sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out, [&]() { if (t + 1 < A.T) sf_step_group(D, A, group, t + 1); });
     }
   }
 }
@@ -206,12 +224,12 @@ __global__ void __launch_bounds__(SF_BLOCK, 1) sf_render_kernel(SfDev D, unsigne
       if (mine) {
         SfEnv e;
         sf_load_env(D, env, e);
-        sf_make_env_rec(D, e, env, B.env[lane]);
-      } else B.env[lane].env = -1;
+        sf_make_env_rec(D, e, env, B.env_next[lane]);
+      } else B.env_next[lane].env = -1;
       __syncwarp();
-      sf_round_scan(B, lane, 0);
+      sf_publish_recs(D, B, lane);
     }
-    sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out);
+    sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out, []() {});
   }
 }
 
@@ -221,6 +239,7 @@ __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
   SfEnv e;
   sf_load_env(D, env, e);
   sf_srand(D, env, e, seeds ? seeds[env] : 1u);
+  D.expstamp[env] = 0;  // the rand() call counter restarts: no cached explosion belongs to a life of the new stream
   sf_store_env(D, env, e);
 }
 
@@ -318,6 +337,7 @@ __global__ void sf_set_state_kernel(SfDev D, int first, int count, const sf_stat
     D.svel[(size_t)s * D.n_pad + i] = make_double2(r.shell_vx[s], r.shell_vy[s]);
     D.sang[(size_t)s * D.n_pad + i] = r.shell_angle[s];
   }
+  D.expstamp[i] = 0;  // a forced state may place a dead ship anywhere
   sf_store_env(D, i, e);
 }
 
@@ -395,6 +415,7 @@ static size_t layout(SfDev& d, char* base) {
   d.spos = carve<double2>(p, np * SF_DEV_SHELLS); d.svel = carve<double2>(p, np * SF_DEV_SHELLS); d.sang = carve<double>(p, np * SF_DEV_SHELLS);
   d.rng = carve<unsigned>(p, np * SF_RNG_WORDS);
   d.expc = carve<unsigned char>(p, np * SF_EXP_W * SF_EXP_W);
+  d.expstamp = carve<unsigned>(p, np);
   d.epi = carve<unsigned long long>(p, SF_NUM_EPISODE_STATS);
   d.tab = carve<SfTables>(p, 1);
   return (size_t)(p - base);

@@ -75,7 +75,7 @@ struct __align__(16) SfEnvRec {
   int ebox;                   // dead ship: explosion sprite box origin (bx0+64) | (by0+64)<<8
   int shell_vis;              // shells further than 21 from the fortress (quirk Q9), bit per slot
   int building;               // dead ship whose explosion sprite is not cached yet: its arcs are scan-converted this round
-  int pad1;
+  unsigned life;              // rand() calls consumed when this ship spawned + 1: names the explosion of this life
 };
 // one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = warp<<8 | region id, -1: none
 struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
@@ -91,6 +91,7 @@ struct __align__(16) SfBlockSmem {
   int4 xtap[84];   // INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
   int4 ytap[84];
   SfEnvRec env[SF_GROUP_ENVS];
+  SfEnvRec env_next[SF_GROUP_ENVS];  // records of the next tick (the stepping warp runs one tick ahead of the frames)
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
   int next_task, netask, pad1, pad2;  // phase C work queue; env tasks of the round
@@ -928,7 +929,7 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
   }
   const int env = B.env[e].env;
   sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
-  if (store_sprite && lane == 0) D.q0[env].x = (int)(B.env[e].core | SF_CORE_EXP_CACHED);
+  if (store_sprite && lane == 0) D.expstamp[env] = B.env[e].life;
   (void)W;
 }
 
@@ -946,7 +947,8 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 }
 
 // All frames of the group. Every thread of the block calls this after warp 0 has written the env records and
-// run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed.
+// run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed. run_ahead() is executed by warp 0
+// at the start of the (first round's) window phase: nothing in that phase reads what the step writes.
 #ifdef SF_PHASE_TIMING
 __device__ unsigned long long sf_dbg_cycles[16];
 #define SF_TICK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
@@ -956,7 +958,8 @@ __device__ unsigned long long sf_dbg_cycles[16];
 #define SF_WTICK(k) ((void)0)
 #endif
 
-__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, const SfFrameOut& out) {
+template <class Ahead>
+__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, const SfFrameOut& out, Ahead run_ahead) {
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
 #endif
@@ -982,6 +985,7 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     __syncthreads();
     SF_TICK(2); SF_WTICK(8);
     // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
+    if (warp == 0 && r0 == 0) run_ahead();  // warp 0 steps the next tick while the others start on the windows
     if (!out.native) {
       const int netask = B.netask;
 #pragma unroll 1

@@ -22,7 +22,6 @@
 #define SF_CORE_THRUST (1u << 24)
 #define SF_CORE_LEFT (1u << 25)
 #define SF_CORE_RIGHT (1u << 26)
-#define SF_CORE_EXP_CACHED (1u << 27)  // ship-explosion sprite cache holds the current death (render memo)
 // q0.y "pmask": bits 0..19 missile slots alive, bits 20..23 shell slots alive
 #define SF_PMASK_MISSILES 0xFFFFFu
 #define SF_PMASK_SHELL_SHIFT 20
@@ -48,6 +47,7 @@ struct SfDev {
   double* sang;  // [4][n_pad] shell angle (real valued, game.cpp:166)
   unsigned* rng; // [31][n_pad]
   unsigned char* expc;        // [n][28*28] ship-explosion sprite cache (render memo; not game state)
+  unsigned* expstamp;         // [n] which life's explosion the cache holds: rand() calls consumed at its spawn + 1 (0: none)
   unsigned long long* epi;    // [SF_NUM_EPISODE_STATS] finished-episode accumulators
   const SfTables* tab;
   // preset (configs.cpp:51-89)

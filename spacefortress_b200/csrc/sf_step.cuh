@@ -119,7 +119,7 @@ __device__ __forceinline__ void sf_reward(SfEnv& e, float& tick_reward, float am
 
 __device__ __forceinline__ void sf_kill_ship(SfEnv& e) {  // game.cpp:274-280
   if (e.q0.x & SF_CORE_SHIP_ALIVE) {
-    e.q0.x &= ~(SF_CORE_SHIP_ALIVE | SF_CORE_EXP_CACHED);
+    e.q0.x &= ~SF_CORE_SHIP_ALIVE;
     e.q0.z = 0;
     e.st0.w += 1;
   }
