@@ -699,8 +699,8 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
 #ifdef SF_PHASE_TIMING
 extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
   return SF_OK;
 }
 #endif

@@ -63,6 +63,9 @@ struct __align__(16) SfWarpSmem {
   unsigned short glist[SF_MAX_GROUPS];      //  704 B per batch: quad | k<<5 : sub-rows g0 + 8k .. g0 + 8k + 7 of a quad
   int nregion, nstroke, nitems, acc_used;
   int ngroups, pad0, pad1, pad2;
+#ifdef SF_PHASE_TIMING
+  long long prof_last, prof_pad;
+#endif
 };
 
 // what the renderer needs to know about one env of the block's group (written by the lane that stepped it)
@@ -101,6 +104,12 @@ struct __align__(16) SfBlockSmem {
   alignas(16) unsigned char bg_obs[84 * 84];                 // default observation: source of the bulk chunk stores
   alignas(16) unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];  // hexagons on black, native
   unsigned char col_out0[SF_NAT_W + 2], col_out1[SF_NAT_W + 2], row_out0[SF_NAT_H], row_out1[SF_NAT_H];  // native -> output footprint
+  unsigned char fort_rect[SF_FORT_STATES][4];
+  alignas(16) unsigned magic[SF_MAGIC_N];      // scan converter reciprocals
+  double2 cs_deg[360];                         // cos, sin of integer degrees (host libm)
+  double wf_line[3][4][4];                     // wireframe models
+  int wf_nlines[4];
+  unsigned colour_white, padc[3];
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
@@ -110,6 +119,22 @@ __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_ca
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
 __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
 #define SF_RENDER_SMEM_BYTES(warps) (sizeof(SfBlockSmem) + sizeof(SfWarpSmem) * (warps))
+
+// debug build (-DSF_PHASE_TIMING): cycles of block 0 per phase / per code section (tools/gpu_phase_timing.py)
+#ifdef SF_PHASE_TIMING
+__device__ unsigned long long sf_dbg_cycles[32];
+__device__ __forceinline__ void sf_prof(int k) {  // time since this warp's previous mark goes to bucket k
+  if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) {
+    SfWarpSmem& W = sf_my_smem();
+    const long long now = clock64();
+    atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now - W.prof_last));
+    W.prof_last = now;
+  }
+}
+#define SF_PROF(k) sf_prof(k)
+#else
+#define SF_PROF(k) ((void)0)
+#endif
 
 __device__ __forceinline__ int sf_warp_min(int v) {
 #pragma unroll
@@ -138,7 +163,12 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < SF_NAT_H * SF_NAT_STRIDE / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_nat)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_nat) + k);
   for (int k = threadIdx.x; k < SF_NAT_W; k += blockDim.x) { B.col_out0[k] = (unsigned char)T->col_out0[k]; B.col_out1[k] = (unsigned char)T->col_out1[k]; }
   for (int k = threadIdx.x; k < SF_NAT_H; k += blockDim.x) { B.row_out0[k] = (unsigned char)T->row_out0[k]; B.row_out1[k] = (unsigned char)T->row_out1[k]; }
-  if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; }
+  for (int k = threadIdx.x; k < SF_FORT_STATES * 4; k += blockDim.x) B.fort_rect[k >> 2][k & 3] = T->fort_rect[k >> 2][k & 3];
+  for (int k = threadIdx.x; k < SF_MAGIC_N; k += blockDim.x) B.magic[k] = T->magic[k];
+  for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
+  for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
+  if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
+  if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; B.colour_white = T->colour_white; }
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -159,6 +189,23 @@ __device__ __forceinline__ void sf_for_rect(int lane, int w, int h, F body) {
     for (int r = lane >> s; r < h; r += rstep) body(c, r);
 }
 
+// the same, as load / store pairs with up to four loads in flight: store(c, r, load(c, r))
+template <class L, class S>
+__device__ __forceinline__ void sf_for_rect4(int lane, int w, int h, L load, S store) {
+  const int s = w <= 8 ? 3 : (w <= 16 ? 4 : 5);
+  const int c = lane & ((1 << s) - 1), rstep = 32 >> s;
+  if (c < w)
+    for (int r = lane >> s; r < h; r += 4 * rstep) {
+      const int r1 = r + rstep, r2 = r + 2 * rstep, r3 = r + 3 * rstep;
+      auto v0 = load(c, r);
+      auto v1 = load(c, r1 < h ? r1 : r), v2 = load(c, r2 < h ? r2 : r), v3 = load(c, r3 < h ? r3 : r);
+      store(c, r, v0);
+      if (r1 < h) store(c, r1, v1);
+      if (r2 < h) store(c, r2, v2);
+      if (r3 < h) store(c, r3, v3);
+    }
+}
+
 // ---- edge records --------------------------------------------------------------------------------------
 // An edge from (xa, ga) to (xb, gb), ga < gb grid rows, crosses sub-row s at x(s) = xa + floor((s - ga) * dx / dy).
 // The record is referenced to the end where the product is non-negative: dx >= 0: x0 = xa, yref = ga; dx < 0:
@@ -167,7 +214,7 @@ __device__ __forceinline__ void sf_for_rect(int lane, int w, int h, F body) {
 // n * dy < 2^32: always true for the strokes drawn here, at most ~30 px tall and ~10 px wide).
 __device__ __forceinline__ int4 sf_make_edge(const SfTables* T, int xa, int ga, int xb, int gb) {  // ga < gb
   const int dy = gb - ga, dx = xb - xa;
-  const unsigned M = T->magic[min(dy, SF_MAGIC_N - 1)];  // device strokes are far shorter than 512 sub-rows (34 px)
+  const unsigned M = sf_block_smem().magic[min(dy, SF_MAGIC_N - 1)];  // device strokes are far shorter than 512 sub-rows (34 px)
   const int a = ga + SF_YBIAS, b = gb + SF_YBIAS;
   if (dy == 1) return make_int4(xa, a | (b << 16), 0, 0);  // one sample, at the top row: x = xa (2^32/1 has no 32-bit magic)
   return dx >= 0 ? make_int4(xa, a | (b << 16), dx, (int)M) : make_int4(xb, b | (a << 16), dx, (int)M);
@@ -390,6 +437,7 @@ __device__ __noinline__ void sf_batch_accumulate() {
     }
   }
   __syncwarp();
+  SF_PROF(19);
   // ---- phase 2 ----
   int s_first = 0;  // stroke containing the first item of the pass (warp uniform)
 #pragma unroll 1
@@ -434,6 +482,7 @@ __device__ __noinline__ void sf_batch_accumulate() {
     }
   }
   __syncwarp();
+  SF_PROF(20);
 }
 
 // ---- windows ---------------------------------------------------------------------------------------------
@@ -483,7 +532,9 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
   const unsigned core = rec.core;
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
   const int nx1 = nx0 + SF_WIN_W(win), ny1 = ny0 + (int)SF_WIN_H(win);  // exclusive
+  SF_PROF(31);
   sf_patch_init(W, T, lane, win);
+  SF_PROF(22);
   // regions of this env (one per visible stroke, in draw order) that reach into the window
   int sr = -1, tag = SF_TAG_PROJECTILE;
   bool hit = false;
@@ -497,6 +548,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
   }
   unsigned rmask = __ballot_sync(0xffffffffu, hit);
   const bool first_is_ship = __shfl_sync(0xffffffffu, tag, 0) == SF_TAG_SHIP;
+  SF_PROF(23);
   // ---- ship wireframe | ship explosion (draw.cpp:233-237) ----
   if (core & SF_CORE_SHIP_ALIVE) {
     if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r >> 8, s0r & 255, win); rmask &= ~1u; }
@@ -536,15 +588,17 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
       } else {
         const unsigned char* src = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
         unsigned char* dst = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
-        sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_PATCH_STRIDE + c] = src[r * SF_EXP_W + c]; });
+        sf_for_rect4(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { return src[r * SF_EXP_W + c]; },
+                     [&](int c, int r, unsigned char v) { dst[r * SF_PATCH_STRIDE + c] = v; });
       }
       __syncwarp();
     }
   }
+  SF_PROF(24);
   // ---- fortress wireframe | fortress explosion (draw.cpp:238-242) ----
   {
     const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-    const unsigned char* fr = T->fort_rect[fst];
+    const unsigned char* fr = B.fort_rect[fst];
     if ((int)fr[0] < nx1 && (int)fr[2] >= nx0 && (int)fr[1] < ny1 && (int)fr[3] >= ny0) {
       if (fst < 36) {
         const int n = T->fort_list_n[fst];
@@ -554,7 +608,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
           const int x = xy & 255, y = xy >> 8;
           if (x >= nx0 && x < nx1 && y >= ny0 && y < ny1) {
             unsigned char* px = &W.patch[(y - ny0) * SF_PATCH_STRIDE + (x - nx0)];
-            *px = (unsigned char)sf_blend(*px, T->colour_white, T->fort_list_a[fst][k]);
+            *px = (unsigned char)sf_blend(*px, B.colour_white, T->fort_list_a[fst][k]);
           }
         }
       } else {
@@ -580,6 +634,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
       __syncwarp();
     }
   }
+  SF_PROF(25);
   // ---- missiles, then shells (draw.cpp:243-253): the env's strokes are stored in draw order ----
 #pragma unroll 1
   while (rmask) {
@@ -588,6 +643,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
     const int sq = __shfl_sync(0xffffffffu, sr, q);
     sf_blend_region(sq >> 8, sq & 255, win);
   }
+  SF_PROF(26);
   // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
   {
     const int ix0 = max(SF_TEXT_X0, nx0), ix1 = min(SF_TEXT_X0 + SF_TEXT_W, nx1);
@@ -662,8 +718,10 @@ __device__ __forceinline__ void sf_window_orect(const SfTables* T, unsigned char
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
   sf_composite(T, expcache, e, win, store_sprite);
+  SF_PROF(27);
   sf_window_out(win, orect, obs84);
   __syncwarp();
+  SF_PROF(28);
 }
 
 // ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
@@ -672,6 +730,7 @@ __device__ __forceinline__ void sf_window_orect(const SfTables* T, unsigned char
 // quads. *rid_out = region of the lane's slot (-1 invisible, -2 deferred). Returns the number of slots consumed
 // (8, or the first slot deferred to the next batch).
 __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle, int* rid_out) {
+  SF_PROF(31);
   const int slot = lane >> 2, line = lane & 3;
   SfQuadGeom G;
   G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
@@ -680,9 +739,11 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
     // quick cull: every model fits in a 37-unit radius (7.4 px) around its origin
     double dxv = SF_DADD(SF_DMUL(px, SF_CTM_SCALE), SF_CTM_X0), dyv = SF_DADD(SF_DMUL(py, SF_CTM_SCALE), SF_CTM_Y0);
     bool visible = !(dxv < -9.0 || dxv > SF_NAT_W + 9.0 || dyv < -9.0 || dyv > SF_NAT_H + 9.0);
-    if (visible && line < T->wf_nlines[kind]) {
-      SfWireXf m = sf_wire_xf(px, py, T->cos_deg[angle], T->sin_deg[angle]);
-      const double* L = T->wf_line[kind][line];
+    const SfBlockSmem& B = sf_block_smem();
+    if (visible && line < B.wf_nlines[kind]) {
+      const double2 cs = B.cs_deg[angle];
+      SfWireXf m = sf_wire_xf(px, py, cs.x, cs.y);
+      const double* L = B.wf_line[kind][line];
       SfPt a = sf_xform_wire(m, L[0], L[1]), b = sf_xform_wire(m, L[2], L[3]);
       SfQuad q;
       if (sf_stroke_quad(a, b, q)) {
@@ -698,13 +759,16 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
     ymin_g = min(ymin_g, __shfl_xor_sync(0xffffffffu, ymin_g, o)); ymax_g = max(ymax_g, __shfl_xor_sync(0xffffffffu, ymax_g, o));
     xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
   }
+  SF_PROF(16);
   // one region + stroke per slot, opened in slot order by the slot's first lane
   int fd = 32, item0 = 0;
-  int rid = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, T->colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE,
+  int rid = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, sf_block_smem().colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE,
                             slot * 4, 4, &fd, &item0);
+  SF_PROF(17);
   rid = __shfl_sync(0xffffffffu, rid, lane & ~3);
   item0 = __shfl_sync(0xffffffffu, item0, lane & ~3);
   sf_publish_quads(W, lane, G, has, rid, line, item0, false);
+  SF_PROF(18);
   *rid_out = rid;
   return fd >> 2;
 }
@@ -717,6 +781,7 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 // quad and the 16 quads of the circle abut along shared radial edges (identical edge records give identical
 // crossings), so no stroke needs a union: all spans go straight to the coverage cells.
 __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, double px, double py) {
+  SF_PROF(31);
   const SfPt c = sf_xform_base(px, py);
   const int apw = (SF_EXP_STROKES - 1 + nwarps - 1) / nwarps;
   const int a0 = warp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);
@@ -744,6 +809,7 @@ __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B,
       if (lane == 0) B.arc_region[SF_EXP_STROKES - 1] = rid >= 0 ? ((warp << 8) | rid) : -1;
     }
     sf_publish_quads(W, lane, G, has, rid, 0, 0, true);
+    SF_PROF(21);
     sf_batch_accumulate();
   }
 }
@@ -950,7 +1016,6 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 // run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed. run_ahead() is executed by warp 0
 // at the start of the (first round's) window phase: nothing in that phase reads what the step writes.
 #ifdef SF_PHASE_TIMING
-__device__ unsigned long long sf_dbg_cycles[16];
 #define SF_TICK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
 #define SF_WTICK(k) do { if (lane == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - w_last_)); w_last_ = now_; } } while (0)
 #else
@@ -994,6 +1059,7 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
         if (lane == 0) t = atomicAdd(&B.next_task, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= netask + nst) break;
+        SF_PROF(29);
         sf_phase_window(D, B, W, lane, t, netask, out);
       }
     } else {
