@@ -92,9 +92,10 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
 // warp 0, after the frames of the previous tick: the staged records become current; a dead ship whose explosion
 // is not the cached one gets it scan-converted this tick
 __device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, int lane) {
-  SfEnvRec r = B.env_next[lane];
+  SfTeamSmem& Tm = sf_team_smem();
+  SfEnvRec r = Tm.env_next[lane];
   if (r.env >= 0) r.building = (!(r.core & SF_CORE_SHIP_ALIVE) && D.expstamp[r.env] != r.life) ? 1 : 0;
-  B.env[lane] = r;
+  Tm.env[lane] = r;
   __syncwarp();
   sf_round_scan(B, lane, 0);
 }
@@ -146,13 +147,14 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   }
   if (mine) {
     sf_store_env(D, env, e);
-    sf_make_env_rec(D, e, env, B.env_next[lane]);
-  } else B.env_next[lane].env = -1;
+    sf_make_env_rec(D, e, env, sf_team_smem().env_next[lane]);
+  } else sf_team_smem().env_next[lane].env = -1;
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / SF_TEAM_WARPS, first_of_team = (warp % SF_TEAM_WARPS) == 0;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
@@ -160,16 +162,17 @@ __global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(const __grid_co
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+  // every team of warps renders its own groups, on its own barrier
 #pragma unroll 1
-  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
-    if (warp == 0) sf_step_group(D, A, group, 0);
+  for (int group = blockIdx.x * SF_TEAMS + team; group < A.ngroups; group += gridDim.x * SF_TEAMS) {
+    if (first_of_team) sf_step_group(D, A, group, 0);
 #pragma unroll 1
     for (int t = 0; t < A.T; t++) {
-      if (warp == 0) sf_publish_recs(D, B, lane);
+      if (first_of_team) sf_publish_recs(D, B, lane);
       out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
       // the step of tick t+1 runs while the other warps composite the windows of tick t: it writes the SoA state
       // and the staged records, which the frames of tick t no longer read
-      sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out, [&]() { if (t + 1 < A.T) sf_step_group(D, A, group, t + 1); });
+      sf_block_frames(D, B, W, lane, out, [&]() { if (t + 1 < A.T) sf_step_group(D, A, group, t + 1); });
     }
   }
 }
@@ -216,20 +219,21 @@ __global__ void __launch_bounds__(SF_BLOCK, 1) sf_render_kernel(SfDev D, unsigne
   out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = obs;
+  const int team = warp / SF_TEAM_WARPS;
 #pragma unroll 1
-  for (int group = blockIdx.x; group < ngroups; group += gridDim.x) {
-    if (warp == 0) {
+  for (int group = blockIdx.x * SF_TEAMS + team; group < ngroups; group += gridDim.x * SF_TEAMS) {
+    if ((warp % SF_TEAM_WARPS) == 0) {
       const int env = group * EB + lane;
       const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
       if (mine) {
         SfEnv e;
         sf_load_env(D, env, e);
-        sf_make_env_rec(D, e, env, B.env_next[lane]);
-      } else B.env_next[lane].env = -1;
+        sf_make_env_rec(D, e, env, sf_team_smem().env_next[lane]);
+      } else sf_team_smem().env_next[lane].env = -1;
       __syncwarp();
       sf_publish_recs(D, B, lane);
     }
-    sf_block_frames(D, B, W, lane, warp, SF_WARPS_PER_BLOCK, out, []() {});
+    sf_block_frames(D, B, W, lane, out, []() {});
   }
 }
 
@@ -515,12 +519,12 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 // the SMs (4096 envs -> 28 per block, 147 blocks); beyond that a group is a full warp of 32 stepping lanes and
 // the blocks are persistent over their groups.
 static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) {
-  const int n = h->dev.n, sms = h->num_sms;
-  int eb = n <= sms * SF_GROUP_ENVS ? (n + sms - 1) / sms : SF_GROUP_ENVS;
+  const int n = h->dev.n, sms = h->num_sms, teams = sms * SF_TEAMS;  // every team of warps renders its own group
+  int eb = n <= teams * SF_GROUP_ENVS ? (n + teams - 1) / teams : SF_GROUP_ENVS;
   if (const char* ov = getenv("SF_ENVS_PER_BLOCK")) { int e = atoi(ov); if (e >= 1 && e <= SF_GROUP_ENVS) eb = e; }  // tuning knob
   *EB = eb;
   *ngroups = (n + eb - 1) / eb;
-  *blocks = std::min(*ngroups, sms);
+  *blocks = std::min((*ngroups + SF_TEAMS - 1) / SF_TEAMS, sms);
 }
 
 static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {

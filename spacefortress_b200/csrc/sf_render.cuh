@@ -89,10 +89,15 @@ struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
 #define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
 #define SF_ROUND_STROKES (8 * SF_RENDER_WARPS)   // strokes pooled per round: at most one batch of 8 per warp
 
-// per-block shared memory
-struct __align__(16) SfBlockSmem {
-  int4 xtap[84];   // INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
-  int4 ytap[84];
+#ifndef SF_TEAMS
+#define SF_TEAMS 1           // independent teams of warps per block: each renders its own group of envs and has its own
+#endif                       // barrier, so one team's barrier waits are filled with the other team's work
+#define SF_TEAM_WARPS (SF_RENDER_WARPS / SF_TEAMS)
+#undef SF_ROUND_STROKES
+#define SF_ROUND_STROKES (8 * SF_TEAM_WARPS)
+
+// per-team shared memory: the group of envs a team renders this tick
+struct __align__(16) SfTeamSmem {
   SfEnvRec env[SF_GROUP_ENVS];
   SfEnvRec env_next[SF_GROUP_ENVS];  // records of the next tick (the stepping warp runs one tick ahead of the frames)
   SfStrokeRec stroke[SF_ROUND_STROKES];
@@ -100,7 +105,12 @@ struct __align__(16) SfBlockSmem {
   int next_task, netask, pad1, pad2;  // phase C work queue; env tasks of the round
   unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   int arc_region[SF_EXP_STROKES + 3];  // build: region (warp<<8 | id, -1 none) of the 84 arcs and of the circle, stroke order
-  // copies of the static tables that every window touches
+};
+
+// per-block shared memory: copies of the static tables that every window touches, and the teams
+struct __align__(16) SfBlockSmem {
+  int4 xtap[84];   // INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
+  int4 ytap[84];
   alignas(16) unsigned char bg_obs[84 * 84];                 // default observation: source of the bulk chunk stores
   alignas(16) unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];  // hexagons on black, native
   unsigned char col_out0[SF_NAT_W + 2], col_out1[SF_NAT_W + 2], row_out0[SF_NAT_H], row_out1[SF_NAT_H];  // native -> output footprint
@@ -110,12 +120,17 @@ struct __align__(16) SfBlockSmem {
   double wf_line[3][4][4];                     // wireframe models
   int wf_nlines[4];
   unsigned colour_white, padc[3];
+  SfTeamSmem team[SF_TEAMS];
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
+__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[(threadIdx.x >> 5) / SF_TEAM_WARPS]; }
+__device__ __forceinline__ void sf_team_sync() {  // barrier of this warp's team (named barrier 1 + team)
+  asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) / SF_TEAM_WARPS)), "r"(32 * SF_TEAM_WARPS) : "memory");
+}
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
 __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
 #define SF_RENDER_SMEM_BYTES(warps) (sizeof(SfBlockSmem) + sizeof(SfWarpSmem) * (warps))
@@ -168,7 +183,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
-  if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; B.colour_white = T->colour_white; }
+  if (threadIdx.x == 0) { for (int k = 0; k < SF_TEAMS; k++) { B.team[k].next_task = 0; B.team[k].netask = 0; } B.colour_white = T->colour_white; }
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -527,7 +542,7 @@ __device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
 __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, bool store_sprite) {
   SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
-  const SfEnvRec& rec = B.env[e];
+  const SfEnvRec& rec = sf_team_smem().env[e];
   const int lane = threadIdx.x & 31;
   const unsigned core = rec.core;
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
@@ -539,7 +554,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
   int sr = -1, tag = SF_TAG_PROJECTILE;
   bool hit = false;
   if (lane < rec.ns) {
-    sr = B.stroke[rec.s0 + lane].region;
+    sr = sf_team_smem().stroke[rec.s0 + lane].region;
     if (sr >= 0) {
       const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
       hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
@@ -565,7 +580,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
           int ar = -1;
           bool ahit = false;
           if (k0 + lane < SF_EXP_STROKES) {
-            ar = B.arc_region[k0 + lane];
+            ar = sf_team_smem().arc_region[k0 + lane];
             if (ar >= 0) {
               const int4 R = sf_warp_smem(ar >> 8).region[ar & 255];
               ahit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
@@ -780,15 +795,15 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 // the env's 28x28 sprite cache (final native pixels: it is the first layer on the background). Every arc is ONE
 // quad and the 16 quads of the circle abut along shared radial edges (identical edge records give identical
 // crossings), so no stroke needs a union: all spans go straight to the coverage cells.
-__device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, double px, double py) {
+__device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int nwarps, double px, double py) {
   SF_PROF(31);
   const SfPt c = sf_xform_base(px, py);
   const int apw = (SF_EXP_STROKES - 1 + nwarps - 1) / nwarps;
-  const int a0 = warp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);
+  const int a0 = lwarp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);  // warp: index in the block (names the owner of a region), lwarp: in the team
 #pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     const bool circle = pass == 1;
-    if (circle ? warp != nwarps - 1 : a0 >= a1) continue;
+    if (circle ? lwarp != nwarps - 1 : a0 >= a1) continue;
     const int s = circle ? SF_EXP_STROKES - 1 + lane : a0 + lane;
     const bool mine = circle ? lane < 16 : s < a1;
     SfQuadGeom G;
@@ -801,12 +816,12 @@ __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B,
     int fd, item0, rid;
     if (!circle) {
       rid = sf_open_regions(W, lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1, &fd, &item0);
-      if (mine) B.arc_region[s] = rid >= 0 ? ((warp << 8) | rid) : -1;
+      if (mine) sf_team_smem().arc_region[s] = rid >= 0 ? ((warp << 8) | rid) : -1;
     } else {
       const int ymin_g = sf_warp_min(G.ymin_g), ymax_g = sf_warp_max(G.ymax_g), xmin = sf_warp_min(G.xmin), xmax = sf_warp_max(G.xmax);
       rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 1, &fd, &item0);
       rid = __shfl_sync(0xffffffffu, rid, 0);
-      if (lane == 0) B.arc_region[SF_EXP_STROKES - 1] = rid >= 0 ? ((warp << 8) | rid) : -1;
+      if (lane == 0) sf_team_smem().arc_region[SF_EXP_STROKES - 1] = rid >= 0 ? ((warp << 8) | rid) : -1;
     }
     sf_publish_quads(W, lane, G, has, rid, 0, 0, true);
     SF_PROF(21);
@@ -845,24 +860,24 @@ __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigne
 
 // warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
 __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_begin) {
-  const bool cand = lane >= r_begin && B.env[lane].env >= 0;
-  const int cnt = cand ? B.env[lane].ns : 0;
+  const bool cand = lane >= r_begin && sf_team_smem().env[lane].env >= 0;
+  const int cnt = cand ? sf_team_smem().env[lane].ns : 0;
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const unsigned builders = __ballot_sync(0xffffffffu, cand && B.env[lane].building);
+  const unsigned builders = __ballot_sync(0xffffffffu, cand && sf_team_smem().env[lane].building);
   const unsigned second = builders & (builders - 1);  // a round scan-converts the explosion of at most one env
   const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES) | (second ? ~((second & (0u - second)) - 1u) : 0u);
   const int r1 = over ? __ffs(over) - 1 : 32;
-  if (lane < r1) B.env[lane].s0 = incl - cnt;
+  if (lane < r1) sf_team_smem().env[lane].s0 = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
-  if (lane == 0) { B.r0 = r_begin; B.r1 = r1; B.nstrokes = r1 > 0 ? total : 0; B.build_env = builders ? __ffs(builders) - 1 : -1; }
+  if (lane == 0) { sf_team_smem().r0 = r_begin; sf_team_smem().r1 = r1; sf_team_smem().nstrokes = r1 > 0 ? total : 0; sf_team_smem().build_env = builders ? __ffs(builders) - 1 : -1; }
 }
 
 // phase A for env slot e (whole warp)
 __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, const SfFrameOut& out) {
   const SfTables* T = D.tab;
-  SfEnvRec& rec = B.env[e];
+  SfEnvRec& rec = sf_team_smem().env[e];
   const int env = rec.env;
   if (env < 0) return;
   unsigned core = rec.core;
@@ -875,9 +890,9 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
       rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
     }
     if ((dead || score) && !out.native) {  // window tasks of this env that do not belong to a stroke
-      int k = atomicAdd(&B.netask, (dead ? 4 : 0) + (score ? 1 : 0));
-      if (dead) for (int q = 0; q < 4; q++) B.etask[k++] = (unsigned short)(e | (q << 5));
-      if (score) B.etask[k] = (unsigned short)(e | (4 << 5));
+      int k = atomicAdd(&sf_team_smem().netask, (dead ? 4 : 0) + (score ? 1 : 0));
+      if (dead) for (int q = 0; q < 4; q++) sf_team_smem().etask[k++] = (unsigned short)(e | (q << 5));
+      if (score) sf_team_smem().etask[k] = (unsigned short)(e | (4 << 5));
     }
   }
   // ---- static base of the observation: 441 16-byte chunks. Background chunks go out as two bulk copies from the
@@ -930,7 +945,7 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
     }
     const unsigned m = __ballot_sync(0xffffffffu, want);
     if (want) {
-      SfStrokeRec& S = B.stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
+      SfStrokeRec& S = sf_team_smem().stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
       S.x = x; S.y = y; S.desc = kind | (angle << 2) | (e << 12); S.region = -1;
     }
   }
@@ -938,7 +953,7 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
 }
 
 // phase B for this warp: scan-convert strokes [first, first + cnt) of the round's list
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int first, int cnt) {
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int first, int cnt) {
   const SfTables* T = D.tab;
   sf_frame_begin(W, lane);
 #pragma unroll 1
@@ -948,17 +963,17 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
     int kind = -1, angle = 0;
     double x = 0, y = 0;
     if (valid) {
-      const SfStrokeRec& S = B.stroke[first + s + slot];
+      const SfStrokeRec& S = sf_team_smem().stroke[first + s + slot];
       x = S.x; y = S.y; kind = S.desc & 3; angle = (S.desc >> 2) & 1023;
     }
     int rid;
     const int used = sf_wire_geometry(W, lane, T, kind, x, y, angle, &rid);
-    if (valid && slot < used && (lane & 3) == 0) B.stroke[first + s + slot].region = rid >= 0 ? ((warp << 8) | rid) : -1;
+    if (valid && slot < used && (lane & 3) == 0) sf_team_smem().stroke[first + s + slot].region = rid >= 0 ? ((warp << 8) | rid) : -1;
     sf_batch_accumulate();
     s += used;
   }
-  const int be = B.build_env;
-  if (be >= 0 && be < B.r1) sf_phase_arcs(T, B, W, lane, warp, SF_RENDER_WARPS, B.env[be].px, B.env[be].py);
+  const int be = sf_team_smem().build_env;
+  if (be >= 0 && be < sf_team_smem().r1) sf_phase_arcs(T, B, W, lane, warp, lwarp, SF_TEAM_WARPS, sf_team_smem().env[be].px, sf_team_smem().env[be].py);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
@@ -967,9 +982,9 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
   int e, j0, i0, j1, i1;
   bool store_sprite = false;
   if (t < netask) {
-    const int et = B.etask[t], kind = et >> 5;
+    const int et = sf_team_smem().etask[t], kind = et >> 5;
     e = et & 31;
-    const SfEnvRec& rec = B.env[e];
+    const SfEnvRec& rec = sf_team_smem().env[e];
     int x0, y0, x1, y1;
     if (kind < 4) {  // dead ship: a quarter (in output rows) of the explosion box
       const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
@@ -986,22 +1001,22 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
       store_sprite = rec.building != 0;
     }
   } else {
-    const SfStrokeRec& S = B.stroke[t - netask];
+    const SfStrokeRec& S = sf_team_smem().stroke[t - netask];
     const int sr = S.region;
     if (sr < 0) return;
     e = S.desc >> 12;
     const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
     j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
-  const int env = B.env[e].env;
+  const int env = sf_team_smem().env[e].env;
   sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
-  if (store_sprite && lane == 0) D.expstamp[env] = B.env[e].life;
+  if (store_sprite && lane == 0) D.expstamp[env] = sf_team_smem().env[e].life;
   (void)W;
 }
 
 // native output (SSF_Env.step returns the 92x90 frame): tile `tile` (30x30 windows, 3 x 4 of them) of env slot e
 __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, int tile, const SfFrameOut& out) {
-  const int env = B.env[e].env;
+  const int env = sf_team_smem().env[e].env;
   if (env < 0) return;
   const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
@@ -1024,39 +1039,42 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 #endif
 
 template <class Ahead>
-__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nwarps, const SfFrameOut& out, Ahead run_ahead) {
+__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out, Ahead run_ahead) {
+  const int gwarp = threadIdx.x >> 5, warp = gwarp % SF_TEAM_WARPS;  // warp index in the block / in its team
+  const int nwarps = SF_TEAM_WARPS;
+  SfTeamSmem& Tm = sf_team_smem();
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
 #endif
 #pragma unroll 1
   for (;;) {
-    __syncthreads();  // records + scan visible
+    sf_team_sync();  // records + scan visible
     SF_TICK(0); SF_WTICK(8);
-    const int r0 = B.r0, r1 = B.r1, nst = B.nstrokes;
+    const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
     // ---- A: env tasks ----
 #pragma unroll 1
     for (int e = r0 + warp; e < r1; e += nwarps) sf_phase_env(D, B, W, lane, e, out);
     SF_WTICK(9);
-    __syncthreads();
+    sf_team_sync();
     SF_TICK(1); SF_WTICK(8);
     // ---- B: stroke tasks, spread evenly (<= 8 per warp: nst <= 8 * nwarps) ----
     {
       const int spw = min(8, max(1, (nst + nwarps - 1) / nwarps));
       const int first = warp * spw;
-      sf_phase_strokes(D, B, W, lane, warp, first, max(0, min(spw, nst - first)));
+      sf_phase_strokes(D, B, W, lane, gwarp, warp, first, max(0, min(spw, nst - first)));
     }
     SF_WTICK(10);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's chunk copies have landed
-    __syncthreads();
+    sf_team_sync();
     SF_TICK(2); SF_WTICK(8);
     // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
-    if (warp == 0 && r0 == 0) run_ahead();  // warp 0 steps the next tick while the others start on the windows
+    if (warp == 0 && r0 == 0) run_ahead();  // the team's first warp steps the next tick while the others start on the windows
     if (!out.native) {
-      const int netask = B.netask;
+      const int netask = Tm.netask;
 #pragma unroll 1
       for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(&B.next_task, 1);
+        if (lane == 0) t = atomicAdd(&Tm.next_task, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= netask + nst) break;
         SF_PROF(29);
@@ -1067,15 +1085,15 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
       for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
     }
     SF_WTICK(11);
-    __syncthreads();  // every warp is done reading the others' cells
+    sf_team_sync();  // every warp is done reading the others' cells
     SF_TICK(3); SF_WTICK(8);
-    if (threadIdx.x == 0) { B.next_task = 0; B.netask = 0; }
+    if (warp == 0 && lane == 0) { Tm.next_task = 0; Tm.netask = 0; }
     sf_frame_end(W, lane);
     // more envs than one round could take?
     bool more = false;
-    for (int e = r1; e < SF_GROUP_ENVS; e++) more |= B.env[e].env >= 0;
+    for (int e = r1; e < SF_GROUP_ENVS; e++) more |= Tm.env[e].env >= 0;
     if (!more) break;
-    __syncthreads();  // everybody has read r1 / the records
+    sf_team_sync();  // everybody has read r1 / the records
     if (warp == 0) sf_round_scan(B, lane, r1);
   }
 }
