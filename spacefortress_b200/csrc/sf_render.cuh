@@ -453,46 +453,42 @@ __device__ __noinline__ void sf_batch_accumulate() {
   }
   __syncwarp();
   SF_PROF(19);
-  // ---- phase 2 ----
-  int s_first = 0;  // stroke containing the first item of the pass (warp uniform)
+  // ---- phase 2: stroke by stroke (warp uniform), 32 items per pass, rows fastest (item = sub * h + row) so that a
+  //      pass spreads its same-cell atomics over the rows of the region ----
 #pragma unroll 1
-  for (int it0 = 0; it0 < nitems; it0 += 32) {
-    const int it = it0 + lane;
-    const bool valid = it < nitems;
-    while (s_first + 1 < ns && W.stroke[s_first + 1].y <= it0) s_first++;
-    int si = s_first;
-    while (valid && si + 1 < ns && W.stroke[si + 1].y <= it) si++;
+  for (int si = 0; si < ns; si++) {
     const int2 S = W.stroke[si];
+    if (((S.x >> 16) & 255) <= 1) continue;  // a single quad: its spans went straight to the cells
     const int4 R = W.region[S.x & 255];
     const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-    // item index -> (row, sub): full blocks of 4 rows, then the remaining 1..3 rows
-    const int li = valid ? it - S.y : 0;
-    const int nfull = h >> 2, rem = h & 3;
-    int r, sub;
-    if (li < nfull * 60) {
-      int blk = sf_div_small(li, 60, 1.0f / 60.0f), t = li - blk * 60;
-      sub = t >> 2; r = blk * 4 + (t & 3);
-    } else {
-      int t = li - nfull * 60;
-      sub = rem == 3 ? sf_div_small(t, 3, 1.0f / 3.0f) : (rem == 2 ? t >> 1 : t);
-      r = nfull * 4 + t - sub * rem;
-    }
-    uint4 K = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
-    if (valid && ((S.x >> 16) & 255) > 1) K = W.span[S.y + r * SF_GRID_Y + sub];
-    if (!__any_sync(0xffffffffu, K.x != SF_SPAN_NONE || K.y != SF_SPAN_NONE || K.z != SF_SPAN_NONE || K.w != SF_SPAN_NONE)) continue;
-    // sort by start (none == 0xFFFFFFFF sinks to the end)
-    unsigned k0 = min(K.x, K.y), k1 = max(K.x, K.y), k2 = min(K.z, K.w), k3 = max(K.z, K.w), t0;
-    t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
-    t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
-    t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-    const int cell0 = (R.w & 0xFFF) + r * w;
-    int reach = 0;
-    if (k0 != SF_SPAN_NONE) { int a = (int)(k0 >> 16), b = (int)(k0 & 0xFFFFu); reach = b; sf_emit_span(acc32, cell0, a, b); }
-    if (__any_sync(0xffffffffu, k1 != SF_SPAN_NONE)) {
-      if (k1 != SF_SPAN_NONE) { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-      if (__any_sync(0xffffffffu, k2 != SF_SPAN_NONE)) {
-        if (k2 != SF_SPAN_NONE) { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-        if (k3 != SF_SPAN_NONE) { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+    const int n = h * SF_GRID_Y;
+    const float inv_h = 1.0f / (float)h;
+    const int acc_off = R.w & 0xFFF;
+#pragma unroll 1
+    for (int li0 = 0; li0 < n; li0 += 32) {
+      const int li = li0 + lane;
+      uint4 K = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
+      int r = 0;
+      if (li < n) {
+        const int sub = sf_div_small(li, h, inv_h);
+        r = li - sub * h;
+        K = W.span[S.y + r * SF_GRID_Y + sub];
+      }
+      // sort by start (none == 0xFFFFFFFF sinks to the end)
+      unsigned k0 = min(K.x, K.y), k1 = max(K.x, K.y), k2 = min(K.z, K.w), k3 = max(K.z, K.w), t0;
+      t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
+      t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
+      t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
+      if (!__any_sync(0xffffffffu, k0 != SF_SPAN_NONE)) continue;
+      const int cell0 = acc_off + r * w;
+      int reach = 0;
+      if (k0 != SF_SPAN_NONE) { int a = (int)(k0 >> 16), b = (int)(k0 & 0xFFFFu); reach = b; sf_emit_span(acc32, cell0, a, b); }
+      if (__any_sync(0xffffffffu, k1 != SF_SPAN_NONE)) {
+        if (k1 != SF_SPAN_NONE) { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+        if (__any_sync(0xffffffffu, k2 != SF_SPAN_NONE)) {
+          if (k2 != SF_SPAN_NONE) { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+          if (k3 != SF_SPAN_NONE) { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+        }
       }
     }
   }
@@ -952,23 +948,25 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
   (void)W;
 }
 
-// phase B for this warp: scan-convert strokes [first, first + cnt) of the round's list
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int first, int cnt) {
+// phase B for this warp: scan-convert strokes lwarp, lwarp + stride, ... (cnt of them) of the round's list. The list
+// is env-major (ship, missiles, shells), so a strided share mixes the kinds evenly over the warps.
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int stride, int cnt) {
   const SfTables* T = D.tab;
   sf_frame_begin(W, lane);
 #pragma unroll 1
   for (int s = 0; s < cnt;) {
     const int slot = lane >> 2;
     const bool valid = s + slot < cnt;
+    const int idx = lwarp + (s + slot) * stride;
     int kind = -1, angle = 0;
     double x = 0, y = 0;
     if (valid) {
-      const SfStrokeRec& S = sf_team_smem().stroke[first + s + slot];
+      const SfStrokeRec& S = sf_team_smem().stroke[idx];
       x = S.x; y = S.y; kind = S.desc & 3; angle = (S.desc >> 2) & 1023;
     }
     int rid;
     const int used = sf_wire_geometry(W, lane, T, kind, x, y, angle, &rid);
-    if (valid && slot < used && (lane & 3) == 0) sf_team_smem().stroke[first + s + slot].region = rid >= 0 ? ((warp << 8) | rid) : -1;
+    if (valid && slot < used && (lane & 3) == 0) sf_team_smem().stroke[idx].region = rid >= 0 ? ((warp << 8) | rid) : -1;
     sf_batch_accumulate();
     s += used;
   }
@@ -1057,12 +1055,8 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     SF_WTICK(9);
     sf_team_sync();
     SF_TICK(1); SF_WTICK(8);
-    // ---- B: stroke tasks, spread evenly (<= 8 per warp: nst <= 8 * nwarps) ----
-    {
-      const int spw = min(8, max(1, (nst + nwarps - 1) / nwarps));
-      const int first = warp * spw;
-      sf_phase_strokes(D, B, W, lane, gwarp, warp, first, max(0, min(spw, nst - first)));
-    }
+    // ---- B: stroke tasks, a strided share per warp (<= 8 each: nst <= 8 * nwarps) ----
+    sf_phase_strokes(D, B, W, lane, gwarp, warp, nwarps, nst > warp ? (nst - warp + nwarps - 1) / nwarps : 0);
     SF_WTICK(10);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's chunk copies have landed
     sf_team_sync();
