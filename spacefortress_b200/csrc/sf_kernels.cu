@@ -82,6 +82,10 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
   r.kill_bar = (e.q1.z > 10 && e.q1.y < 250) ? 1 : 0;
   r.env = env;
   r.s0 = 0; r.ebox = 0;
+  if (!(r.core & SF_CORE_SHIP_ALIVE)) {  // explosion sprite box (draw.cpp:235-237)
+    const SfPt c = sf_xform_base(r.px, r.py);
+    r.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
+  }
   r.life = (unsigned)e.st3.z + 1u;
   r.building = 0;  // decided by sf_publish_recs, when the frames of the previous tick are done
   int vis;
@@ -703,8 +707,8 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
 #ifdef SF_PHASE_TIMING
 extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 32);
-  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 64);
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
   return SF_OK;
 }
 #endif

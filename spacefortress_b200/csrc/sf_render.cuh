@@ -86,6 +86,7 @@ struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
 #ifndef SF_RENDER_WARPS
 #define SF_RENDER_WARPS 16   // warps per block (one block per SM): 16 x 11.8 KB of scratch
 #endif
+#define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
 #define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
 #define SF_ROUND_STROKES (8 * SF_RENDER_WARPS)   // strokes pooled per round: at most one batch of 8 per warp
 
@@ -115,6 +116,10 @@ struct __align__(16) SfBlockSmem {
   alignas(16) unsigned char bg_nat[SF_NAT_H * SF_NAT_STRIDE];  // hexagons on black, native
   unsigned char col_out0[SF_NAT_W + 2], col_out1[SF_NAT_W + 2], row_out0[SF_NAT_H], row_out1[SF_NAT_H];  // native -> output footprint
   unsigned char fort_rect[SF_FORT_STATES][4];
+  unsigned short fort_list_xy[36][SF_FORT_LIST_SMEM];  // lit pixels of the fortress sprites (native x | y<<8) ...
+  unsigned char fort_list_a[36][SF_FORT_LIST_SMEM];    // ... and their coverage; 0 pads the tail (a blend with alpha 0 changes nothing)
+  unsigned char fort_list_n[36];
+  unsigned char fort_sparse[SF_FORT_STATES][16];  // first 16 chunks a fortress state changes (255: none); a live fortress changes <= 14
   alignas(16) unsigned magic[SF_MAGIC_N];      // scan converter reciprocals
   double2 cs_deg[360];                         // cos, sin of integer degrees (host libm)
   double wf_line[3][4][4];                     // wireframe models
@@ -137,7 +142,7 @@ __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(thread
 
 // debug build (-DSF_PHASE_TIMING): cycles of block 0 per phase / per code section (tools/gpu_phase_timing.py)
 #ifdef SF_PHASE_TIMING
-__device__ unsigned long long sf_dbg_cycles[32];
+__device__ unsigned long long sf_dbg_cycles[64];  // 32..47: phase B busy cycles per warp, 48..63: phase C
 __device__ __forceinline__ void sf_prof(int k) {  // time since this warp's previous mark goes to bucket k
   if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) {
     SfWarpSmem& W = sf_my_smem();
@@ -179,6 +184,12 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < SF_NAT_W; k += blockDim.x) { B.col_out0[k] = (unsigned char)T->col_out0[k]; B.col_out1[k] = (unsigned char)T->col_out1[k]; }
   for (int k = threadIdx.x; k < SF_NAT_H; k += blockDim.x) { B.row_out0[k] = (unsigned char)T->row_out0[k]; B.row_out1[k] = (unsigned char)T->row_out1[k]; }
   for (int k = threadIdx.x; k < SF_FORT_STATES * 4; k += blockDim.x) B.fort_rect[k >> 2][k & 3] = T->fort_rect[k >> 2][k & 3];
+  for (int k = threadIdx.x; k < 36 * SF_FORT_LIST_SMEM; k += blockDim.x) {
+    const int st = k / SF_FORT_LIST_SMEM, i = k - st * SF_FORT_LIST_SMEM;
+    B.fort_list_xy[st][i] = T->fort_list_xy[st][i]; B.fort_list_a[st][i] = i < T->fort_list_n[st] ? T->fort_list_a[st][i] : 0;
+  }
+  if (threadIdx.x < 36) B.fort_list_n[threadIdx.x] = (unsigned char)min(T->fort_list_n[threadIdx.x], 255);
+  for (int k = threadIdx.x; k < SF_FORT_STATES * 16; k += blockDim.x) B.fort_sparse[k >> 4][k & 15] = T->fort_sparse[k >> 4][k & 15];
   for (int k = threadIdx.x; k < SF_MAGIC_N; k += blockDim.x) B.magic[k] = T->magic[k];
   for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
@@ -597,10 +608,23 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
           sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_EXP_W + c] = src[r * SF_PATCH_STRIDE + c]; });
         }
       } else {
-        const unsigned char* src = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
-        unsigned char* dst = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
-        sf_for_rect4(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { return src[r * SF_EXP_W + c]; },
-                     [&](int c, int r, unsigned char v) { dst[r * SF_PATCH_STRIDE + c] = v; });
+        // cached sprite: whole 28-byte rows as 32-bit words, all loads in flight before the first use
+        const unsigned* src32 = reinterpret_cast<const unsigned*>(expcache + (iy0 - by0) * SF_EXP_W);
+        const int nw = (SF_EXP_W / 4) * (iy1 - iy0);
+        unsigned v[7];
+#pragma unroll
+        for (int u = 0; u < 7; u++) v[u] = lane + 32 * u < nw ? src32[lane + 32 * u] : 0u;
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+          const int k = lane + 32 * u;
+          if (k < nw) {
+            const int row = (k * 9363) >> 16, x4 = bx0 + (k - row * (SF_EXP_W / 4)) * 4;  // k / 7, exact for k < 196
+            unsigned char* dst = W.patch + (iy0 + row - ny0) * SF_PATCH_STRIDE - nx0;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              if (x4 + b >= ix0 && x4 + b < ix1) dst[x4 + b] = (unsigned char)(v[u] >> (8 * b));
+          }
+        }
       }
       __syncwarp();
     }
@@ -612,14 +636,16 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
     const unsigned char* fr = B.fort_rect[fst];
     if ((int)fr[0] < nx1 && (int)fr[2] >= nx0 && (int)fr[1] < ny1 && (int)fr[3] >= ny0) {
       if (fst < 36) {
-        const int n = T->fort_list_n[fst];
+        const int n = B.fort_list_n[fst];
+        const bool in_smem = n <= SF_FORT_LIST_SMEM;  // always, for the sprites of the reference's fortress
 #pragma unroll 1
         for (int k = lane; k < n; k += 32) {
-          const int xy = T->fort_list_xy[fst][k];
+          const int xy = in_smem ? B.fort_list_xy[fst][k] : T->fort_list_xy[fst][k];
+          const unsigned a = in_smem ? B.fort_list_a[fst][k] : T->fort_list_a[fst][k];
           const int x = xy & 255, y = xy >> 8;
           if (x >= nx0 && x < nx1 && y >= ny0 && y < ny1) {
             unsigned char* px = &W.patch[(y - ny0) * SF_PATCH_STRIDE + (x - nx0)];
-            *px = (unsigned char)sf_blend(*px, B.colour_white, T->fort_list_a[fst][k]);
+            *px = (unsigned char)sf_blend(*px, B.colour_white, a);
           }
         }
       } else {
@@ -868,84 +894,96 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
   if (lane < r1) sf_team_smem().env[lane].s0 = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
   if (lane == 0) { sf_team_smem().r0 = r_begin; sf_team_smem().r1 = r1; sf_team_smem().nstrokes = r1 > 0 ? total : 0; sf_team_smem().build_env = builders ? __ffs(builders) - 1 : -1; }
+  // window tasks of the round that do not belong to a stroke: 4 quarters of a dead ship's explosion box, the strip
+  // of a non-zero score (the static base shows "0000000")
+  {
+    const bool in_round = cand && lane < r1;
+    const bool dead = in_round && !(sf_team_smem().env[lane].core & SF_CORE_SHIP_ALIVE), score = in_round && sf_team_smem().env[lane].points_i > 0;
+    const int cntt = (dead ? 4 : 0) + (score ? 1 : 0);
+    int inclt = cntt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclt, o); if (lane >= o) inclt += t; }
+    int k = inclt - cntt;
+    if (dead) for (int q = 0; q < 4; q++) sf_team_smem().etask[k++] = (unsigned short)(lane | (q << 5));
+    if (score) sf_team_smem().etask[k] = (unsigned short)(lane | (4 << 5));
+    if (lane == 31) sf_team_smem().netask = inclt;
+  }
+  __syncwarp();
 }
 
-// phase A for env slot e (whole warp)
-__device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, const SfFrameOut& out) {
+// Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
+// out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes)...
+__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
+  const int env = sf_team_smem().env[e].env;
+  if (env < 0 || lane != 0) return;
+  const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
+  unsigned char* gb = out.obs + (size_t)env * out.obs_bytes;
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// ... and, once the bulk copies of this warp have landed, the few 16-byte chunks that the fortress state (about 12
+// for a live fortress, 53 for its explosion) and a non-empty vulnerability bar change are patched from the
+// pre-resampled state tables.
+__device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
   const SfTables* T = D.tab;
-  SfEnvRec& rec = sf_team_smem().env[e];
+  const SfEnvRec& rec = sf_team_smem().env[e];
   const int env = rec.env;
   if (env < 0) return;
-  unsigned core = rec.core;
+  const unsigned core = rec.core;
+  const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+  const int bst = rec.kill_bar ? 11 : min(rec.vuln, 10);
+  int4* g = reinterpret_cast<int4*>(out.obs + (size_t)env * out.obs_bytes);
+  const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
+  const int fc0 = T->fort_chunk0;
+  // lanes 0..15: fortress chunks (index list in shared memory), lanes 0..20: bar chunks; both loads in flight
+  const int c0 = lane < 16 ? B.fort_sparse[fst][lane] : 255;
+  const bool bar = bst != 0 && lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0;
+  int4 v0, vb;
+  if (c0 != 255) v0 = __ldg(&ft[c0]);
+  if (bar) vb = __ldg(reinterpret_cast<const int4*>(T->obs_bar[bst]) + lane);
+  if (c0 != 255) g[fc0 + c0] = v0;
+  if (bar) g[SF_BAR_CHUNK0 + lane] = vb;
+  if (fst == 36) {  // fortress explosion: the rest of its 53 chunks
+    const int nsp = T->fort_sparse_n[fst];
+#pragma unroll 1
+    for (int k = 16 + lane; k < nsp; k += 32) { const int c = T->fort_sparse[fst][k]; g[fc0 + c] = __ldg(&ft[c]); }
+  }
+}
+
+// phase A for env slot e (whole warp): its entries of the round's stroke list:
+// [ship] + live missiles (slot order) + visible shells (slot order)
+__device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, const SfFrameOut& out) {
+  const SfEnvRec& rec = sf_team_smem().env[e];
+  const int env = rec.env;
+  if (env < 0) return;
+  const unsigned core = rec.core;
   const int np = D.n_pad;
-  // ---- ship explosion box (draw.cpp:235-237) ----
+  bool want = false;
+  int kind = 0, angle = 0;
+  double x = 0, y = 0;
   if (lane == 0) {
-    const bool dead = !(core & SF_CORE_SHIP_ALIVE), score = rec.points_i > 0;
-    if (dead) {
-      SfPt c = sf_xform_base(rec.px, rec.py);
-      rec.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
+    if (core & SF_CORE_SHIP_ALIVE) { want = true; kind = 0; x = rec.px; y = rec.py; angle = (int)(core & SF_CORE_ANGLE_MASK); }
+  } else if (lane <= SF_MAX_MISSILES) {
+    const int s = lane - 1;
+    if ((rec.pmask >> s) & 1u) {
+      const double2 p = D.mpos[(size_t)s * np + env];
+      want = true; kind = 1; x = p.x; y = p.y; angle = D.mang[(size_t)s * np + env];
     }
-    if ((dead || score) && !out.native) {  // window tasks of this env that do not belong to a stroke
-      int k = atomicAdd(&sf_team_smem().netask, (dead ? 4 : 0) + (score ? 1 : 0));
-      if (dead) for (int q = 0; q < 4; q++) sf_team_smem().etask[k++] = (unsigned short)(e | (q << 5));
-      if (score) sf_team_smem().etask[k] = (unsigned short)(e | (4 << 5));
-    }
-  }
-  // ---- static base of the observation: 441 16-byte chunks. Background chunks go out as two bulk copies from the
-  //      block's copy of the default observation (TMA engine, asynchronous; sf_block_frames waits for them before
-  //      the windows overwrite pixels); the fortress and bar chunks come from the pre-resampled state tables ----
-  if (!out.native) {
-    const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-    const int bst = rec.kill_bar ? 11 : min(rec.vuln, 10);
-    const int fc0 = T->fort_chunk0, nfc = T->fort_nchunks, fc1 = fc0 + nfc;
-    unsigned char* gb = out.obs + (size_t)env * out.obs_bytes;
-    if (lane == 0) {
-      const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(fc0 * 16) : "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb + fc1 * 16), "r"(src + fc1 * 16), "r"((SF_BAR_CHUNK0 - fc1) * 16) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    int4* g = reinterpret_cast<int4*>(gb);
-    const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
-    const int4* bt = reinterpret_cast<const int4*>(T->obs_bar[bst]);
-    {  // up to 160 fortress chunks: 5 loads in flight per lane
-      int4 v[5];
-#pragma unroll
-      for (int u = 0; u < 5; u++) if (lane + 32 * u < nfc) v[u] = __ldg(&ft[lane + 32 * u]);
-#pragma unroll
-      for (int u = 0; u < 5; u++) if (lane + 32 * u < nfc) g[fc0 + lane + 32 * u] = v[u];
-    }
-    if (lane < SF_OBS_CHUNKS - SF_BAR_CHUNK0) g[SF_BAR_CHUNK0 + lane] = __ldg(&bt[lane]);
-  }
-  // ---- stroke list: [ship] + live missiles (slot order) + visible shells (slot order) ----
-  {
-    bool want = false;
-    int kind = 0, angle = 0;
-    double x = 0, y = 0;
-    if (lane == 0) {
-      if (core & SF_CORE_SHIP_ALIVE) { want = true; kind = 0; x = rec.px; y = rec.py; angle = (int)(core & SF_CORE_ANGLE_MASK); }
-    } else if (lane <= SF_MAX_MISSILES) {
-      const int s = lane - 1;
-      if ((rec.pmask >> s) & 1u) {
-        const double2 p = D.mpos[(size_t)s * np + env];
-        want = true; kind = 1; x = p.x; y = p.y; angle = D.mang[(size_t)s * np + env];
-      }
-    } else if (lane <= SF_MAX_MISSILES + SF_DEV_SHELLS) {
-      const int s = lane - 1 - SF_MAX_MISSILES;
-      if ((rec.shell_vis >> s) & 1) {
-        const double2 p = D.spos[(size_t)s * np + env];
-        want = true; kind = 2; x = p.x; y = p.y;
-        angle = __double2int_rz(D.sang[(size_t)s * np + env]);  // `int angle` truncation, quirk Q10
-        if (angle >= 360) angle -= 360;
-      }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (want) {
-      SfStrokeRec& S = sf_team_smem().stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
-      S.x = x; S.y = y; S.desc = kind | (angle << 2) | (e << 12); S.region = -1;
+  } else if (lane <= SF_MAX_MISSILES + SF_DEV_SHELLS) {
+    const int s = lane - 1 - SF_MAX_MISSILES;
+    if ((rec.shell_vis >> s) & 1) {
+      const double2 p = D.spos[(size_t)s * np + env];
+      want = true; kind = 2; x = p.x; y = p.y;
+      angle = __double2int_rz(D.sang[(size_t)s * np + env]);  // `int angle` truncation, quirk Q10
+      if (angle >= 360) angle -= 360;
     }
   }
-  (void)W;
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (want) {
+    SfStrokeRec& S = sf_team_smem().stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
+    S.x = x; S.y = y; S.desc = kind | (angle << 2) | (e << 12); S.region = -1;
+  }
+  (void)W; (void)B; (void)out;
 }
 
 // phase B for this warp: scan-convert strokes lwarp, lwarp + stride, ... (cnt of them) of the round's list. The list
@@ -1056,9 +1094,21 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     sf_team_sync();
     SF_TICK(1); SF_WTICK(8);
     // ---- B: stroke tasks, a strided share per warp (<= 8 each: nst <= 8 * nwarps) ----
+    if (!out.native) {
+#pragma unroll 1
+      for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_issue(B, lane, e, out);
+    }
     sf_phase_strokes(D, B, W, lane, gwarp, warp, nwarps, nst > warp ? (nst - warp + nwarps - 1) / nwarps : 0);
+    if (!out.native) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
+      __syncwarp();
+#pragma unroll 1
+      for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_patch(D, B, lane, e, out);
+    }
+#ifdef SF_PHASE_TIMING
+    if (lane == 0 && blockIdx.x == 0) atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_));
+#endif
     SF_WTICK(10);
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's chunk copies have landed
     sf_team_sync();
     SF_TICK(2); SF_WTICK(8);
     // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
@@ -1078,10 +1128,13 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
 #pragma unroll 1
       for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
     }
+#ifdef SF_PHASE_TIMING
+    if (lane == 0 && blockIdx.x == 0) atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_));
+#endif
     SF_WTICK(11);
     sf_team_sync();  // every warp is done reading the others' cells
     SF_TICK(3); SF_WTICK(8);
-    if (warp == 0 && lane == 0) { Tm.next_task = 0; Tm.netask = 0; }
+    if (warp == 0 && lane == 0) Tm.next_task = 0;
     sf_frame_end(W, lane);
     // more envs than one round could take?
     bool more = false;

@@ -464,6 +464,16 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     if (c1 < c0 || c1 - c0 + 1 > SF_FORT_CHUNKS || c1 >= SF_BAR_CHUNK0) { snprintf(err, errcap, "fortress chunk range %d..%d", c0, c1); return 1; }
     t->fort_chunk0 = c0; t->fort_nchunks = c1 - c0 + 1;
     for (int st = 0; st < SF_FORT_STATES; st++) memcpy(t->obs_fort[st], &obs[st][c0 * 16], (size_t)t->fort_nchunks * 16);
+    for (int st = 0; st < SF_FORT_STATES; st++) {
+      int n = 0;
+      for (int c = 0; c < t->fort_nchunks; c++)
+        if (memcmp(&t->obs_fort[st][c * 16], &t->bg_obs[(c0 + c) * 16], 16)) {
+          if (n >= 64 || c > 254) { snprintf(err, errcap, "fortress state %d changes more than 64 chunks", st); return 1; }
+          t->fort_sparse[st][n++] = (unsigned char)c;
+        }
+      t->fort_sparse_n[st] = (unsigned char)n;
+      for (int k = n; k < 64; k++) t->fort_sparse[st][k] = 255;
+    }
   }
   return 0;
 }

@@ -86,6 +86,9 @@ struct SfTables {
   int fort_chunk0, fort_nchunks;
   alignas(16) unsigned char obs_fort[SF_FORT_STATES][SF_FORT_CHUNKS * 16];
   alignas(16) unsigned char obs_bar[SF_BAR_STATES][(SF_OBS_CHUNKS - SF_BAR_CHUNK0) * 16];
+  // the chunks of obs_fort[st] that differ from the default observation (index relative to fort_chunk0), 255-terminated
+  unsigned char fort_sparse[SF_FORT_STATES][64];
+  unsigned char fort_sparse_n[SF_FORT_STATES];
   int text_guard_row;  // moving rects with y0 <= this native row force the general text path
   int bar_guard_row;   // moving rects with y1 >= this native row force the general bar path
 };

@@ -11,7 +11,7 @@ env.rollout(300, want=("reward",))
 out = {"obs": torch.empty((T, n, 1, 84, 84), dtype=torch.uint8, device="cuda")}
 env.rollout(T, out=out); torch.cuda.synchronize()
 L = _lib.lib()
-buf = (C.c_ulonglong * 32)()
+buf = (C.c_ulonglong * 64)()
 L.sf_debug_cycles.restype = C.c_int; L.sf_debug_cycles.argtypes = [C.c_void_p, C.c_int]
 L.sf_debug_cycles(buf, 1)
 s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
@@ -25,6 +25,8 @@ print("  sum %8.0f cycles per tick = %.1f us" % (sum(v[:4]) / T, sum(v[:4]) / T 
 W = 16
 print("  all warps: waiting at barriers (+frame_end/step) %8.0f per warp-tick; busy A %6.0f  B %6.0f  C %6.0f" % (v[8] / T / W, v[9] / T / W, v[10] / T / W, v[11] / T / W))
 sec = {16: "B geometry (xform, stroke quad, edges)", 17: "B open_regions", 18: "B publish_quads", 19: "B clear + phase 1 (spans)", 20: "B phase 2 (union + emit)", 21: "B arcs geometry", 22: "C patch init", 23: "C region test", 24: "C ship layer / explosion", 25: "C fortress layer", 26: "C projectile blends", 27: "C text + bar", 28: "C window_out", 29: "C task fetch", 31: "(other)"}
+print("  phase B busy cycles per tick, by warp:", " ".join("%.0f" % (v[32 + k] / T) for k in range(16)))
+print("  phase C busy cycles per tick, by warp:", " ".join("%.0f" % (v[48 + k] / T) for k in range(16)))
 print("  sections, cycles per warp-tick (sum over the 16 warps / 16):")
 for k in sorted(sec): print("    %-40s %8.0f" % (sec[k], v[k] / T / W))
 subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
