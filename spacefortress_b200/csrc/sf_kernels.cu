@@ -2,10 +2,10 @@
 // simulator. sm_100a only; no CPU fallback: every entry point fails with SF_ERR_CUDA without a device.
 //
 // Kernels
-//   sf_rollout_kernel<RENDER>   fused step + render + auto-reset for T consecutive ticks (T=1 == sf_step).
-//                               A warp owns E consecutive envs: lanes < E step one env each (SoA, 128-bit
-//                               loads/stores), then the whole warp rasterises those envs one after another
-//                               out of shared memory and streams the 84x84 frames to HBM.
+//   sf_rollout_kernel           fused step + render + auto-reset for T consecutive ticks (T=1 == sf_step). One block
+//                               of 16 warps per SM owns groups of <= 32 envs: warp 0 steps them one env per lane
+//                               (SoA, 128-bit loads/stores) one tick ahead, all warps run the block-cooperative
+//                               frame pipeline of sf_render.cuh and stream the 84x84 frames to HBM.
 //   sf_step_only_kernel         state-only variant (render off), one env per thread.
 //   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel
 #include <cuda_runtime.h>
