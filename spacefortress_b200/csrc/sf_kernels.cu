@@ -95,10 +95,21 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
 
 // warp 0, after the frames of the previous tick: the staged records become current; a dead ship whose explosion
 // is not the cached one gets it scan-converted this tick
-__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, int lane) {
+__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, int lane, bool native) {
   SfTeamSmem& Tm = sf_team_smem();
   SfEnvRec r = Tm.env_next[lane];
-  if (r.env >= 0) r.building = (!(r.core & SF_CORE_SHIP_ALIVE) && D.expstamp[r.env] != r.life) ? 1 : 0;
+  if (r.env >= 0 && !(r.core & SF_CORE_SHIP_ALIVE)) {
+    r.building = D.expstamp[r.env] != r.life ? 1 : 0;
+    if (!native) {
+      // which quarters of the resampled explosion box are cached for exactly this life / fortress / bar / score
+      const int fst = (r.core & SF_CORE_FORT_ALIVE) ? (int)((r.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
+      const int bst = r.kill_bar ? 11 : min(r.vuln, 10);
+      const unsigned key = (unsigned)fst | ((unsigned)bst << 6) | (((unsigned)r.points_i & 0x3FFFFu) << 10);
+      const uint2 m = D.expo_meta[r.env];
+      if (!r.building && m.x == r.life && (m.y & 0x0FFFFFFFu) == key) r.building |= (int)(m.y >> 28) << 4;
+      else D.expo_meta[r.env] = make_uint2(r.life, key);
+    }
+  }
   Tm.env[lane] = r;
   __syncwarp();
   sf_round_scan(B, lane, 0);
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(const __grid_co
     if (first_of_team) sf_step_group(D, A, group, 0);
 #pragma unroll 1
     for (int t = 0; t < A.T; t++) {
-      if (first_of_team) sf_publish_recs(D, B, lane);
+      if (first_of_team) sf_publish_recs(D, B, lane, out.native != 0);
       out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
       // the step of tick t+1 runs while the other warps composite the windows of tick t: it writes the SoA state
       // and the staged records, which the frames of tick t no longer read
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(SF_BLOCK, 1) sf_render_kernel(SfDev D, unsigne
         sf_make_env_rec(D, e, env, sf_team_smem().env_next[lane]);
       } else sf_team_smem().env_next[lane].env = -1;
       __syncwarp();
-      sf_publish_recs(D, B, lane);
+      sf_publish_recs(D, B, lane, out.native != 0);
     }
     sf_block_frames(D, B, W, lane, out, []() {});
   }
@@ -248,6 +259,7 @@ __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
   sf_load_env(D, env, e);
   sf_srand(D, env, e, seeds ? seeds[env] : 1u);
   D.expstamp[env] = 0;  // the rand() call counter restarts: no cached explosion belongs to a life of the new stream
+  D.expo_meta[env] = make_uint2(0u, 0u);
   sf_store_env(D, env, e);
 }
 
@@ -346,6 +358,7 @@ __global__ void sf_set_state_kernel(SfDev D, int first, int count, const sf_stat
     D.sang[(size_t)s * D.n_pad + i] = r.shell_angle[s];
   }
   D.expstamp[i] = 0;  // a forced state may place a dead ship anywhere
+  D.expo_meta[i] = make_uint2(0u, 0u);
   sf_store_env(D, i, e);
 }
 
@@ -424,6 +437,8 @@ static size_t layout(SfDev& d, char* base) {
   d.rng = carve<unsigned>(p, np * SF_RNG_WORDS);
   d.expc = carve<unsigned char>(p, np * SF_EXP_W * SF_EXP_W);
   d.expstamp = carve<unsigned>(p, np);
+  d.expo = carve<unsigned char>(p, np * SF_EXPO_BYTES);
+  d.expo_meta = carve<uint2>(p, np);
   d.epi = carve<unsigned long long>(p, SF_NUM_EPISODE_STATS);
   d.tab = carve<SfTables>(p, 1);
   return (size_t)(p - base);
@@ -707,8 +722,8 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
 #ifdef SF_PHASE_TIMING
 extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 64);
-  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(h_out, sf_dbg_cycles, sizeof(unsigned long long) * 96);
+  if (reset) { unsigned long long z[96] = {0}; cudaMemcpyToSymbol(sf_dbg_cycles, z, sizeof(z)); }
   return SF_OK;
 }
 #endif

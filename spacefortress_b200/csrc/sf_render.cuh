@@ -29,11 +29,8 @@
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
-#define SF_ACC_CELLS 1280    // 16-bit coverage cells: ship <= 100, 20 missiles <= 40 each, 3 shells <= 36 each
 #define SF_BATCH_QUADS 32
-#define SF_MAX_REGIONS 32
-#define SF_SPAN_ITEMS 256    // (stroke, sub-row) items of one batch whose quads must be unioned
-#define SF_MAX_GROUPS 352    // (quad, 8 sub-rows) work groups of one batch: 32 quads x <= 8 groups, or <= 4*256/8 + 32
+#define SF_MAX_GROUPS 256    // (stroke, 8 sub-rows) work groups of one batch: 8 wireframes x <= 30, or 32 one-quad strokes x <= 8
 // A window is the INTER_AREA footprint closure of a box of at most 28x28 native pixels (the explosion sprite):
 // +1 column each side (<= 2 taps in x), +2 rows each side (<= 3 taps in y) -> at most 30 x 32. Rows are 32 bytes
 // apart; the resampler always reads 2 x 3 taps (missing ones have weight 0), i.e. up to row h+1 and column w.
@@ -45,23 +42,44 @@
 #define SF_TAG_SHIP 0
 #define SF_TAG_PROJECTILE 1
 #define SF_SPAN_NONE 0xFFFFFFFFu
-#define SF_QF_DIRECT 1       // quad flag: its stroke has no other quad -> spans go straight to the coverage cells
 #define SF_QF_IRREGULAR 2    // quad flag: not a 2+2 edge split, test all four edges
 
-// per-warp shared memory (11.6 KB)
+#ifndef SF_RENDER_WARPS
+#define SF_RENDER_WARPS 16   // warps per block (one block per SM)
+#endif
+#define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
+#define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
+#ifndef SF_ROUND_STROKES
+#define SF_ROUND_STROKES 256                     // strokes pooled per round (a round takes as many envs of the group as fit)
+#endif
+// Block-wide pools of a round: one region (bounding box in native pixels + coverage cells) per visible stroke.
+// The round scan admits envs by WORST-CASE need, so the pools cannot overflow: a ship wireframe spans at most
+// 44 user units (8.8 px) + the line width in any direction, a missile 25 (5 px), a shell 24 (4.8 px).
+#define SF_CELLS_SHIP 144
+#define SF_CELLS_MISSILE 49
+#define SF_CELLS_SHELL 49
+#define SF_CELLS_EXPLOSION 2048                  // 84 arcs (each within a ring segment of <= 4x4 px) + the r=7 circle
+#ifndef SF_POOL_CELLS
+#define SF_POOL_CELLS 12288                      // 16-bit coverage cells
+#endif
+#define SF_POOL_REGIONS (SF_ROUND_STROKES + SF_EXP_STROKES + 3)
+
+#define SF_TEAMS 1
+#define SF_TEAM_WARPS SF_RENDER_WARPS
+#ifndef SF_DEAL_DIV
+#define SF_DEAL_DIV 1
+#endif
+
+// per-warp shared memory (3.6 KB): the records of the batch being scan-converted; the window being composited
+// aliases the edge records (compositing starts after the block's last batch)
 struct __align__(16) SfWarpSmem {
-  // union scratch of a batch; the window patch aliases it (compositing starts after the last batch)
   union {
-    uint4 span[SF_SPAN_ITEMS];              // 4096 B per item: <= 4 spans (lo<<16 | hi, relative to the region), sorted later
-    unsigned char patch[SF_PATCH_BYTES];    // 1152 B the window being composited (native pixels)
+    int4 edge[SF_BATCH_QUADS * 4];          // 2048 B per quad: down A,B, up A,B = {x0, yref | yother<<16 (biased), dx, magic}
+    unsigned char patch[SF_PATCH_BYTES];    // 1152 B native pixels of the window
   };
-  int4 edge[SF_BATCH_QUADS * 4];            // 2048 B per quad: down A,B, up A,B = {x0, yref | yother<<16 (biased), dx, magic}
-  int4 qinfo[SF_BATCH_QUADS * 2];           // 1024 B per quad: {g0 | g1<<16, splitD | splitU<<16, xlo, xhi}, {sink, top, w, flags}
-  unsigned short acc[SF_ACC_CELLS];         // 2560 B coverage cells of every region of the frame
-  int4 region[SF_MAX_REGIONS];              //  512 B {x0, y0, w | h<<16, acc_off | tag<<12 | colour<<16}, draw order
-  int2 stroke[SF_MAX_REGIONS];              //  256 B per batch: {region | quad0<<8 | nq<<16, first item}
-  unsigned short glist[SF_MAX_GROUPS];      //  704 B per batch: quad | k<<5 : sub-rows g0 + 8k .. g0 + 8k + 7 of a quad
-  int nregion, nstroke, nitems, acc_used;
+  int4 qinfo[SF_BATCH_QUADS];               //  512 B per quad: {g0 | g1<<16 (biased, clipped to the region), splitD | splitU<<16, flags, 0}
+  int4 srec[SF_BATCH_QUADS];                //  512 B per stroke slot: {x0 | w<<8 | nq<<16 | quad0<<24, top (biased), first cell, s0 | s1<<16}
+  unsigned short glist[SF_MAX_GROUPS];      //  512 B slot | k<<5 : sub-rows s0 + 8k .. s0 + 8k + 7 of a stroke
   int ngroups, pad0, pad1, pad2;
 #ifdef SF_PHASE_TIMING
   long long prof_last, prof_pad;
@@ -77,35 +95,26 @@ struct __align__(16) SfEnvRec {
   int s0, ns;                 // this env's strokes in the round's list (draw order)
   int ebox;                   // dead ship: explosion sprite box origin (bx0+64) | (by0+64)<<8
   int shell_vis;              // shells further than 21 from the fortress (quirk Q9), bit per slot
-  int building;               // dead ship whose explosion sprite is not cached yet: its arcs are scan-converted this round
+  int building;               // bit 0: dead ship whose explosion sprite is not cached yet: its arcs are scan-converted this round;
+                              // bits 4..7: quarters of its resampled explosion box that are valid in D.expo (copied, not recomputed)
   unsigned life;              // rand() calls consumed when this ship spawned + 1: names the explosion of this life
 };
-// one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = warp<<8 | region id, -1: none
+// one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = index into the block's list, -1: none
 struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
 
-#ifndef SF_RENDER_WARPS
-#define SF_RENDER_WARPS 16   // warps per block (one block per SM): 16 x 11.8 KB of scratch
-#endif
-#define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
-#define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
-#define SF_ROUND_STROKES (8 * SF_RENDER_WARPS)   // strokes pooled per round: at most one batch of 8 per warp
-
-#ifndef SF_TEAMS
-#define SF_TEAMS 1           // independent teams of warps per block: each renders its own group of envs and has its own
-#endif                       // barrier, so one team's barrier waits are filled with the other team's work
-#define SF_TEAM_WARPS (SF_RENDER_WARPS / SF_TEAMS)
-#undef SF_ROUND_STROKES
-#define SF_ROUND_STROKES (8 * SF_TEAM_WARPS)
-
-// per-team shared memory: the group of envs a team renders this tick
+// the group of envs the block renders this tick, and the pools of the current round
 struct __align__(16) SfTeamSmem {
   SfEnvRec env[SF_GROUP_ENVS];
   SfEnvRec env_next[SF_GROUP_ENVS];  // records of the next tick (the stepping warp runs one tick ahead of the frames)
   SfStrokeRec stroke[SF_ROUND_STROKES];
+  int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
-  int next_task, netask, pad1, pad2;  // phase C work queue; env tasks of the round
+  int next_task, netask, next_stroke, chunk;  // phase C work queue; env tasks of the round; phase B work queue and its grab size
+  int more, padm0, padm1, padm2;     // envs of the group are left for another round
+  int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
-  int arc_region[SF_EXP_STROKES + 3];  // build: region (warp<<8 | id, -1 none) of the 84 arcs and of the circle, stroke order
+  short arc_region[SF_EXP_STROKES + 3];  // build: region (-1 none) of the 84 arcs and of the circle, stroke order
+  alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
 };
 
 // per-block shared memory: copies of the static tables that every window touches, and the teams
@@ -142,7 +151,7 @@ __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(thread
 
 // debug build (-DSF_PHASE_TIMING): cycles of block 0 per phase / per code section (tools/gpu_phase_timing.py)
 #ifdef SF_PHASE_TIMING
-__device__ unsigned long long sf_dbg_cycles[64];  // 32..47: phase B busy cycles per warp, 48..63: phase C
+__device__ unsigned long long sf_dbg_cycles[96];  // 32..47: phase B busy cycles per warp, 48..63: phase C
 __device__ __forceinline__ void sf_prof(int k) {  // time since this warp's previous mark goes to bucket k
   if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) {
     SfWarpSmem& W = sf_my_smem();
@@ -151,9 +160,15 @@ __device__ __forceinline__ void sf_prof(int k) {  // time since this warp's prev
     W.prof_last = now;
   }
 }
+__device__ __forceinline__ void sf_prof_reset() { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) sf_my_smem().prof_last = clock64(); }
+__device__ __forceinline__ void sf_prof_count(int k, int v) { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) atomicAdd(&sf_dbg_cycles[k], (unsigned long long)v); }
 #define SF_PROF(k) sf_prof(k)
+#define SF_PROF_RESET() sf_prof_reset()
+#define SF_PROF_COUNT(k, v) sf_prof_count(k, v)
 #else
 #define SF_PROF(k) ((void)0)
+#define SF_PROF_RESET() ((void)0)
+#define SF_PROF_COUNT(k, v) ((void)0)
 #endif
 
 __device__ __forceinline__ int sf_warp_min(int v) {
@@ -194,15 +209,19 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
-  if (threadIdx.x == 0) { for (int k = 0; k < SF_TEAMS; k++) { B.team[k].next_task = 0; B.team[k].netask = 0; } B.colour_white = T->colour_white; }
+  for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[0].cells)[k] = 0u;
+  if (threadIdx.x == 0) {
+    SfTeamSmem& Tm = B.team[0];
+    Tm.next_task = 0; Tm.netask = 0; Tm.next_stroke = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+    B.colour_white = T->colour_white;
+  }
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 }
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
-  for (int k = lane; k < SF_ACC_CELLS / 2; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
+  if (lane == 0) W.ngroups = 0;
   __syncwarp();
 }
 
@@ -296,34 +315,17 @@ __device__ __noinline__ void sf_store_quad_edges(const SfTables* T, int qi, int 
 }
 
 // ---- batch machinery ---------------------------------------------------------------------------------------
-// A frame owns the region list and the coverage cells; a batch owns the edge / quad / stroke / span records.
-__device__ __forceinline__ void sf_frame_begin(SfWarpSmem& W, int lane) {
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
-  __syncwarp();
-}
-// zero the coverage cells handed out since sf_frame_begin and forget the regions
-__device__ __forceinline__ void sf_frame_end(SfWarpSmem& W, int lane) {
-  __syncwarp();
-  const int nw = (W.acc_used + 1) >> 1;
-  for (int k = lane; k < nw; k += 32) reinterpret_cast<unsigned*>(W.acc)[k] = 0u;
-  __syncwarp();
-  if (lane == 0) { W.nregion = 0; W.nstroke = 0; W.nitems = 0; W.acc_used = 0; W.ngroups = 0; }
-  __syncwarp();
-}
+// The block owns the region list and the coverage cells of a round; a warp owns the edge / quad / stroke records
+// of the batch it is scan-converting.
 
 // floor division of a grid row by 15
 __device__ __forceinline__ int sf_row_of(int g) { return (g >= 0) ? g / SF_GRID_Y : -((-g + SF_GRID_Y - 1) / SF_GRID_Y); }
 
-// Append one region + open one stroke per participating lane (`want`), in lane order, with warp scans: region ids
-// continue the frame's list, accumulator offsets continue its pool, first-item indices are exclusive prefixes of
-// this batch (strokes with nq == 1 need no union and take no items). Returns the lane's region id, -1 when the
-// stroke is off the surface (or a pool is full: cannot happen for the strokes drawn here, see the size notes
-// above), or -2 when the union scratch of this batch is full: the stroke and every later one is DEFERRED to the
-// next batch (*first_deferred = lane of the first such stroke, 32 if none).
-__device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax,
-                                               unsigned colour, int tag, int quad0, int nq, int* first_deferred, int* item0_out) {
-  __syncwarp();
-  const int base_r = W.nregion, base_c = W.acc_used;
+// Append one region per participating lane (`want`) to the block's list, in lane order: region ids and coverage
+// cells come from the block-wide pools (one atomic per batch each). Returns the lane's region id, or -1 when the
+// stroke is off the surface (or a pool is full: cannot happen, the round scan admits envs by worst-case need).
+__device__ __forceinline__ int sf_open_regions(int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax, unsigned colour, int tag) {
+  SfTeamSmem& Tm = sf_team_smem();
   int cx0 = 0, py0 = 0, w = 0, h = 0;
   bool ok = want && ymin_g < ymax_g;
   if (ok) {
@@ -331,54 +333,42 @@ __device__ __forceinline__ int sf_open_regions(SfWarpSmem& W, int lane, bool wan
     cx0 = max(xmin >> 8, 0); int cx1 = min((xmax - 1) >> 8, SF_NAT_W - 1);
     ok = py0 <= py1 && cx0 <= cx1;
     w = cx1 - cx0 + 1; h = py1 - py0 + 1;
+    if (w > 255 || h > 255) ok = false;
   }
-  int items = (ok && nq > 1) ? h * SF_GRID_Y : 0;
-  if (items > SF_SPAN_ITEMS) { ok = false; items = 0; }  // no stroke drawn here is 17 rows tall
-  // inclusive scans of items (deferral) and cells (pool)
-  int iv = items;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-  const unsigned defer_mask = __ballot_sync(0xffffffffu, ok && iv > SF_SPAN_ITEMS);
-  const int fd = defer_mask ? __ffs(defer_mask) - 1 : 32;
-  *first_deferred = fd;
-  const bool deferred = lane >= fd;
-  if (deferred) { ok = false; }
   const int cells = ok ? w * h : 0;
-  int incl_cells = cells;
+  int incl = cells;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl_cells, o); if (lane >= o) incl_cells += t; }
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned m1 = __ballot_sync(0xffffffffu, ok);
-  if (ok && (base_c + incl_cells > SF_ACC_CELLS || base_r + __popc(m1 & lt) >= SF_MAX_REGIONS)) ok = false;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
   const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-  const int sid = __popc(okmask & lt);
-  const int rid = ok ? base_r + sid : (deferred && want ? -2 : -1);
-  if (ok) {
-    W.region[rid] = make_int4(cx0, py0, w | (h << 16), (base_c + incl_cells - cells) | (tag << 12) | ((int)colour << 16));
-    W.stroke[sid] = make_int2(rid | (quad0 << 8) | (nq << 16), iv - items);
-  }
-  *item0_out = iv - items;
-  const int last = 31 - __clz((int)(okmask | 1u));  // highest participating lane (lane 0 when none: it counts 0 then)
-  const int used = __shfl_sync(0xffffffffu, ok ? incl_cells : 0, last);
-  const int nit = __shfl_sync(0xffffffffu, ok ? iv : 0, last);
-  if (lane == 31) { W.nregion = base_r + __popc(okmask); W.nstroke = __popc(okmask); W.nitems = nit; W.acc_used = base_c + used; }
-  __syncwarp();
+  int base_c = 0, base_r = 0;
+  if (lane == 31) { base_c = atomicAdd(&Tm.cells_used, incl); base_r = atomicAdd(&Tm.nregions, __popc(okmask)); }
+  base_c = __shfl_sync(0xffffffffu, base_c, 31); base_r = __shfl_sync(0xffffffffu, base_r, 31);
+  const int rid = base_r + __popc(okmask & ((1u << lane) - 1u));
+  if (ok && (base_c + incl > SF_POOL_CELLS || rid >= SF_POOL_REGIONS)) ok = false;
+  if (!ok) return -1;
+  Tm.region[rid] = make_int4(cx0, py0, w | (h << 16), (base_c + incl - cells) | (tag << 15) | ((int)colour << 16));
   return rid;
 }
 
-// Every lane that built a quad publishes it for the scan converter: live sub-rows clipped to the region, edge
-// splits, clip range in x and where its spans go (the union scratch, or straight to the cells when the stroke
-// has no other quad). j = index of the quad in its stroke, item0 = first item of the stroke.
-__device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const SfQuadGeom& G, bool has, int rid, int j, int item0, bool direct) {
+// Publish the batch for the scan converter. Every lane that built a quad (`has`) stores its live sub-rows clipped to
+// the region of its stroke; the first lane of every stroke slot (`head`: nq consecutive lanes starting here hold the
+// quads of the stroke, [s0, s1) = union of their live sub-rows) stores the stroke record and appends the stroke's
+// work groups of 8 consecutive sub-rows. rid = the stroke's region (-1: none).
+__device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const SfQuadGeom& G, bool has, int rid, bool head, int slot, int nq, int ymin_g, int ymax_g) {
+  const SfTeamSmem& Tm = sf_team_smem();
   int len = 0;
+  int4 R = make_int4(0, 0, 0, 0);
+  if (rid >= 0) R = Tm.region[rid];
+  const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
+  const int top = R.y * SF_GRID_Y + SF_YBIAS;
   if (has && rid >= 0) {
-    const int4 R = W.region[rid];
-    const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-    const int top = R.y * SF_GRID_Y + SF_YBIAS;
     const int g0 = max(G.ymin_g + SF_YBIAS, top), g1 = min(G.ymax_g + SF_YBIAS, top + h * SF_GRID_Y);
-    len = max(g1 - g0, 0);
-    W.qinfo[lane * 2 + 0] = make_int4(g0 | (g1 << 16), G.split, R.x << 8, (R.x + w) << 8);
-    W.qinfo[lane * 2 + 1] = make_int4(direct ? (R.w & 0xFFF) : (item0 * 4 + j), top, w, G.flags | (direct ? SF_QF_DIRECT : 0));
+    W.qinfo[lane] = make_int4(g0 | (max(g1, g0) << 16), G.split, G.flags, 0);
+  } else W.qinfo[lane] = make_int4(0, 0, 0, 0);  // g0 == g1: never live
+  if (head && rid >= 0) {
+    const int s0 = max(ymin_g + SF_YBIAS, top), s1 = min(ymax_g + SF_YBIAS, top + h * SF_GRID_Y);
+    len = max(s1 - s0, 0);
+    W.srec[slot] = make_int4(R.x | (w << 8) | (nq << 16) | (lane << 24), top, R.w & 0x7FFF, s0 | (max(s1, s0) << 16));
   }
   // work groups of 8 consecutive sub-rows
   const int n8 = (len + 7) >> 3;
@@ -388,7 +378,7 @@ __device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const 
   const int total = __shfl_sync(0xffffffffu, gs, 31);
   gs -= n8;
   for (int k = 0; k < n8; k++)
-    if (gs + k < SF_MAX_GROUPS) W.glist[gs + k] = (unsigned short)(lane | (k << 5));
+    if (gs + k < SF_MAX_GROUPS) W.glist[gs + k] = (unsigned short)(slot | (k << 5));
   if (lane == 0) W.ngroups = min(total, SF_MAX_GROUPS);
   __syncwarp();
 }
@@ -420,88 +410,83 @@ __device__ __noinline__ void sf_quad_span_irregular(int qi, int sb, int& lo, int
   }
 }
 
-// Scan-convert the batch.
-//  Phase 1: one lane per live (quad, sub-row): exact edge crossings -> span, clipped to the region. A quad that is
-//           alone in its stroke adds the span to the coverage cells; otherwise it goes to slot j of the stroke's
-//           (row, sub-row) item in the union scratch.
-//  Phase 2: one lane per item: sort the <= 4 spans, add each one minus the union of its predecessors (non-zero
-//           winding of equally oriented convex quads == union). Items are visited in blocks of 4 pixel rows
-//           (row fastest, then sub-row) so that a pass spreads its same-cell atomics over 4 rows.
+// span of quad q on sub-row sb clipped to [xlo, xhi) and made relative to xlo, packed lo<<16 | hi; SF_SPAN_NONE when
+// the quad has no sample there
+__device__ __forceinline__ unsigned sf_quad_span(const SfWarpSmem& W, int q, int sb, int xlo, int xhi) {
+  const int4 Q = W.qinfo[q];
+  if (sb < (Q.x & 0xFFFF) || sb >= (int)((unsigned)Q.x >> 16)) return SF_SPAN_NONE;
+  int lo, hi;
+  if (Q.z & SF_QF_IRREGULAR) sf_quad_span_irregular(q, sb, lo, hi);
+  else {
+    const int4 Ed = W.edge[q * 4 + (sb >= (Q.y & 0xFFFF) ? 1 : 0)];
+    const int4 Eu = W.edge[q * 4 + 2 + (sb >= (int)((unsigned)Q.y >> 16) ? 1 : 0)];
+    const int xd = sf_edge_x(Ed, sb), xu = sf_edge_x(Eu, sb);
+    lo = min(xd, xu); hi = max(xd, xu);
+  }
+  lo = max(lo, xlo) - xlo; hi = min(hi, xhi) - xlo;
+  return lo < hi ? (((unsigned)lo << 16) | (unsigned)hi) : SF_SPAN_NONE;
+}
+
+// the same for a stroked segment (a parallelogram: opposite edges run in opposite directions, so it is never
+// irregular), branch free: the loads of all quads of a stroke can be in flight together. A quad slot without a quad
+// has g0 == g1 (never live); whatever its edge records hold is evaluated and discarded.
+__device__ __forceinline__ unsigned sf_quad_span_regular(const SfWarpSmem& W, int q, int sb, int xlo, int xhi) {
+  const int4 Q = W.qinfo[q];
+  const int4 Ed = W.edge[q * 4 + (sb >= (Q.y & 0xFFFF) ? 1 : 0)];
+  const int4 Eu = W.edge[q * 4 + 2 + (sb >= (int)((unsigned)Q.y >> 16) ? 1 : 0)];
+  const int xd = sf_edge_x(Ed, sb), xu = sf_edge_x(Eu, sb);
+  const int lo = max(min(xd, xu), xlo) - xlo, hi = min(max(xd, xu), xhi) - xlo;
+  const bool live = sb >= (Q.x & 0xFFFF) && sb < (int)((unsigned)Q.x >> 16) && lo < hi;
+  return live ? (((unsigned)lo << 16) | (unsigned)hi) : SF_SPAN_NONE;
+}
+
+// Scan-convert the batch: one lane per (stroke, sub-row). The lane computes the exact span of every quad of the
+// stroke that is live on its sub-row (integer edge stepping), sorts the <= 4 spans and adds each one minus the
+// union of its predecessors to the coverage cells of the stroke's region (non-zero winding of equally oriented
+// convex quads == union). 8 lanes share a work group of 8 consecutive sub-rows of one stroke.
 __device__ __noinline__ void sf_batch_accumulate() {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  const int nitems = W.nitems, ns = W.nstroke, ngroups = W.ngroups;
-  unsigned* acc32 = reinterpret_cast<unsigned*>(W.acc);
-  for (int k = lane; k < nitems; k += 32) W.span[k] = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
-  __syncwarp();
-  // ---- phase 1 ----
+  const int ngroups = W.ngroups;
+  SF_PROF_COUNT(68, ngroups);
+  unsigned* acc32 = reinterpret_cast<unsigned*>(sf_team_smem().cells);
 #pragma unroll 1
   for (int g0 = 0; g0 < ngroups; g0 += 4) {
     const int gi = g0 + (lane >> 3);
-    if (gi < ngroups) {
-      const int ent = W.glist[gi];
-      const int q = ent & 31;
-      const int4 Q0 = W.qinfo[q * 2], Q1 = W.qinfo[q * 2 + 1];
-      const int sb = (Q0.x & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
-      if (sb < (int)((unsigned)Q0.x >> 16)) {
-        int lo, hi;
-        if (Q1.w & SF_QF_IRREGULAR) sf_quad_span_irregular(q, sb, lo, hi);
-        else {
-          const int4 Ed = W.edge[q * 4 + (sb >= (Q0.y & 0xFFFF) ? 1 : 0)];
-          const int4 Eu = W.edge[q * 4 + 2 + (sb >= (int)((unsigned)Q0.y >> 16) ? 1 : 0)];
-          const int xd = sf_edge_x(Ed, sb), xu = sf_edge_x(Eu, sb);
-          lo = min(xd, xu); hi = max(xd, xu);
-        }
-        lo = max(lo, Q0.z) - Q0.z; hi = min(hi, Q0.w) - Q0.z;
-        if (lo < hi) {
-          const int d = sb - Q1.y;  // sub-row index inside the region
-          if (Q1.w & SF_QF_DIRECT) sf_emit_span(acc32, Q1.x + sf_div15(d) * Q1.z, lo, hi);
-          else reinterpret_cast<unsigned*>(W.span)[Q1.x + d * 4] = ((unsigned)lo << 16) | (unsigned)hi;
-        }
-      }
+    if (gi >= ngroups) continue;
+    const int ent = W.glist[gi];
+    const int4 S = W.srec[ent & 31];
+    const int sb = (S.w & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
+    if (sb >= (int)((unsigned)S.w >> 16)) continue;
+    const int nq = (S.x >> 16) & 255, q0 = (int)((unsigned)S.x >> 24);
+    const int w = (S.x >> 8) & 255;
+    const int xlo = (S.x & 255) << 8, xhi = xlo + (w << 8);
+    const int cell0 = S.z + sf_div15(sb - S.y) * w;
+    if (nq == 1) {  // explosion arcs, circle chords
+      const unsigned k = sf_quad_span(W, q0, sb, xlo, xhi);
+      if (k != SF_SPAN_NONE) sf_emit_span(acc32, cell0, (int)(k >> 16), (int)(k & 0xFFFFu));
+      continue;
     }
-  }
-  __syncwarp();
-  SF_PROF(19);
-  // ---- phase 2: stroke by stroke (warp uniform), 32 items per pass, rows fastest (item = sub * h + row) so that a
-  //      pass spreads its same-cell atomics over the rows of the region ----
-#pragma unroll 1
-  for (int si = 0; si < ns; si++) {
-    const int2 S = W.stroke[si];
-    if (((S.x >> 16) & 255) <= 1) continue;  // a single quad: its spans went straight to the cells
-    const int4 R = W.region[S.x & 255];
-    const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
-    const int n = h * SF_GRID_Y;
-    const float inv_h = 1.0f / (float)h;
-    const int acc_off = R.w & 0xFFF;
-#pragma unroll 1
-    for (int li0 = 0; li0 < n; li0 += 32) {
-      const int li = li0 + lane;
-      uint4 K = make_uint4(SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE, SF_SPAN_NONE);
-      int r = 0;
-      if (li < n) {
-        const int sub = sf_div_small(li, h, inv_h);
-        r = li - sub * h;
-        K = W.span[S.y + r * SF_GRID_Y + sub];
-      }
-      // sort by start (none == 0xFFFFFFFF sinks to the end)
-      unsigned k0 = min(K.x, K.y), k1 = max(K.x, K.y), k2 = min(K.z, K.w), k3 = max(K.z, K.w), t0;
-      t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
-      t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
-      t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-      if (!__any_sync(0xffffffffu, k0 != SF_SPAN_NONE)) continue;
-      const int cell0 = acc_off + r * w;
-      int reach = 0;
-      if (k0 != SF_SPAN_NONE) { int a = (int)(k0 >> 16), b = (int)(k0 & 0xFFFFu); reach = b; sf_emit_span(acc32, cell0, a, b); }
-      if (__any_sync(0xffffffffu, k1 != SF_SPAN_NONE)) {
-        if (k1 != SF_SPAN_NONE) { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-        if (__any_sync(0xffffffffu, k2 != SF_SPAN_NONE)) {
-          if (k2 != SF_SPAN_NONE) { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-          if (k3 != SF_SPAN_NONE) { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-        }
-      }
-    }
+    // wireframes: 3 or 4 stroked segments
+    unsigned k0 = sf_quad_span_regular(W, q0, sb, xlo, xhi);
+    unsigned k1 = sf_quad_span_regular(W, q0 + 1, sb, xlo, xhi);
+    unsigned k2 = sf_quad_span_regular(W, q0 + 2, sb, xlo, xhi);
+    unsigned k3 = nq > 3 ? sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi) : SF_SPAN_NONE;
+    // sort by start (none == 0xFFFFFFFF sinks to the end)
+    unsigned t0 = min(k0, k1), t1 = max(k0, k1), t2 = min(k2, k3), t3 = max(k2, k3);
+    k0 = min(t0, t2); k2 = max(t0, t2);
+    k1 = min(t1, t3); k3 = max(t1, t3);
+    t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
+    if (k0 == SF_SPAN_NONE) continue;
+    int reach = (int)(k0 & 0xFFFFu);
+    sf_emit_span(acc32, cell0, (int)(k0 >> 16), reach);
+    if (k1 == SF_SPAN_NONE) continue;
+    { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+    if (k2 == SF_SPAN_NONE) continue;
+    { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+    if (k3 == SF_SPAN_NONE) continue;
+    { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
   }
   __syncwarp();
   SF_PROF(20);
@@ -521,10 +506,10 @@ __device__ __forceinline__ void sf_patch_init(SfWarpSmem& W, const SfTables* T, 
   __syncwarp();
 }
 
-// Blend region `rid` of warp `owner` (its coverage cells) into this warp's window (clipped to it).
-__device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
+// Blend region `rid` of the round (its coverage cells) into this warp's window (clipped to it).
+__device__ __noinline__ void sf_blend_region(int rid, int win) {
   SfWarpSmem& W = sf_my_smem();
-  const SfWarpSmem& O = sf_warp_smem(owner);
+  const SfTeamSmem& O = sf_team_smem();
   const int lane = threadIdx.x & 31;
   const int4 R = O.region[rid];
   const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
@@ -533,7 +518,7 @@ __device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
   const int iy0 = max(R.y, ny0), iy1 = min(R.y + h, ny0 + (int)SF_WIN_H(win));
   if (ix0 >= ix1 || iy0 >= iy1) return;
   const unsigned colour = ((unsigned)R.w >> 16) & 255u;
-  const unsigned short* cells = O.acc + (R.w & 0xFFF) + (iy0 - R.y) * w + (ix0 - R.x);
+  const unsigned short* cells = O.cells + (R.w & 0x7FFF) + (iy0 - R.y) * w + (ix0 - R.x);
   unsigned char* p0 = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
   sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) {
     unsigned L = cells[r * w + c];
@@ -546,7 +531,8 @@ __device__ __noinline__ void sf_blend_region(int owner, int rid, int win) {
 }
 
 // Composite every layer of env slot `e` that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
-__device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, bool store_sprite) {
+// Returns true when no wireframe of the env reaches into the window.
+__device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, bool store_sprite) {
   SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
   const SfEnvRec& rec = sf_team_smem().env[e];
@@ -563,24 +549,25 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
   if (lane < rec.ns) {
     sr = sf_team_smem().stroke[rec.s0 + lane].region;
     if (sr >= 0) {
-      const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
+      const int4 R = sf_team_smem().region[sr];
       hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
-      tag = (R.w >> 12) & 1;
+      tag = (R.w >> 15) & 1;
     }
   }
   unsigned rmask = __ballot_sync(0xffffffffu, hit);
+  const bool no_wireframe = rmask == 0u;
   const bool first_is_ship = __shfl_sync(0xffffffffu, tag, 0) == SF_TAG_SHIP;
   SF_PROF(23);
   // ---- ship wireframe | ship explosion (draw.cpp:233-237) ----
   if (core & SF_CORE_SHIP_ALIVE) {
-    if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r >> 8, s0r & 255, win); rmask &= ~1u; }
+    if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r, win); rmask &= ~1u; }
   } else {
     const int ebox = rec.ebox;
     const int bx0 = (ebox & 255) - 64, by0 = ((ebox >> 8) & 255) - 64;
     const int ix0 = max(max(bx0, 0), nx0), ix1 = min(min(bx0 + SF_EXP_W, SF_NAT_W), nx1);
     const int iy0 = max(max(by0, 0), ny0), iy1 = min(min(by0 + SF_EXP_W, SF_NAT_H), ny1);
     if (ix0 < ix1 && iy0 < iy1) {
-      if (rec.building) {
+      if (rec.building & 1) {
         // first dead frame: the arcs were scan-converted this round (sf_phase_arcs); blend them in stroke order
 #pragma unroll 1
         for (int k0 = 0; k0 < SF_EXP_STROKES; k0 += 32) {
@@ -589,7 +576,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
           if (k0 + lane < SF_EXP_STROKES) {
             ar = sf_team_smem().arc_region[k0 + lane];
             if (ar >= 0) {
-              const int4 R = sf_warp_smem(ar >> 8).region[ar & 255];
+              const int4 R = sf_team_smem().region[ar];
               ahit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
             }
           }
@@ -599,7 +586,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
             const int q = __ffs(am) - 1;
             am &= am - 1;
             const int aq = __shfl_sync(0xffffffffu, ar, q);
-            sf_blend_region(aq >> 8, aq & 255, win);
+            sf_blend_region(aq, win);
           }
         }
         if (store_sprite) {  // this window covers the whole box: keep the sprite (first layer on the background)
@@ -678,7 +665,7 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
     const int q = __ffs(rmask) - 1;
     rmask &= rmask - 1;
     const int sq = __shfl_sync(0xffffffffu, sr, q);
-    sf_blend_region(sq >> 8, sq & 255, win);
+    sf_blend_region(sq, win);
   }
   SF_PROF(26);
   // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
@@ -720,12 +707,15 @@ __device__ __noinline__ void sf_composite(const SfTables* T, unsigned char* expc
       __syncwarp();
     }
   }
+  return no_wireframe;
 }
 
 // Resample the window (cv2 INTER_AREA: float accumulation in table order, round-half-even; a missing tap has
 // weight +0 and reads a byte of the patch that is never used) and overwrite the output rectangle
 // orect = j0 | i0<<8 | ow<<16 | oh<<24.
-__device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __restrict__ obs84) {
+// `cache` (or NULL): the same pixels also go to the env's resampled explosion box, whose origin is output pixel
+// corigin = cj0 | ci0<<8.
+__device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __restrict__ obs84, unsigned char* __restrict__ cache, int corigin) {
   const SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
   const int lane = threadIdx.x & 31;
@@ -742,31 +732,35 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
     float sum = __fmul_rn(__int_as_float(ty.y), b0);
     sum = __fadd_rn(sum, __fmul_rn(__int_as_float(ty.z), b1));
     sum = __fadd_rn(sum, __fmul_rn(__int_as_float(ty.w), b2));
-    obs84[i * 84 + j] = (unsigned char)__float2int_rn(sum);
+    const unsigned char v = (unsigned char)__float2int_rn(sum);
+    obs84[i * 84 + j] = v;
+    if (cache) cache[(i - (corigin >> 8)) * SF_EXPO_STRIDE + (j - (corigin & 255))] = v;
   });
 }
 
 // Window of the output rectangle [j0..j1] x [i0..i1] of env slot e: composite its native footprint + resample.
-__device__ __forceinline__ void sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84, bool store_sprite) {
+// Returns true when the pixels were also written to `cache` (no wireframe reaches into the window).
+__device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84, bool store_sprite,
+                                                unsigned char* cache, int corigin) {
   const SfBlockSmem& B = sf_block_smem();
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
   const int nx0 = tx0 & 255, nx1 = (tx1 & 255) + (tx1 >> 8) - 1, ny0 = ty0 & 255, ny1 = (ty1 & 255) + (ty1 >> 8) - 1;
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
-  sf_composite(T, expcache, e, win, store_sprite);
+  const bool pure = sf_composite(T, expcache, e, win, store_sprite);
   SF_PROF(27);
-  sf_window_out(win, orect, obs84);
+  sf_window_out(win, orect, obs84, pure ? cache : nullptr, corigin);
   __syncwarp();
   SF_PROF(28);
+  return pure && cache;
 }
 
 // ---- wireframe strokes (R3 drawWireFrame, draw.cpp:82-100) --------------------------------------------------------
 // Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
 // Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke and publishes the
-// quads. *rid_out = region of the lane's slot (-1 invisible, -2 deferred). Returns the number of slots consumed
-// (8, or the first slot deferred to the next batch).
-__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle, int* rid_out) {
+// quads. Returns the region of the lane's slot (-1 invisible).
+__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
   SF_PROF(31);
   const int slot = lane >> 2, line = lane & 3;
   SfQuadGeom G;
@@ -797,17 +791,13 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
     xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
   }
   SF_PROF(16);
-  // one region + stroke per slot, opened in slot order by the slot's first lane
-  int fd = 32, item0 = 0;
-  int rid = sf_open_regions(W, lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, sf_block_smem().colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE,
-                            slot * 4, 4, &fd, &item0);
+  // one region per slot, opened in slot order by the slot's first lane
+  int rid = sf_open_regions(lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, sf_block_smem().colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE);
   SF_PROF(17);
   rid = __shfl_sync(0xffffffffu, rid, lane & ~3);
-  item0 = __shfl_sync(0xffffffffu, item0, lane & ~3);
-  sf_publish_quads(W, lane, G, has, rid, line, item0, false);
+  sf_publish_quads(W, lane, G, has, rid, line == 0 && kind >= 0, slot, kind >= 0 ? sf_block_smem().wf_nlines[kind] : 0, ymin_g, ymax_g);
   SF_PROF(18);
-  *rid_out = rid;
-  return fd >> 2;
+  return rid;
 }
 
 // ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
@@ -835,17 +825,18 @@ __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B,
       sf_store_quad_edges(T, lane, c.x + o[0], c.y + o[1], c.x + o[2], c.y + o[3], c.x + o[4], c.y + o[5], c.x + o[6], c.y + o[7], G);
     }
     const bool has = mine && G.ymin_g < G.ymax_g;
-    int fd, item0, rid;
+    int rid;
     if (!circle) {
-      rid = sf_open_regions(W, lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE, lane, 1, &fd, &item0);
-      if (mine) sf_team_smem().arc_region[s] = rid >= 0 ? ((warp << 8) | rid) : -1;
+      rid = sf_open_regions(lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE);
+      if (mine) sf_team_smem().arc_region[s] = (short)rid;
     } else {
       const int ymin_g = sf_warp_min(G.ymin_g), ymax_g = sf_warp_max(G.ymax_g), xmin = sf_warp_min(G.xmin), xmax = sf_warp_max(G.xmax);
-      rid = sf_open_regions(W, lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE, 0, 1, &fd, &item0);
+      rid = sf_open_regions(lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE);
       rid = __shfl_sync(0xffffffffu, rid, 0);
-      if (lane == 0) sf_team_smem().arc_region[SF_EXP_STROKES - 1] = rid >= 0 ? ((warp << 8) | rid) : -1;
+      if (lane == 0) sf_team_smem().arc_region[SF_EXP_STROKES - 1] = (short)rid;
     }
-    sf_publish_quads(W, lane, G, has, rid, 0, 0, true);
+    // every quad is a one-quad stroke of its own (the 16 quads of the circle share one region)
+    sf_publish_quads(W, lane, G, has, rid, has, lane, 1, G.ymin_g, G.ymax_g);
     SF_PROF(21);
     sf_batch_accumulate();
   }
@@ -884,27 +875,45 @@ __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigne
 __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_begin) {
   const bool cand = lane >= r_begin && sf_team_smem().env[lane].env >= 0;
   const int cnt = cand ? sf_team_smem().env[lane].ns : 0;
-  int incl = cnt;
+  int need = 0;  // worst-case coverage cells of this env's regions
+  if (cand) {
+    const SfEnvRec& rec = sf_team_smem().env[lane];
+    need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE +
+           __popc(rec.shell_vis) * SF_CELLS_SHELL + ((rec.building & 1) ? SF_CELLS_EXPLOSION : 0);
+  }
+  int incl = cnt, incl_need = need;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const unsigned builders = __ballot_sync(0xffffffffu, cand && sf_team_smem().env[lane].building);
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, incl_need, o);
+    if (lane >= o) { incl += t; incl_need += u; }
+  }
+  const unsigned builders = __ballot_sync(0xffffffffu, cand && (sf_team_smem().env[lane].building & 1));
   const unsigned second = builders & (builders - 1);  // a round scan-converts the explosion of at most one env
-  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES) | (second ? ~((second & (0u - second)) - 1u) : 0u);
+  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (second ? ~((second & (0u - second)) - 1u) : 0u);
   const int r1 = over ? __ffs(over) - 1 : 32;
   if (lane < r1) sf_team_smem().env[lane].s0 = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
-  if (lane == 0) { sf_team_smem().r0 = r_begin; sf_team_smem().r1 = r1; sf_team_smem().nstrokes = r1 > 0 ? total : 0; sf_team_smem().build_env = builders ? __ffs(builders) - 1 : -1; }
+  const unsigned later = __ballot_sync(0xffffffffu, lane >= r1 && sf_team_smem().env[lane].env >= 0);
+  if (lane == 0) {
+    SfTeamSmem& Tm = sf_team_smem();
+    Tm.more = later != 0u;
+    const int nst = r1 > 0 ? total : 0;
+    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = builders ? __ffs(builders) - 1 : -1;
+    // phase B hands the strokes out in equal grabs of <= 8 (one batch), about SF_DEAL_DIV per warp
+    Tm.chunk = min(max((nst + SF_RENDER_WARPS * SF_DEAL_DIV - 1) / (SF_RENDER_WARPS * SF_DEAL_DIV), 1), 8);
+  }
   // window tasks of the round that do not belong to a stroke: 4 quarters of a dead ship's explosion box, the strip
   // of a non-zero score (the static base shows "0000000")
   {
     const bool in_round = cand && lane < r1;
     const bool dead = in_round && !(sf_team_smem().env[lane].core & SF_CORE_SHIP_ALIVE), score = in_round && sf_team_smem().env[lane].points_i > 0;
-    const int cntt = (dead ? 4 : 0) + (score ? 1 : 0);
+    const int qvalid = dead ? (sf_team_smem().env[lane].building >> 4) & 15 : 0;
+    const int cntt = (dead ? 4 - __popc(qvalid) : 0) + (score ? 1 : 0);
     int inclt = cntt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclt, o); if (lane >= o) inclt += t; }
     int k = inclt - cntt;
-    if (dead) for (int q = 0; q < 4; q++) sf_team_smem().etask[k++] = (unsigned short)(lane | (q << 5));
+    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) sf_team_smem().etask[k++] = (unsigned short)(lane | (q << 5));
     if (score) sf_team_smem().etask[k] = (unsigned short)(lane | (4 << 5));
     if (lane == 31) sf_team_smem().netask = inclt;
   }
@@ -948,6 +957,37 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
 #pragma unroll 1
     for (int k = 16 + lane; k < nsp; k += 32) { const int c = T->fort_sparse[fst][k]; g[fc0 + c] = __ldg(&ft[c]); }
   }
+  // dead ship: the quarters of its resampled explosion box that are still valid are copied, not recomputed (a
+  // wireframe that reaches into the box gets its own window in phase C, which composites the explosion under it)
+  const int qvalid = !(core & SF_CORE_SHIP_ALIVE) ? (rec.building >> 4) & 15 : 0;
+  if (qvalid) {
+    __syncwarp();  // the chunk stores above and the byte stores below (other lanes) can touch the same bytes: order them
+    const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
+    const int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1, y1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
+    if (x0 <= x1 && y0 <= y1) {
+      const int j0 = B.col_out0[x0], j1 = B.col_out1[x1], i0 = B.row_out0[y0], i1 = B.row_out1[y1];
+      const int hb = (i1 - i0 + 4) >> 2, ow = j1 - j0 + 1, oh = i1 - i0 + 1;
+      const unsigned* src = reinterpret_cast<const unsigned*>(D.expo + (size_t)env * SF_EXPO_BYTES);
+      unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + i0 * 84 + j0;
+      unsigned v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = lane + 32 * u, r = k >> 3;
+        const int q = (r >= hb) + (r >= 2 * hb) + (r >= 3 * hb);
+        v[u] = (r < oh && ((qvalid >> q) & 1)) ? __ldcg(&src[k]) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = lane + 32 * u, r = k >> 3, c = (k & 7) * 4;
+        const int q = (r >= hb) + (r >= 2 * hb) + (r >= 3 * hb);
+        if (r < oh && ((qvalid >> q) & 1)) {
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            if (c + b < ow) dst[r * 84 + c + b] = (unsigned char)(v[u] >> (8 * b));
+        }
+      }
+    }
+  }
 }
 
 // phase A for env slot e (whole warp): its entries of the round's stroke list:
@@ -986,30 +1026,36 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
   (void)W; (void)B; (void)out;
 }
 
-// phase B for this warp: scan-convert strokes lwarp, lwarp + stride, ... (cnt of them) of the round's list. The list
-// is env-major (ship, missiles, shells), so a strided share mixes the kinds evenly over the warps.
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int stride, int cnt) {
+// phase B for this warp: grab batches of Tm.chunk consecutive strokes of the round's list (first come first served)
+// and scan-convert them into the block's coverage cells; then this warp's share of the explosion being built.
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nst) {
   const SfTables* T = D.tab;
-  sf_frame_begin(W, lane);
+  SfTeamSmem& Tm = sf_team_smem();
+  const int chunk = Tm.chunk;
 #pragma unroll 1
-  for (int s = 0; s < cnt;) {
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(&Tm.next_stroke, chunk);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    SF_PROF(64);
+    if (s >= nst) break;
+    SF_PROF_COUNT(67, 1);
     const int slot = lane >> 2;
-    const bool valid = s + slot < cnt;
-    const int idx = lwarp + (s + slot) * stride;
+    const bool valid = slot < chunk && s + slot < nst;
+    const int idx = s + slot;
     int kind = -1, angle = 0;
     double x = 0, y = 0;
     if (valid) {
-      const SfStrokeRec& S = sf_team_smem().stroke[idx];
+      const SfStrokeRec& S = Tm.stroke[idx];
       x = S.x; y = S.y; kind = S.desc & 3; angle = (S.desc >> 2) & 1023;
     }
-    int rid;
-    const int used = sf_wire_geometry(W, lane, T, kind, x, y, angle, &rid);
-    if (valid && slot < used && (lane & 3) == 0) sf_team_smem().stroke[idx].region = rid >= 0 ? ((warp << 8) | rid) : -1;
+    const int rid = sf_wire_geometry(W, lane, T, kind, x, y, angle);
+    if (valid && (lane & 3) == 0) Tm.stroke[idx].region = rid;
     sf_batch_accumulate();
-    s += used;
   }
-  const int be = sf_team_smem().build_env;
-  if (be >= 0 && be < sf_team_smem().r1) sf_phase_arcs(T, B, W, lane, warp, lwarp, SF_TEAM_WARPS, sf_team_smem().env[be].px, sf_team_smem().env[be].py);
+  const int be = Tm.build_env;
+  // (warp 0 steps the next tick in this phase and takes no arcs)
+  if (be >= 0 && be < Tm.r1 && warp > 0) sf_phase_arcs(T, B, W, lane, warp, warp - 1, SF_TEAM_WARPS - 1, Tm.env[be].px, Tm.env[be].py);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
@@ -1017,6 +1063,7 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
   const SfTables* T = D.tab;
   int e, j0, i0, j1, i1;
   bool store_sprite = false;
+  int quarter = -1, corigin = 0;
   if (t < netask) {
     const int et = sf_team_smem().etask[t], kind = et >> 5;
     e = et & 31;
@@ -1032,21 +1079,25 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
     j0 = B.col_out0[x0]; j1 = B.col_out1[x1]; i0 = B.row_out0[y0]; i1 = B.row_out1[y1];
     if (kind < 4) {
       const int hb = (i1 - i0 + 4) >> 2;
+      corigin = j0 | (i0 << 8);
       i0 += kind * hb; i1 = min(i1, i0 + hb - 1);
       if (i0 > i1) return;
-      store_sprite = rec.building != 0;
+      store_sprite = (rec.building & 1) != 0;
+      quarter = kind;
     }
   } else {
     const SfStrokeRec& S = sf_team_smem().stroke[t - netask];
     const int sr = S.region;
     if (sr < 0) return;
     e = S.desc >> 12;
-    const int4 R = sf_warp_smem(sr >> 8).region[sr & 255];
+    const int4 R = sf_team_smem().region[sr];
     j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
   const int env = sf_team_smem().env[e].env;
-  sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite);
+  const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite,
+                                      quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin);
   if (store_sprite && lane == 0) D.expstamp[env] = sf_team_smem().env[e].life;
+  if (cached && lane == 0) atomicOr(&D.expo_meta[env].y, 1u << (28 + quarter));
   (void)W;
 }
 
@@ -1057,7 +1108,7 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
   const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
   const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
-  sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win, false);  // native frames never fill the sprite cache
+  (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win, false);  // native frames never fill the sprite cache
   unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + ty * SF_NAT_W + tx;
   sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
   __syncwarp();
@@ -1087,7 +1138,9 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     sf_team_sync();  // records + scan visible
     SF_TICK(0); SF_WTICK(8);
     const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
+    const bool more = Tm.more != 0;  // more envs than this round could take?
     // ---- A: env tasks ----
+    if (warp == nwarps - 1 && lane == 0) { Tm.next_task = 0; Tm.next_stroke = 0; Tm.nregions = 0; Tm.cells_used = 0; }
 #pragma unroll 1
     for (int e = r0 + warp; e < r1; e += nwarps) sf_phase_env(D, B, W, lane, e, out);
     SF_WTICK(9);
@@ -1098,21 +1151,29 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
 #pragma unroll 1
       for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_issue(B, lane, e, out);
     }
-    sf_phase_strokes(D, B, W, lane, gwarp, warp, nwarps, nst > warp ? (nst - warp + nwarps - 1) / nwarps : 0);
+    SF_PROF_RESET();
+    // warp 0 steps the next tick first: the step writes the SoA state and the staged records, which nothing reads
+    // after phase A (the other warps drain the stroke queue meanwhile)
+    // (phase A of every round reads the projectile positions from the SoA state: only the LAST round may overlap the step)
+    if (warp == 0 && !more) { run_ahead(); SF_PROF(70); }
+    sf_phase_strokes(D, B, W, lane, warp, nst);
+    SF_PROF(69);
     if (!out.native) {
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
       __syncwarp();
+      SF_PROF(65);
 #pragma unroll 1
       for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_patch(D, B, lane, e, out);
+      SF_PROF(66);
     }
 #ifdef SF_PHASE_TIMING
-    if (lane == 0 && blockIdx.x == 0) atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_));
+    if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_b, (int)(clock64() - w_last_)); }
 #endif
     SF_WTICK(10);
     sf_team_sync();
     SF_TICK(2); SF_WTICK(8);
     // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
-    if (warp == 0 && r0 == 0) run_ahead();  // the team's first warp steps the next tick while the others start on the windows
+    SF_PROF_RESET();  // the team's first warp steps the next tick while the others start on the windows
     if (!out.native) {
       const int netask = Tm.netask;
 #pragma unroll 1
@@ -1129,16 +1190,26 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
       for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
     }
 #ifdef SF_PHASE_TIMING
-    if (lane == 0 && blockIdx.x == 0) atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_));
+    if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
 #endif
     SF_WTICK(11);
     sf_team_sync();  // every warp is done reading the others' cells
     SF_TICK(3); SF_WTICK(8);
-    if (warp == 0 && lane == 0) Tm.next_task = 0;
-    sf_frame_end(W, lane);
-    // more envs than one round could take?
-    bool more = false;
-    for (int e = r1; e < SF_GROUP_ENVS; e++) more |= Tm.env[e].env >= 0;
+#ifdef SF_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+      atomicAdd(&sf_dbg_cycles[71], (unsigned long long)Tm.dbg_max_b); atomicAdd(&sf_dbg_cycles[72], (unsigned long long)Tm.dbg_max_c);
+      atomicAdd(&sf_dbg_cycles[73], 1ull); atomicAdd(&sf_dbg_cycles[74], (unsigned long long)(Tm.netask + nst)); atomicAdd(&sf_dbg_cycles[75], (unsigned long long)Tm.netask);
+      atomicAdd(&sf_dbg_cycles[76], (unsigned long long)(Tm.build_env >= 0));
+      Tm.dbg_max_b = 0; Tm.dbg_max_c = 0;
+    }
+#endif
+    // zero the coverage cells handed out this round (the queues and pools restart in phase A of the next round: at
+    // least one barrier away from here and from their next use)
+    {
+      const int nw = (Tm.cells_used + 1) >> 1;
+      for (int k = threadIdx.x; k < nw; k += blockDim.x) reinterpret_cast<unsigned*>(Tm.cells)[k] = 0u;
+    }
+
     if (!more) break;
     sf_team_sync();  // everybody has read r1 / the records
     if (warp == 0) sf_round_scan(B, lane, r1);

@@ -48,6 +48,8 @@ struct SfDev {
   unsigned* rng; // [31][n_pad]
   unsigned char* expc;        // [n][28*28] ship-explosion sprite cache (render memo; not game state)
   unsigned* expstamp;         // [n] which life's explosion the cache holds: rand() calls consumed at its spawn + 1 (0: none)
+  unsigned char* expo;        // [n][32*32] RESAMPLED explosion box (output pixels, row stride 32) without any wireframe layer
+  uint2* expo_meta;           // [n] {life, fortress state | bar state<<6 | (points & 0x3FFFF)<<10 | valid quarters<<28}: what expo holds
   unsigned long long* epi;    // [SF_NUM_EPISODE_STATS] finished-episode accumulators
   const SfTables* tab;
   // preset (configs.cpp:51-89)

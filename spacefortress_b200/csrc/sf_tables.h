@@ -14,6 +14,8 @@
 #define SF_FORT_X0 37
 #define SF_FORT_Y0 39
 #define SF_EXP_W 28                // explosion box: centre px - 13 .. centre px + 14
+#define SF_EXPO_STRIDE 32           // resampled explosion box cache: 28 native columns / rows feed <= 28 output ones
+#define SF_EXPO_BYTES (32 * SF_EXPO_STRIDE)
 #define SF_EXP_LAYERS 4
 #define SF_FEXP_X0 (45 - 13)
 #define SF_FEXP_Y0 (47 - 13)
