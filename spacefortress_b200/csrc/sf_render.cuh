@@ -114,6 +114,7 @@ struct __align__(16) SfTeamSmem {
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   short arc_region[SF_EXP_STROKES + 3];  // build: region (-1 none) of the 84 arcs and of the circle, stroke order
+  unsigned arc_mask[SF_EXP_W * SF_EXP_W][3];  // build: per pixel of the explosion box, the strokes whose region holds it (zero between builds)
   alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
 };
 
@@ -142,8 +143,11 @@ struct __align__(16) SfBlockSmem {
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
 __device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[(threadIdx.x >> 5) / SF_TEAM_WARPS]; }
-__device__ __forceinline__ void sf_team_sync() {  // barrier of this warp's team (named barrier 1 + team)
-  asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) / SF_TEAM_WARPS)), "r"(32 * SF_TEAM_WARPS) : "memory");
+__device__ __forceinline__ void sf_team_sync() {  // every warp of the block (named barrier 1)
+  asm volatile("bar.sync 1, %0;" :: "r"(32 * SF_RENDER_WARPS) : "memory");
+}
+__device__ __forceinline__ void sf_render_sync() {  // the warps that draw: all but warp 0, which steps (named barrier 2)
+  asm volatile("bar.sync 2, %0;" :: "r"(32 * (SF_RENDER_WARPS - 1)) : "memory");
 }
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
 __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
@@ -210,6 +214,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
   for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[0].cells)[k] = 0u;
+  for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 3; k += blockDim.x) (&B.team[0].arc_mask[0][0])[k] = 0u;
   if (threadIdx.x == 0) {
     SfTeamSmem& Tm = B.team[0];
     Tm.next_task = 0; Tm.netask = 0; Tm.next_stroke = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
@@ -532,7 +537,7 @@ __device__ __noinline__ void sf_blend_region(int rid, int win) {
 
 // Composite every layer of env slot `e` that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
 // Returns true when no wireframe of the env reaches into the window.
-__device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, bool store_sprite) {
+__device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expcache, int e, int win) {
   SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
   const SfEnvRec& rec = sf_team_smem().env[e];
@@ -567,40 +572,13 @@ __device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expc
     const int ix0 = max(max(bx0, 0), nx0), ix1 = min(min(bx0 + SF_EXP_W, SF_NAT_W), nx1);
     const int iy0 = max(max(by0, 0), ny0), iy1 = min(min(by0 + SF_EXP_W, SF_NAT_H), ny1);
     if (ix0 < ix1 && iy0 < iy1) {
-      if (rec.building & 1) {
-        // first dead frame: the arcs were scan-converted this round (sf_phase_arcs); blend them in stroke order
-#pragma unroll 1
-        for (int k0 = 0; k0 < SF_EXP_STROKES; k0 += 32) {
-          int ar = -1;
-          bool ahit = false;
-          if (k0 + lane < SF_EXP_STROKES) {
-            ar = sf_team_smem().arc_region[k0 + lane];
-            if (ar >= 0) {
-              const int4 R = sf_team_smem().region[ar];
-              ahit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
-            }
-          }
-          unsigned am = __ballot_sync(0xffffffffu, ahit);
-#pragma unroll 1
-          while (am) {
-            const int q = __ffs(am) - 1;
-            am &= am - 1;
-            const int aq = __shfl_sync(0xffffffffu, ar, q);
-            sf_blend_region(aq, win);
-          }
-        }
-        if (store_sprite) {  // this window covers the whole box: keep the sprite (first layer on the background)
-          unsigned char* dst = expcache + (iy0 - by0) * SF_EXP_W + (ix0 - bx0);
-          const unsigned char* src = W.patch + (iy0 - ny0) * SF_PATCH_STRIDE + (ix0 - nx0);
-          sf_for_rect(lane, ix1 - ix0, iy1 - iy0, [&](int c, int r) { dst[r * SF_EXP_W + c] = src[r * SF_PATCH_STRIDE + c]; });
-        }
-      } else {
+      {
         // cached sprite: whole 28-byte rows as 32-bit words, all loads in flight before the first use
         const unsigned* src32 = reinterpret_cast<const unsigned*>(expcache + (iy0 - by0) * SF_EXP_W);
         const int nw = (SF_EXP_W / 4) * (iy1 - iy0);
         unsigned v[7];
 #pragma unroll
-        for (int u = 0; u < 7; u++) v[u] = lane + 32 * u < nw ? src32[lane + 32 * u] : 0u;
+        for (int u = 0; u < 7; u++) v[u] = lane + 32 * u < nw ? __ldcg(&src32[lane + 32 * u]) : 0u;
 #pragma unroll
         for (int u = 0; u < 7; u++) {
           const int k = lane + 32 * u;
@@ -740,7 +718,7 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
 
 // Window of the output rectangle [j0..j1] x [i0..i1] of env slot e: composite its native footprint + resample.
 // Returns true when the pixels were also written to `cache` (no wireframe reaches into the window).
-__device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84, bool store_sprite,
+__device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84,
                                                 unsigned char* cache, int corigin) {
   const SfBlockSmem& B = sf_block_smem();
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
@@ -748,7 +726,7 @@ __device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
-  const bool pure = sf_composite(T, expcache, e, win, store_sprite);
+  const bool pure = sf_composite(T, expcache, e, win);
   SF_PROF(27);
   sf_window_out(win, orect, obs84, pure ? cache : nullptr, corigin);
   __syncwarp();
@@ -810,6 +788,7 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int nwarps, double px, double py) {
   SF_PROF(31);
   const SfPt c = sf_xform_base(px, py);
+  const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;  // the explosion box (sf_make_env_rec)
   const int apw = (SF_EXP_STROKES - 1 + nwarps - 1) / nwarps;
   const int a0 = lwarp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);  // warp: index in the block (names the owner of a region), lwarp: in the team
 #pragma unroll 1
@@ -835,11 +814,57 @@ __device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B,
       rid = __shfl_sync(0xffffffffu, rid, 0);
       if (lane == 0) sf_team_smem().arc_region[SF_EXP_STROKES - 1] = (short)rid;
     }
+    // every pixel of the stroke's region learns that this stroke may cover it
+    if (rid >= 0 && (circle ? lane == 0 : mine)) {
+      const int4 R = sf_team_smem().region[rid];
+      const int w = R.z & 0xFFFF, n = w * ((R.z >> 16) & 0xFFFF);
+      const int sidx = circle ? SF_EXP_STROKES - 1 : s;
+      int x = R.x - bx0, y = R.y - by0;
+      for (int k = 0; k < n; k++) {
+        if ((unsigned)x < (unsigned)SF_EXP_W && (unsigned)y < (unsigned)SF_EXP_W) atomicOr(&sf_team_smem().arc_mask[y * SF_EXP_W + x][sidx >> 5], 1u << (sidx & 31));
+        if (++x == R.x - bx0 + w) { x = R.x - bx0; y++; }
+      }
+    }
     // every quad is a one-quad stroke of its own (the 16 quads of the circle share one region)
     sf_publish_quads(W, lane, G, has, rid, has, lane, 1, G.ymin_g, G.ymax_g);
     SF_PROF(21);
     sf_batch_accumulate();
   }
+}
+
+// Phase B2 (rounds that build an explosion, after every arc is scan-converted): one lane per pixel of the 28x28 box
+// blends the strokes whose region holds the pixel, in stroke order, over the background (hexagons) and stores the
+// sprite in the env's cache; the windows of phase C read it like any cached sprite. wi / nw: this warp's index
+// among the drawing warps and their number.
+__device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int lane, int wi, int nw) {
+  SfTeamSmem& Tm = sf_team_smem();
+  const int be = Tm.build_env;
+  SfEnvRec& rec = Tm.env[be];
+  const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
+  unsigned char* sprite = D.expc + (size_t)rec.env * (SF_EXP_W * SF_EXP_W);
+#pragma unroll 1
+  for (int p = wi * 32 + lane; p < SF_EXP_W * SF_EXP_W; p += nw * 32) {
+    const int y = p / SF_EXP_W, x = p - y * SF_EXP_W;
+    const int nx = bx0 + x, ny = by0 + y;
+    unsigned v = 0;
+    if ((unsigned)nx < (unsigned)SF_NAT_W && (unsigned)ny < (unsigned)SF_NAT_H) {
+      v = B.bg_nat[ny * SF_NAT_STRIDE + nx];
+#pragma unroll 1
+      for (int wd = 0; wd < 3; wd++) {
+        unsigned m = Tm.arc_mask[p][wd];
+        while (m) {
+          const int sidx = wd * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          const int4 R = Tm.region[Tm.arc_region[sidx]];
+          const unsigned L = Tm.cells[(R.w & 0x7FFF) + (ny - R.y) * (R.z & 0xFFFF) + (nx - R.x)];
+          if (L) v = sf_blend(v, ((unsigned)R.w >> 16) & 255u, sf_len_to_alpha(L));
+        }
+      }
+    }
+    sprite[p] = (unsigned char)v;
+    Tm.arc_mask[p][0] = 0u; Tm.arc_mask[p][1] = 0u; Tm.arc_mask[p][2] = 0u;
+  }
+  if (wi == 0 && lane == 0) D.expstamp[rec.env] = rec.life;
 }
 
 // ================================================================================================================
@@ -900,7 +925,7 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
     const int nst = r1 > 0 ? total : 0;
     Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = builders ? __ffs(builders) - 1 : -1;
     // phase B hands the strokes out in equal grabs of <= 8 (one batch), about SF_DEAL_DIV per warp
-    Tm.chunk = min(max((nst + SF_RENDER_WARPS * SF_DEAL_DIV - 1) / (SF_RENDER_WARPS * SF_DEAL_DIV), 1), 8);
+    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) * SF_DEAL_DIV - 1) / ((SF_RENDER_WARPS - 1) * SF_DEAL_DIV), 1), 8);
   }
   // window tasks of the round that do not belong to a stroke: 4 quarters of a dead ship's explosion box, the strip
   // of a non-zero score (the static base shows "0000000")
@@ -1028,7 +1053,7 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
 
 // phase B for this warp: grab batches of Tm.chunk consecutive strokes of the round's list (first come first served)
 // and scan-convert them into the block's coverage cells; then this warp's share of the explosion being built.
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int nst) {
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst) {
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team_smem();
   const int chunk = Tm.chunk;
@@ -1054,15 +1079,13 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
     sf_batch_accumulate();
   }
   const int be = Tm.build_env;
-  // (warp 0 steps the next tick in this phase and takes no arcs)
-  if (be >= 0 && be < Tm.r1 && warp > 0) sf_phase_arcs(T, B, W, lane, warp, warp - 1, SF_TEAM_WARPS - 1, Tm.env[be].px, Tm.env[be].py);
+  if (be >= 0 && be < Tm.r1) sf_phase_arcs(T, B, W, lane, wi, wi, nw, Tm.env[be].px, Tm.env[be].py);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
 __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int netask, const SfFrameOut& out) {
   const SfTables* T = D.tab;
   int e, j0, i0, j1, i1;
-  bool store_sprite = false;
   int quarter = -1, corigin = 0;
   if (t < netask) {
     const int et = sf_team_smem().etask[t], kind = et >> 5;
@@ -1082,7 +1105,6 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
       corigin = j0 | (i0 << 8);
       i0 += kind * hb; i1 = min(i1, i0 + hb - 1);
       if (i0 > i1) return;
-      store_sprite = (rec.building & 1) != 0;
       quarter = kind;
     }
   } else {
@@ -1094,9 +1116,8 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
     j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
   const int env = sf_team_smem().env[e].env;
-  const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes, store_sprite,
+  const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes,
                                       quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin);
-  if (store_sprite && lane == 0) D.expstamp[env] = sf_team_smem().env[e].life;
   if (cached && lane == 0) atomicOr(&D.expo_meta[env].y, 1u << (28 + quarter));
   (void)W;
 }
@@ -1108,7 +1129,7 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
   const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
   const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
-  (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win, false);  // native frames never fill the sprite cache
+  (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win);
   unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + ty * SF_NAT_W + tx;
   sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
   __syncwarp();
@@ -1118,7 +1139,7 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 // run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed. run_ahead() is executed by warp 0
 // at the start of the (first round's) window phase: nothing in that phase reads what the step writes.
 #ifdef SF_PHASE_TIMING
-#define SF_TICK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
+#define SF_TICK(k) do { if (threadIdx.x == 32 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
 #define SF_WTICK(k) do { if (lane == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - w_last_)); w_last_ = now_; } } while (0)
 #else
 #define SF_TICK(k) ((void)0)
@@ -1127,11 +1148,13 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 
 template <class Ahead>
 __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out, Ahead run_ahead) {
-  const int gwarp = threadIdx.x >> 5, warp = gwarp % SF_TEAM_WARPS;  // warp index in the block / in its team
-  const int nwarps = SF_TEAM_WARPS;
+  const int warp = threadIdx.x >> 5;
+  const bool stepper = warp == 0;        // warp 0 steps the next tick while the other warps draw this one
+  const int wi = warp - 1, nw = SF_RENDER_WARPS - 1;  // index among the drawing warps, and their number
   SfTeamSmem& Tm = sf_team_smem();
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
+  const int gwarp = warp;
 #endif
 #pragma unroll 1
   for (;;) {
@@ -1140,63 +1163,76 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
     const bool more = Tm.more != 0;  // more envs than this round could take?
     // ---- A: env tasks ----
-    if (warp == nwarps - 1 && lane == 0) { Tm.next_task = 0; Tm.next_stroke = 0; Tm.nregions = 0; Tm.cells_used = 0; }
+    if (stepper) {
+      if (lane == 0) { Tm.next_task = 0; Tm.next_stroke = 0; Tm.nregions = 0; Tm.cells_used = 0; }
+    } else {
 #pragma unroll 1
-    for (int e = r0 + warp; e < r1; e += nwarps) sf_phase_env(D, B, W, lane, e, out);
+      for (int e = r0 + wi; e < r1; e += nw) sf_phase_env(D, B, W, lane, e, out);
+    }
     SF_WTICK(9);
     sf_team_sync();
     SF_TICK(1); SF_WTICK(8);
-    // ---- B: stroke tasks, a strided share per warp (<= 8 each: nst <= 8 * nwarps) ----
-    if (!out.native) {
-#pragma unroll 1
-      for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_issue(B, lane, e, out);
-    }
-    SF_PROF_RESET();
-    // warp 0 steps the next tick first: the step writes the SoA state and the staged records, which nothing reads
-    // after phase A (the other warps drain the stroke queue meanwhile)
-    // (phase A of every round reads the projectile positions from the SoA state: only the LAST round may overlap the step)
-    if (warp == 0 && !more) { run_ahead(); SF_PROF(70); }
-    sf_phase_strokes(D, B, W, lane, warp, nst);
-    SF_PROF(69);
-    if (!out.native) {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
-      __syncwarp();
-      SF_PROF(65);
-#pragma unroll 1
-      for (int e = r0 + warp; e < r1; e += nwarps) sf_env_base_patch(D, B, lane, e, out);
-      SF_PROF(66);
-    }
-#ifdef SF_PHASE_TIMING
-    if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_b, (int)(clock64() - w_last_)); }
-#endif
-    SF_WTICK(10);
-    sf_team_sync();
-    SF_TICK(2); SF_WTICK(8);
-    // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
-    SF_PROF_RESET();  // the team's first warp steps the next tick while the others start on the windows
-    if (!out.native) {
-      const int netask = Tm.netask;
-#pragma unroll 1
-      for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&Tm.next_task, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= netask + nst) break;
-        SF_PROF(29);
-        sf_phase_window(D, B, W, lane, t, netask, out);
-      }
+    if (stepper) {
+      // The step writes the SoA state and the staged records, which nothing of this tick reads after phase A. Phase A
+      // of every round reads the projectile positions from the SoA state: only the LAST round may overlap the step.
+      SF_PROF_RESET();
+      if (!more) { run_ahead(); SF_PROF(70); }
     } else {
+      // ---- B: stroke tasks from the block's queue ----
+      if (!out.native) {
 #pragma unroll 1
-      for (int t = warp; t < (r1 - r0) * 12; t += nwarps) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
-    }
+        for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
+      }
+      SF_PROF_RESET();
+      sf_phase_strokes(D, B, W, lane, wi, nw, nst);
+      SF_PROF(69);
+      if (!out.native) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
+        __syncwarp();
+        SF_PROF(65);
+#pragma unroll 1
+        for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
+        SF_PROF(66);
+      }
 #ifdef SF_PHASE_TIMING
-    if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
+      if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_b, (int)(clock64() - w_last_)); }
 #endif
-    SF_WTICK(11);
-    sf_team_sync();  // every warp is done reading the others' cells
+      SF_WTICK(10);
+      sf_render_sync();
+      SF_TICK(2); SF_WTICK(8);
+      // ---- B2: the sprite of the explosion whose arcs were scan-converted in B ----
+      if (Tm.build_env >= 0 && Tm.build_env < r1) {
+        sf_phase_sprite(D, B, lane, wi, nw);
+        SF_WTICK(10);
+        sf_render_sync();
+        SF_WTICK(8);
+      }
+      // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
+      SF_PROF_RESET();
+      if (!out.native) {
+        const int netask = Tm.netask;
+#pragma unroll 1
+        for (;;) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(&Tm.next_task, 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= netask + nst) break;
+          SF_PROF(29);
+          sf_phase_window(D, B, W, lane, t, netask, out);
+        }
+      } else {
+#pragma unroll 1
+        for (int t = wi; t < (r1 - r0) * 12; t += nw) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
+      }
+#ifdef SF_PHASE_TIMING
+      if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
+#endif
+      SF_WTICK(11);
+    }
+    sf_team_sync();  // every warp is done reading the cells; the step of the next tick is done
     SF_TICK(3); SF_WTICK(8);
 #ifdef SF_PHASE_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 32 && blockIdx.x == 0) {
       atomicAdd(&sf_dbg_cycles[71], (unsigned long long)Tm.dbg_max_b); atomicAdd(&sf_dbg_cycles[72], (unsigned long long)Tm.dbg_max_c);
       atomicAdd(&sf_dbg_cycles[73], 1ull); atomicAdd(&sf_dbg_cycles[74], (unsigned long long)(Tm.netask + nst)); atomicAdd(&sf_dbg_cycles[75], (unsigned long long)Tm.netask);
       atomicAdd(&sf_dbg_cycles[76], (unsigned long long)(Tm.build_env >= 0));
@@ -1206,12 +1242,11 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     // zero the coverage cells handed out this round (the queues and pools restart in phase A of the next round: at
     // least one barrier away from here and from their next use)
     {
-      const int nw = (Tm.cells_used + 1) >> 1;
-      for (int k = threadIdx.x; k < nw; k += blockDim.x) reinterpret_cast<unsigned*>(Tm.cells)[k] = 0u;
+      const int nz = (Tm.cells_used + 1) >> 1;
+      for (int k = threadIdx.x; k < nz; k += blockDim.x) reinterpret_cast<unsigned*>(Tm.cells)[k] = 0u;
     }
-
     if (!more) break;
     sf_team_sync();  // everybody has read r1 / the records
-    if (warp == 0) sf_round_scan(B, lane, r1);
+    if (stepper) sf_round_scan(B, lane, r1);
   }
 }
