@@ -27,6 +27,9 @@
 
 #define SF_WARPS_PER_BLOCK SF_RENDER_WARPS  // sf_render.cuh: one block per SM
 #define SF_BLOCK (32 * SF_WARPS_PER_BLOCK)
+#ifndef SF_BLOCKS_PER_SM
+#define SF_BLOCKS_PER_SM 1  // resident blocks per SM (each with its own stepping warp, pools and barriers)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // synthetic policy: stateless counter hash; same function on host and device
@@ -167,7 +170,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(SF_BLOCK, 1) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
+__global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / SF_TEAM_WARPS, first_of_team = (warp % SF_TEAM_WARPS) == 0;
   SfBlockSmem& B = sf_block_smem();
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
 }
 
 // render the current state (Game.draw): the same block-cooperative pipeline without the step
-__global__ void __launch_bounds__(SF_BLOCK, 1) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask, int EB, int ngroups) {
+__global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask, int EB, int ngroups) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
@@ -538,7 +541,7 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 // the SMs (4096 envs -> 28 per block, 147 blocks); beyond that a group is a full warp of 32 stepping lanes and
 // the blocks are persistent over their groups.
 static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) {
-  const int n = h->dev.n, sms = h->num_sms, teams = sms * SF_TEAMS;  // every team of warps renders its own group
+  const int n = h->dev.n, sms = h->num_sms * SF_BLOCKS_PER_SM, teams = sms * SF_TEAMS;  // every team of warps renders its own group
   int eb = n <= teams * SF_GROUP_ENVS ? (n + teams - 1) / teams : SF_GROUP_ENVS;
   if (const char* ov = getenv("SF_ENVS_PER_BLOCK")) { int e = atoi(ov); if (e >= 1 && e <= SF_GROUP_ENVS) eb = e; }  // tuning knob
   *EB = eb;

@@ -58,11 +58,10 @@
 #define SF_CELLS_SHIP 144
 #define SF_CELLS_MISSILE 49
 #define SF_CELLS_SHELL 49
-#define SF_CELLS_EXPLOSION 2048                  // 84 arcs (each within a ring segment of <= 4x4 px) + the r=7 circle
 #ifndef SF_POOL_CELLS
 #define SF_POOL_CELLS 12288                      // 16-bit coverage cells
 #endif
-#define SF_POOL_REGIONS (SF_ROUND_STROKES + SF_EXP_STROKES + 3)
+#define SF_POOL_REGIONS SF_ROUND_STROKES
 
 #define SF_TEAMS 1
 #define SF_TEAM_WARPS SF_RENDER_WARPS
@@ -113,8 +112,8 @@ struct __align__(16) SfTeamSmem {
   int more, padm0, padm1, padm2;     // envs of the group are left for another round
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
-  short arc_region[SF_EXP_STROKES + 3];  // build: region (-1 none) of the 84 arcs and of the circle, stroke order
-  unsigned arc_mask[SF_EXP_W * SF_EXP_W][3];  // build: per pixel of the explosion box, the strokes whose region holds it (zero between builds)
+  unsigned short exp_len[SF_EXPT_ITEMS][SF_EXPT_NC];  // build: summed span lengths of the (quad, pixel row) items of the explosion, per cell
+  alignas(16) unsigned arc_mask[SF_EXP_W * SF_EXP_W][4];  // build: per pixel of the explosion box, the quads that cover it (zero between builds)
   alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
 };
 
@@ -214,7 +213,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
   for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[0].cells)[k] = 0u;
-  for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 3; k += blockDim.x) (&B.team[0].arc_mask[0][0])[k] = 0u;
+  for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[0].arc_mask[0][0])[k] = 0u;
   if (threadIdx.x == 0) {
     SfTeamSmem& Tm = B.team[0];
     Tm.next_task = 0; Tm.netask = 0; Tm.next_stroke = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
@@ -779,68 +778,57 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 }
 
 // ---- ship explosion (R5 drawExplosion, draw.cpp:116-145): 84 arcs (one stroke each) + the r=7 circle -------------
-// The explosion is identical for the 30 ticks a ship stays dead. On the first dead frame its 85 strokes are
-// scan-converted by ALL warps of the block (this warp: arcs [a0, a1), the last warp: the circle) into coverage
-// cells like any other stroke; the window of the explosion box blends them in stroke order and keeps the result in
-// the env's 28x28 sprite cache (final native pixels: it is the first layer on the background). Every arc is ONE
-// quad and the 16 quads of the circle abut along shared radial edges (identical edge records give identical
-// crossings), so no stroke needs a union: all spans go straight to the coverage cells.
-__device__ __forceinline__ void sf_phase_arcs(const SfTables* T, SfBlockSmem& B, SfWarpSmem& W, int lane, int warp, int lwarp, int nwarps, double px, double py) {
-  SF_PROF(31);
-  const SfPt c = sf_xform_base(px, py);
-  const int bx0 = (c.x >> 8) - 13, by0 = (c.y >> 8) - 13;  // the explosion box (sf_make_env_rec)
-  const int apw = (SF_EXP_STROKES - 1 + nwarps - 1) / nwarps;
-  const int a0 = lwarp * apw, a1 = min(SF_EXP_STROKES - 1, a0 + apw);  // warp: index in the block (names the owner of a region), lwarp: in the team
+// The explosion is identical for the 30 ticks a ship stays dead. On the first dead frame it is scan-converted from
+// the tables of its y phase (SfExpPhase, sf_tables.h): one lane per (quad, pixel row) item adds the <= 15 tabulated
+// spans of the item, shifted by the centre's x, into the item's <= SF_EXPT_NC cells (registers: nobody else adds to
+// them) and tells every pixel it covers which quad did. wi / nw: this warp's index among the drawing warps.
+__device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int lane, int wi, int nw) {
+  SfTeamSmem& Tm = sf_team_smem();
+  const SfEnvRec& rec = Tm.env[Tm.build_env];
+  const SfPt c = sf_xform_base(rec.px, rec.py);
+  const SfExpPhase& P = D.tab->exp_phase[c.y & 255];
+  const int Y = c.y >> 8, bx0 = (c.x >> 8) - 13, by0 = Y - 13;  // the explosion box (sf_make_env_rec)
+  const int n = __ldg(&P.n_items);
 #pragma unroll 1
-  for (int pass = 0; pass < 2; pass++) {
-    const bool circle = pass == 1;
-    if (circle ? lwarp != nwarps - 1 : a0 >= a1) continue;
-    const int s = circle ? SF_EXP_STROKES - 1 + lane : a0 + lane;
-    const bool mine = circle ? lane < 16 : s < a1;
-    SfQuadGeom G;
-    G.ymin_g = 1 << 30; G.ymax_g = -(1 << 30); G.xmin = 1 << 30; G.xmax = -(1 << 30); G.split = 0; G.flags = 0;
-    if (mine) {
-      const short* o = T->exp_quad[s];
-      sf_store_quad_edges(T, lane, c.x + o[0], c.y + o[1], c.x + o[2], c.y + o[3], c.x + o[4], c.y + o[5], c.x + o[6], c.y + o[7], G);
-    }
-    const bool has = mine && G.ymin_g < G.ymax_g;
-    int rid;
-    if (!circle) {
-      rid = sf_open_regions(lane, mine, G.ymin_g, G.ymax_g, G.xmin, G.xmax, mine ? T->exp_colour[s] : 0u, SF_TAG_PROJECTILE);
-      if (mine) sf_team_smem().arc_region[s] = (short)rid;
-    } else {
-      const int ymin_g = sf_warp_min(G.ymin_g), ymax_g = sf_warp_max(G.ymax_g), xmin = sf_warp_min(G.xmin), xmax = sf_warp_max(G.xmax);
-      rid = sf_open_regions(lane, lane == 0, ymin_g, ymax_g, xmin, xmax, T->exp_colour[SF_EXP_STROKES - 1], SF_TAG_PROJECTILE);
-      rid = __shfl_sync(0xffffffffu, rid, 0);
-      if (lane == 0) sf_team_smem().arc_region[SF_EXP_STROKES - 1] = (short)rid;
-    }
-    // every pixel of the stroke's region learns that this stroke may cover it
-    if (rid >= 0 && (circle ? lane == 0 : mine)) {
-      const int4 R = sf_team_smem().region[rid];
-      const int w = R.z & 0xFFFF, n = w * ((R.z >> 16) & 0xFFFF);
-      const int sidx = circle ? SF_EXP_STROKES - 1 : s;
-      int x = R.x - bx0, y = R.y - by0;
-      for (int k = 0; k < n; k++) {
-        if ((unsigned)x < (unsigned)SF_EXP_W && (unsigned)y < (unsigned)SF_EXP_W) atomicOr(&sf_team_smem().arc_mask[y * SF_EXP_W + x][sidx >> 5], 1u << (sidx & 31));
-        if (++x == R.x - bx0 + w) { x = R.x - bx0; y++; }
+  for (int it = wi * 32 + lane; it < n; it += nw * 32) {
+    const uint2 Iw = __ldg(reinterpret_cast<const uint2*>(&P.item[it]));
+    const int quad = Iw.x & 255, row = Y + (int)(signed char)((Iw.x >> 8) & 255), ns = (Iw.x >> 16) & 255, span0 = Iw.y & 0xFFFF;
+    const int colmin = (c.x + __ldg(&P.qxmin[quad])) >> 8;
+    const int shift = c.x - (colmin << 8);
+    int acc[SF_EXPT_NC];
+#pragma unroll
+    for (int cc = 0; cc < SF_EXPT_NC; cc++) acc[cc] = 0;
+    if (row >= 0 && row < SF_NAT_H) {
+      unsigned sp[SF_GRID_Y];
+#pragma unroll
+      for (int k = 0; k < SF_GRID_Y; k++) sp[k] = k < ns ? __ldg(reinterpret_cast<const unsigned*>(&P.span[span0 + k][0])) : 0u;
+#pragma unroll
+      for (int k = 0; k < SF_GRID_Y; k++) {
+        const int a = (int)(short)(sp[k] & 0xFFFFu) + shift, b = (int)(short)(sp[k] >> 16) + shift;  // an unused slot has a == b
+#pragma unroll
+        for (int cc = 0; cc < SF_EXPT_NC; cc++) acc[cc] += max(min(b, (cc + 1) << 8) - max(a, cc << 8), 0);
       }
     }
-    // every quad is a one-quad stroke of its own (the 16 quads of the circle share one region)
-    sf_publish_quads(W, lane, G, has, rid, has, lane, 1, G.ymin_g, G.ymax_g);
-    SF_PROF(21);
-    sf_batch_accumulate();
+#pragma unroll
+    for (int cc = 0; cc < SF_EXPT_NC; cc++) {
+      Tm.exp_len[it][cc] = (unsigned short)acc[cc];
+      const int col = colmin + cc;
+      if (acc[cc] && (unsigned)col < (unsigned)SF_NAT_W && (unsigned)(row - by0) < (unsigned)SF_EXP_W && (unsigned)(col - bx0) < (unsigned)SF_EXP_W) atomicOr(&Tm.arc_mask[(row - by0) * SF_EXP_W + (col - bx0)][quad >> 5], 1u << (quad & 31));
+    }
   }
 }
 
-// Phase B2 (rounds that build an explosion, after every arc is scan-converted): one lane per pixel of the 28x28 box
-// blends the strokes whose region holds the pixel, in stroke order, over the background (hexagons) and stores the
-// sprite in the env's cache; the windows of phase C read it like any cached sprite. wi / nw: this warp's index
-// among the drawing warps and their number.
+// Phase B2 (rounds that build an explosion, after sf_phase_exp_items): one lane per pixel of the 28x28 box blends
+// the strokes that cover the pixel, in stroke order (arc s == quad s; the 16 chords of the circle, quads 84..99,
+// are ONE stroke: their lengths add up), over the background (hexagons) and stores the sprite in the env's cache;
+// the windows of phase C read it like any cached sprite. wi / nw: this warp's index among the drawing warps.
 __device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int lane, int wi, int nw) {
   SfTeamSmem& Tm = sf_team_smem();
-  const int be = Tm.build_env;
-  SfEnvRec& rec = Tm.env[be];
-  const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
+  const SfTables* T = D.tab;
+  SfEnvRec& rec = Tm.env[Tm.build_env];
+  const SfPt c = sf_xform_base(rec.px, rec.py);
+  const SfExpPhase& P = T->exp_phase[c.y & 255];
+  const int Y = c.y >> 8, bx0 = (c.x >> 8) - 13, by0 = Y - 13;
   unsigned char* sprite = D.expc + (size_t)rec.env * (SF_EXP_W * SF_EXP_W);
 #pragma unroll 1
   for (int p = wi * 32 + lane; p < SF_EXP_W * SF_EXP_W; p += nw * 32) {
@@ -849,20 +837,25 @@ __device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, 
     unsigned v = 0;
     if ((unsigned)nx < (unsigned)SF_NAT_W && (unsigned)ny < (unsigned)SF_NAT_H) {
       v = B.bg_nat[ny * SF_NAT_STRIDE + nx];
+      const uint4 M = *reinterpret_cast<const uint4*>(Tm.arc_mask[p]);
+      unsigned circle = 0;
 #pragma unroll 1
-      for (int wd = 0; wd < 3; wd++) {
-        unsigned m = Tm.arc_mask[p][wd];
+      for (int wd = 0; wd < 4; wd++) {
+        unsigned m = wd == 0 ? M.x : wd == 1 ? M.y : wd == 2 ? M.z : M.w;
         while (m) {
-          const int sidx = wd * 32 + __ffs(m) - 1;
+          const int q = wd * 32 + __ffs(m) - 1;
           m &= m - 1;
-          const int4 R = Tm.region[Tm.arc_region[sidx]];
-          const unsigned L = Tm.cells[(R.w & 0x7FFF) + (ny - R.y) * (R.z & 0xFFFF) + (nx - R.x)];
-          if (L) v = sf_blend(v, ((unsigned)R.w >> 16) & 255u, sf_len_to_alpha(L));
+          const int it = __ldg(&P.item0[q]) + (ny - Y - (int)__ldg(&P.row0[q]));
+          const int colmin = (c.x + __ldg(&P.qxmin[q])) >> 8;
+          const unsigned L = Tm.exp_len[it][nx - colmin];
+          if (q < SF_EXP_STROKES - 1) v = sf_blend(v, T->exp_colour[q], sf_len_to_alpha(L));
+          else circle += L;
         }
       }
+      if (circle) v = sf_blend(v, T->exp_colour[SF_EXP_STROKES - 1], sf_len_to_alpha(circle));
+      *reinterpret_cast<uint4*>(Tm.arc_mask[p]) = make_uint4(0u, 0u, 0u, 0u);
     }
     sprite[p] = (unsigned char)v;
-    Tm.arc_mask[p][0] = 0u; Tm.arc_mask[p][1] = 0u; Tm.arc_mask[p][2] = 0u;
   }
   if (wi == 0 && lane == 0) D.expstamp[rec.env] = rec.life;
 }
@@ -904,7 +897,7 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
   if (cand) {
     const SfEnvRec& rec = sf_team_smem().env[lane];
     need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE +
-           __popc(rec.shell_vis) * SF_CELLS_SHELL + ((rec.building & 1) ? SF_CELLS_EXPLOSION : 0);
+           __popc(rec.shell_vis) * SF_CELLS_SHELL;
   }
   int incl = cnt, incl_need = need;
 #pragma unroll
@@ -1057,6 +1050,8 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team_smem();
   const int chunk = Tm.chunk;
+  if (Tm.build_env >= 0 && Tm.build_env < Tm.r1) sf_phase_exp_items(D, lane, wi, nw);
+  SF_PROF(21);
 #pragma unroll 1
   for (;;) {
     int s = 0;
@@ -1078,8 +1073,6 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
     if (valid && (lane & 3) == 0) Tm.stroke[idx].region = rid;
     sf_batch_accumulate();
   }
-  const int be = Tm.build_env;
-  if (be >= 0 && be < Tm.r1) sf_phase_arcs(T, B, W, lane, wi, wi, nw, Tm.env[be].px, Tm.env[be].py);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke

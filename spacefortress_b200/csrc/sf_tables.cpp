@@ -285,6 +285,51 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     if (q != SF_EXP_QUADS || stroke != SF_EXP_STROKES) { snprintf(err, errcap, "explosion table size"); return 1; }
   }
 
+  // ---- the same quads scan-converted for each of the 256 y phases of the centre (SfExpPhase, sf_tables.h) ----
+  {
+    auto floordiv = [](int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+    for (int phy = 0; phy < 256; phy++) {
+      SfExpPhase& P = t->exp_phase[phy];
+      memset(&P, 0, sizeof(P));
+      int ni = 0, ns = 0;
+      for (int q = 0; q < SF_EXP_QUADS; q++) {
+        const short* o = t->exp_quad[q];
+        int x[4], g[4];
+        for (int k = 0; k < 4; k++) { x[k] = o[2 * k]; g[k] = sf_grid_y(phy + o[2 * k + 1]); }  // rows relative to 15 * (c.y >> 8)
+        const int gmin = std::min(std::min(g[0], g[1]), std::min(g[2], g[3])), gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
+        P.item0[q] = (unsigned short)ni;
+        P.qxmin[q] = (short)std::min(std::min(x[0], x[1]), std::min(x[2], x[3]));
+        P.row0[q] = (signed char)floordiv(gmin, SF_GRID_Y);
+        int nd = 0, nu = 0;
+        for (int k = 0; k < 4; k++) { const int d = g[(k + 1) & 3] - g[k]; nd += d > 0; nu += d < 0; }
+        if (nd == 0 || nu == 0) continue;  // covers no sample row
+        for (int r = floordiv(gmin, SF_GRID_Y); r <= floordiv(gmax - 1, SF_GRID_Y); r++) {
+          if (ni >= SF_EXPT_ITEMS) { snprintf(err, errcap, "explosion phase table: items"); return 1; }
+          SfExpItem& I = P.item[ni++];
+          I.quad = (unsigned char)q; I.row = (signed char)r; I.span0 = (unsigned short)ns; I.n = 0;
+          for (int sr = std::max(gmin, r * SF_GRID_Y); sr < std::min(gmax, (r + 1) * SF_GRID_Y); sr++) {
+            // crossings of the edges that are live on sample row sr: x = xa + floor((sr - ga) * dx / dy)
+            int lo = 1 << 30, hi = -(1 << 30);
+            for (int k = 0; k < 4; k++) {
+              int xa = x[k], ga = g[k], xb = x[(k + 1) & 3], gb = g[(k + 1) & 3];
+              if (ga == gb) continue;
+              if (ga > gb) { std::swap(xa, xb); std::swap(ga, gb); }
+              if (sr < ga || sr >= gb) continue;
+              const int xs = xa + (int)fdiv((long long)(sr - ga) * (xb - xa), gb - ga);
+              lo = std::min(lo, xs); hi = std::max(hi, xs);
+            }
+            if (ns >= SF_EXPT_SPANS) { snprintf(err, errcap, "explosion phase table: spans"); return 1; }
+            if (lo > hi) { lo = 0; hi = 0; }
+            if (lo < hi && (lo < -13 * 256 || hi > 14 * 256 + 1 || r < -13 || r > 14)) { snprintf(err, errcap, "explosion phase table: box"); return 1; }
+            if (((lo - P.qxmin[q]) >> 8) >= SF_EXPT_NC || (hi > lo && ((hi - 1 - P.qxmin[q]) >> 8) + 1 >= SF_EXPT_NC)) { snprintf(err, errcap, "explosion phase table: cells per item"); return 1; }
+            P.span[ns][0] = (short)lo; P.span[ns][1] = (short)hi; ns++; I.n++;
+          }
+        }
+      }
+      P.n_items = ni; P.n_spans = ns;
+    }
+  }
+
   // ---- fortress explosion as ordered (alpha, colour) layers at the fixed fortress position ----
   {
     SfPt c = sf_xform_base(SF_FORT_X, SF_FORT_Y);

@@ -38,6 +38,25 @@
 #define SF_FORT_STATES 37          // 36 sector angles + destroyed (explosion)
 #define SF_FORT_CHUNKS 160         // upper bound of output chunks influenced by the fortress/explosion box
 
+// Ship explosion, scan-converted ahead of time. The 100 quads of drawExplosion (draw.cpp:116-145) are fixed
+// relative to the 24.8 fixed-point centre c. In x the scan conversion is translation invariant; in y the rounding of
+// the corners to the 1/15 px sample grid depends only on c.y & 255. So for each of the 256 y phases the exact span
+// [lo, hi) of every quad on every sample row is tabulated relative to c (x in 1/256 px, rows relative to the
+// centre's pixel row), grouped into (quad, pixel row) items; the device only adds the spans of an item into its
+// <= SF_EXPT_NC cells.
+#define SF_EXPT_ITEMS 224
+#define SF_EXPT_SPANS 1792
+#define SF_EXPT_NC 6
+struct alignas(8) SfExpItem { unsigned char quad; signed char row; unsigned char n, pad; unsigned short span0; unsigned short pad2; };  // n spans from span0, pixel row `row`
+struct alignas(16) SfExpPhase {
+  int n_items, n_spans, pad[2];
+  SfExpItem item[SF_EXPT_ITEMS];
+  short span[SF_EXPT_SPANS][2];           // lo, hi relative to c.x
+  unsigned short item0[SF_EXP_QUADS];     // first item of a quad (its pixel rows are consecutive items)
+  signed char row0[SF_EXP_QUADS];         // first pixel row of a quad relative to the centre's
+  short qxmin[SF_EXP_QUADS];              // leftmost corner of a quad relative to c.x: its cells start at (c.x + qxmin) >> 8
+};
+
 struct SfTap { int si, cnt; float a[SF_MAX_TAPS]; };  // consecutive source indices si..si+cnt-1 and their weights
 
 struct SfTables {
@@ -91,6 +110,7 @@ struct SfTables {
   // the chunks of obs_fort[st] that differ from the default observation (index relative to fort_chunk0), 255-terminated
   unsigned char fort_sparse[SF_FORT_STATES][64];
   unsigned char fort_sparse_n[SF_FORT_STATES];
+  SfExpPhase exp_phase[256];
   int text_guard_row;  // moving rects with y0 <= this native row force the general text path
   int bar_guard_row;   // moving rects with y1 >= this native row force the general bar path
 };
