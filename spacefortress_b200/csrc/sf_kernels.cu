@@ -102,13 +102,14 @@ __device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, 
   SfTeamSmem& Tm = sf_team_smem();
   SfEnvRec r = Tm.env_next[lane];
   if (r.env >= 0 && !(r.core & SF_CORE_SHIP_ALIVE)) {
-    r.building = D.expstamp[r.env] != r.life ? 1 : 0;
+    const unsigned stamp = __ldcg(&D.expstamp[r.env]);  // both loads in flight together
+    const uint2 m = __ldcg(&D.expo_meta[r.env]);
+    r.building = stamp != r.life ? 1 : 0;
     if (!native) {
       // which quarters of the resampled explosion box are cached for exactly this life / fortress / bar / score
       const int fst = (r.core & SF_CORE_FORT_ALIVE) ? (int)((r.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
       const int bst = r.kill_bar ? 11 : min(r.vuln, 10);
       const unsigned key = (unsigned)fst | ((unsigned)bst << 6) | (((unsigned)r.points_i & 0x3FFFFu) << 10);
-      const uint2 m = D.expo_meta[r.env];
       if (!r.building && m.x == r.life && (m.y & 0x0FFFFFFFu) == key) r.building |= (int)(m.y >> 28) << 4;
       else D.expo_meta[r.env] = make_uint2(r.life, key);
     }

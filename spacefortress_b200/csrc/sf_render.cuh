@@ -448,6 +448,19 @@ __device__ __forceinline__ unsigned sf_quad_span_regular(const SfWarpSmem& W, in
 // stroke that is live on its sub-row (integer edge stepping), sorts the <= 4 spans and adds each one minus the
 // union of its predecessors to the coverage cells of the stroke's region (non-zero winding of equally oriented
 // convex quads == union). 8 lanes share a work group of 8 consecutive sub-rows of one stroke.
+__device__ __forceinline__ void sf_emit_span_pred(unsigned* acc32, int cell0, int a, int b) {
+  // straight-line version of sf_emit_span: the two partial cells are predicated, only the run of full cells in
+  // between (near-horizontal spans) loops
+  const bool any = a < b;
+  const int c1 = a >> 8, c2 = (b - 1) >> 8;
+  const int ci = cell0 + c1, cj = cell0 + c2;
+  const unsigned len1 = (unsigned)(min(b, (c1 + 1) << 8) - a), len2 = (unsigned)(b - (c2 << 8));
+  if (any) atomicAdd(&acc32[ci >> 1], len1 << ((ci & 1) << 4));
+  if (any && c2 > c1) atomicAdd(&acc32[cj >> 1], len2 << ((cj & 1) << 4));
+  if (any && c2 > c1 + 1)
+    for (int c = c1 + 1; c < c2; c++) { const int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
+}
+
 __device__ __noinline__ void sf_batch_accumulate() {
   SfWarpSmem& W = sf_my_smem();
   const int lane = threadIdx.x & 31;
@@ -457,40 +470,32 @@ __device__ __noinline__ void sf_batch_accumulate() {
   unsigned* acc32 = reinterpret_cast<unsigned*>(sf_team_smem().cells);
 #pragma unroll 1
   for (int g0 = 0; g0 < ngroups; g0 += 4) {
-    const int gi = g0 + (lane >> 3);
-    if (gi >= ngroups) continue;
+    const int gi = min(g0 + (lane >> 3), ngroups - 1);
     const int ent = W.glist[gi];
     const int4 S = W.srec[ent & 31];
     const int sb = (S.w & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
-    if (sb >= (int)((unsigned)S.w >> 16)) continue;
-    const int nq = (S.x >> 16) & 255, q0 = (int)((unsigned)S.x >> 24);
+    const bool valid = g0 + (lane >> 3) < ngroups && sb < (int)((unsigned)S.w >> 16);
+    const int q0 = (int)((unsigned)S.x >> 24);
     const int w = (S.x >> 8) & 255;
     const int xlo = (S.x & 255) << 8, xhi = xlo + (w << 8);
-    const int cell0 = S.z + sf_div15(sb - S.y) * w;
-    if (nq == 1) {  // explosion arcs, circle chords
-      const unsigned k = sf_quad_span(W, q0, sb, xlo, xhi);
-      if (k != SF_SPAN_NONE) sf_emit_span(acc32, cell0, (int)(k >> 16), (int)(k & 0xFFFFu));
-      continue;
-    }
-    // wireframes: 3 or 4 stroked segments
+    const int cell0 = S.z + sf_div15(max(sb - S.y, 0)) * w;
+    // wireframes: 3 or 4 stroked segments (a slot without a quad is never live); all loads in flight together
     unsigned k0 = sf_quad_span_regular(W, q0, sb, xlo, xhi);
     unsigned k1 = sf_quad_span_regular(W, q0 + 1, sb, xlo, xhi);
     unsigned k2 = sf_quad_span_regular(W, q0 + 2, sb, xlo, xhi);
-    unsigned k3 = nq > 3 ? sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi) : SF_SPAN_NONE;
+    unsigned k3 = sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi);
+    if (!valid) { k0 = SF_SPAN_NONE; k1 = SF_SPAN_NONE; k2 = SF_SPAN_NONE; k3 = SF_SPAN_NONE; }
     // sort by start (none == 0xFFFFFFFF sinks to the end)
     unsigned t0 = min(k0, k1), t1 = max(k0, k1), t2 = min(k2, k3), t3 = max(k2, k3);
     k0 = min(t0, t2); k2 = max(t0, t2);
     k1 = min(t1, t3); k3 = max(t1, t3);
     t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-    if (k0 == SF_SPAN_NONE) continue;
-    int reach = (int)(k0 & 0xFFFFu);
-    sf_emit_span(acc32, cell0, (int)(k0 >> 16), reach);
-    if (k1 == SF_SPAN_NONE) continue;
-    { int a = max((int)(k1 >> 16), reach), b = (int)(k1 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-    if (k2 == SF_SPAN_NONE) continue;
-    { int a = max((int)(k2 >> 16), reach), b = (int)(k2 & 0xFFFFu); reach = max(reach, b); if (a < b) sf_emit_span(acc32, cell0, a, b); }
-    if (k3 == SF_SPAN_NONE) continue;
-    { int a = max((int)(k3 >> 16), reach), b = (int)(k3 & 0xFFFFu); if (a < b) sf_emit_span(acc32, cell0, a, b); }
+    // each span minus the union of its predecessors; none: a = 0xFFFF > b
+    int reach = 0;
+    { const int a = (int)(k0 >> 16), b = k0 == SF_SPAN_NONE ? 0 : (int)(k0 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = b; }
+    { const int a = max((int)(k1 >> 16), reach), b = k1 == SF_SPAN_NONE ? 0 : (int)(k1 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
+    { const int a = max((int)(k2 >> 16), reach), b = k2 == SF_SPAN_NONE ? 0 : (int)(k2 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
+    { const int a = max((int)(k3 >> 16), reach), b = k3 == SF_SPAN_NONE ? 0 : (int)(k3 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); }
   }
   __syncwarp();
   SF_PROF(20);
