@@ -49,9 +49,7 @@
 #endif
 #define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
 #define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
-#ifndef SF_ROUND_STROKES
-#define SF_ROUND_STROKES 256                     // strokes pooled per round (a round takes as many envs of the group as fit)
-#endif
+#define SF_ROUND_STROKES (8 * (SF_RENDER_WARPS - 1))  // strokes pooled per round: one batch of <= 8 per drawing warp (a round takes as many envs of the group as fit)
 // Block-wide pools of a round: one region (bounding box in native pixels + coverage cells) per visible stroke.
 // The round scan admits envs by WORST-CASE need, so the pools cannot overflow: a ship wireframe spans at most
 // 44 user units (8.8 px) + the line width in any direction, a missile 25 (5 px), a shell 24 (4.8 px).
@@ -461,44 +459,40 @@ __device__ __forceinline__ void sf_emit_span_pred(unsigned* acc32, int cell0, in
     for (int c = c1 + 1; c < c2; c++) { const int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
 }
 
-__device__ __noinline__ void sf_batch_accumulate() {
-  SfWarpSmem& W = sf_my_smem();
+// One pass (4 work groups = 32 (stroke, sub-row) items) of the batch that warp `owner` published, starting at its
+// work group g0. Any warp of the block can run any pass: the records are read-only after the block barrier that
+// follows the geometry, and the cells are updated with atomics.
+__device__ __noinline__ void sf_accumulate_pass(int owner, int g0) {
+  const SfWarpSmem& W = sf_warp_smem(owner);
   const int lane = threadIdx.x & 31;
-  __syncwarp();
   const int ngroups = W.ngroups;
-  SF_PROF_COUNT(68, ngroups);
   unsigned* acc32 = reinterpret_cast<unsigned*>(sf_team_smem().cells);
-#pragma unroll 1
-  for (int g0 = 0; g0 < ngroups; g0 += 4) {
-    const int gi = min(g0 + (lane >> 3), ngroups - 1);
-    const int ent = W.glist[gi];
-    const int4 S = W.srec[ent & 31];
-    const int sb = (S.w & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
-    const bool valid = g0 + (lane >> 3) < ngroups && sb < (int)((unsigned)S.w >> 16);
-    const int q0 = (int)((unsigned)S.x >> 24);
-    const int w = (S.x >> 8) & 255;
-    const int xlo = (S.x & 255) << 8, xhi = xlo + (w << 8);
-    const int cell0 = S.z + sf_div15(max(sb - S.y, 0)) * w;
-    // wireframes: 3 or 4 stroked segments (a slot without a quad is never live); all loads in flight together
-    unsigned k0 = sf_quad_span_regular(W, q0, sb, xlo, xhi);
-    unsigned k1 = sf_quad_span_regular(W, q0 + 1, sb, xlo, xhi);
-    unsigned k2 = sf_quad_span_regular(W, q0 + 2, sb, xlo, xhi);
-    unsigned k3 = sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi);
-    if (!valid) { k0 = SF_SPAN_NONE; k1 = SF_SPAN_NONE; k2 = SF_SPAN_NONE; k3 = SF_SPAN_NONE; }
-    // sort by start (none == 0xFFFFFFFF sinks to the end)
-    unsigned t0 = min(k0, k1), t1 = max(k0, k1), t2 = min(k2, k3), t3 = max(k2, k3);
-    k0 = min(t0, t2); k2 = max(t0, t2);
-    k1 = min(t1, t3); k3 = max(t1, t3);
-    t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-    // each span minus the union of its predecessors; none: a = 0xFFFF > b
-    int reach = 0;
-    { const int a = (int)(k0 >> 16), b = k0 == SF_SPAN_NONE ? 0 : (int)(k0 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = b; }
-    { const int a = max((int)(k1 >> 16), reach), b = k1 == SF_SPAN_NONE ? 0 : (int)(k1 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
-    { const int a = max((int)(k2 >> 16), reach), b = k2 == SF_SPAN_NONE ? 0 : (int)(k2 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
-    { const int a = max((int)(k3 >> 16), reach), b = k3 == SF_SPAN_NONE ? 0 : (int)(k3 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); }
-  }
-  __syncwarp();
-  SF_PROF(20);
+  const int gi = min(g0 + (lane >> 3), ngroups - 1);
+  const int ent = W.glist[gi];
+  const int4 S = W.srec[ent & 31];
+  const int sb = (S.w & 0xFFFF) + ((ent >> 5) << 3) + (lane & 7);
+  const bool valid = g0 + (lane >> 3) < ngroups && sb < (int)((unsigned)S.w >> 16);
+  const int q0 = (int)((unsigned)S.x >> 24);
+  const int w = (S.x >> 8) & 255;
+  const int xlo = (S.x & 255) << 8, xhi = xlo + (w << 8);
+  const int cell0 = S.z + sf_div15(max(sb - S.y, 0)) * w;
+  // wireframes: 3 or 4 stroked segments (a slot without a quad is never live); all loads in flight together
+  unsigned k0 = sf_quad_span_regular(W, q0, sb, xlo, xhi);
+  unsigned k1 = sf_quad_span_regular(W, q0 + 1, sb, xlo, xhi);
+  unsigned k2 = sf_quad_span_regular(W, q0 + 2, sb, xlo, xhi);
+  unsigned k3 = sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi);
+  if (!valid) { k0 = SF_SPAN_NONE; k1 = SF_SPAN_NONE; k2 = SF_SPAN_NONE; k3 = SF_SPAN_NONE; }
+  // sort by start (none == 0xFFFFFFFF sinks to the end)
+  unsigned t0 = min(k0, k1), t1 = max(k0, k1), t2 = min(k2, k3), t3 = max(k2, k3);
+  k0 = min(t0, t2); k2 = max(t0, t2);
+  k1 = min(t1, t3); k3 = max(t1, t3);
+  t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
+  // each span minus the union of its predecessors; none: a = 0xFFFF > b
+  int reach = 0;
+  { const int a = (int)(k0 >> 16), b = k0 == SF_SPAN_NONE ? 0 : (int)(k0 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = b; }
+  { const int a = max((int)(k1 >> 16), reach), b = k1 == SF_SPAN_NONE ? 0 : (int)(k1 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
+  { const int a = max((int)(k2 >> 16), reach), b = k2 == SF_SPAN_NONE ? 0 : (int)(k2 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); reach = max(reach, b); }
+  { const int a = max((int)(k3 >> 16), reach), b = k3 == SF_SPAN_NONE ? 0 : (int)(k3 & 0xFFFFu); sf_emit_span_pred(acc32, cell0, a, b); }
 }
 
 // ---- windows ---------------------------------------------------------------------------------------------
@@ -922,8 +916,8 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
     Tm.more = later != 0u;
     const int nst = r1 > 0 ? total : 0;
     Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = builders ? __ffs(builders) - 1 : -1;
-    // phase B hands the strokes out in equal grabs of <= 8 (one batch), about SF_DEAL_DIV per warp
-    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) * SF_DEAL_DIV - 1) / ((SF_RENDER_WARPS - 1) * SF_DEAL_DIV), 1), 8);
+    // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
+    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
   }
   // window tasks of the round that do not belong to a stroke: 4 quarters of a dead ship's explosion box, the strip
   // of a non-zero score (the static base shows "0000000")
@@ -1049,21 +1043,18 @@ __device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfW
   (void)W; (void)B; (void)out;
 }
 
-// phase B for this warp: grab batches of Tm.chunk consecutive strokes of the round's list (first come first served)
-// and scan-convert them into the block's coverage cells; then this warp's share of the explosion being built.
+// phase B for this warp. B1: warp wi builds the geometry of batch wi (Tm.chunk consecutive strokes of the round's
+// list: at most one batch per warp) and publishes its records; after a barrier of the drawing warps, B3: the
+// passes of ALL batches are dealt round-robin over ALL drawing warps, so the scan conversion is balanced whatever
+// the size of the individual strokes.
 __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst) {
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team_smem();
   const int chunk = Tm.chunk;
   if (Tm.build_env >= 0 && Tm.build_env < Tm.r1) sf_phase_exp_items(D, lane, wi, nw);
   SF_PROF(21);
-#pragma unroll 1
-  for (;;) {
-    int s = 0;
-    if (lane == 0) s = atomicAdd(&Tm.next_stroke, chunk);
-    s = __shfl_sync(0xffffffffu, s, 0);
-    SF_PROF(64);
-    if (s >= nst) break;
+  const int s = wi * chunk;
+  if (s < nst) {
     SF_PROF_COUNT(67, 1);
     const int slot = lane >> 2;
     const bool valid = slot < chunk && s + slot < nst;
@@ -1076,8 +1067,25 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
     }
     const int rid = sf_wire_geometry(W, lane, T, kind, x, y, angle);
     if (valid && (lane & 3) == 0) Tm.stroke[idx].region = rid;
-    sf_batch_accumulate();
+  } else {
+    if (lane == 0) W.ngroups = 0;
   }
+  sf_render_sync();  // every batch is published
+  SF_PROF(64);
+  // passes of warp l's batch: (ngroups + 3) / 4; every warp computes the same prefix sums
+  const int mine = lane < nw ? (sf_warp_smem(lane + 1).ngroups + 3) >> 2 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  SF_PROF_COUNT(68, total);
+#pragma unroll 1
+  for (int g = wi; g < total; g += nw) {
+    const int owner = __popc(__ballot_sync(0xffffffffu, incl <= g));  // first warp whose inclusive count exceeds g
+    const int first = __shfl_sync(0xffffffffu, incl - mine, owner);
+    sf_accumulate_pass(owner + 1, (g - first) << 2);
+  }
+  SF_PROF(20);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
