@@ -8,7 +8,7 @@ def run(gametype, n, T, warm=200, render=True):
     env.reset(to_numpy=False)
     env.rollout(warm, want=("reward",))  # state-only warm-up is fine: it advances the same state
     out = {"obs": torch.empty((T, n, 1, 84, 84), dtype=torch.uint8, device="cuda")} if render else {"reward": torch.empty((T, n), dtype=torch.int32, device="cuda")}
-    env.rollout(2, out={k: v[:2] for k, v in out.items()})
+    env.rollout(T, out=out)  # warm: fills the explosion caches of the ships that are dead right now
     torch.cuda.synchronize()
     best = 1e9
     for _ in range(3):

@@ -6,7 +6,7 @@ subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.
 import torch
 from spacefortress_b200 import SFVecEnv, _lib
 n, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 64
-env = SFVecEnv("autoturn", num_envs=n, device=0); env.reset(to_numpy=False)
+env = SFVecEnv(os.environ.get("SF_GT", "autoturn"), num_envs=n, device=0); env.reset(to_numpy=False)
 env.rollout(300, want=("reward",))
 out = {"obs": torch.empty((T, n, 1, 84, 84), dtype=torch.uint8, device="cuda")}
 env.rollout(T, out=out); torch.cuda.synchronize()
