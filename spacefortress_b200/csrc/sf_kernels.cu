@@ -173,7 +173,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
 
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int team = warp / SF_TEAM_WARPS, first_of_team = (warp % SF_TEAM_WARPS) == 0;
+  const bool stepper = warp == 0;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   // every team of warps renders its own groups, on its own barrier
 #pragma unroll 1
-  for (int group = blockIdx.x * SF_TEAMS + team; group < A.ngroups; group += gridDim.x * SF_TEAMS) {
-    if (first_of_team) sf_step_group(D, A, group, 0);
+  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
+    if (stepper) sf_step_group(D, A, group, 0);
 #pragma unroll 1
     for (int t = 0; t < A.T; t++) {
-      if (first_of_team) sf_publish_recs(D, B, lane, out.native != 0);
+      if (stepper) sf_publish_recs(D, B, lane, out.native != 0);
       out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
       // the step of tick t+1 runs while the other warps composite the windows of tick t: it writes the SoA state
       // and the staged records, which the frames of tick t no longer read
@@ -238,10 +238,9 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
   out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = obs;
-  const int team = warp / SF_TEAM_WARPS;
 #pragma unroll 1
-  for (int group = blockIdx.x * SF_TEAMS + team; group < ngroups; group += gridDim.x * SF_TEAMS) {
-    if ((warp % SF_TEAM_WARPS) == 0) {
+  for (int group = blockIdx.x; group < ngroups; group += gridDim.x) {
+    if (warp == 0) {
       const int env = group * EB + lane;
       const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
       if (mine) {
@@ -542,12 +541,12 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
 // the SMs (4096 envs -> 28 per block, 147 blocks); beyond that a group is a full warp of 32 stepping lanes and
 // the blocks are persistent over their groups.
 static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) {
-  const int n = h->dev.n, sms = h->num_sms * SF_BLOCKS_PER_SM, teams = sms * SF_TEAMS;  // every team of warps renders its own group
+  const int n = h->dev.n, sms = h->num_sms * SF_BLOCKS_PER_SM, teams = sms;
   int eb = n <= teams * SF_GROUP_ENVS ? (n + teams - 1) / teams : SF_GROUP_ENVS;
   if (const char* ov = getenv("SF_ENVS_PER_BLOCK")) { int e = atoi(ov); if (e >= 1 && e <= SF_GROUP_ENVS) eb = e; }  // tuning knob
   *EB = eb;
   *ngroups = (n + eb - 1) / eb;
-  *blocks = std::min((*ngroups + SF_TEAMS - 1) / SF_TEAMS, sms);
+  *blocks = std::min(*ngroups, sms);
 }
 
 static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {

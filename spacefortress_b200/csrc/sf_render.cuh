@@ -1,4 +1,5 @@
-// sf_render.cuh — warp-cooperative rasteriser: one warp draws one env's frame.
+// sf_render.cuh — block-cooperative rasteriser: the 15 drawing warps of a block draw the frames of a group of <= 32
+// envs per tick while warp 0 steps the group's next tick.
 // Replaces drawGameStateScaled (draw.cpp:256-270), the RGBA2GRAY conversion (ssf_env.py:205, identity on grey
 // input) and cv2.resize(INTER_AREA, 84x84) (rl/envs.py:29).
 //
@@ -6,24 +7,27 @@
 //   black, 2 hexagons -> ship wireframe | ship explosion -> fortress wireframe | fortress explosion
 //   -> missiles -> shells further than 21 from the fortress -> score digits -> vulnerability bar.
 //
-// Organisation (one block per SM renders a group of <= 32 envs per tick; 11.8 KB of scratch per warp; see the
-// block-cooperative pipeline at the end of this file):
-//  * The observation is first written from STATIC, pre-resampled 16-byte chunk tables (background with the
-//    "0000000" score and the empty bar, the fortress sprite of the current sector angle, the bar state):
-//    441 coalesced 128-bit stores.
-//  * Everything that moves (ship, missiles, shells, the ship explosion, a non-zero score) is a small box. Its
-//    strokes are scan-converted in BATCHES: lanes build the stroked quads (fp64 CTM, 24.8 fixed point), then
-//    (1) every live (quad, sub-row) pair of the batch gets a lane that computes the exact span (integer edge
-//    stepping) into a per-(stroke, sub-row) scratch, (2) every (stroke, sub-row) gets a lane that merges the
-//    <= 4 spans (non-zero winding == union for equally oriented convex quads) and adds the lengths to 16-bit
-//    coverage cells that stay in shared memory until the frame is done.
-//  * For every moving box a WINDOW is composited: the native pixels that the box's output pixels read
-//    (INTER_AREA footprint closure, at most 30x32) are initialised from the background and EVERY layer that
-//    intersects the window is blended in draw order, clipped to it. The window is resampled and its output
-//    pixels overwrite the static ones. Windows are independent of each other (overlapping windows recompute
-//    the same pixels), so no full-frame tile exists anywhere.
-//  * The ship explosion is identical for the 30 ticks a ship stays dead: it is rasterised once and kept in
-//    a per-env 28x28 sprite cache (memo, not game state).
+// Organisation (one block per SM; see the pipeline at the end of this file):
+//  * The default observation (hexagons, "0000000", empty bar; 7056 B) of every env goes out as ONE TMA bulk copy from
+//    shared memory; the few 16-byte chunks that the fortress state and a non-empty bar change are patched from
+//    pre-resampled tables, and the resampled explosion box of a dead ship is copied from a per-env cache.
+//  * Everything that moves (ship, missiles, shells) is a wireframe STROKE of 3-4 stroked segments (quads). The strokes
+//    of all envs of the round are pooled. B1: every drawing warp builds the geometry of one batch of <= 8 strokes
+//    (fp64 CTM, 24.8 fixed point, edge records with magic reciprocals) and opens one REGION per stroke (bounding box
+//    in native pixels + 16-bit coverage cells) in block-wide pools. B3: the scan-conversion passes of all batches are
+//    dealt round-robin over all drawing warps: one lane per (stroke, sub-row) computes the exact spans of the
+//    stroke's quads (integer edge stepping), makes them disjoint (non-zero winding of equally oriented convex quads
+//    == union) and adds the lengths to the cells with shared-memory atomics.
+//  * C: for every visible stroke (and every stale quarter of a dead ship's explosion box, and a non-zero score) a
+//    WINDOW is composited: the native pixels that the box's output pixels read (INTER_AREA footprint closure, at
+//    most 30x32) are initialised from the background and EVERY layer of the env that intersects the window is
+//    blended in draw order, clipped to it. The window is resampled with cv2's float arithmetic and its output pixels
+//    overwrite the static ones. Windows are independent of each other (overlapping windows recompute the same
+//    pixels), so no full-frame tile exists anywhere.
+//  * The ship explosion (85 strokes) is identical for the 30 ticks a ship stays dead. On the first dead frame it is
+//    scan-converted from per-y-phase span tables (SfExpPhase) with register accumulation, composited once per pixel
+//    (phase B2) and kept as a 28x28 native sprite per env; the resampled box is cached per quarter as soon as no
+//    wireframe reaches into it, and from then on copied instead of recomputed (memos, not game state).
 #pragma once
 #include "sf_geom.h"
 #include "sf_state.cuh"
@@ -61,11 +65,6 @@
 #endif
 #define SF_POOL_REGIONS SF_ROUND_STROKES
 
-#define SF_TEAMS 1
-#define SF_TEAM_WARPS SF_RENDER_WARPS
-#ifndef SF_DEAL_DIV
-#define SF_DEAL_DIV 1
-#endif
 
 // per-warp shared memory (3.6 KB): the records of the batch being scan-converted; the window being composited
 // aliases the edge records (compositing starts after the block's last batch)
@@ -106,7 +105,7 @@ struct __align__(16) SfTeamSmem {
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
-  int next_task, netask, next_stroke, chunk;  // phase C work queue; env tasks of the round; phase B work queue and its grab size
+  int next_task, netask, pad_q, chunk;  // phase C work queue; env tasks of the round; strokes per batch of phase B1
   int more, padm0, padm1, padm2;     // envs of the group are left for another round
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
@@ -132,14 +131,14 @@ struct __align__(16) SfBlockSmem {
   double wf_line[3][4][4];                     // wireframe models
   int wf_nlines[4];
   unsigned colour_white, padc[3];
-  SfTeamSmem team[SF_TEAMS];
+  SfTeamSmem team[1];
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
-__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[(threadIdx.x >> 5) / SF_TEAM_WARPS]; }
+__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[0]; }
 __device__ __forceinline__ void sf_team_sync() {  // every warp of the block (named barrier 1)
   asm volatile("bar.sync 1, %0;" :: "r"(32 * SF_RENDER_WARPS) : "memory");
 }
@@ -214,7 +213,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[0].arc_mask[0][0])[k] = 0u;
   if (threadIdx.x == 0) {
     SfTeamSmem& Tm = B.team[0];
-    Tm.next_task = 0; Tm.netask = 0; Tm.next_stroke = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+    Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
     B.colour_white = T->colour_white;
   }
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
@@ -385,53 +384,10 @@ __device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const 
   __syncwarp();
 }
 
-// add the span [a, b) (24.8, relative to the region's left edge) of one sub-row to the cells of its pixel row.
-// 16-bit cells, 32-bit atomics: a cell never exceeds 15*256, so the two halves of a word cannot carry into each other
-__device__ __forceinline__ void sf_emit_span(unsigned* acc32, int cell0, int a, int b) {
-  // first cell (partial), last cell (partial), full cells in between (only for near-horizontal spans)
-  const int c1 = a >> 8, c2 = (b - 1) >> 8;
-  const int ci = cell0 + c1;
-  const int len1 = min(b, (c1 + 1) << 8) - a;
-  atomicAdd(&acc32[ci >> 1], (unsigned)len1 << ((ci & 1) << 4));
-  if (c2 > c1) {
-    const int cj = cell0 + c2;
-    atomicAdd(&acc32[cj >> 1], (unsigned)(b - (c2 << 8)) << ((cj & 1) << 4));
-    for (int c = c1 + 1; c < c2; c++) { const int cm = cell0 + c; atomicAdd(&acc32[cm >> 1], 256u << ((cm & 1) << 4)); }
-  }
-}
-
-// span of an irregular quad: min / max over the edges that are live on sub-row sb
-__device__ __noinline__ void sf_quad_span_irregular(int qi, int sb, int& lo, int& hi) {
-  const SfWarpSmem& W = sf_my_smem();
-  lo = 1 << 30; hi = -(1 << 30);
-#pragma unroll 1
-  for (int k = 0; k < 4; k++) {
-    const int4 E = W.edge[qi * 4 + k];
-    const int ya = E.y & 0xFFFF, yb = (int)((unsigned)E.y >> 16);
-    if (sb >= min(ya, yb) && sb < max(ya, yb)) { int x = sf_edge_x(E, sb); lo = min(lo, x); hi = max(hi, x); }
-  }
-}
-
-// span of quad q on sub-row sb clipped to [xlo, xhi) and made relative to xlo, packed lo<<16 | hi; SF_SPAN_NONE when
-// the quad has no sample there
-__device__ __forceinline__ unsigned sf_quad_span(const SfWarpSmem& W, int q, int sb, int xlo, int xhi) {
-  const int4 Q = W.qinfo[q];
-  if (sb < (Q.x & 0xFFFF) || sb >= (int)((unsigned)Q.x >> 16)) return SF_SPAN_NONE;
-  int lo, hi;
-  if (Q.z & SF_QF_IRREGULAR) sf_quad_span_irregular(q, sb, lo, hi);
-  else {
-    const int4 Ed = W.edge[q * 4 + (sb >= (Q.y & 0xFFFF) ? 1 : 0)];
-    const int4 Eu = W.edge[q * 4 + 2 + (sb >= (int)((unsigned)Q.y >> 16) ? 1 : 0)];
-    const int xd = sf_edge_x(Ed, sb), xu = sf_edge_x(Eu, sb);
-    lo = min(xd, xu); hi = max(xd, xu);
-  }
-  lo = max(lo, xlo) - xlo; hi = min(hi, xhi) - xlo;
-  return lo < hi ? (((unsigned)lo << 16) | (unsigned)hi) : SF_SPAN_NONE;
-}
-
-// the same for a stroked segment (a parallelogram: opposite edges run in opposite directions, so it is never
-// irregular), branch free: the loads of all quads of a stroke can be in flight together. A quad slot without a quad
-// has g0 == g1 (never live); whatever its edge records hold is evaluated and discarded.
+// Span of quad q (a stroked segment: a parallelogram, opposite edges run in opposite directions, so each side has at
+// most two edges) on sub-row sb, clipped to [xlo, xhi) and made relative to xlo, packed lo<<16 | hi; SF_SPAN_NONE when
+// the quad has no sample there. Branch free: the loads of all quads of a stroke can be in flight together. A quad
+// slot without a quad has g0 == g1 (never live); whatever its edge records hold is evaluated and discarded.
 __device__ __forceinline__ unsigned sf_quad_span_regular(const SfWarpSmem& W, int q, int sb, int xlo, int xhi) {
   const int4 Q = W.qinfo[q];
   const int4 Ed = W.edge[q * 4 + (sb >= (Q.y & 0xFFFF) ? 1 : 0)];
@@ -480,7 +436,8 @@ __device__ __noinline__ void sf_accumulate_pass(int owner, int g0) {
   unsigned k0 = sf_quad_span_regular(W, q0, sb, xlo, xhi);
   unsigned k1 = sf_quad_span_regular(W, q0 + 1, sb, xlo, xhi);
   unsigned k2 = sf_quad_span_regular(W, q0 + 2, sb, xlo, xhi);
-  unsigned k3 = sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi);
+  unsigned k3 = SF_SPAN_NONE;
+  if (__any_sync(0xffffffffu, ((S.x >> 16) & 255) > 3)) k3 = sf_quad_span_regular(W, q0 + 3, sb, xlo, xhi);  // only shells have a 4th segment
   if (!valid) { k0 = SF_SPAN_NONE; k1 = SF_SPAN_NONE; k2 = SF_SPAN_NONE; k3 = SF_SPAN_NONE; }
   // sort by start (none == 0xFFFFFFFF sinks to the end)
   unsigned t0 = min(k0, k1), t1 = max(k0, k1), t2 = min(k2, k3), t3 = max(k2, k3);
@@ -1170,7 +1127,7 @@ __device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, 
     const bool more = Tm.more != 0;  // more envs than this round could take?
     // ---- A: env tasks ----
     if (stepper) {
-      if (lane == 0) { Tm.next_task = 0; Tm.next_stroke = 0; Tm.nregions = 0; Tm.cells_used = 0; }
+      if (lane == 0) { Tm.next_task = 0; Tm.nregions = 0; Tm.cells_used = 0; }
     } else {
 #pragma unroll 1
       for (int e = r0 + wi; e < r1; e += nw) sf_phase_env(D, B, W, lane, e, out);

@@ -230,6 +230,42 @@ def test_frames_from_crafted_states():
     env.close()
 
 
+def test_explosion_all_phases_and_box_cache():
+    """The ship explosion is scan-converted from per-y-phase span tables (csrc/sf_tables.h SfExpPhase): put a dead
+    ship at every one of the 256 sub-pixel y phases (x phases spread over 0..255), with and without wireframes
+    reaching into the explosion box, and compare with the oracle. Rendering the same state again takes the sprite
+    and resampled-box memo paths and must give the same frames."""
+    n = 512
+    env = make("autoturn", n)
+    env.reset()
+    rng = np.random.RandomState(11)
+    recs = []
+    for i in range(n):
+        r = OracleEnv("autoturn", 1).get_state()
+        phy, phx = i % 256, (i * 37 + 11) % 256
+        cx, cy = int(rng.randint(8, 82)) * 256 + phx, int(rng.randint(14, 80)) * 256 + phy   # 24.8 device centre
+        r.ship_x = 5.0 * (cx / 256.0 + 26.0); r.ship_y = 5.0 * (cy / 256.0 + 16.0)           # inverse of the base CTM
+        r.ship_alive = 0; r.ship_angle = float(rng.randint(360))
+        r.fortress_alive = int(i % 7 != 3)
+        r.fortress_angle = float(10 * rng.randint(36)); r.fortress_last_angle = r.fortress_angle
+        if i >= 256:  # missiles flying through the explosion box
+            for s in range(int(rng.randint(1, 4))):
+                r.missile_mask |= 1 << s
+                r.missile_x[s] = r.ship_x + float(rng.uniform(-70, 70)); r.missile_y[s] = r.ship_y + float(rng.uniform(-70, 70)); r.missile_angle[s] = float(rng.randint(360))
+        r.points = float([0, 3][i % 2]); r.vulnerability = int(i % 12)
+        recs.append(r)
+    env.set_state([to_gpu_record(r) for r in recs])
+    obs = env.render_frames(native=False)
+    for i, r in enumerate(recs):
+        assert_frame_close(draw_obs(r), obs[i], ("obs", i, "phase", i % 256))
+    assert np.array_equal(env.render_frames(native=False), obs)   # cached sprite; quarters without wireframes copied
+    assert np.array_equal(env.render_frames(native=False), obs)
+    nat = env.render_frames(native=True)
+    for i in range(0, n, 5):
+        assert_frame_close(draw_native(recs[i]), nat[i], ("native", i))
+    env.close()
+
+
 def test_rollout_equals_stepwise_and_synthetic_stream():
     torch = torch_cuda()
     n, T = 96, 64
