@@ -90,33 +90,10 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
     r.ebox = (((c.x >> 8) - 13) + 64) | ((((c.y >> 8) - 13) + 64) << 8);
   }
   r.life = (unsigned)e.st3.z + 1u;
-  r.building = 0;  // decided by sf_publish_recs, when the frames of the previous tick are done
+  r.building = 0;  // decided by sf_publish_recs
   int vis;
   r.ns = sf_count_strokes(D, env, r.core, r.pmask, &vis);
   r.shell_vis = vis;
-}
-
-// warp 0, after the frames of the previous tick: the staged records become current; a dead ship whose explosion
-// is not the cached one gets it scan-converted this tick
-__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfBlockSmem& B, int lane, bool native) {
-  SfTeamSmem& Tm = sf_team_smem();
-  SfEnvRec r = Tm.env_next[lane];
-  if (r.env >= 0 && !(r.core & SF_CORE_SHIP_ALIVE)) {
-    const unsigned stamp = __ldcg(&D.expstamp[r.env]);  // both loads in flight together
-    const uint2 m = __ldcg(&D.expo_meta[r.env]);
-    r.building = stamp != r.life ? 1 : 0;
-    if (!native) {
-      // which quarters of the resampled explosion box are cached for exactly this life / fortress / bar / score
-      const int fst = (r.core & SF_CORE_FORT_ALIVE) ? (int)((r.core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
-      const int bst = r.kill_bar ? 11 : min(r.vuln, 10);
-      const unsigned key = (unsigned)fst | ((unsigned)bst << 6) | (((unsigned)r.points_i & 0x3FFFFu) << 10);
-      if (!r.building && m.x == r.life && (m.y & 0x0FFFFFFFu) == key) r.building |= (int)(m.y >> 28) << 4;
-      else D.expo_meta[r.env] = make_uint2(r.life, key);
-    }
-  }
-  Tm.env[lane] = r;
-  __syncwarp();
-  sf_round_scan(B, lane, 0);
 }
 
 struct SfRollArgs {
@@ -138,8 +115,7 @@ struct SfRollArgs {
 // warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
 // warps run the block-cooperative frame pipeline (sf_render.cuh).
 // one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
-__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t) {
-  SfBlockSmem& B = sf_block_smem();
+__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfTeamSmem& Tm) {
   const int lane = threadIdx.x & 31;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const int env = group * A.EB + lane;
@@ -166,14 +142,13 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   }
   if (mine) {
     sf_store_env(D, env, e);
-    sf_make_env_rec(D, e, env, sf_team_smem().env_next[lane]);
-  } else sf_team_smem().env_next[lane].env = -1;
+    sf_make_env_rec(D, e, env, Tm.env[lane]);
+  } else Tm.env[lane].env = -1;
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool stepper = warp == 0;
+  const int lane = threadIdx.x & 31;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
@@ -181,19 +156,13 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  // every team of warps renders its own groups, on its own barrier
+  out.obs = A.obs;
+  SfStageState st;
+  st.stage = 0; st.prev_used = 0;
+  // the block is persistent over its groups; the step of tick t + 1 (warp 0) runs while the other warps draw tick t
 #pragma unroll 1
-  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
-    if (stepper) sf_step_group(D, A, group, 0);
-#pragma unroll 1
-    for (int t = 0; t < A.T; t++) {
-      if (stepper) sf_publish_recs(D, B, lane, out.native != 0);
-      out.obs = A.obs + (size_t)t * D.n * out.obs_bytes;
-      // the step of tick t+1 runs while the other warps composite the windows of tick t: it writes the SoA state
-      // and the staged records, which the frames of tick t no longer read
-      sf_block_frames(D, B, W, lane, out, [&]() { if (t + 1 < A.T) sf_step_group(D, A, group, t + 1); });
-    }
-  }
+  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x)
+    sf_block_ticks(D, B, W, lane, out, (size_t)D.n * out.obs_bytes, A.T, st, [&](int t, SfTeamSmem& Tm) { sf_step_group(D, A, group, t, Tm); });
 }
 
 // state-only: one env per thread
@@ -229,7 +198,7 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
 
 // render the current state (Game.draw): the same block-cooperative pipeline without the step
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(SfDev D, unsigned char* obs, int flags, const unsigned char* mask, int EB, int ngroups) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.tab);
@@ -238,21 +207,20 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
   out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = obs;
+  SfStageState st;
+  st.stage = 0; st.prev_used = 0;
 #pragma unroll 1
-  for (int group = blockIdx.x; group < ngroups; group += gridDim.x) {
-    if (warp == 0) {
+  for (int group = blockIdx.x; group < ngroups; group += gridDim.x)
+    sf_block_ticks(D, B, W, lane, out, 0, 1, st, [&](int, SfTeamSmem& Tm) {
       const int env = group * EB + lane;
       const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
       if (mine) {
         SfEnv e;
         sf_load_env(D, env, e);
-        sf_make_env_rec(D, e, env, sf_team_smem().env_next[lane]);
-      } else sf_team_smem().env_next[lane].env = -1;
+        sf_make_env_rec(D, e, env, Tm.env[lane]);
+      } else Tm.env[lane].env = -1;
       __syncwarp();
-      sf_publish_recs(D, B, lane, out.native != 0);
-    }
-    sf_block_frames(D, B, W, lane, out, []() {});
-  }
+    });
 }
 
 __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {

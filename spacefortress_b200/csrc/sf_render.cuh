@@ -76,7 +76,7 @@ struct __align__(16) SfWarpSmem {
   int4 qinfo[SF_BATCH_QUADS];               //  512 B per quad: {g0 | g1<<16 (biased, clipped to the region), splitD | splitU<<16, flags, 0}
   int4 srec[SF_BATCH_QUADS];                //  512 B per stroke slot: {x0 | w<<8 | nq<<16 | quad0<<24, top (biased), first cell, s0 | s1<<16}
   unsigned short glist[SF_MAX_GROUPS];      //  512 B slot | k<<5 : sub-rows s0 + 8k .. s0 + 8k + 7 of a stroke
-  int ngroups, pad0, pad1, pad2;
+  int ngroups, stage, pad1, pad2;           // stage: which of the two SfTeamSmem copies this warp is drawing from
 #ifdef SF_PHASE_TIMING
   long long prof_last, prof_pad;
 #endif
@@ -95,13 +95,20 @@ struct __align__(16) SfEnvRec {
                               // bits 4..7: quarters of its resampled explosion box that are valid in D.expo (copied, not recomputed)
   unsigned life;              // rand() calls consumed when this ship spawned + 1: names the explosion of this life
 };
+// what, besides the explosion itself, lies under a dead ship's explosion box: fortress state | bar state | score
+__device__ __forceinline__ unsigned sf_expo_key(const SfEnvRec& r) {
+  const int fst = (r.core & (1u << 22)) ? (int)((r.core >> 9) & 63u) : 36;   // SF_CORE_FORT_ALIVE, SF_CORE_FANG_SHIFT
+  const int bst = r.kill_bar ? 11 : min(r.vuln, 10);
+  return (unsigned)fst | ((unsigned)bst << 6) | (((unsigned)r.points_i & 0x3FFFFu) << 10);
+}
 // one moving wireframe of the round: desc = kind | angle<<2 | env slot<<12; region = index into the block's list, -1: none
 struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
 
-// the group of envs the block renders this tick, and the pools of the current round
+// One STAGE = one round of one tick of the block's group of envs: the records, the round's stroke list and control
+// values (written by the stepping warp while the previous stage is drawn) and the pools the drawing warps fill.
+// Two copies: stage s is drawn from copy s & 1 while warp 0 prepares stage s + 1 in the other one.
 struct __align__(16) SfTeamSmem {
   SfEnvRec env[SF_GROUP_ENVS];
-  SfEnvRec env_next[SF_GROUP_ENVS];  // records of the next tick (the stepping warp runs one tick ahead of the frames)
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
@@ -131,14 +138,16 @@ struct __align__(16) SfBlockSmem {
   double wf_line[3][4][4];                     // wireframe models
   int wf_nlines[4];
   unsigned colour_white, padc[3];
-  SfTeamSmem team[1];
+  SfTeamSmem team[2];
 };
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
-__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[0]; }
+__device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp);
+// the stage copy this warp is drawing from (drawing warps; warp 0 addresses the copies explicitly)
+__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[sf_warp_smem(threadIdx.x >> 5).stage]; }
 __device__ __forceinline__ void sf_team_sync() {  // every warp of the block (named barrier 1)
   asm volatile("bar.sync 1, %0;" :: "r"(32 * SF_RENDER_WARPS) : "memory");
 }
@@ -209,20 +218,22 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
-  for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[0].cells)[k] = 0u;
-  for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[0].arc_mask[0][0])[k] = 0u;
-  if (threadIdx.x == 0) {
-    SfTeamSmem& Tm = B.team[0];
-    Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
-    B.colour_white = T->colour_white;
+  for (int c = 0; c < 2; c++) {
+    for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[c].cells)[k] = 0u;
+    for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[c].arc_mask[0][0])[k] = 0u;
+    if (threadIdx.x == 0) {
+      SfTeamSmem& Tm = B.team[c];
+      Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+    }
   }
+  if (threadIdx.x == 0) B.colour_white = T->colour_white;
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 }
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
-  if (lane == 0) W.ngroups = 0;
+  if (lane == 0) { W.ngroups = 0; W.stage = 0; }
   __syncwarp();
 }
 
@@ -846,12 +857,12 @@ __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigne
 }
 
 // warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
-__device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_begin) {
-  const bool cand = lane >= r_begin && sf_team_smem().env[lane].env >= 0;
-  const int cnt = cand ? sf_team_smem().env[lane].ns : 0;
+__device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin) {
+  const bool cand = lane >= r_begin && Tm.env[lane].env >= 0;
+  const int cnt = cand ? Tm.env[lane].ns : 0;
   int need = 0;  // worst-case coverage cells of this env's regions
   if (cand) {
-    const SfEnvRec& rec = sf_team_smem().env[lane];
+    const SfEnvRec& rec = Tm.env[lane];
     need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE +
            __popc(rec.shell_vis) * SF_CELLS_SHELL;
   }
@@ -861,15 +872,14 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
     int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, incl_need, o);
     if (lane >= o) { incl += t; incl_need += u; }
   }
-  const unsigned builders = __ballot_sync(0xffffffffu, cand && (sf_team_smem().env[lane].building & 1));
+  const unsigned builders = __ballot_sync(0xffffffffu, cand && (Tm.env[lane].building & 1));
   const unsigned second = builders & (builders - 1);  // a round scan-converts the explosion of at most one env
   const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (second ? ~((second & (0u - second)) - 1u) : 0u);
   const int r1 = over ? __ffs(over) - 1 : 32;
-  if (lane < r1) sf_team_smem().env[lane].s0 = incl - cnt;
+  if (lane < r1) Tm.env[lane].s0 = incl - cnt;
   const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
-  const unsigned later = __ballot_sync(0xffffffffu, lane >= r1 && sf_team_smem().env[lane].env >= 0);
+  const unsigned later = __ballot_sync(0xffffffffu, lane >= r1 && Tm.env[lane].env >= 0);
   if (lane == 0) {
-    SfTeamSmem& Tm = sf_team_smem();
     Tm.more = later != 0u;
     const int nst = r1 > 0 ? total : 0;
     Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = builders ? __ffs(builders) - 1 : -1;
@@ -880,16 +890,16 @@ __device__ __forceinline__ void sf_round_scan(SfBlockSmem& B, int lane, int r_be
   // of a non-zero score (the static base shows "0000000")
   {
     const bool in_round = cand && lane < r1;
-    const bool dead = in_round && !(sf_team_smem().env[lane].core & SF_CORE_SHIP_ALIVE), score = in_round && sf_team_smem().env[lane].points_i > 0;
-    const int qvalid = dead ? (sf_team_smem().env[lane].building >> 4) & 15 : 0;
+    const bool dead = in_round && !(Tm.env[lane].core & SF_CORE_SHIP_ALIVE), score = in_round && Tm.env[lane].points_i > 0;
+    const int qvalid = dead ? (Tm.env[lane].building >> 4) & 15 : 0;
     const int cntt = (dead ? 4 - __popc(qvalid) : 0) + (score ? 1 : 0);
     int inclt = cntt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclt, o); if (lane >= o) inclt += t; }
     int k = inclt - cntt;
-    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) sf_team_smem().etask[k++] = (unsigned short)(lane | (q << 5));
-    if (score) sf_team_smem().etask[k] = (unsigned short)(lane | (4 << 5));
-    if (lane == 31) sf_team_smem().netask = inclt;
+    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) Tm.etask[k++] = (unsigned short)(lane | (q << 5));
+    if (score) Tm.etask[k] = (unsigned short)(lane | (4 << 5));
+    if (lane == 31) Tm.netask = inclt;
   }
   __syncwarp();
 }
@@ -964,40 +974,29 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
   }
 }
 
-// phase A for env slot e (whole warp): its entries of the round's stroke list:
-// [ship] + live missiles (slot order) + visible shells (slot order)
-__device__ __forceinline__ void sf_phase_env(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, const SfFrameOut& out) {
-  const SfEnvRec& rec = sf_team_smem().env[e];
-  const int env = rec.env;
-  if (env < 0) return;
-  const unsigned core = rec.core;
-  const int np = D.n_pad;
-  bool want = false;
-  int kind = 0, angle = 0;
-  double x = 0, y = 0;
-  if (lane == 0) {
-    if (core & SF_CORE_SHIP_ALIVE) { want = true; kind = 0; x = rec.px; y = rec.py; angle = (int)(core & SF_CORE_ANGLE_MASK); }
-  } else if (lane <= SF_MAX_MISSILES) {
-    const int s = lane - 1;
-    if ((rec.pmask >> s) & 1u) {
-      const double2 p = D.mpos[(size_t)s * np + env];
-      want = true; kind = 1; x = p.x; y = p.y; angle = D.mang[(size_t)s * np + env];
+// Stepping warp, after the round scan of the stage it prepares: the stroke list of the round's envs [r0, r1), one
+// env per lane, from the SoA state: [ship] + live missiles (slot order) + visible shells (slot order) == draw order.
+__device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm, int lane) {
+  const SfEnvRec& rec = Tm.env[lane];
+  if (lane >= Tm.r0 && lane < Tm.r1 && rec.env >= 0) {
+    const int env = rec.env, np = D.n_pad;
+    const unsigned core = rec.core;
+    SfStrokeRec* S = &Tm.stroke[rec.s0];
+    if (core & SF_CORE_SHIP_ALIVE) { S->x = rec.px; S->y = rec.py; S->desc = 0 | ((int)(core & SF_CORE_ANGLE_MASK) << 2) | (lane << 12); S->region = -1; S++; }
+    for (unsigned m = rec.pmask & SF_PMASK_MISSILES; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const double2 p = D.mpos[(size_t)k * np + env];
+      S->x = p.x; S->y = p.y; S->desc = 1 | ((int)D.mang[(size_t)k * np + env] << 2) | (lane << 12); S->region = -1; S++;
     }
-  } else if (lane <= SF_MAX_MISSILES + SF_DEV_SHELLS) {
-    const int s = lane - 1 - SF_MAX_MISSILES;
-    if ((rec.shell_vis >> s) & 1) {
-      const double2 p = D.spos[(size_t)s * np + env];
-      want = true; kind = 2; x = p.x; y = p.y;
-      angle = __double2int_rz(D.sang[(size_t)s * np + env]);  // `int angle` truncation, quirk Q10
+    for (unsigned m = (unsigned)rec.shell_vis; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const double2 p = D.spos[(size_t)k * np + env];
+      int angle = __double2int_rz(D.sang[(size_t)k * np + env]);  // `int angle` truncation, quirk Q10
       if (angle >= 360) angle -= 360;
+      S->x = p.x; S->y = p.y; S->desc = 2 | (angle << 2) | (lane << 12); S->region = -1; S++;
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, want);
-  if (want) {
-    SfStrokeRec& S = sf_team_smem().stroke[rec.s0 + __popc(m & ((1u << lane) - 1u))];
-    S.x = x; S.y = y; S.desc = kind | (angle << 2) | (e << 12); S.region = -1;
-  }
-  (void)W; (void)B; (void)out;
+  __syncwarp();
 }
 
 // phase B for this warp. B1: warp wi builds the geometry of batch wi (Tm.chunk consecutive strokes of the round's
@@ -1008,7 +1007,13 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team_smem();
   const int chunk = Tm.chunk;
-  if (Tm.build_env >= 0 && Tm.build_env < Tm.r1) sf_phase_exp_items(D, lane, wi, nw);
+  // B2 first: the explosion of the ship that died this tick (its sprite stamp is then visible to the stepping warp
+  // long before it looks at the next tick)
+  if (Tm.build_env >= 0 && Tm.build_env < Tm.r1) {
+    sf_phase_exp_items(D, lane, wi, nw);
+    sf_render_sync();
+    sf_phase_sprite(D, B, lane, wi, nw);
+  }
   SF_PROF(21);
   const int s = wi * chunk;
   if (s < nst) {
@@ -1081,7 +1086,18 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
   const int env = sf_team_smem().env[e].env;
   const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes,
                                       quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin);
-  if (cached && lane == 0) atomicOr(&D.expo_meta[env].y, 1u << (28 + quarter));
+  if (cached && lane == 0) {
+    // mark the quarter valid, unless the stepping warp has already re-keyed the cache for the next tick
+    const SfEnvRec& rec = sf_team_smem().env[e];
+    const unsigned long long want = (unsigned long long)rec.life | ((unsigned long long)sf_expo_key(rec) << 32);
+    unsigned long long* m = reinterpret_cast<unsigned long long*>(&D.expo_meta[env]);
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(m);
+    while ((old & 0x0FFFFFFFFFFFFFFFull) == want) {
+      const unsigned long long prev = atomicCAS(m, old, old | (1ull << (60 + quarter)));
+      if (prev == old) break;
+      old = prev;
+    }
+  }
   (void)W;
 }
 
@@ -1098,9 +1114,6 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
   __syncwarp();
 }
 
-// All frames of the group. Every thread of the block calls this after warp 0 has written the env records and
-// run sf_round_scan(B, lane, 0); a __syncthreads() has NOT yet been executed. run_ahead() is executed by warp 0
-// at the start of the (first round's) window phase: nothing in that phase reads what the step writes.
 #ifdef SF_PHASE_TIMING
 #define SF_TICK(k) do { if (threadIdx.x == 32 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - t_last_)); t_last_ = now_; } } while (0)
 #define SF_WTICK(k) do { if (lane == 0 && blockIdx.x == 0) { long long now_ = clock64(); atomicAdd(&sf_dbg_cycles[k], (unsigned long long)(now_ - w_last_)); w_last_ = now_; } } while (0)
@@ -1109,107 +1122,161 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 #define SF_WTICK(k) ((void)0)
 #endif
 
-template <class Ahead>
-__device__ __forceinline__ void sf_block_frames(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out, Ahead run_ahead) {
+// warp 0, one env per lane, on the records of the stage being prepared: a dead ship whose explosion sprite is not the
+// cached one gets it built in this tick; which quarters of its resampled explosion box are still valid. Runs while
+// the previous tick is drawn: a sprite stamp or valid bit that is set later than this is read only delays the use of
+// the memo by a tick (the rebuild is idempotent); sf_phase_window sets valid bits with a compare-and-swap against
+// the key, so a key written here is never combined with the bits of another one.
+__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfTeamSmem& Tm, int lane, bool native) {
+  SfEnvRec& r = Tm.env[lane];
+  if (r.env >= 0 && !(r.core & SF_CORE_SHIP_ALIVE)) {
+    const unsigned stamp = __ldcg(&D.expstamp[r.env]);  // both loads in flight together
+    const unsigned long long mw = __ldcg(reinterpret_cast<const unsigned long long*>(&D.expo_meta[r.env]));
+    const unsigned mx = (unsigned)mw, my = (unsigned)(mw >> 32);
+    int building = stamp != r.life ? 1 : 0;
+    if (!native) {
+      const unsigned key = sf_expo_key(r);
+      if (!building && mx == r.life && (my & 0x0FFFFFFFu) == key) building |= (int)(my >> 28) << 4;
+      else atomicExch(reinterpret_cast<unsigned long long*>(&D.expo_meta[r.env]), (unsigned long long)r.life | ((unsigned long long)key << 32));
+    }
+    r.building = building;
+  }
+  __syncwarp();
+}
+
+// what persists from one group of envs to the next in a persistent block
+struct SfStageState {
+  int stage;      // copy (0 / 1) the next stage is drawn from
+  int prev_used;  // coverage cells the previous stage used in the OTHER copy: zeroed while the next stage is drawn
+};
+
+// warp 0: everything the drawing warps need to draw a stage whose env records are in Tm.env: explosion memo state,
+// the round's envs and tasks, its stroke list; the pools restart
+__device__ __forceinline__ void sf_prepare_stage(const SfDev& D, SfTeamSmem& Tm, int lane, int r_begin) {
+  sf_round_scan(Tm, lane, r_begin);
+  sf_gather_strokes(D, Tm, lane);
+  if (lane == 0) { Tm.next_task = 0; Tm.nregions = 0; Tm.cells_used = 0; }
+  __syncwarp();
+}
+
+// One stage drawn by the 15 drawing warps (see the pipeline description above): B1 geometry, B3 passes, base
+// patches, B2 explosion sprite, C windows.
+__device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out) {
   const int warp = threadIdx.x >> 5;
-  const bool stepper = warp == 0;        // warp 0 steps the next tick while the other warps draw this one
   const int wi = warp - 1, nw = SF_RENDER_WARPS - 1;  // index among the drawing warps, and their number
   SfTeamSmem& Tm = sf_team_smem();
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
   const int gwarp = warp;
 #endif
+  const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
+  // ---- B: stroke tasks ----
+  if (!out.native) {
+#pragma unroll 1
+    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
+  }
+  SF_PROF_RESET();
+  sf_phase_strokes(D, B, W, lane, wi, nw, nst);
+  SF_PROF(69);
+  if (!out.native) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
+    __syncwarp();
+    SF_PROF(65);
+#pragma unroll 1
+    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
+    SF_PROF(66);
+  }
+#ifdef SF_PHASE_TIMING
+  if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_b, (int)(clock64() - w_last_)); }
+#endif
+  SF_WTICK(10);
+  sf_render_sync();
+  SF_TICK(2); SF_WTICK(8);
+  // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
+  SF_PROF_RESET();
+  if (!out.native) {
+    const int netask = Tm.netask;
+#pragma unroll 1
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&Tm.next_task, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= netask + nst) break;
+      SF_PROF(29);
+      sf_phase_window(D, B, W, lane, t, netask, out);
+    }
+  } else {
+#pragma unroll 1
+    for (int t = wi; t < (r1 - r0) * 12; t += nw) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
+  }
+#ifdef SF_PHASE_TIMING
+  if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
+  SF_WTICK(11);
+  if (threadIdx.x == 32 && blockIdx.x == 0) {
+    atomicAdd(&sf_dbg_cycles[71], (unsigned long long)Tm.dbg_max_b); atomicAdd(&sf_dbg_cycles[72], (unsigned long long)Tm.dbg_max_c);
+    atomicAdd(&sf_dbg_cycles[73], 1ull); atomicAdd(&sf_dbg_cycles[74], (unsigned long long)(Tm.netask + nst)); atomicAdd(&sf_dbg_cycles[75], (unsigned long long)Tm.netask);
+    atomicAdd(&sf_dbg_cycles[76], (unsigned long long)(Tm.build_env >= 0));
+    Tm.dbg_max_b = 0; Tm.dbg_max_c = 0;
+  }
+#endif
+}
+
+// All frames of T consecutive ticks of one group. Every thread of the block calls this. prep(t, Tm) is executed by
+// warp 0 only and writes the env records of tick t into Tm.env (one env per lane, env = -1: unused); for a rollout
+// it is the step of tick t, which therefore runs while the other warps draw tick t - 1.
+// Stage s (a round of a tick) is drawn from copy s & 1 by the drawing warps while warp 0 prepares stage s + 1 in the
+// other copy; ONE block barrier per stage separates them. Nothing of a stage that is being drawn reads the SoA
+// state, so the step may overwrite it; the strokes of a LATER round of the same tick are gathered (from the state)
+// before the step of the next tick, which runs during the tick's last round.
+template <class Prep>
+__device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, SfFrameOut out, size_t tick_bytes, int T,
+                                               SfStageState& st, Prep prep) {
+  const bool stepper = (threadIdx.x >> 5) == 0;
+  unsigned char* const obs0 = out.obs;
+#ifdef SF_PHASE_TIMING
+  long long t_last_ = clock64(), w_last_ = t_last_;
+#endif
+  if (stepper) {
+    SfTeamSmem& Tm = B.team[st.stage];
+    prep(0, Tm);
+    sf_publish_recs(D, Tm, lane, out.native != 0);
+    sf_prepare_stage(D, Tm, lane, 0);
+  }
+  int t = 0;
 #pragma unroll 1
   for (;;) {
-    sf_team_sync();  // records + scan visible
+    sf_team_sync();  // the stage is prepared; every warp is done with the previous one
     SF_TICK(0); SF_WTICK(8);
-    const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
-    const bool more = Tm.more != 0;  // more envs than this round could take?
-    // ---- A: env tasks ----
+    SfTeamSmem& Tm = B.team[st.stage];
+    SfTeamSmem& Nx = B.team[st.stage ^ 1];
+    const bool more = Tm.more != 0;            // more envs of the group than this round could take?
+    const bool last = !more && t + 1 >= T;
     if (stepper) {
-      if (lane == 0) { Tm.next_task = 0; Tm.nregions = 0; Tm.cells_used = 0; }
-    } else {
-#pragma unroll 1
-      for (int e = r0 + wi; e < r1; e += nw) sf_phase_env(D, B, W, lane, e, out);
-    }
-    SF_WTICK(9);
-    sf_team_sync();
-    SF_TICK(1); SF_WTICK(8);
-    if (stepper) {
-      // The step writes the SoA state and the staged records, which nothing of this tick reads after phase A. Phase A
-      // of every round reads the projectile positions from the SoA state: only the LAST round may overlap the step.
       SF_PROF_RESET();
-      if (!more) { run_ahead(); SF_PROF(70); }
-    } else {
-      // ---- B: stroke tasks from the block's queue ----
-      if (!out.native) {
-#pragma unroll 1
-        for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
-      }
-      SF_PROF_RESET();
-      sf_phase_strokes(D, B, W, lane, wi, nw, nst);
-      SF_PROF(69);
-      if (!out.native) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
+      if (more) {
+        Nx.env[lane] = Tm.env[lane];
         __syncwarp();
-        SF_PROF(65);
-#pragma unroll 1
-        for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
-        SF_PROF(66);
+        sf_prepare_stage(D, Nx, lane, Tm.r1);
+      } else if (!last) {
+        prep(t + 1, Nx);
+        SF_PROF(70);
+        sf_publish_recs(D, Nx, lane, out.native != 0);
+        sf_prepare_stage(D, Nx, lane, 0);
       }
-#ifdef SF_PHASE_TIMING
-      if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[32 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_b, (int)(clock64() - w_last_)); }
-#endif
-      SF_WTICK(10);
-      sf_render_sync();
-      SF_TICK(2); SF_WTICK(8);
-      // ---- B2: the sprite of the explosion whose arcs were scan-converted in B ----
-      if (Tm.build_env >= 0 && Tm.build_env < r1) {
-        sf_phase_sprite(D, B, lane, wi, nw);
-        SF_WTICK(10);
-        sf_render_sync();
-        SF_WTICK(8);
+    } else {
+      if (lane == 0) W.stage = st.stage;
+      __syncwarp();
+      // zero the coverage cells of the stage before this one (the other copy)
+      {
+        const int nz = (st.prev_used + 1) >> 1;
+        for (int k = threadIdx.x - 32; k < nz; k += 32 * (SF_RENDER_WARPS - 1)) reinterpret_cast<unsigned*>(Nx.cells)[k] = 0u;
       }
-      // ---- C: window tasks, handed out first come first served (env tasks first: the big ones) ----
-      SF_PROF_RESET();
-      if (!out.native) {
-        const int netask = Tm.netask;
-#pragma unroll 1
-        for (;;) {
-          int t = 0;
-          if (lane == 0) t = atomicAdd(&Tm.next_task, 1);
-          t = __shfl_sync(0xffffffffu, t, 0);
-          if (t >= netask + nst) break;
-          SF_PROF(29);
-          sf_phase_window(D, B, W, lane, t, netask, out);
-        }
-      } else {
-#pragma unroll 1
-        for (int t = wi; t < (r1 - r0) * 12; t += nw) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
-      }
-#ifdef SF_PHASE_TIMING
-      if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
-#endif
-      SF_WTICK(11);
+      out.obs = obs0 + (size_t)t * tick_bytes;
+      sf_draw_stage(D, B, W, lane, out);
+      st.prev_used = Tm.cells_used;
     }
-    sf_team_sync();  // every warp is done reading the cells; the step of the next tick is done
-    SF_TICK(3); SF_WTICK(8);
-#ifdef SF_PHASE_TIMING
-    if (threadIdx.x == 32 && blockIdx.x == 0) {
-      atomicAdd(&sf_dbg_cycles[71], (unsigned long long)Tm.dbg_max_b); atomicAdd(&sf_dbg_cycles[72], (unsigned long long)Tm.dbg_max_c);
-      atomicAdd(&sf_dbg_cycles[73], 1ull); atomicAdd(&sf_dbg_cycles[74], (unsigned long long)(Tm.netask + nst)); atomicAdd(&sf_dbg_cycles[75], (unsigned long long)Tm.netask);
-      atomicAdd(&sf_dbg_cycles[76], (unsigned long long)(Tm.build_env >= 0));
-      Tm.dbg_max_b = 0; Tm.dbg_max_c = 0;
-    }
-#endif
-    // zero the coverage cells handed out this round (the queues and pools restart in phase A of the next round: at
-    // least one barrier away from here and from their next use)
-    {
-      const int nz = (Tm.cells_used + 1) >> 1;
-      for (int k = threadIdx.x; k < nz; k += blockDim.x) reinterpret_cast<unsigned*>(Tm.cells)[k] = 0u;
-    }
-    if (!more) break;
-    sf_team_sync();  // everybody has read r1 / the records
-    if (stepper) sf_round_scan(B, lane, r1);
+    st.stage ^= 1;
+    if (!more) t++;
+    if (last) break;
   }
 }
