@@ -115,7 +115,7 @@ struct SfRollArgs {
 // warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
 // warps run the block-cooperative frame pipeline (sf_render.cuh).
 // one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
-__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfTeamSmem& Tm) {
+__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfEnvRec* recs) {
   const int lane = threadIdx.x & 31;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const int env = group * A.EB + lane;
@@ -142,8 +142,8 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   }
   if (mine) {
     sf_store_env(D, env, e);
-    sf_make_env_rec(D, e, env, Tm.env[lane]);
-  } else Tm.env[lane].env = -1;
+    sf_make_env_rec(D, e, env, recs[lane]);
+  } else recs[lane].env = -1;
   __syncwarp();
 }
 
@@ -157,12 +157,13 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = A.obs;
+  out.tick_bytes = (size_t)D.n * out.obs_bytes;
   SfStageState st;
   st.stage = 0; st.prev_used = 0;
   // the block is persistent over its groups; the step of tick t + 1 (warp 0) runs while the other warps draw tick t
 #pragma unroll 1
   for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x)
-    sf_block_ticks(D, B, W, lane, out, (size_t)D.n * out.obs_bytes, A.T, st, [&](int t, SfTeamSmem& Tm) { sf_step_group(D, A, group, t, Tm); });
+    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, group, t, &Tm.env[32 * h]); });
 }
 
 // state-only: one env per thread
@@ -207,11 +208,12 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
   out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = obs;
+  out.tick_bytes = 0;
   SfStageState st;
   st.stage = 0; st.prev_used = 0;
 #pragma unroll 1
   for (int group = blockIdx.x; group < ngroups; group += gridDim.x)
-    sf_block_ticks(D, B, W, lane, out, 0, 1, st, [&](int, SfTeamSmem& Tm) {
+    sf_block_ticks(D, B, W, lane, out, 1, st, [&](int, SfTeamSmem& Tm, int) {
       const int env = group * EB + lane;
       const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
       if (mine) {

@@ -53,6 +53,10 @@
 #endif
 #define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
 #define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
+#ifndef SF_STAGE_TICKS
+#define SF_STAGE_TICKS 2                         // consecutive ticks of the group drawn together in one stage (1 or 2)
+#endif
+#define SF_STAGE_SLOTS (SF_GROUP_ENVS * SF_STAGE_TICKS)  // env slot = 32 * (tick within the stage) + lane of the env
 #define SF_ROUND_STROKES (8 * (SF_RENDER_WARPS - 1))  // strokes pooled per round: one batch of <= 8 per drawing warp (a round takes as many envs of the group as fit)
 // Block-wide pools of a round: one region (bounding box in native pixels + coverage cells) per visible stroke.
 // The round scan admits envs by WORST-CASE need, so the pools cannot overflow: a ship wireframe spans at most
@@ -108,14 +112,14 @@ struct __align__(8) SfStrokeRec { double x, y; int desc, region; };
 // values (written by the stepping warp while the previous stage is drawn) and the pools the drawing warps fill.
 // Two copies: stage s is drawn from copy s & 1 while warp 0 prepares stage s + 1 in the other one.
 struct __align__(16) SfTeamSmem {
-  SfEnvRec env[SF_GROUP_ENVS];
+  SfEnvRec env[SF_STAGE_SLOTS];
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
   int next_task, netask, pad_q, chunk;  // phase C work queue; env tasks of the round; strokes per batch of phase B1
-  int more, padm0, padm1, padm2;     // envs of the group are left for another round
+  int more, nticks, padm1, padm2;    // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS)
   int nregions, cells_used, dbg_max_b, dbg_max_c;
-  unsigned short etask[SF_GROUP_ENVS * 5];  // env slot | kind<<5: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
+  unsigned short etask[SF_STAGE_SLOTS * 5];  // env slot | kind<<6: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   unsigned short exp_len[SF_EXPT_ITEMS][SF_EXPT_NC];  // build: summed span lengths of the (quad, pixel row) items of the explosion, per cell
   alignas(16) unsigned arc_mask[SF_EXP_W * SF_EXP_W][4];  // build: per pixel of the explosion box, the quads that cover it (zero between builds)
   alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
@@ -838,10 +842,15 @@ __device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, 
 //                    (reading the cells of whichever warp scan-converted them) + resample + overwrite the pixels
 // ================================================================================================================
 struct SfFrameOut {
-  unsigned char* obs;   // frames of this tick, env-major
+  unsigned char* obs;   // frames of the stage's first tick, env-major
   size_t obs_bytes;     // 84*84 or 92*90
+  size_t tick_bytes;    // from one tick's frames to the next one's
   int native;           // 92x90 output (SSF_Env.step)
 };
+// frame of env slot e (tick e >> 5 of the stage) whose env index is `env`
+__device__ __forceinline__ unsigned char* sf_frame_ptr(const SfFrameOut& out, int e, int env) {
+  return out.obs + (size_t)(e >> 5) * out.tick_bytes + (size_t)env * out.obs_bytes;
+}
 
 // per-env stroke count (written by the env's lane before the scan)
 __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigned core, unsigned pmask, int* shell_vis) {
@@ -857,49 +866,60 @@ __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigne
 }
 
 // warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
-__device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin) {
-  const bool cand = lane >= r_begin && Tm.env[lane].env >= 0;
-  const int cnt = cand ? Tm.env[lane].ns : 0;
-  int need = 0;  // worst-case coverage cells of this env's regions
-  if (cand) {
-    const SfEnvRec& rec = Tm.env[lane];
-    need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE +
-           __popc(rec.shell_vis) * SF_CELLS_SHELL;
-  }
-  int incl = cnt, incl_need = need;
+__device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin, int nslots) {
+  int carry_cnt = 0, carry_need = 0, carry_task = 0;
+  int r1 = nslots, nst = 0, build_env = -1, nbuilders = 0;
+  bool closed = false;   // the round's last slot is known
+  unsigned later_any = 0u;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, incl_need, o);
-    if (lane >= o) { incl += t; incl_need += u; }
-  }
-  const unsigned builders = __ballot_sync(0xffffffffu, cand && (Tm.env[lane].building & 1));
-  const unsigned second = builders & (builders - 1);  // a round scan-converts the explosion of at most one env
-  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (second ? ~((second & (0u - second)) - 1u) : 0u);
-  const int r1 = over ? __ffs(over) - 1 : 32;
-  if (lane < r1) Tm.env[lane].s0 = incl - cnt;
-  const int total = __shfl_sync(0xffffffffu, incl, max(r1 - 1, 0));
-  const unsigned later = __ballot_sync(0xffffffffu, lane >= r1 && Tm.env[lane].env >= 0);
-  if (lane == 0) {
-    Tm.more = later != 0u;
-    const int nst = r1 > 0 ? total : 0;
-    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = builders ? __ffs(builders) - 1 : -1;
-    // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
-    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
-  }
-  // window tasks of the round that do not belong to a stroke: 4 quarters of a dead ship's explosion box, the strip
-  // of a non-zero score (the static base shows "0000000")
-  {
-    const bool in_round = cand && lane < r1;
-    const bool dead = in_round && !(Tm.env[lane].core & SF_CORE_SHIP_ALIVE), score = in_round && Tm.env[lane].points_i > 0;
-    const int qvalid = dead ? (Tm.env[lane].building >> 4) & 15 : 0;
+  for (int h = 0; h < SF_STAGE_TICKS; h++) {
+    const int slot = 32 * h + lane;
+    SfEnvRec& rec = Tm.env[slot];
+    const bool cand = slot >= r_begin && slot < nslots && rec.env >= 0;
+    const int cnt = cand ? rec.ns : 0;
+    int need = 0;  // worst-case coverage cells of this env's regions
+    if (cand) need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE + __popc(rec.shell_vis) * SF_CELLS_SHELL;
+    int incl = cnt, incl_need = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, incl_need, o);
+      if (lane >= o) { incl += t; incl_need += u; }
+    }
+    incl += carry_cnt; incl_need += carry_need;
+    const unsigned builders = __ballot_sync(0xffffffffu, cand && (rec.building & 1));
+    // a round builds the explosion of at most one env: the round ends before the second builder
+    const unsigned second = nbuilders ? builders : (builders & (builders - 1));
+    const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (second ? ~((second & (0u - second)) - 1u) : 0u);
+    if (!closed && over) { r1 = 32 * h + __ffs(over) - 1; closed = true; }
+    if (build_env < 0 && builders) build_env = 32 * h + __ffs(builders) - 1;
+    nbuilders += __popc(builders);
+    const bool in_round = cand && slot < r1;
+    if (in_round) rec.s0 = incl - cnt;
+    // strokes of the round = inclusive count of its last slot
+    const unsigned inr = __ballot_sync(0xffffffffu, in_round);
+    if (inr) nst = __shfl_sync(0xffffffffu, incl, 31 - __clz((int)inr));
+    later_any |= __ballot_sync(0xffffffffu, cand && slot >= r1);
+    carry_cnt = __shfl_sync(0xffffffffu, incl, 31); carry_need = __shfl_sync(0xffffffffu, incl_need, 31);
+    // window tasks of the round that do not belong to a stroke: the stale quarters of a dead ship's explosion box,
+    // the strip of a non-zero score (the static base shows "0000000")
+    const bool dead = in_round && !(rec.core & SF_CORE_SHIP_ALIVE), score = in_round && rec.points_i > 0;
+    const int qvalid = dead ? (rec.building >> 4) & 15 : 0;
     const int cntt = (dead ? 4 - __popc(qvalid) : 0) + (score ? 1 : 0);
     int inclt = cntt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclt, o); if (lane >= o) inclt += t; }
+    inclt += carry_task;
     int k = inclt - cntt;
-    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) Tm.etask[k++] = (unsigned short)(lane | (q << 5));
-    if (score) Tm.etask[k] = (unsigned short)(lane | (4 << 5));
-    if (lane == 31) Tm.netask = inclt;
+    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) Tm.etask[k++] = (unsigned short)(slot | (q << 6));
+    if (score) Tm.etask[k] = (unsigned short)(slot | (4 << 6));
+    carry_task = __shfl_sync(0xffffffffu, inclt, 31);
+  }
+  if (lane == 0) {
+    Tm.more = later_any != 0u;
+    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = (build_env >= 0 && build_env < r1) ? build_env : -1;
+    // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
+    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
+    Tm.netask = carry_task;
   }
   __syncwarp();
 }
@@ -910,7 +930,7 @@ __device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane
   const int env = sf_team_smem().env[e].env;
   if (env < 0 || lane != 0) return;
   const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
-  unsigned char* gb = out.obs + (size_t)env * out.obs_bytes;
+  unsigned char* gb = sf_frame_ptr(out, e, env);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -925,7 +945,7 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
   const unsigned core = rec.core;
   const int fst = (core & SF_CORE_FORT_ALIVE) ? (int)((core >> SF_CORE_FANG_SHIFT) & 63u) : 36;
   const int bst = rec.kill_bar ? 11 : min(rec.vuln, 10);
-  int4* g = reinterpret_cast<int4*>(out.obs + (size_t)env * out.obs_bytes);
+  int4* g = reinterpret_cast<int4*>(sf_frame_ptr(out, e, env));
   const int4* ft = reinterpret_cast<const int4*>(T->obs_fort[fst]);
   const int fc0 = T->fort_chunk0;
   // lanes 0..15: fortress chunks (index list in shared memory), lanes 0..20: bar chunks; both loads in flight
@@ -952,7 +972,7 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
       const int j0 = B.col_out0[x0], j1 = B.col_out1[x1], i0 = B.row_out0[y0], i1 = B.row_out1[y1];
       const int hb = (i1 - i0 + 4) >> 2, ow = j1 - j0 + 1, oh = i1 - i0 + 1;
       const unsigned* src = reinterpret_cast<const unsigned*>(D.expo + (size_t)env * SF_EXPO_BYTES);
-      unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + i0 * 84 + j0;
+      unsigned char* dst = sf_frame_ptr(out, e, env) + i0 * 84 + j0;
       unsigned v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -974,26 +994,28 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
   }
 }
 
-// Stepping warp, after the round scan of the stage it prepares: the stroke list of the round's envs [r0, r1), one
-// env per lane, from the SoA state: [ship] + live missiles (slot order) + visible shells (slot order) == draw order.
-__device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm, int lane) {
-  const SfEnvRec& rec = Tm.env[lane];
-  if (lane >= Tm.r0 && lane < Tm.r1 && rec.env >= 0) {
+// Stepping warp, after the round scan of the stage it prepares: the strokes of the round's slots of tick `h` of the
+// stage, one env per lane, from the SoA state (which holds exactly that tick): [ship] + live missiles (slot order) +
+// visible shells (slot order) == draw order.
+__device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm, int lane, int h) {
+  const int slot = 32 * h + lane;
+  const SfEnvRec& rec = Tm.env[slot];
+  if (slot >= Tm.r0 && slot < Tm.r1 && rec.env >= 0) {
     const int env = rec.env, np = D.n_pad;
     const unsigned core = rec.core;
     SfStrokeRec* S = &Tm.stroke[rec.s0];
-    if (core & SF_CORE_SHIP_ALIVE) { S->x = rec.px; S->y = rec.py; S->desc = 0 | ((int)(core & SF_CORE_ANGLE_MASK) << 2) | (lane << 12); S->region = -1; S++; }
+    if (core & SF_CORE_SHIP_ALIVE) { S->x = rec.px; S->y = rec.py; S->desc = 0 | ((int)(core & SF_CORE_ANGLE_MASK) << 2) | (slot << 12); S->region = -1; S++; }
     for (unsigned m = rec.pmask & SF_PMASK_MISSILES; m; m &= m - 1) {
       const int k = __ffs(m) - 1;
       const double2 p = D.mpos[(size_t)k * np + env];
-      S->x = p.x; S->y = p.y; S->desc = 1 | ((int)D.mang[(size_t)k * np + env] << 2) | (lane << 12); S->region = -1; S++;
+      S->x = p.x; S->y = p.y; S->desc = 1 | ((int)D.mang[(size_t)k * np + env] << 2) | (slot << 12); S->region = -1; S++;
     }
     for (unsigned m = (unsigned)rec.shell_vis; m; m &= m - 1) {
       const int k = __ffs(m) - 1;
       const double2 p = D.spos[(size_t)k * np + env];
       int angle = __double2int_rz(D.sang[(size_t)k * np + env]);  // `int angle` truncation, quirk Q10
       if (angle >= 360) angle -= 360;
-      S->x = p.x; S->y = p.y; S->desc = 2 | (angle << 2) | (lane << 12); S->region = -1; S++;
+      S->x = p.x; S->y = p.y; S->desc = 2 | (angle << 2) | (slot << 12); S->region = -1; S++;
     }
   }
   __syncwarp();
@@ -1056,8 +1078,8 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
   int e, j0, i0, j1, i1;
   int quarter = -1, corigin = 0;
   if (t < netask) {
-    const int et = sf_team_smem().etask[t], kind = et >> 5;
-    e = et & 31;
+    const int et = sf_team_smem().etask[t], kind = et >> 6;
+    e = et & 63;
     const SfEnvRec& rec = sf_team_smem().env[e];
     int x0, y0, x1, y1;
     if (kind < 4) {  // dead ship: a quarter (in output rows) of the explosion box
@@ -1084,7 +1106,7 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
     j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
   const int env = sf_team_smem().env[e].env;
-  const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, out.obs + (size_t)env * out.obs_bytes,
+  const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, sf_frame_ptr(out, e, env),
                                       quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin);
   if (cached && lane == 0) {
     // mark the quarter valid, unless the stepping warp has already re-keyed the cache for the next tick
@@ -1109,7 +1131,7 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
   const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
   (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win);
-  unsigned char* dst = out.obs + (size_t)env * out.obs_bytes + ty * SF_NAT_W + tx;
+  unsigned char* dst = sf_frame_ptr(out, e, env) + ty * SF_NAT_W + tx;
   sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
   __syncwarp();
 }
@@ -1127,16 +1149,19 @@ __device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem
 // the previous tick is drawn: a sprite stamp or valid bit that is set later than this is read only delays the use of
 // the memo by a tick (the rebuild is idempotent); sf_phase_window sets valid bits with a compare-and-swap against
 // the key, so a key written here is never combined with the bits of another one.
-__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfTeamSmem& Tm, int lane, bool native) {
-  SfEnvRec& r = Tm.env[lane];
+__device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfTeamSmem& Tm, int lane, int h, bool native) {
+  SfEnvRec& r = Tm.env[32 * h + lane];
   if (r.env >= 0 && !(r.core & SF_CORE_SHIP_ALIVE)) {
     const unsigned stamp = __ldcg(&D.expstamp[r.env]);  // both loads in flight together
     const unsigned long long mw = __ldcg(reinterpret_cast<const unsigned long long*>(&D.expo_meta[r.env]));
     const unsigned mx = (unsigned)mw, my = (unsigned)(mw >> 32);
     int building = stamp != r.life ? 1 : 0;
+    // second tick of the stage: the ship died in the first one, whose slot builds the sprite for both
+    if (h > 0 && building && !(Tm.env[lane].core & SF_CORE_SHIP_ALIVE) && Tm.env[lane].env == r.env && Tm.env[lane].life == r.life) building = 0;
     if (!native) {
       const unsigned key = sf_expo_key(r);
-      if (!building && mx == r.life && (my & 0x0FFFFFFFu) == key) building |= (int)(my >> 28) << 4;
+      const bool same = mx == r.life && (my & 0x0FFFFFFFu) == key;
+      if (same) { if (!building) building |= (int)(my >> 28) << 4; }
       else atomicExch(reinterpret_cast<unsigned long long*>(&D.expo_meta[r.env]), (unsigned long long)r.life | ((unsigned long long)key << 32));
     }
     r.building = building;
@@ -1150,13 +1175,34 @@ struct SfStageState {
   int prev_used;  // coverage cells the previous stage used in the OTHER copy: zeroed while the next stage is drawn
 };
 
-// warp 0: everything the drawing warps need to draw a stage whose env records are in Tm.env: explosion memo state,
-// the round's envs and tasks, its stroke list; the pools restart
-__device__ __forceinline__ void sf_prepare_stage(const SfDev& D, SfTeamSmem& Tm, int lane, int r_begin) {
-  sf_round_scan(Tm, lane, r_begin);
-  sf_gather_strokes(D, Tm, lane);
+// warp 0: restart the pools of the copy whose stage it has just prepared
+__device__ __forceinline__ void sf_restart_pools(SfTeamSmem& Tm, int lane) {
   if (lane == 0) { Tm.next_task = 0; Tm.nregions = 0; Tm.cells_used = 0; }
   __syncwarp();
+}
+
+// warp 0: the first round of a new stage in Tm: up to SF_STAGE_TICKS consecutive ticks starting at tick t (nt of them
+// are left). prep(t, Tm, h) writes the env records of tick t into slots 32h .. 32h + 31 and leaves the SoA state at
+// that tick. The strokes of a tick are gathered from the state before it moves on, so the first tick must fit the
+// round in one piece; if it does not, the stage covers that tick only (and takes several rounds).
+template <class Prep>
+__device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, SfTeamSmem& Tm, int lane, int t, int nt, bool native, Prep prep) {
+  prep(t, Tm, 0);
+  sf_publish_recs(D, Tm, lane, 0, native);
+  sf_round_scan(Tm, lane, 0, SF_GROUP_ENVS);
+  sf_gather_strokes(D, Tm, lane, 0);
+  int nticks = 1;
+#if SF_STAGE_TICKS > 1
+  if (nt > 1 && !Tm.more) {
+    prep(t + 1, Tm, 1);
+    sf_publish_recs(D, Tm, lane, 1, native);
+    sf_round_scan(Tm, lane, 0, 2 * SF_GROUP_ENVS);
+    sf_gather_strokes(D, Tm, lane, 1);
+    nticks = 2;
+  }
+#endif
+  if (lane == 0) Tm.nticks = nticks;
+  sf_restart_pools(Tm, lane);
 }
 
 // One stage drawn by the 15 drawing warps (see the pipeline description above): B1 geometry, B3 passes, base
@@ -1221,27 +1267,21 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
 #endif
 }
 
-// All frames of T consecutive ticks of one group. Every thread of the block calls this. prep(t, Tm) is executed by
-// warp 0 only and writes the env records of tick t into Tm.env (one env per lane, env = -1: unused); for a rollout
-// it is the step of tick t, which therefore runs while the other warps draw tick t - 1.
-// Stage s (a round of a tick) is drawn from copy s & 1 by the drawing warps while warp 0 prepares stage s + 1 in the
-// other copy; ONE block barrier per stage separates them. Nothing of a stage that is being drawn reads the SoA
-// state, so the step may overwrite it; the strokes of a LATER round of the same tick are gathered (from the state)
-// before the step of the next tick, which runs during the tick's last round.
+// All frames of T consecutive ticks of one group. Every thread of the block calls this. prep(t, Tm, h) is executed by
+// warp 0 only and writes the env records of tick t into Tm.env[32h ..] (one env per lane, env = -1: unused); for a
+// rollout it is the step of tick t, which therefore runs while the other warps draw the ticks before it.
+// A STAGE is a round of up to SF_STAGE_TICKS consecutive ticks. Stage s is drawn from copy s & 1 by the drawing warps
+// while warp 0 prepares stage s + 1 in the other copy; ONE block barrier per stage separates them. Nothing of a
+// stage that is being drawn reads the SoA state, so the steps may overwrite it; the strokes of a LATER round of the
+// same stage are gathered (from the state, which still holds the stage's last tick) before the next step.
 template <class Prep>
-__device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, SfFrameOut out, size_t tick_bytes, int T,
-                                               SfStageState& st, Prep prep) {
+__device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, SfFrameOut out, int T, SfStageState& st, Prep prep) {
   const bool stepper = (threadIdx.x >> 5) == 0;
   unsigned char* const obs0 = out.obs;
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
 #endif
-  if (stepper) {
-    SfTeamSmem& Tm = B.team[st.stage];
-    prep(0, Tm);
-    sf_publish_recs(D, Tm, lane, out.native != 0);
-    sf_prepare_stage(D, Tm, lane, 0);
-  }
+  if (stepper) sf_prepare_first_round(D, B.team[st.stage], lane, 0, T, out.native != 0, prep);
   int t = 0;
 #pragma unroll 1
   for (;;) {
@@ -1249,19 +1289,22 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
     SF_TICK(0); SF_WTICK(8);
     SfTeamSmem& Tm = B.team[st.stage];
     SfTeamSmem& Nx = B.team[st.stage ^ 1];
-    const bool more = Tm.more != 0;            // more envs of the group than this round could take?
-    const bool last = !more && t + 1 >= T;
+    const bool more = Tm.more != 0;            // more env slots in the stage than this round could take?
+    const int nticks = Tm.nticks;
+    const bool last = !more && t + nticks >= T;
     if (stepper) {
       SF_PROF_RESET();
       if (more) {
-        Nx.env[lane] = Tm.env[lane];
+#pragma unroll
+        for (int h = 0; h < SF_STAGE_TICKS; h++) Nx.env[32 * h + lane] = Tm.env[32 * h + lane];
+        if (lane == 0) Nx.nticks = nticks;
         __syncwarp();
-        sf_prepare_stage(D, Nx, lane, Tm.r1);
+        sf_round_scan(Nx, lane, Tm.r1, SF_GROUP_ENVS * nticks);
+        sf_gather_strokes(D, Nx, lane, nticks - 1);  // the slots that are left are of the stage's last tick (see above)
+        sf_restart_pools(Nx, lane);
       } else if (!last) {
-        prep(t + 1, Nx);
+        sf_prepare_first_round(D, Nx, lane, t + nticks, T - (t + nticks), out.native != 0, prep);
         SF_PROF(70);
-        sf_publish_recs(D, Nx, lane, out.native != 0);
-        sf_prepare_stage(D, Nx, lane, 0);
       }
     } else {
       if (lane == 0) W.stage = st.stage;
@@ -1271,12 +1314,12 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
         const int nz = (st.prev_used + 1) >> 1;
         for (int k = threadIdx.x - 32; k < nz; k += 32 * (SF_RENDER_WARPS - 1)) reinterpret_cast<unsigned*>(Nx.cells)[k] = 0u;
       }
-      out.obs = obs0 + (size_t)t * tick_bytes;
+      out.obs = obs0 + (size_t)t * out.tick_bytes;
       sf_draw_stage(D, B, W, lane, out);
       st.prev_used = Tm.cells_used;
     }
     st.stage ^= 1;
-    if (!more) t++;
+    if (!more) t += nticks;
     if (last) break;
   }
 }
