@@ -49,7 +49,7 @@
 #define SF_QF_IRREGULAR 2    // quad flag: not a 2+2 edge split, test all four edges
 
 #ifndef SF_RENDER_WARPS
-#define SF_RENDER_WARPS 16   // warps per block (one block per SM)
+#define SF_RENDER_WARPS 24   // warps per block (one block per SM): warp 0 steps, the others draw; 80 registers per thread
 #endif
 #define SF_FORT_LIST_SMEM 48                     // lit pixels of a fortress sprite kept in shared memory (the sprites have <= 42)
 #define SF_GROUP_ENVS 32                         // envs a block renders per tick: one per lane of the stepping warp
@@ -117,7 +117,7 @@ struct __align__(16) SfTeamSmem {
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
   int next_task, netask, pad_q, chunk;  // phase C work queue; env tasks of the round; strokes per batch of phase B1
-  int more, nticks, padm1, padm2;    // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS)
+  int more, nticks, build_env2, padm2;    // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS)
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_STAGE_SLOTS * 5];  // env slot | kind<<6: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   unsigned short exp_len[SF_EXPT_ITEMS][SF_EXPT_NC];  // build: summed span lengths of the (quad, pixel row) items of the explosion, per cell
@@ -753,9 +753,9 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 // the tables of its y phase (SfExpPhase, sf_tables.h): one lane per (quad, pixel row) item adds the <= 15 tabulated
 // spans of the item, shifted by the centre's x, into the item's <= SF_EXPT_NC cells (registers: nobody else adds to
 // them) and tells every pixel it covers which quad did. wi / nw: this warp's index among the drawing warps.
-__device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int lane, int wi, int nw) {
+__device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int be, int lane, int wi, int nw) {
   SfTeamSmem& Tm = sf_team_smem();
-  const SfEnvRec& rec = Tm.env[Tm.build_env];
+  const SfEnvRec& rec = Tm.env[be];
   const SfPt c = sf_xform_base(rec.px, rec.py);
   const SfExpPhase& P = D.tab->exp_phase[c.y & 255];
   const int Y = c.y >> 8, bx0 = (c.x >> 8) - 13, by0 = Y - 13;  // the explosion box (sf_make_env_rec)
@@ -793,10 +793,10 @@ __device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int lane, int
 // the strokes that cover the pixel, in stroke order (arc s == quad s; the 16 chords of the circle, quads 84..99,
 // are ONE stroke: their lengths add up), over the background (hexagons) and stores the sprite in the env's cache;
 // the windows of phase C read it like any cached sprite. wi / nw: this warp's index among the drawing warps.
-__device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int lane, int wi, int nw) {
+__device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int be, int lane, int wi, int nw) {
   SfTeamSmem& Tm = sf_team_smem();
   const SfTables* T = D.tab;
-  SfEnvRec& rec = Tm.env[Tm.build_env];
+  SfEnvRec& rec = Tm.env[be];
   const SfPt c = sf_xform_base(rec.px, rec.py);
   const SfExpPhase& P = T->exp_phase[c.y & 255];
   const int Y = c.y >> 8, bx0 = (c.x >> 8) - 13, by0 = Y - 13;
@@ -868,7 +868,7 @@ __device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigne
 // warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
 __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin, int nslots) {
   int carry_cnt = 0, carry_need = 0, carry_task = 0;
-  int r1 = nslots, nst = 0, build_env = -1, nbuilders = 0;
+  int r1 = nslots, nst = 0, build_env = -1, build_env2 = -1, nbuilders = 0;
   bool closed = false;   // the round's last slot is known
   unsigned later_any = 0u;
 #pragma unroll
@@ -887,11 +887,15 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
     }
     incl += carry_cnt; incl_need += carry_need;
     const unsigned builders = __ballot_sync(0xffffffffu, cand && (rec.building & 1));
-    // a round builds the explosion of at most one env: the round ends before the second builder
-    const unsigned second = nbuilders ? builders : (builders & (builders - 1));
-    const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (second ? ~((second & (0u - second)) - 1u) : 0u);
+    // a round builds the explosions of at most two envs: the round ends before the third builder
+    unsigned third = builders;
+    for (int k = nbuilders; k < 2 && third; k++) third &= third - 1;
+    const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (third ? ~((third & (0u - third)) - 1u) : 0u);
     if (!closed && over) { r1 = 32 * h + __ffs(over) - 1; closed = true; }
-    if (build_env < 0 && builders) build_env = 32 * h + __ffs(builders) - 1;
+    for (unsigned bm = builders; bm && build_env2 < 0; bm &= bm - 1) {
+      const int sl = 32 * h + __ffs(bm) - 1;
+      if (build_env < 0) build_env = sl; else build_env2 = sl;
+    }
     nbuilders += __popc(builders);
     const bool in_round = cand && slot < r1;
     if (in_round) rec.s0 = incl - cnt;
@@ -916,7 +920,9 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
   }
   if (lane == 0) {
     Tm.more = later_any != 0u;
-    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst; Tm.build_env = (build_env >= 0 && build_env < r1) ? build_env : -1;
+    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst;
+    Tm.build_env = (build_env >= 0 && build_env < r1) ? build_env : -1;
+    Tm.build_env2 = (Tm.build_env >= 0 && build_env2 >= 0 && build_env2 < r1) ? build_env2 : -1;
     // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
     Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
     Tm.netask = carry_task;
@@ -970,9 +976,10 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
     const int x0 = max(bx0, 0), y0 = max(by0, 0), x1 = min(bx0 + SF_EXP_W, SF_NAT_W) - 1, y1 = min(by0 + SF_EXP_W, SF_NAT_H) - 1;
     if (x0 <= x1 && y0 <= y1) {
       const int j0 = B.col_out0[x0], j1 = B.col_out1[x1], i0 = B.row_out0[y0], i1 = B.row_out1[y1];
-      const int hb = (i1 - i0 + 4) >> 2, ow = j1 - j0 + 1, oh = i1 - i0 + 1;
+      const int hb = (i1 - i0 + 4) >> 2, oh = i1 - i0 + 1;
+      const int ja = j0 & ~3;  // the cache columns start at a 32-bit word of the observation row (rows are 84 = 4 * 21 bytes)
       const unsigned* src = reinterpret_cast<const unsigned*>(D.expo + (size_t)env * SF_EXPO_BYTES);
-      unsigned char* dst = sf_frame_ptr(out, e, env) + i0 * 84 + j0;
+      unsigned char* dst = sf_frame_ptr(out, e, env) + i0 * 84 + ja;
       unsigned v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -982,12 +989,16 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int k = lane + 32 * u, r = k >> 3, c = (k & 7) * 4;
+        const int k = lane + 32 * u, r = k >> 3, c = ja + (k & 7) * 4;   // observation columns c .. c + 3
         const int q = (r >= hb) + (r >= 2 * hb) + (r >= 3 * hb);
-        if (r < oh && ((qvalid >> q) & 1)) {
+        if (r < oh && ((qvalid >> q) & 1) && c + 3 >= j0 && c <= j1) {
+          unsigned char* p = dst + r * 84 + (c - ja);
+          if (c >= j0 && c + 3 <= j1) *reinterpret_cast<unsigned*>(p) = v[u];
+          else {
 #pragma unroll
-          for (int b = 0; b < 4; b++)
-            if (c + b < ow) dst[r * 84 + c + b] = (unsigned char)(v[u] >> (8 * b));
+            for (int b = 0; b < 4; b++)
+              if (c + b >= j0 && c + b <= j1) p[b] = (unsigned char)(v[u] >> (8 * b));
+          }
         }
       }
     }
@@ -1031,10 +1042,17 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   const int chunk = Tm.chunk;
   // B2 first: the explosion of the ship that died this tick (its sprite stamp is then visible to the stepping warp
   // long before it looks at the next tick)
-  if (Tm.build_env >= 0 && Tm.build_env < Tm.r1) {
-    sf_phase_exp_items(D, lane, wi, nw);
+  // (a round takes at most two; they share the item lengths and the pixel masks, one after the other)
+  if (Tm.build_env >= 0) {
+    sf_phase_exp_items(D, Tm.build_env, lane, wi, nw);
     sf_render_sync();
-    sf_phase_sprite(D, B, lane, wi, nw);
+    sf_phase_sprite(D, B, Tm.build_env, lane, wi, nw);
+    if (Tm.build_env2 >= 0) {
+      sf_render_sync();
+      sf_phase_exp_items(D, Tm.build_env2, lane, wi, nw);
+      sf_render_sync();
+      sf_phase_sprite(D, B, Tm.build_env2, lane, wi, nw);
+    }
   }
   SF_PROF(21);
   const int s = wi * chunk;
@@ -1092,7 +1110,7 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
     j0 = B.col_out0[x0]; j1 = B.col_out1[x1]; i0 = B.row_out0[y0]; i1 = B.row_out1[y1];
     if (kind < 4) {
       const int hb = (i1 - i0 + 4) >> 2;
-      corigin = j0 | (i0 << 8);
+      corigin = (j0 & ~3) | (i0 << 8);  // cache columns are aligned with the 32-bit words of the observation row
       i0 += kind * hb; i1 = min(i1, i0 + hb - 1);
       if (i0 > i1) return;
       quarter = kind;
