@@ -282,6 +282,48 @@ def test_rollout_equals_stepwise_and_synthetic_stream():
     a.close(); b.close()
 
 
+def test_rollout_with_many_strokes_and_odd_lengths_equals_stepwise():
+    """The fused rollout draws two consecutive ticks per stage and splits a stage into rounds when the stroke or
+    cell pools are full; a single step draws one tick per stage. From crowded states (up to 20 missiles and 3 shells
+    per env, a third of the ships dead: several rounds per stage) both must give the same frames, for even and odd
+    numbers of ticks."""
+    torch = torch_cuda()
+    n = 64
+    rng = np.random.RandomState(21)
+    recs = []
+    for i in range(n):
+        r = OracleEnv("youturn", 1).get_state()
+        r.ship_x = float(rng.uniform(250, 460)); r.ship_y = float(rng.uniform(200, 430)); r.ship_angle = float(rng.randint(360))
+        r.ship_alive = int(i % 3 != 0)
+        for s in rng.choice(20, int(rng.randint(8, 21)), replace=False):
+            r.missile_mask |= 1 << int(s)
+            r.missile_x[s] = float(rng.uniform(200, 520)); r.missile_y[s] = float(rng.uniform(150, 480)); r.missile_angle[s] = float(rng.randint(360))
+        for s in range(int(rng.randint(0, 4))):
+            r.shell_mask |= 1 << s
+            ang = float(rng.uniform(0, 360)); rad = float(rng.uniform(30, 150))
+            r.shell_x[s] = 355 + rad * np.cos(np.deg2rad(ang)); r.shell_y[s] = 315 + rad * np.sin(np.deg2rad(ang)); r.shell_angle[s] = ang
+            r.shell_vx[s] = 6 * np.cos(np.deg2rad(ang)); r.shell_vy[s] = 6 * np.sin(np.deg2rad(ang))
+        recs.append(to_gpu_record(r))
+    for T in (1, 2, 5, 8):
+        a = make("youturn", n); b = make("youturn", n)
+        a.reset(); b.reset()
+        a.set_state(recs); b.set_state(recs)
+        acts = a.synthetic_actions(T, action_seed=9)
+        out = a.rollout(T, action_seed=9)
+        for t in range(T):
+            obs, rew, done, info = b.step(torch.from_numpy(acts[t]).cuda())
+            assert torch.equal(out["obs"][t], obs), (T, t)
+            assert torch.equal(out["reward"][t], rew), (T, t)
+        assert bytes(a.get_state()) == bytes(b.get_state())
+        a.close(); b.close()
+    # and the first frames against the oracle
+    a = make("youturn", n); a.reset(); a.set_state(recs)
+    obs = a.render_frames(native=False)
+    for i in range(0, n, 7):
+        assert_frame_close(draw_obs(to_oracle_record(recs[i])), obs[i], ("crowded", i))
+    a.close()
+
+
 def test_shard_invariance_two_slabs_equal_one():
     """N envs in one slab == the same envs split over two slabs (what two ranks would own), bitwise;
     episode statistics add up."""
