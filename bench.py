@@ -244,7 +244,7 @@ def ours(args):
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs": n * world, "gametype": GAMETYPE, "kernel": "sf_rollout_kernel, T=K steps per launch (one block per SM: a stepping warp one tick ahead + 15 drawing warps in a block-cooperative frame pipeline)", "presteps": args.presteps,
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs": n * world, "gametype": GAMETYPE, "kernel": "sf_rollout_kernel, T=K steps per launch (one block of 24 warps per SM: a stepping warp up to two ticks ahead + 23 drawing warps in a block-cooperative frame pipeline)", "presteps": args.presteps,
                    "l2": "obs output %.1f MB/step streams into a K-step buffer (%.0f MB) larger than L2; env state (%.1f MB) is intentionally cache resident"
                          % (n * 7056 / 1e6, K * n * 7056 / 1e6, env.state_bytes() / 1e6),
                    "timing": "median of %d launches of K steps each, CUDA events on the launching stream, max over ranks" % args.repeats, "launch_ms_all": [round(x, 4) for x in reps]},

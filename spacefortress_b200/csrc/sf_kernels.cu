@@ -3,9 +3,10 @@
 //
 // Kernels
 //   sf_rollout_kernel           fused step + render + auto-reset for T consecutive ticks (T=1 == sf_step). One block
-//                               of 16 warps per SM owns groups of <= 32 envs: warp 0 steps them one env per lane
-//                               (SoA, 128-bit loads/stores) one tick ahead, all warps run the block-cooperative
-//                               frame pipeline of sf_render.cuh and stream the 84x84 frames to HBM.
+//                               of 24 warps per SM owns groups of <= 32 envs: warp 0 steps them one env per lane
+//                               (SoA, 128-bit loads/stores) up to two ticks ahead and prepares the next stage, the
+//                               other warps run the block-cooperative frame pipeline of sf_render.cuh and stream the
+//                               84x84 frames to HBM.
 //   sf_step_only_kernel         state-only variant (render off), one env per thread.
 //   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel
 #include <cuda_runtime.h>

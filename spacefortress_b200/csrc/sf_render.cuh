@@ -1,5 +1,5 @@
-// sf_render.cuh — block-cooperative rasteriser: the 15 drawing warps of a block draw the frames of a group of <= 32
-// envs per tick while warp 0 steps the group's next tick.
+// sf_render.cuh — block-cooperative rasteriser: the 23 drawing warps of a block draw the frames of a group of <= 32
+// envs, two ticks per stage, while warp 0 steps the group's next ticks and prepares the next stage.
 // Replaces drawGameStateScaled (draw.cpp:256-270), the RGBA2GRAY conversion (ssf_env.py:205, identity on grey
 // input) and cv2.resize(INTER_AREA, 84x84) (rl/envs.py:29).
 //
