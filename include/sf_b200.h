@@ -113,6 +113,12 @@ long long sf_state_bytes(const sf_handle* h);          /* device bytes held per 
  * so that results are shard-invariant across GPUs. */
 int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_global_env, void* stream);
 
+/* Extension for BASELINE.json configs[4] (auto-reset under episode-length variance): episode i continues from
+ * tick h_ticks[i] (Game::mTick; mTime = 34 * tick, game.cpp:425-427), everything else is untouched. The
+ * reference has fixed episodes of 5295 ticks (game.cpp:487-489); staggering the clocks makes the envs of a
+ * batch finish at different steps. Same effect as sf_get_state / edit tick and time / sf_set_state. */
+int sf_set_ticks(sf_handle* h, const int32_t* h_ticks);
+
 /* SSF_Env.__init__/reset for all envs (d_mask==NULL) or for envs with d_mask[i]!=0: new Game
  * (game.cpp:18-82); prev_vlner is cleared only when clear_prev_vlner!=0 (= __init__, ssf_env.py:92).
  * d_obs (may be NULL) receives the first frame, layout per flags. */

@@ -237,6 +237,14 @@ __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
   sf_store_env(D, env, e);
 }
 
+__global__ void sf_set_ticks_kernel(SfDev D, const int* ticks) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n) return;
+  int4 q = D.q3[env];
+  q.z = max(ticks[env], 0);
+  D.q3[env] = q;
+}
+
 __global__ void sf_reset_kernel(SfDev D, const unsigned char* mask, int clear_prev_vlner) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= D.n) return;
@@ -525,6 +533,21 @@ static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const un
   group_shape(h, &EB, &ngroups, &blocks);
   sf_render_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(h->dev, d_obs, flags, d_mask, EB, ngroups);
   CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+
+extern "C" int sf_set_ticks(sf_handle* h, const int32_t* h_ticks) {
+  if (!h || !h_ticks) return fail(SF_ERR_INVALID, "handle or ticks is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(int) * (size_t)h->dev.n));
+  cudaError_t ce = cudaMemcpy(d, h_ticks, sizeof(int) * (size_t)h->dev.n, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    sf_set_ticks_kernel<<<(h->dev.n + 127) / 128, 128>>>(h->dev, d);
+    ce = cudaDeviceSynchronize();
+  }
+  cudaFree(d);
+  if (ce != cudaSuccess) return fail(SF_ERR_CUDA, std::string("sf_set_ticks: ") + cudaGetErrorString(ce));
   return SF_OK;
 }
 

@@ -106,6 +106,13 @@ class SFVecEnv(object):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ API
+    def set_ticks(self, ticks):
+        """Extension (BASELINE.json configs[4]): env i continues its episode from tick ticks[i], so that the envs of
+        the batch reach the fixed episode end (5295 ticks, game.cpp:487-489) at different steps."""
+        arr = np.ascontiguousarray(ticks, dtype=np.int32)
+        assert arr.shape == (self.num_envs,)
+        _lib.check(self.L.sf_set_ticks(self.h, arr.ctypes.data_as(C.c_void_p)))
+
     def seed_streams(self, seeds=None, first_global_env=0):
         """Per-env libc-rand() stream seeds (default: 1 for every env, the reference's behaviour since it
         never calls srand — game.cpp:137-148). An int s gives seeds s+i (rl/envs.py:13 `seed + rank`)."""

@@ -380,6 +380,40 @@ def test_auto_reset_and_episode_stats():
     env.close()
 
 
+def test_staggered_episode_ends_auto_reset_and_stats():
+    """BASELINE.json configs[4]: auto-reset under episode-length variance. The clocks of the envs are staggered
+    (sf_set_ticks), so they finish at different steps; done flags, rewards, the first frames of the new episodes and
+    the episode statistics must equal the oracle's, step by step."""
+    torch = torch_cuda()
+    n, T = 24, 48
+    rng = np.random.RandomState(3)
+    ticks = (5295 - 1 - rng.randint(0, 40, size=n)).astype(np.int32)
+    env = make("youturn", n, seeds=np.arange(1, n + 1))
+    env.reset()
+    env.set_ticks(ticks)
+    orc = [OracleEnv("youturn", s) for s in range(1, n + 1)]
+    for i in range(n):
+        r = orc[i].get_state(); r.tick = int(ticks[i]); r.time = int(ticks[i]) * 34; orc[i].set_state(r)
+    acts = env.synthetic_actions(T, action_seed=2)
+    out = env.rollout(T, action_seed=2)
+    done = out["done"].cpu().numpy(); rew = out["reward"].cpu().numpy(); obs = out["obs"].cpu().numpy()
+    episodes, sum_len = 0, 0
+    for i in range(n):
+        for t in range(T):
+            r, d, k, _ = orc[i].step(orc[i].keymask(int(acts[t, i])))
+            assert r == int(rew[t, i]) and bool(d) == bool(done[t, i]), (i, t)
+            if d:
+                assert t == 5295 - 1 - int(ticks[i]), (i, t)
+                episodes += 1; sum_len += orc[i].get_state().tick
+                orc[i].reset()
+            if d or t % 11 == 0:
+                assert_frame_close(orc[i].obs(), obs[t, i, 0], ("frame", i, t))
+    assert len(set(int(np.argmax(done[:, i])) for i in range(n))) > 5  # the ends really are spread
+    st = env.episode_stats()
+    assert st["episodes"] == episodes == n and st["sum_length"] == sum_len
+    env.close()
+
+
 def test_vecenv_numpy_api_matches_reference_usage():
     """rl/train.py:30-41,60,80-85 usage pattern with the drop-in classes."""
     torch_cuda()
