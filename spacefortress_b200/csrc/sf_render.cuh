@@ -1040,20 +1040,10 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team_smem();
   const int chunk = Tm.chunk;
-  // B2 first: the explosion of the ship that died this tick (its sprite stamp is then visible to the stepping warp
-  // long before it looks at the next tick)
-  // (a round takes at most two; they share the item lengths and the pixel masks, one after the other)
-  if (Tm.build_env >= 0) {
-    sf_phase_exp_items(D, Tm.build_env, lane, wi, nw);
-    sf_render_sync();
-    sf_phase_sprite(D, B, Tm.build_env, lane, wi, nw);
-    if (Tm.build_env2 >= 0) {
-      sf_render_sync();
-      sf_phase_exp_items(D, Tm.build_env2, lane, wi, nw);
-      sf_render_sync();
-      sf_phase_sprite(D, B, Tm.build_env2, lane, wi, nw);
-    }
-  }
+  // B2, first half: the items of the explosion of a ship that died in this stage. They are dealt from the LAST
+  // drawing warp down: the geometry batches go to the first warps, so the two overlap.
+  const int be = Tm.build_env;
+  if (be >= 0) sf_phase_exp_items(D, be, lane, nw - 1 - wi, nw);
   SF_PROF(21);
   const int s = wi * chunk;
   if (s < nst) {
@@ -1072,8 +1062,19 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   } else {
     if (lane == 0) W.ngroups = 0;
   }
-  sf_render_sync();  // every batch is published
+  sf_render_sync();  // every batch is published, the explosion items are done
   SF_PROF(64);
+  // B2, second half: the sprite (its stamp is visible to the stepping warp long before it looks at the next stage). A
+  // round takes at most two explosions; they share the item lengths and the pixel masks, one after the other.
+  if (be >= 0) {
+    sf_phase_sprite(D, B, be, lane, wi, nw);
+    if (Tm.build_env2 >= 0) {
+      sf_render_sync();
+      sf_phase_exp_items(D, Tm.build_env2, lane, wi, nw);
+      sf_render_sync();
+      sf_phase_sprite(D, B, Tm.build_env2, lane, wi, nw);
+    }
+  }
   // passes of warp l's batch: (ngroups + 3) / 4; every warp computes the same prefix sums
   const int mine = lane < nw ? (sf_warp_smem(lane + 1).ngroups + 3) >> 2 : 0;
   int incl = mine;
