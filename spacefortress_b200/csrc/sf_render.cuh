@@ -980,25 +980,39 @@ __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockS
       const int ja = j0 & ~3;  // the cache columns start at a 32-bit word of the observation row (rows are 84 = 4 * 21 bytes)
       const unsigned* src = reinterpret_cast<const unsigned*>(D.expo + (size_t)env * SF_EXPO_BYTES);
       unsigned char* dst = sf_frame_ptr(out, e, env) + i0 * 84 + ja;
+      // valid rows as a bit mask (row r belongs to quarter r / hb)
+      unsigned rows = 0u;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if ((qvalid >> q) & 1) { const int ra = q * hb, rb = min(ra + hb, oh); if (ra < rb) rows |= ((rb - ra >= 32 ? 0u : (1u << (rb - ra))) - 1u) << ra; }
+      const int wfull0 = (j0 - ja + 3) >> 2, wfull1 = (j1 + 1 - ja) >> 2;  // words [wfull0, wfull1) lie inside [j0, j1]
+      // whole words: 8 per row
       unsigned v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int k = lane + 32 * u, r = k >> 3;
-        const int q = (r >= hb) + (r >= 2 * hb) + (r >= 3 * hb);
-        v[u] = (r < oh && ((qvalid >> q) & 1)) ? __ldcg(&src[k]) : 0u;
+        const int k = lane + 32 * u, w = k & 7;
+        const bool on = ((rows >> (k >> 3)) & 1u) && w >= wfull0 && w < wfull1;
+        v[u] = on ? __ldcg(&src[k]) : 0u;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int k = lane + 32 * u, r = k >> 3, c = ja + (k & 7) * 4;   // observation columns c .. c + 3
-        const int q = (r >= hb) + (r >= 2 * hb) + (r >= 3 * hb);
-        if (r < oh && ((qvalid >> q) & 1) && c + 3 >= j0 && c <= j1) {
-          unsigned char* p = dst + r * 84 + (c - ja);
-          if (c >= j0 && c + 3 <= j1) *reinterpret_cast<unsigned*>(p) = v[u];
-          else {
+        const int k = lane + 32 * u, w = k & 7;
+        if (((rows >> (k >> 3)) & 1u) && w >= wfull0 && w < wfull1) *reinterpret_cast<unsigned*>(dst + (k >> 3) * 84 + 4 * w) = v[u];
+      }
+      // the (at most two) partial words at the ends of a row: lane = row
+      if ((rows >> lane) & 1u) {
+        const int wl = wfull0 - 1, wr = wfull1;   // partial iff they hold a column of [j0, j1]
+        if (wl >= 0) {
+          const unsigned x = __ldcg(&src[lane * 8 + wl]);
+          unsigned char* p = dst + lane * 84 + 4 * wl;
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-              if (c + b >= j0 && c + b <= j1) p[b] = (unsigned char)(v[u] >> (8 * b));
-          }
+          for (int b = 0; b < 4; b++) { const int c = ja + 4 * wl + b; if (c >= j0 && c <= j1) p[b] = (unsigned char)(x >> (8 * b)); }
+        }
+        if (wr != wl && ja + 4 * wr <= j1) {
+          const unsigned x = __ldcg(&src[lane * 8 + wr]);
+          unsigned char* p = dst + lane * 84 + 4 * wr;
+#pragma unroll
+          for (int b = 0; b < 4; b++) { const int c = ja + 4 * wr + b; if (c >= j0 && c <= j1) p[b] = (unsigned char)(x >> (8 * b)); }
         }
       }
     }
