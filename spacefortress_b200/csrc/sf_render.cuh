@@ -120,6 +120,9 @@ struct __align__(16) SfTeamSmem {
   int more, nticks, build_env2, padm2;    // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS)
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_STAGE_SLOTS * 5];  // env slot | kind<<6: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
+  unsigned short exp_item0[SF_EXP_QUADS];   // build: copies of the y phase's per-quad table entries (SfExpPhase) for the sprite pass
+  short exp_qxmin[SF_EXP_QUADS];
+  signed char exp_row0[SF_EXP_QUADS];
   unsigned short exp_len[SF_EXPT_ITEMS][SF_EXPT_NC];  // build: summed span lengths of the (quad, pixel row) items of the explosion, per cell
   alignas(16) unsigned arc_mask[SF_EXP_W * SF_EXP_W][4];  // build: per pixel of the explosion box, the quads that cover it (zero between builds)
   alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
@@ -142,6 +145,7 @@ struct __align__(16) SfBlockSmem {
   double wf_line[3][4][4];                     // wireframe models
   int wf_nlines[4];
   unsigned colour_white, padc[3];
+  unsigned char exp_colour[SF_EXP_STROKES + 3];
   SfTeamSmem team[2];
 };
 
@@ -231,6 +235,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
     }
   }
   if (threadIdx.x == 0) B.colour_white = T->colour_white;
+  for (int k = threadIdx.x; k < SF_EXP_STROKES; k += blockDim.x) B.exp_colour[k] = T->exp_colour[k];
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -760,6 +765,7 @@ __device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int be, int l
   const SfExpPhase& P = D.tab->exp_phase[c.y & 255];
   const int Y = c.y >> 8, bx0 = (c.x >> 8) - 13, by0 = Y - 13;  // the explosion box (sf_make_env_rec)
   const int n = __ldg(&P.n_items);
+  for (int q = wi * 32 + lane; q < SF_EXP_QUADS; q += nw * 32) { Tm.exp_item0[q] = __ldg(&P.item0[q]); Tm.exp_row0[q] = __ldg(&P.row0[q]); Tm.exp_qxmin[q] = __ldg(&P.qxmin[q]); }
 #pragma unroll 1
   for (int it = wi * 32 + lane; it < n; it += nw * 32) {
     const uint2 Iw = __ldg(reinterpret_cast<const uint2*>(&P.item[it]));
@@ -816,14 +822,14 @@ __device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, 
         while (m) {
           const int q = wd * 32 + __ffs(m) - 1;
           m &= m - 1;
-          const int it = __ldg(&P.item0[q]) + (ny - Y - (int)__ldg(&P.row0[q]));
-          const int colmin = (c.x + __ldg(&P.qxmin[q])) >> 8;
+          const int it = Tm.exp_item0[q] + (ny - Y - (int)Tm.exp_row0[q]);
+          const int colmin = (c.x + Tm.exp_qxmin[q]) >> 8;
           const unsigned L = Tm.exp_len[it][nx - colmin];
-          if (q < SF_EXP_STROKES - 1) v = sf_blend(v, T->exp_colour[q], sf_len_to_alpha(L));
+          if (q < SF_EXP_STROKES - 1) v = sf_blend(v, B.exp_colour[q], sf_len_to_alpha(L));
           else circle += L;
         }
       }
-      if (circle) v = sf_blend(v, T->exp_colour[SF_EXP_STROKES - 1], sf_len_to_alpha(circle));
+      if (circle) v = sf_blend(v, B.exp_colour[SF_EXP_STROKES - 1], sf_len_to_alpha(circle));
       *reinterpret_cast<uint4*>(Tm.arc_mask[p]) = make_uint4(0u, 0u, 0u, 0u);
     }
     sprite[p] = (unsigned char)v;
@@ -932,14 +938,22 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
 
 // Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
 // out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes)...
-__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
-  const int env = sf_team_smem().env[e].env;
-  if (env < 0 || lane != 0) return;
+// (stepping warp, one env slot per lane and tick of the stage, for the stage it has just prepared; every lane waits
+// for its own copies with sf_base_wait before the stage barrier)
+__device__ __forceinline__ void sf_base_issue_stage(const SfBlockSmem& B, const SfTeamSmem& Tm, int lane, const SfFrameOut& out) {
+  if (out.native) return;
   const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
-  unsigned char* gb = sf_frame_ptr(out, e, env);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#pragma unroll
+  for (int h = 0; h < SF_STAGE_TICKS; h++) {
+    const int e = 32 * h + lane;
+    if (e >= Tm.r0 && e < Tm.r1 && Tm.env[e].env >= 0) {
+      unsigned char* gb = sf_frame_ptr(out, e, Tm.env[e].env);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
 }
+__device__ __forceinline__ void sf_base_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // ... and, once the bulk copies of this warp have landed, the few 16-byte chunks that the fortress state (about 12
 // for a live fortress, 53 for its explosion) and a non-empty vulnerability bar change are patched from the
 // pre-resampled state tables.
@@ -1219,7 +1233,8 @@ __device__ __forceinline__ void sf_restart_pools(SfTeamSmem& Tm, int lane) {
 // that tick. The strokes of a tick are gathered from the state before it moves on, so the first tick must fit the
 // round in one piece; if it does not, the stage covers that tick only (and takes several rounds).
 template <class Prep>
-__device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, SfTeamSmem& Tm, int lane, int t, int nt, bool native, Prep prep) {
+__device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, const SfBlockSmem& B, SfTeamSmem& Tm, int lane, int t, int nt, SfFrameOut out, Prep prep) {
+  const bool native = out.native != 0;
   prep(t, Tm, 0);
   sf_publish_recs(D, Tm, lane, 0, native);
   sf_round_scan(Tm, lane, 0, SF_GROUP_ENVS);
@@ -1236,6 +1251,8 @@ __device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, SfTeamSme
 #endif
   if (lane == 0) Tm.nticks = nticks;
   sf_restart_pools(Tm, lane);
+  out.obs += (size_t)t * out.tick_bytes;
+  sf_base_issue_stage(B, Tm, lane, out);
 }
 
 // One stage drawn by the 15 drawing warps (see the pipeline description above): B1 geometry, B3 passes, base
@@ -1250,16 +1267,10 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
 #endif
   const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
   // ---- B: stroke tasks ----
-  if (!out.native) {
-#pragma unroll 1
-    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
-  }
   SF_PROF_RESET();
   sf_phase_strokes(D, B, W, lane, wi, nw, nst);
   SF_PROF(69);
   if (!out.native) {
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
-    __syncwarp();
     SF_PROF(65);
 #pragma unroll 1
     for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
@@ -1314,10 +1325,11 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
 #endif
-  if (stepper) sf_prepare_first_round(D, B.team[st.stage], lane, 0, T, out.native != 0, prep);
+  if (stepper) sf_prepare_first_round(D, B, B.team[st.stage], lane, 0, T, out, prep);
   int t = 0;
 #pragma unroll 1
   for (;;) {
+    if (stepper) sf_base_wait();  // the default observations of the stage have landed
     sf_team_sync();  // the stage is prepared; every warp is done with the previous one
     SF_TICK(0); SF_WTICK(8);
     SfTeamSmem& Tm = B.team[st.stage];
@@ -1335,8 +1347,11 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
         sf_round_scan(Nx, lane, Tm.r1, SF_GROUP_ENVS * nticks);
         sf_gather_strokes(D, Nx, lane, nticks - 1);  // the slots that are left are of the stage's last tick (see above)
         sf_restart_pools(Nx, lane);
+        out.obs = obs0 + (size_t)t * out.tick_bytes;
+        sf_base_issue_stage(B, Nx, lane, out);
       } else if (!last) {
-        sf_prepare_first_round(D, Nx, lane, t + nticks, T - (t + nticks), out.native != 0, prep);
+        out.obs = obs0;
+        sf_prepare_first_round(D, B, Nx, lane, t + nticks, T - (t + nticks), out, prep);
         SF_PROF(70);
       }
     } else {
