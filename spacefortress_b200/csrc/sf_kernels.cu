@@ -716,6 +716,14 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
   return SF_OK;
 }
 
+#ifdef SF_BARRIER_TIMING
+extern "C" int sf_barrier_cycles(unsigned long long* h_out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h_out, sf_bar_cycles, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf_bar_cycles, z, sizeof(z)); }
+  return SF_OK;
+}
+#endif
 #ifdef SF_PHASE_TIMING
 extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
   cudaDeviceSynchronize();

@@ -156,11 +156,27 @@ __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_ca
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp);
 // the stage copy this warp is drawing from (drawing warps; warp 0 addresses the copies explicitly)
 __device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[sf_warp_smem(threadIdx.x >> 5).stage]; }
+#ifdef SF_BARRIER_TIMING  // tools/gpu_barrier_timing.py: cycles the warps spend at the barriers
+__device__ unsigned long long sf_bar_cycles[8];  // [0] stage barrier (drawing warps), [1] drawing-warp barriers, [2] stage barrier (warp 0)
+__device__ __forceinline__ void sf_bar_add(int k, long long t0) { if ((threadIdx.x & 31) == 0) atomicAdd(&sf_bar_cycles[k], (unsigned long long)(clock64() - t0)); }
+#endif
 __device__ __forceinline__ void sf_team_sync() {  // every warp of the block (named barrier 1)
+#ifdef SF_BARRIER_TIMING
+  const long long t0 = clock64();
+#endif
   asm volatile("bar.sync 1, %0;" :: "r"(32 * SF_RENDER_WARPS) : "memory");
+#ifdef SF_BARRIER_TIMING
+  sf_bar_add(threadIdx.x < 32 ? 2 : 0, t0);
+#endif
 }
 __device__ __forceinline__ void sf_render_sync() {  // the warps that draw: all but warp 0, which steps (named barrier 2)
+#ifdef SF_BARRIER_TIMING
+  const long long t0 = clock64();
+#endif
   asm volatile("bar.sync 2, %0;" :: "r"(32 * (SF_RENDER_WARPS - 1)) : "memory");
+#ifdef SF_BARRIER_TIMING
+  sf_bar_add(1, t0);
+#endif
 }
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
 __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
