@@ -954,22 +954,14 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
 
 // Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
 // out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes)...
-// (stepping warp, one env slot per lane and tick of the stage, for the stage it has just prepared; every lane waits
-// for its own copies with sf_base_wait before the stage barrier)
-__device__ __forceinline__ void sf_base_issue_stage(const SfBlockSmem& B, const SfTeamSmem& Tm, int lane, const SfFrameOut& out) {
-  if (out.native) return;
+__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
+  const int env = sf_team_smem().env[e].env;
+  if (env < 0 || lane != 0) return;
   const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
-#pragma unroll
-  for (int h = 0; h < SF_STAGE_TICKS; h++) {
-    const int e = 32 * h + lane;
-    if (e >= Tm.r0 && e < Tm.r1 && Tm.env[e].env >= 0) {
-      unsigned char* gb = sf_frame_ptr(out, e, Tm.env[e].env);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  }
+  unsigned char* gb = sf_frame_ptr(out, e, env);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void sf_base_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // ... and, once the bulk copies of this warp have landed, the few 16-byte chunks that the fortress state (about 12
 // for a live fortress, 53 for its explosion) and a non-empty vulnerability bar change are patched from the
 // pre-resampled state tables.
@@ -1251,24 +1243,37 @@ __device__ __forceinline__ void sf_restart_pools(SfTeamSmem& Tm, int lane) {
 template <class Prep>
 __device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, const SfBlockSmem& B, SfTeamSmem& Tm, int lane, int t, int nt, SfFrameOut out, Prep prep) {
   const bool native = out.native != 0;
+#ifdef SF_BARRIER_TIMING
+  long long tb_ = clock64();
+#define SF_BT(k) do { sf_bar_add(k, tb_); tb_ = clock64(); } while (0)
+#else
+#define SF_BT(k) ((void)0)
+#endif
   prep(t, Tm, 0);
+  SF_BT(3);
   sf_publish_recs(D, Tm, lane, 0, native);
+  SF_BT(4);
   sf_round_scan(Tm, lane, 0, SF_GROUP_ENVS);
+  SF_BT(5);
   sf_gather_strokes(D, Tm, lane, 0);
+  SF_BT(6);
   int nticks = 1;
 #if SF_STAGE_TICKS > 1
   if (nt > 1 && !Tm.more) {
     prep(t + 1, Tm, 1);
+    SF_BT(3);
     sf_publish_recs(D, Tm, lane, 1, native);
+    SF_BT(4);
     sf_round_scan(Tm, lane, 0, 2 * SF_GROUP_ENVS);
+    SF_BT(5);
     sf_gather_strokes(D, Tm, lane, 1);
+    SF_BT(6);
     nticks = 2;
   }
 #endif
   if (lane == 0) Tm.nticks = nticks;
   sf_restart_pools(Tm, lane);
-  out.obs += (size_t)t * out.tick_bytes;
-  sf_base_issue_stage(B, Tm, lane, out);
+  SF_BT(7);
 }
 
 // One stage drawn by the 15 drawing warps (see the pipeline description above): B1 geometry, B3 passes, base
@@ -1283,10 +1288,16 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
 #endif
   const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
   // ---- B: stroke tasks ----
+  if (!out.native) {  // (issuing a bulk copy costs a few hundred cycles: spread over the drawing warps, not on the stepping warp)
+#pragma unroll 1
+    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
+  }
   SF_PROF_RESET();
   sf_phase_strokes(D, B, W, lane, wi, nw, nst);
   SF_PROF(69);
   if (!out.native) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
+    __syncwarp();
     SF_PROF(65);
 #pragma unroll 1
     for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
@@ -1345,7 +1356,6 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
   int t = 0;
 #pragma unroll 1
   for (;;) {
-    if (stepper) sf_base_wait();  // the default observations of the stage have landed
     sf_team_sync();  // the stage is prepared; every warp is done with the previous one
     SF_TICK(0); SF_WTICK(8);
     SfTeamSmem& Tm = B.team[st.stage];
@@ -1363,10 +1373,7 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
         sf_round_scan(Nx, lane, Tm.r1, SF_GROUP_ENVS * nticks);
         sf_gather_strokes(D, Nx, lane, nticks - 1);  // the slots that are left are of the stage's last tick (see above)
         sf_restart_pools(Nx, lane);
-        out.obs = obs0 + (size_t)t * out.tick_bytes;
-        sf_base_issue_stage(B, Nx, lane, out);
       } else if (!last) {
-        out.obs = obs0;
         sf_prepare_first_round(D, B, Nx, lane, t + nticks, T - (t + nticks), out, prep);
         SF_PROF(70);
       }

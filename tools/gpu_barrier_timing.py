@@ -26,4 +26,6 @@ W = 24
 print("%s n=%d: launch %.3f ms = %.0f cycles; %.3e steps/s" % (gt, n, ms, cyc, n * T / ms * 1e3))
 print("per drawing warp: stage barrier %.1f %%, drawing-warp barriers %.1f %% of the launch; stepping warp at the stage barrier %.1f %%"
       % (100 * v[0] / (blocks * (W - 1)) / cyc, 100 * v[1] / (blocks * (W - 1)) / cyc, 100 * v[2] / blocks / cyc))
+print("stepping warp, share of the launch: steps %.1f %%, memo state %.1f %%, round scans %.1f %%, stroke gathering %.1f %%, pools + base copies %.1f %%"
+      % tuple(100 * v[k] / blocks / cyc for k in (3, 4, 5, 6, 7)))
 subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
