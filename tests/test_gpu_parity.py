@@ -324,6 +324,26 @@ def test_rollout_with_many_strokes_and_odd_lengths_equals_stepwise():
     a.close()
 
 
+def test_soak_fused_rollout_equals_single_steps_many_envs():
+    """Every block of the GPU busy (4096 envs, the bench workload), 192 ticks into the steady state: the pipelined
+    multi-tick kernel and single steps must agree on every frame (a race between the stepping warp and the
+    drawing warps, or between two stages, would show up as a sporadic mismatch). tools/gpu_soak.py runs longer."""
+    torch = torch_cuda()
+    n, T = 4096, 64
+    a = make("autoturn", n); b = make("autoturn", n)
+    a.reset(to_numpy=False); b.reset(to_numpy=False)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for chunk in range(3):
+        acts = torch.randint(0, a.num_actions, (T, n), generator=g, device="cuda", dtype=torch.int32)
+        out = a.rollout(T, actions=acts)
+        for t in range(T):
+            obs, rew, done, info = b.step(acts[t])
+            assert torch.equal(out["obs"][t], obs), (chunk, t)
+            assert torch.equal(out["reward"][t], rew) and torch.equal(out["done"][t].bool(), done), (chunk, t)
+    assert bytes(a.get_state()) == bytes(b.get_state())
+    a.close(); b.close()
+
+
 def test_shard_invariance_two_slabs_equal_one():
     """N envs in one slab == the same envs split over two slabs (what two ranks would own), bitwise;
     episode statistics add up."""
