@@ -118,6 +118,7 @@ struct SfRollArgs {
 // one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
 __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfEnvRec* recs) {
   const int lane = threadIdx.x & 31;
+  const SfHot* H = &sf_block_smem().hot;  // the step's tables from shared memory
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const int env = group * A.EB + lane;
   const bool mine = lane < A.EB && env < D.n;
@@ -129,7 +130,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
                       : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
     int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
     SfStepOut o;
-    sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+    sf_env_step(D, H, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
     size_t oi = (size_t)t * D.n + env;
     if (A.reward) A.reward[oi] = o.reward;
     if (A.done) A.done[oi] = o.done;
@@ -139,7 +140,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   }
   if (__any_sync(0xffffffffu, finished)) {
     sf_accumulate_episode(D, e, finished, lane);
-    if (finished) sf_new_game(D, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
+    if (finished) sf_new_game(D, H, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
     sf_store_env(D, env, e);
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
                         : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
       int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
       SfStepOut o;
-      sf_env_step(D, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
+      sf_env_step(D, &D.tab->hot, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
       size_t oi = (size_t)t * D.n + env;
       if (A.reward) A.reward[oi] = o.reward;
       if (A.done) A.done[oi] = o.done;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
     }
     if (__any_sync(0xffffffffu, finished)) {
       sf_accumulate_episode(D, e, finished, lane);
-      if (finished) sf_new_game(D, env, e);
+      if (finished) sf_new_game(D, &D.tab->hot, env, e);
     }
   }
   if (mine) sf_store_env(D, env, e);
@@ -252,7 +253,7 @@ __global__ void sf_reset_kernel(SfDev D, const unsigned char* mask, int clear_pr
   SfEnv e;
   sf_load_env(D, env, e);
   if (clear_prev_vlner) e.q1.w = 0;
-  sf_new_game(D, env, e);
+  sf_new_game(D, &D.tab->hot, env, e);
   sf_store_env(D, env, e);
 }
 

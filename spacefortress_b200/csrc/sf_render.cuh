@@ -141,7 +141,7 @@ struct __align__(16) SfBlockSmem {
   unsigned char fort_list_n[36];
   unsigned char fort_sparse[SF_FORT_STATES][16];  // first 16 chunks a fortress state changes (255: none); a live fortress changes <= 14
   alignas(16) unsigned magic[SF_MAGIC_N];      // scan converter reciprocals
-  double2 cs_deg[360];                         // cos, sin of integer degrees (host libm)
+  alignas(16) SfHot hot;                       // cos / sin of integer degrees (host libm), hexagons, atan2 octants: read by the step too
   double wf_line[3][4][4];                     // wireframe models
   int wf_nlines[4];
   unsigned colour_white, padc[3];
@@ -239,7 +239,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   if (threadIdx.x < 36) B.fort_list_n[threadIdx.x] = (unsigned char)min(T->fort_list_n[threadIdx.x], 255);
   for (int k = threadIdx.x; k < SF_FORT_STATES * 16; k += blockDim.x) B.fort_sparse[k >> 4][k & 15] = T->fort_sparse[k >> 4][k & 15];
   for (int k = threadIdx.x; k < SF_MAGIC_N; k += blockDim.x) B.magic[k] = T->magic[k];
-  for (int k = threadIdx.x; k < 360; k += blockDim.x) B.cs_deg[k] = make_double2(T->cos_deg[k], T->sin_deg[k]);
+  for (int k = threadIdx.x; k < (int)(sizeof(SfHot) / sizeof(double)); k += blockDim.x) reinterpret_cast<double*>(&B.hot)[k] = reinterpret_cast<const double*>(&T->hot)[k];
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
   for (int c = 0; c < 2; c++) {
@@ -741,7 +741,7 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
     bool visible = !(dxv < -9.0 || dxv > SF_NAT_W + 9.0 || dyv < -9.0 || dyv > SF_NAT_H + 9.0);
     const SfBlockSmem& B = sf_block_smem();
     if (visible && line < B.wf_nlines[kind]) {
-      const double2 cs = B.cs_deg[angle];
+      const double2 cs = make_double2(B.hot.cs[angle][0], B.hot.cs[angle][1]);
       SfWireXf m = sf_wire_xf(px, py, cs.x, cs.y);
       const double* L = B.wf_line[kind][line];
       SfPt a = sf_xform_wire(m, L[0], L[1]), b = sf_xform_wire(m, L[2], L[3]);

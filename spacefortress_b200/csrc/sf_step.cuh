@@ -70,12 +70,12 @@ __device__ inline void sf_srand(const SfDev& D, int i, SfEnv& e, unsigned seed) 
 }
 
 // ---- S9: Hexagon::isInside (hexagon.cpp:37-48), boundary inclusive ----
-__device__ __forceinline__ bool sf_inside_hex(const SfTables* T, int h, double x, double y) {
+__device__ __forceinline__ bool sf_inside_hex(const SfHot* H, int h, double x, double y) {
   bool in = true;
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    double dx = SF_DSUB(x, T->hex_px[h][k]), dy = SF_DSUB(y, T->hex_py[h][k]);
-    double t = SF_DADD(SF_DMUL(T->hex_nx[h][k], dx), SF_DMUL(T->hex_ny[h][k], dy));
+    double dx = SF_DSUB(x, H->hex[h][k][0]), dy = SF_DSUB(y, H->hex[h][k][1]);
+    double t = SF_DADD(SF_DMUL(H->hex[h][k][2], dx), SF_DMUL(H->hex[h][k][3], dy));
     in = in && !(t < 0);
   }
   return in;
@@ -92,10 +92,10 @@ __device__ __forceinline__ bool sf_outside(double x, double y) {  // game.cpp:12
 // atan2 as the reference's libm gives it where a downstream ceil() could flip (exact octants);
 // elsewhere the CUDA fp64 atan2 (<= 2 ulp) is used — a differing last bit cannot change the
 // quantised angle unless the true angle is within 1e-13 degrees of an integer.
-__device__ __noinline__ double sf_atan2(const SfTables* T, double dy, double dx) {
-  if (dy == 0.0) return dx >= 0 ? T->atan2_oct[0] : T->atan2_oct[4];
-  if (dx == 0.0) return dy > 0 ? T->atan2_oct[2] : T->atan2_oct[6];
-  if (fabs(dx) == fabs(dy)) return dx > 0 ? (dy > 0 ? T->atan2_oct[1] : T->atan2_oct[7]) : (dy > 0 ? T->atan2_oct[3] : T->atan2_oct[5]);
+__device__ __noinline__ double sf_atan2(const SfHot* H, double dy, double dx) {
+  if (dy == 0.0) return dx >= 0 ? H->atan2_oct[0] : H->atan2_oct[4];
+  if (dx == 0.0) return dy > 0 ? H->atan2_oct[2] : H->atan2_oct[6];
+  if (fabs(dx) == fabs(dy)) return dx > 0 ? (dy > 0 ? H->atan2_oct[1] : H->atan2_oct[7]) : (dy > 0 ? H->atan2_oct[3] : H->atan2_oct[5]);
   return atan2(dy, dx);
 }
 #define SF_PI 3.14159265358979323846
@@ -128,7 +128,7 @@ __device__ __forceinline__ void sf_kill_ship(SfEnv& e) {  // game.cpp:274-280
 // S2: resetShip (game.cpp:133-149): rejection-sample an integer spawn inside the big and outside the small
 // hexagon, then the heading. Out of line (rare); takes and returns plain values so the caller's env stays in
 // registers. Returns {x, y, angle, new ring index}; *calls = number of rand() calls consumed.
-__device__ __noinline__ int4 sf_spawn_draw(unsigned* rng, int np, int i, const SfTables* T, int idx, int* calls) {
+__device__ __noinline__ int4 sf_spawn_draw(unsigned* rng, int np, int i, const SfHot* T, int idx, int* calls) {
   int x, y, n = 0;
   for (;;) {
     x = sf_rand_raw(rng, np, i, idx) % 380 + 170;
@@ -140,20 +140,20 @@ __device__ __noinline__ int4 sf_spawn_draw(unsigned* rng, int np, int i, const S
   *calls = n + 1;
   return make_int4(x, y, ang, idx);
 }
-__device__ __forceinline__ void sf_spawn_ship(const SfDev& D, int i, SfEnv& e) {
+__device__ __forceinline__ void sf_spawn_ship(const SfDev& D, const SfHot* H, int i, SfEnv& e) {
   int calls = 0;
-  int4 sp = sf_spawn_draw(D.rng, D.n_pad, i, D.tab, e.st3.y, &calls);
+  int4 sp = sf_spawn_draw(D.rng, D.n_pad, i, H, e.st3.y, &calls);
   e.st3.y = sp.w; e.st3.z += calls;
   e.pos = make_double2((double)sp.x, (double)sp.y);
-  e.vel = make_double2(D.tab->ship_start_vx, D.tab->ship_start_vy);
+  e.vel = make_double2(H->ship_start_vx, H->ship_start_vy);
   e.q0.x = (e.q0.x & ~SF_CORE_ANGLE_MASK) | (unsigned)sp.z | SF_CORE_SHIP_ALIVE;
 }
 
 // S1: Game::Game (game.cpp:18-82) through SSF_Env.reset (ssf_env.py:163-178). prev_vlner (q1.w),
 // the rand stream (st3.yzw) survive; everything else is a fresh Game.
-__device__ inline void sf_new_game(const SfDev& D, int i, SfEnv& e) {
+__device__ inline void sf_new_game(const SfDev& D, const SfHot* H, int i, SfEnv& e) {
   e.q0 = make_int4(0, 0, 0, 0);
-  sf_spawn_ship(D, i, e);
+  sf_spawn_ship(D, H, i, e);
   e.q0.x |= SF_CORE_FORT_ALIVE | (18u << SF_CORE_FANG_SHIFT);  // mAngle=180, mLastAngle=0 (game.cpp:40-41)
   e.q1 = make_int4(0, 250, 0, e.q1.w);                           // mVulnerabilityTimer: 0 + 250 (game.cpp:78)
   e.q2 = make_int4(0, 0, 0, 0);
@@ -169,8 +169,7 @@ __device__ __forceinline__ int sf_first_free(unsigned mask, int n) {
 }
 
 // One SSF_Env.step: keymask -> key events -> stepOneTick(34) -> shaping -> done -> auto-reset.
-__device__ inline void sf_env_step(const SfDev& D, int i, SfEnv& e, int keymask, bool autoreset, bool raw_reward, SfStepOut& out) {
-  const SfTables* T = D.tab;
+__device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv& e, int keymask, bool autoreset, bool raw_reward, SfStepOut& out) {
   const int np = D.n_pad;
   float rew = 0.f;
   unsigned ev = 0;
@@ -210,7 +209,7 @@ __device__ inline void sf_env_step(const SfDev& D, int i, SfEnv& e, int keymask,
 
   // ---- S6 monitorShipRespawn (game.cpp:151-157) ----
   if (!(core & SF_CORE_SHIP_ALIVE) && e.q0.z >= 1000) {
-    sf_spawn_ship(D, i, e);
+    sf_spawn_ship(D, T, i, e);
     e.q0.w = 0;
     ev |= SF_EV_SHIP_RESPAWN;
     core = (unsigned)e.q0.x;
@@ -231,8 +230,8 @@ __device__ inline void sf_env_step(const SfDev& D, int i, SfEnv& e, int keymask,
     }
     core = (core & ~SF_CORE_ANGLE_MASK) | (unsigned)ang;
     if (core & SF_CORE_THRUST) {
-      e.vel.x = SF_DADD(e.vel.x, SF_DMUL(0.3, T->cos_deg[ang]));
-      e.vel.y = SF_DADD(e.vel.y, SF_DMUL(0.3, T->sin_deg[ang]));
+      e.vel.x = SF_DADD(e.vel.x, SF_DMUL(0.3, T->cs[ang][0]));
+      e.vel.y = SF_DADD(e.vel.y, SF_DMUL(0.3, T->cs[ang][1]));
     }
     e.pos.x = SF_DADD(e.pos.x, e.vel.x);
     e.pos.y = SF_DADD(e.pos.y, e.vel.y);
@@ -299,8 +298,8 @@ __device__ inline void sf_env_step(const SfDev& D, int i, SfEnv& e, int keymask,
     int s = __ffs(m) - 1;
     double2 p = D.mpos[(size_t)s * np + i];
     int ang = D.mang[(size_t)s * np + i];
-    p.x = SF_DADD(p.x, SF_DMUL(20.0, T->cos_deg[ang]));
-    p.y = SF_DADD(p.y, SF_DMUL(20.0, T->sin_deg[ang]));
+    p.x = SF_DADD(p.x, SF_DMUL(20.0, T->cs[ang][0]));
+    p.y = SF_DADD(p.y, SF_DMUL(20.0, T->cs[ang][1]));
     D.mpos[(size_t)s * np + i] = p;
     if (sf_touch(p.x, p.y, SF_FORT_X, SF_FORT_Y, 23.0)) {
       e.q0.y &= ~(1 << s);

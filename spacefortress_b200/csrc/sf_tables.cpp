@@ -520,6 +520,11 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
       for (int k = n; k < 64; k++) t->fort_sparse[st][k] = 255;
     }
   }
+  for (int a = 0; a < 360; a++) { t->hot.cs[a][0] = t->cos_deg[a]; t->hot.cs[a][1] = t->sin_deg[a]; }
+  for (int h = 0; h < 2; h++)
+    for (int k = 0; k < 6; k++) { t->hot.hex[h][k][0] = t->hex_px[h][k]; t->hot.hex[h][k][1] = t->hex_py[h][k]; t->hot.hex[h][k][2] = t->hex_nx[h][k]; t->hot.hex[h][k][3] = t->hex_ny[h][k]; }
+  for (int k = 0; k < 8; k++) t->hot.atan2_oct[k] = t->atan2_oct[k];
+  t->hot.ship_start_vx = t->ship_start_vx; t->hot.ship_start_vy = t->ship_start_vy;
   return 0;
 }
 

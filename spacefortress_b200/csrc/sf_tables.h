@@ -57,6 +57,15 @@ struct alignas(16) SfExpPhase {
   short qxmin[SF_EXP_QUADS];              // leftmost corner of a quad relative to c.x: its cells start at (c.x + qxmin) >> 8
 };
 
+// the few tables the game step reads every tick, together: one copy lives in SfTables (global memory: state-only
+// kernel), one in the shared memory of every rendering block
+struct SfHot {
+  double cs[360][2];        // cos, sin of integer degrees (== cos_deg, sin_deg)
+  double hex[2][6][4];      // per hexagon edge: px, py, nx, ny (== hex_px, hex_py, hex_nx, hex_ny)
+  double atan2_oct[8];
+  double ship_start_vx, ship_start_vy;
+};
+
 struct SfTap { int si, cnt; float a[SF_MAX_TAPS]; };  // consecutive source indices si..si+cnt-1 and their weights
 
 struct SfTables {
@@ -111,6 +120,7 @@ struct SfTables {
   unsigned char fort_sparse[SF_FORT_STATES][64];
   unsigned char fort_sparse_n[SF_FORT_STATES];
   SfExpPhase exp_phase[256];
+  alignas(16) SfHot hot;
   int text_guard_row;  // moving rects with y0 <= this native row force the general text path
   int bar_guard_row;   // moving rects with y1 >= this native row force the general bar path
 };
