@@ -168,6 +168,11 @@ def ours(args):
     from spacefortress_b200 import dist as sfdist
     import torch.distributed as dist
 
+    # Native libraries print to stdout (NCCL's version banner at init, for one): stdout is for the ONE JSON line, so
+    # everything else goes to stderr until the line is printed
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, local, world = sfdist.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
@@ -262,8 +267,11 @@ def ours(args):
             line["cpu_baseline"] = b
         except Exception as ex:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+    sys.stdout.flush()
+    os.dup2(json_fd, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     env.close()
     if world > 1:
         dist.barrier()
