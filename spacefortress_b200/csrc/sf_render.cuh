@@ -80,7 +80,7 @@ struct __align__(16) SfWarpSmem {
   int4 qinfo[SF_BATCH_QUADS];               //  512 B per quad: {g0 | g1<<16 (biased, clipped to the region), splitD | splitU<<16, flags, 0}
   int4 srec[SF_BATCH_QUADS];                //  512 B per stroke slot: {x0 | w<<8 | nq<<16 | quad0<<24, top (biased), first cell, s0 | s1<<16}
   unsigned short glist[SF_MAX_GROUPS];      //  512 B slot | k<<5 : sub-rows s0 + 8k .. s0 + 8k + 7 of a stroke
-  int ngroups, stage, pad1, pad2;           // stage: which of the two SfTeamSmem copies this warp is drawing from
+  int ngroups, pad0, pad1, pad2;
 #ifdef SF_PHASE_TIMING
   long long prof_last, prof_pad;
 #endif
@@ -153,9 +153,7 @@ struct __align__(16) SfBlockSmem {
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
 extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
-__device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp);
-// the stage copy this warp is drawing from (drawing warps; warp 0 addresses the copies explicitly)
-__device__ __forceinline__ SfTeamSmem& sf_team_smem() { return sf_block_smem().team[sf_warp_smem(threadIdx.x >> 5).stage]; }
+__device__ __forceinline__ SfTeamSmem& sf_team(int sg) { return sf_block_smem().team[sg]; }  // sg: the stage copy being drawn (0 / 1), handed down in a register
 #ifdef SF_BARRIER_TIMING  // tools/gpu_barrier_timing.py: cycles the warps spend at the barriers
 __device__ unsigned long long sf_bar_cycles[8];  // [0] stage barrier (drawing warps), [1] drawing-warp barriers, [2] stage barrier (warp 0)
 __device__ __forceinline__ void sf_bar_add(int k, long long t0) { if ((threadIdx.x & 31) == 0) atomicAdd(&sf_bar_cycles[k], (unsigned long long)(clock64() - t0)); }
@@ -258,7 +256,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
 }
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
-  if (lane == 0) { W.ngroups = 0; W.stage = 0; }
+  if (lane == 0) W.ngroups = 0;
   __syncwarp();
 }
 
@@ -361,8 +359,8 @@ __device__ __forceinline__ int sf_row_of(int g) { return (g >= 0) ? g / SF_GRID_
 // Append one region per participating lane (`want`) to the block's list, in lane order: region ids and coverage
 // cells come from the block-wide pools (one atomic per batch each). Returns the lane's region id, or -1 when the
 // stroke is off the surface (or a pool is full: cannot happen, the round scan admits envs by worst-case need).
-__device__ __forceinline__ int sf_open_regions(int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax, unsigned colour, int tag) {
-  SfTeamSmem& Tm = sf_team_smem();
+__device__ __forceinline__ int sf_open_regions(int lane, bool want, int ymin_g, int ymax_g, int xmin, int xmax, unsigned colour, int tag, int sg) {
+  SfTeamSmem& Tm = sf_team(sg);
   int cx0 = 0, py0 = 0, w = 0, h = 0;
   bool ok = want && ymin_g < ymax_g;
   if (ok) {
@@ -391,8 +389,8 @@ __device__ __forceinline__ int sf_open_regions(int lane, bool want, int ymin_g, 
 // the region of its stroke; the first lane of every stroke slot (`head`: nq consecutive lanes starting here hold the
 // quads of the stroke, [s0, s1) = union of their live sub-rows) stores the stroke record and appends the stroke's
 // work groups of 8 consecutive sub-rows. rid = the stroke's region (-1: none).
-__device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const SfQuadGeom& G, bool has, int rid, bool head, int slot, int nq, int ymin_g, int ymax_g) {
-  const SfTeamSmem& Tm = sf_team_smem();
+__device__ __forceinline__ void sf_publish_quads(SfWarpSmem& W, int lane, const SfQuadGeom& G, bool has, int rid, bool head, int slot, int nq, int ymin_g, int ymax_g, int sg) {
+  const SfTeamSmem& Tm = sf_team(sg);
   int len = 0;
   int4 R = make_int4(0, 0, 0, 0);
   if (rid >= 0) R = Tm.region[rid];
@@ -454,11 +452,11 @@ __device__ __forceinline__ void sf_emit_span_pred(unsigned* acc32, int cell0, in
 // One pass (4 work groups = 32 (stroke, sub-row) items) of the batch that warp `owner` published, starting at its
 // work group g0. Any warp of the block can run any pass: the records are read-only after the block barrier that
 // follows the geometry, and the cells are updated with atomics.
-__device__ __noinline__ void sf_accumulate_pass(int owner, int g0) {
+__device__ __noinline__ void sf_accumulate_pass(int owner, int g0, int sg) {
   const SfWarpSmem& W = sf_warp_smem(owner);
   const int lane = threadIdx.x & 31;
   const int ngroups = W.ngroups;
-  unsigned* acc32 = reinterpret_cast<unsigned*>(sf_team_smem().cells);
+  unsigned* acc32 = reinterpret_cast<unsigned*>(sf_team(sg).cells);
   const int gi = min(g0 + (lane >> 3), ngroups - 1);
   const int ent = W.glist[gi];
   const int4 S = W.srec[ent & 31];
@@ -503,9 +501,9 @@ __device__ __forceinline__ void sf_patch_init(SfWarpSmem& W, const SfTables* T, 
 }
 
 // Blend region `rid` of the round (its coverage cells) into this warp's window (clipped to it).
-__device__ __noinline__ void sf_blend_region(int rid, int win) {
+__device__ __noinline__ void sf_blend_region(int rid, int win, int sg) {
   SfWarpSmem& W = sf_my_smem();
-  const SfTeamSmem& O = sf_team_smem();
+  const SfTeamSmem& O = sf_team(sg);
   const int lane = threadIdx.x & 31;
   const int4 R = O.region[rid];
   const int w = R.z & 0xFFFF, h = (R.z >> 16) & 0xFFFF;
@@ -528,10 +526,10 @@ __device__ __noinline__ void sf_blend_region(int rid, int win) {
 
 // Composite every layer of env slot `e` that intersects the window, in draw order (draw.cpp:227-269), into W.patch.
 // Returns true when no wireframe of the env reaches into the window.
-__device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expcache, int e, int win) {
+__device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expcache, int e, int win, int sg) {
   SfWarpSmem& W = sf_my_smem();
   const SfBlockSmem& B = sf_block_smem();
-  const SfEnvRec& rec = sf_team_smem().env[e];
+  const SfEnvRec& rec = sf_team(sg).env[e];
   const int lane = threadIdx.x & 31;
   const unsigned core = rec.core;
   const int nx0 = SF_WIN_X0(win), ny0 = SF_WIN_Y0(win);
@@ -543,9 +541,9 @@ __device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expc
   int sr = -1, tag = SF_TAG_PROJECTILE;
   bool hit = false;
   if (lane < rec.ns) {
-    sr = sf_team_smem().stroke[rec.s0 + lane].region;
+    sr = sf_team(sg).stroke[rec.s0 + lane].region;
     if (sr >= 0) {
-      const int4 R = sf_team_smem().region[sr];
+      const int4 R = sf_team(sg).region[sr];
       hit = R.x < nx1 && R.x + (R.z & 0xFFFF) > nx0 && R.y < ny1 && R.y + ((R.z >> 16) & 0xFFFF) > ny0;
       tag = (R.w >> 15) & 1;
     }
@@ -556,7 +554,7 @@ __device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expc
   SF_PROF(23);
   // ---- ship wireframe | ship explosion (draw.cpp:233-237) ----
   if (core & SF_CORE_SHIP_ALIVE) {
-    if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r, win); rmask &= ~1u; }
+    if ((rmask & 1u) && first_is_ship) { const int s0r = __shfl_sync(0xffffffffu, sr, 0); sf_blend_region(s0r, win, sg); rmask &= ~1u; }
   } else {
     const int ebox = rec.ebox;
     const int bx0 = (ebox & 255) - 64, by0 = ((ebox >> 8) & 255) - 64;
@@ -634,7 +632,7 @@ __device__ __noinline__ bool sf_composite(const SfTables* T, unsigned char* expc
     const int q = __ffs(rmask) - 1;
     rmask &= rmask - 1;
     const int sq = __shfl_sync(0xffffffffu, sr, q);
-    sf_blend_region(sq, win);
+    sf_blend_region(sq, win, sg);
   }
   SF_PROF(26);
   // ---- score digits (draw.cpp:160-173,267): "%07d" of (int)mPoints ----
@@ -710,14 +708,14 @@ __device__ __noinline__ void sf_window_out(int win, int orect, unsigned char* __
 // Window of the output rectangle [j0..j1] x [i0..i1] of env slot e: composite its native footprint + resample.
 // Returns true when the pixels were also written to `cache` (no wireframe reaches into the window).
 __device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char* expcache, int e, int j0, int i0, int j1, int i1, unsigned char* obs84,
-                                                unsigned char* cache, int corigin) {
+                                                unsigned char* cache, int corigin, int sg) {
   const SfBlockSmem& B = sf_block_smem();
   const int tx0 = B.xtap[j0].x, tx1 = B.xtap[j1].x, ty0 = B.ytap[i0].x, ty1 = B.ytap[i1].x;
   const int nx0 = tx0 & 255, nx1 = (tx1 & 255) + (tx1 >> 8) - 1, ny0 = ty0 & 255, ny1 = (ty1 & 255) + (ty1 >> 8) - 1;
   if (nx1 - nx0 + 1 > SF_WIN_MAX_W || ny1 - ny0 + 1 > SF_WIN_MAX_H) __trap();  // no moving box is that large
   const int win = nx0 | (ny0 << 8) | ((nx1 - nx0 + 1) << 16) | ((ny1 - ny0 + 1) << 24);
   const int orect = j0 | (i0 << 8) | ((j1 - j0 + 1) << 16) | ((i1 - i0 + 1) << 24);
-  const bool pure = sf_composite(T, expcache, e, win);
+  const bool pure = sf_composite(T, expcache, e, win, sg);
   SF_PROF(27);
   sf_window_out(win, orect, obs84, pure ? cache : nullptr, corigin);
   __syncwarp();
@@ -729,7 +727,7 @@ __device__ __forceinline__ bool sf_window_orect(const SfTables* T, unsigned char
 // Geometry for up to 8 strokes at once: lane = 4*slot + line. kind: 0 ship, 1 missile, 2 shell, -1 none.
 // Every lane passes the description of ITS slot's stroke. Appends one region per visible stroke and publishes the
 // quads. Returns the region of the lane's slot (-1 invisible).
-__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle) {
+__device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const SfTables* T, int kind, double px, double py, int angle, int sg) {
   SF_PROF(31);
   const int slot = lane >> 2, line = lane & 3;
   SfQuadGeom G;
@@ -761,10 +759,10 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
   }
   SF_PROF(16);
   // one region per slot, opened in slot order by the slot's first lane
-  int rid = sf_open_regions(lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, sf_block_smem().colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE);
+  int rid = sf_open_regions(lane, line == 0 && kind >= 0, ymin_g, ymax_g, xmin, xmax, sf_block_smem().colour_white, kind == 0 ? SF_TAG_SHIP : SF_TAG_PROJECTILE, sg);
   SF_PROF(17);
   rid = __shfl_sync(0xffffffffu, rid, lane & ~3);
-  sf_publish_quads(W, lane, G, has, rid, line == 0 && kind >= 0, slot, kind >= 0 ? sf_block_smem().wf_nlines[kind] : 0, ymin_g, ymax_g);
+  sf_publish_quads(W, lane, G, has, rid, line == 0 && kind >= 0, slot, kind >= 0 ? sf_block_smem().wf_nlines[kind] : 0, ymin_g, ymax_g, sg);
   SF_PROF(18);
   return rid;
 }
@@ -774,8 +772,8 @@ __device__ __forceinline__ int sf_wire_geometry(SfWarpSmem& W, int lane, const S
 // the tables of its y phase (SfExpPhase, sf_tables.h): one lane per (quad, pixel row) item adds the <= 15 tabulated
 // spans of the item, shifted by the centre's x, into the item's <= SF_EXPT_NC cells (registers: nobody else adds to
 // them) and tells every pixel it covers which quad did. wi / nw: this warp's index among the drawing warps.
-__device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int be, int lane, int wi, int nw) {
-  SfTeamSmem& Tm = sf_team_smem();
+__device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int be, int lane, int wi, int nw, int sg) {
+  SfTeamSmem& Tm = sf_team(sg);
   const SfEnvRec& rec = Tm.env[be];
   const SfPt c = sf_xform_base(rec.px, rec.py);
   const SfExpPhase& P = D.tab->exp_phase[c.y & 255];
@@ -815,8 +813,8 @@ __device__ __forceinline__ void sf_phase_exp_items(const SfDev& D, int be, int l
 // the strokes that cover the pixel, in stroke order (arc s == quad s; the 16 chords of the circle, quads 84..99,
 // are ONE stroke: their lengths add up), over the background (hexagons) and stores the sprite in the env's cache;
 // the windows of phase C read it like any cached sprite. wi / nw: this warp's index among the drawing warps.
-__device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int be, int lane, int wi, int nw) {
-  SfTeamSmem& Tm = sf_team_smem();
+__device__ __forceinline__ void sf_phase_sprite(const SfDev& D, SfBlockSmem& B, int be, int lane, int wi, int nw, int sg) {
+  SfTeamSmem& Tm = sf_team(sg);
   const SfTables* T = D.tab;
   SfEnvRec& rec = Tm.env[be];
   const SfPt c = sf_xform_base(rec.px, rec.py);
@@ -954,8 +952,8 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
 
 // Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
 // out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes)...
-__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
-  const int env = sf_team_smem().env[e].env;
+__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out, int sg) {
+  const int env = sf_team(sg).env[e].env;
   if (env < 0 || lane != 0) return;
   const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
   unsigned char* gb = sf_frame_ptr(out, e, env);
@@ -965,9 +963,9 @@ __device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane
 // ... and, once the bulk copies of this warp have landed, the few 16-byte chunks that the fortress state (about 12
 // for a live fortress, 53 for its explosion) and a non-empty vulnerability bar change are patched from the
 // pre-resampled state tables.
-__device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockSmem& B, int lane, int e, const SfFrameOut& out) {
+__device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockSmem& B, int lane, int e, const SfFrameOut& out, int sg) {
   const SfTables* T = D.tab;
-  const SfEnvRec& rec = sf_team_smem().env[e];
+  const SfEnvRec& rec = sf_team(sg).env[e];
   const int env = rec.env;
   if (env < 0) return;
   const unsigned core = rec.core;
@@ -1072,14 +1070,14 @@ __device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm
 // list: at most one batch per warp) and publishes its records; after a barrier of the drawing warps, B3: the
 // passes of ALL batches are dealt round-robin over ALL drawing warps, so the scan conversion is balanced whatever
 // the size of the individual strokes.
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst) {
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst, int sg) {
   const SfTables* T = D.tab;
-  SfTeamSmem& Tm = sf_team_smem();
+  SfTeamSmem& Tm = sf_team(sg);
   const int chunk = Tm.chunk;
   // B2, first half: the items of the explosion of a ship that died in this stage. They are dealt from the LAST
   // drawing warp down: the geometry batches go to the first warps, so the two overlap.
   const int be = Tm.build_env;
-  if (be >= 0) sf_phase_exp_items(D, be, lane, nw - 1 - wi, nw);
+  if (be >= 0) sf_phase_exp_items(D, be, lane, nw - 1 - wi, nw, sg);
   SF_PROF(21);
   const int s = wi * chunk;
   if (s < nst) {
@@ -1093,7 +1091,7 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
       const SfStrokeRec& S = Tm.stroke[idx];
       x = S.x; y = S.y; kind = S.desc & 3; angle = (S.desc >> 2) & 1023;
     }
-    const int rid = sf_wire_geometry(W, lane, T, kind, x, y, angle);
+    const int rid = sf_wire_geometry(W, lane, T, kind, x, y, angle, sg);
     if (valid && (lane & 3) == 0) Tm.stroke[idx].region = rid;
   } else {
     if (lane == 0) W.ngroups = 0;
@@ -1103,12 +1101,12 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   // B2, second half: the sprite (its stamp is visible to the stepping warp long before it looks at the next stage). A
   // round takes at most two explosions; they share the item lengths and the pixel masks, one after the other.
   if (be >= 0) {
-    sf_phase_sprite(D, B, be, lane, wi, nw);
+    sf_phase_sprite(D, B, be, lane, wi, nw, sg);
     if (Tm.build_env2 >= 0) {
       sf_render_sync();
-      sf_phase_exp_items(D, Tm.build_env2, lane, wi, nw);
+      sf_phase_exp_items(D, Tm.build_env2, lane, wi, nw, sg);
       sf_render_sync();
-      sf_phase_sprite(D, B, Tm.build_env2, lane, wi, nw);
+      sf_phase_sprite(D, B, Tm.build_env2, lane, wi, nw, sg);
     }
   }
   // passes of warp l's batch: (ngroups + 3) / 4; every warp computes the same prefix sums
@@ -1122,20 +1120,20 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   for (int g = wi; g < total; g += nw) {
     const int owner = __popc(__ballot_sync(0xffffffffu, incl <= g));  // first warp whose inclusive count exceeds g
     const int first = __shfl_sync(0xffffffffu, incl - mine, owner);
-    sf_accumulate_pass(owner + 1, (g - first) << 2);
+    sf_accumulate_pass(owner + 1, (g - first) << 2, sg);
   }
   SF_PROF(20);
 }
 
 // phase C task t of this round: env tasks (quarters of explosion boxes, score strips) first, then one per stroke
-__device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int netask, const SfFrameOut& out) {
+__device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int t, int netask, const SfFrameOut& out, int sg) {
   const SfTables* T = D.tab;
   int e, j0, i0, j1, i1;
   int quarter = -1, corigin = 0;
   if (t < netask) {
-    const int et = sf_team_smem().etask[t], kind = et >> 6;
+    const int et = sf_team(sg).etask[t], kind = et >> 6;
     e = et & 63;
-    const SfEnvRec& rec = sf_team_smem().env[e];
+    const SfEnvRec& rec = sf_team(sg).env[e];
     int x0, y0, x1, y1;
     if (kind < 4) {  // dead ship: a quarter (in output rows) of the explosion box
       const int bx0 = (rec.ebox & 255) - 64, by0 = ((rec.ebox >> 8) & 255) - 64;
@@ -1153,19 +1151,19 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
       quarter = kind;
     }
   } else {
-    const SfStrokeRec& S = sf_team_smem().stroke[t - netask];
+    const SfStrokeRec& S = sf_team(sg).stroke[t - netask];
     const int sr = S.region;
     if (sr < 0) return;
     e = S.desc >> 12;
-    const int4 R = sf_team_smem().region[sr];
+    const int4 R = sf_team(sg).region[sr];
     j0 = B.col_out0[R.x]; j1 = B.col_out1[R.x + (R.z & 0xFFFF) - 1]; i0 = B.row_out0[R.y]; i1 = B.row_out1[R.y + ((R.z >> 16) & 0xFFFF) - 1];
   }
-  const int env = sf_team_smem().env[e].env;
+  const int env = sf_team(sg).env[e].env;
   const bool cached = sf_window_orect(T, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, j0, i0, j1, i1, sf_frame_ptr(out, e, env),
-                                      quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin);
+                                      quarter >= 0 ? D.expo + (size_t)env * SF_EXPO_BYTES : nullptr, corigin, sg);
   if (cached && lane == 0) {
     // mark the quarter valid, unless the stepping warp has already re-keyed the cache for the next tick
-    const SfEnvRec& rec = sf_team_smem().env[e];
+    const SfEnvRec& rec = sf_team(sg).env[e];
     const unsigned long long want = (unsigned long long)rec.life | ((unsigned long long)sf_expo_key(rec) << 32);
     unsigned long long* m = reinterpret_cast<unsigned long long*>(&D.expo_meta[env]);
     unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(m);
@@ -1179,13 +1177,13 @@ __device__ __forceinline__ void sf_phase_window(const SfDev& D, SfBlockSmem& B, 
 }
 
 // native output (SSF_Env.step returns the 92x90 frame): tile `tile` (30x30 windows, 3 x 4 of them) of env slot e
-__device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, int tile, const SfFrameOut& out) {
-  const int env = sf_team_smem().env[e].env;
+__device__ __forceinline__ void sf_phase_native_tile(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int e, int tile, const SfFrameOut& out, int sg) {
+  const int env = sf_team(sg).env[e].env;
   if (env < 0) return;
   const int tx = (tile % 3) * 30, ty = (tile / 3) * 30;
   const int pw = min(30, SF_NAT_W - tx), ph = min(30, SF_NAT_H - ty);
   const int win = tx | (ty << 8) | (pw << 16) | (ph << 24);
-  (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win);
+  (void)sf_composite(D.tab, D.expc + (size_t)env * (SF_EXP_W * SF_EXP_W), e, win, sg);
   unsigned char* dst = sf_frame_ptr(out, e, env) + ty * SF_NAT_W + tx;
   sf_for_rect(lane, pw, ph, [&](int c, int r) { dst[r * SF_NAT_W + c] = W.patch[r * SF_PATCH_STRIDE + c]; });
   __syncwarp();
@@ -1278,10 +1276,10 @@ __device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, const SfB
 
 // One stage drawn by the 15 drawing warps (see the pipeline description above): B1 geometry, B3 passes, base
 // patches, B2 explosion sprite, C windows.
-__device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out) {
+__device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, const SfFrameOut& out, int sg) {
   const int warp = threadIdx.x >> 5;
   const int wi = warp - 1, nw = SF_RENDER_WARPS - 1;  // index among the drawing warps, and their number
-  SfTeamSmem& Tm = sf_team_smem();
+  SfTeamSmem& Tm = sf_team(sg);
 #ifdef SF_PHASE_TIMING
   long long t_last_ = clock64(), w_last_ = t_last_;
   const int gwarp = warp;
@@ -1290,17 +1288,17 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
   // ---- B: stroke tasks ----
   if (!out.native) {  // (issuing a bulk copy costs a few hundred cycles: spread over the drawing warps, not on the stepping warp)
 #pragma unroll 1
-    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out);
+    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out, sg);
   }
   SF_PROF_RESET();
-  sf_phase_strokes(D, B, W, lane, wi, nw, nst);
+  sf_phase_strokes(D, B, W, lane, wi, nw, nst, sg);
   SF_PROF(69);
   if (!out.native) {
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
     __syncwarp();
     SF_PROF(65);
 #pragma unroll 1
-    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out);
+    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out, sg);
     SF_PROF(66);
   }
 #ifdef SF_PHASE_TIMING
@@ -1320,11 +1318,11 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= netask + nst) break;
       SF_PROF(29);
-      sf_phase_window(D, B, W, lane, t, netask, out);
+      sf_phase_window(D, B, W, lane, t, netask, out, sg);
     }
   } else {
 #pragma unroll 1
-    for (int t = wi; t < (r1 - r0) * 12; t += nw) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out);
+    for (int t = wi; t < (r1 - r0) * 12; t += nw) sf_phase_native_tile(D, B, W, lane, r0 + t / 12, t % 12, out, sg);
   }
 #ifdef SF_PHASE_TIMING
   if (lane == 0 && blockIdx.x == 0) { atomicAdd(&sf_dbg_cycles[48 + (gwarp & 15)], (unsigned long long)(clock64() - w_last_)); atomicMax(&Tm.dbg_max_c, (int)(clock64() - w_last_)); }
@@ -1378,15 +1376,13 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
         SF_PROF(70);
       }
     } else {
-      if (lane == 0) W.stage = st.stage;
-      __syncwarp();
       // zero the coverage cells of the stage before this one (the other copy)
       {
         const int nz = (st.prev_used + 1) >> 1;
         for (int k = threadIdx.x - 32; k < nz; k += 32 * (SF_RENDER_WARPS - 1)) reinterpret_cast<unsigned*>(Nx.cells)[k] = 0u;
       }
       out.obs = obs0 + (size_t)t * out.tick_bytes;
-      sf_draw_stage(D, B, W, lane, out);
+      sf_draw_stage(D, B, W, lane, out, st.stage);
       st.prev_used = Tm.cells_used;
     }
     st.stage ^= 1;
