@@ -164,6 +164,15 @@ int sf_set_state(sf_handle* h, int first, int count, const sf_state_record* h_in
  * integer sums make the reduction bitwise shard-invariant. */
 int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream);
 
+/* Consumer-side helper for the on-device rollout (rl/train.py:51-56,92-97: current_obs frame stack, zeroed on done,
+ * scaled by 1/255 in rl/networks.py:35): the 4-frame stack of every env as the policy's first-layer input.
+ * d_frames points at the OLDEST of 4 consecutive time-major frames [4][n][84][84] u8 (frame_stride_bytes apart);
+ * d_valid[i] = frames since env i's last reset, capped at 4 (older frames read as 0). d_out is bf16
+ * [n][21][21][64], i.e. an NHWC tensor of shape (n, 64, 21, 21) in channels_last: channel = frame*16 + (y%4)*4 + (x%4)
+ * of pixel (4*Y + y%4, 4*X + x%4) -- the space-to-depth form in which conv(4->16, k8, s4) is a 2x2 convolution
+ * over 64 channels (same sums). value = bf16(u8 / 255). No handle: a pure function of its arguments. */
+int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream);
+
 /* Static tables built at sf_create (host copies, for tests/inspection): background frames. */
 int sf_background(const sf_handle* h, uint8_t* h_native /*[92*90]*/, uint8_t* h_obs /*[84*84]*/);
 

@@ -537,6 +537,46 @@ static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const un
   return SF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// policy input (consumer side of the on-device rollout): 4-frame stack -> space-to-depth bf16 NHWC
+// ------------------------------------------------------------------------------------------------
+#include <cuda_bf16.h>
+// one thread per 16-byte output chunk: 8 channels = frame f, rows dy0, dy0 + 1, 4 columns of block (Y, X)
+__global__ void __launch_bounds__(256) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
+                                                             uint4* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * (21 * 21 * 8);
+  if (gid >= total) return;
+  const int env = (int)(gid / (21 * 21 * 8));
+  const int r = (int)(gid - (long long)env * (21 * 21 * 8));
+  const int c8 = r & 7, yx = r >> 3;
+  const int Y = yx / 21, X = yx - Y * 21;
+  const int f = c8 >> 1, dy0 = (c8 & 1) * 2;
+  const bool keep = f >= 4 - min(max(valid[env], 0), 4);
+  unsigned a = 0u, b = 0u;
+  if (keep) {
+    const unsigned char* src = frames + (long long)f * fstride + (long long)env * (84 * 84) + (4 * Y + dy0) * 84 + 4 * X;
+    a = *reinterpret_cast<const unsigned*>(src);
+    b = *reinterpret_cast<const unsigned*>(src + 84);
+  }
+  auto cvt2 = [](unsigned lo, unsigned hi) {  // bf16(u8 / 255), like torch: u8 -> bf16 (exact), / 255 in fp32, round to bf16
+    __nv_bfloat162 v = __floats2bfloat162_rn(__fdiv_rn((float)lo, 255.0f), __fdiv_rn((float)hi, 255.0f));
+    return *reinterpret_cast<unsigned*>(&v);
+  };
+  uint4 o;
+  o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
+  o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
+  out[gid] = o;
+}
+
+extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
+  if (!d_frames || !d_valid || !d_out_bf16 || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
+  const long long total = (long long)n * (21 * 21 * 8);
+  sf_policy_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
+  CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+
 extern "C" int sf_set_ticks(sf_handle* h, const int32_t* h_ticks) {
   if (!h || !h_ticks) return fail(SF_ERR_INVALID, "handle or ticks is NULL");
   CUDA_TRY(cudaSetDevice(h->device));

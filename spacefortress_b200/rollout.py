@@ -35,9 +35,20 @@ class SFGRUPolicy(nn.Module):
                 nn.init.orthogonal_(m.weight_ih); nn.init.orthogonal_(m.weight_hh)
                 nn.init.zeros_(m.bias_ih); nn.init.zeros_(m.bias_hh)
 
-    def features(self, obs_u8, state, mask):
+    def conv1_s2d_weight(self):
+        """conv1 (4->16, k8, s4) as a 2x2 convolution over the 64 channels of the space-to-depth input that
+        sf_policy_input builds (channel = frame*16 + (y%4)*4 + (x%4)): the same sums, 10x faster in cuDNN."""
+        w = self.conv1.weight
+        return w.view(16, 4, 2, 4, 2, 4).permute(0, 1, 3, 5, 2, 4).reshape(16, 64, 2, 2).contiguous(memory_format=torch.channels_last)
+
+    def features(self, obs_u8, state, mask, s2d=False):
+        """obs_u8: [N,4,84,84] u8 stack, or with s2d=True the [N,64,21,21] channels_last input of sf_policy_input
+        (already scaled by 1/255 in the policy's dtype)."""
         dt = self.conv1.weight.dtype  # fp32 like the reference, or bf16 via policy.bfloat16()
-        x = F.relu(self.conv1(obs_u8.to(dt) / 255.0))
+        if s2d:
+            x = F.relu(F.conv2d(obs_u8, self.conv1_s2d_weight(), self.conv1.bias))
+        else:
+            x = F.relu(self.conv1(obs_u8.to(dt) / 255.0))
         x = F.relu(self.conv2(x)).flatten(1)
         x = F.relu(self.fc1(x))
         if self.feedforward:
@@ -46,8 +57,8 @@ class SFGRUPolicy(nn.Module):
         return h, h
 
     @torch.no_grad()
-    def act(self, obs_u8, state, mask, deterministic=False):
-        x, state = self.features(obs_u8, state, mask)
+    def act(self, obs_u8, state, mask, deterministic=False, s2d=False):
+        x, state = self.features(obs_u8, state, mask, s2d=s2d)
         logits = self.action(x)
         logp = F.log_softmax(logits, dim=1)
         action = logits.argmax(1, keepdim=True) if deterministic else torch.multinomial(logp.float().exp(), 1)
@@ -73,6 +84,10 @@ class OnDeviceRollout(object):
         self.final_return = torch.zeros(n, dtype=torch.int64, device=dev)
         self.num_destruction = torch.zeros((), dtype=torch.int64, device=dev)
         self._age_idx = torch.arange(self.S, device=dev, dtype=torch.int32).view(1, self.S, 1, 1)
+        # bf16 policy: its first-layer input comes from the fused stack / mask / scale / space-to-depth kernel
+        self.fused_input = next(policy.parameters()).dtype == torch.bfloat16 and self.S == 4
+        if self.fused_input:
+            self.pin = torch.empty((n, 64, 21, 21), dtype=torch.bfloat16, device=dev).contiguous(memory_format=torch.channels_last)
         first = env.reset(to_numpy=False)
         self.frames[self.S - 1].copy_(first[:, 0])
         self.valid.fill_(1)
@@ -83,10 +98,21 @@ class OnDeviceRollout(object):
         keep = self._age_idx >= (self.S - self.valid).view(-1, 1, 1, 1)
         return w * keep.to(torch.uint8)
 
+    def policy_input(self, t):
+        """The 4-frame stack ending at frame t as the policy's space-to-depth bf16 input (one fused kernel)."""
+        from . import _lib
+        import ctypes as C
+        _lib.check(self.env.L.sf_policy_input(C.c_void_p(self.frames[t].data_ptr()), int(self.frames.stride(0)), self.env.num_envs,
+                                              C.c_void_p(self.valid.data_ptr()), C.c_void_p(self.pin.data_ptr()), self.env._stream_ptr()))
+        return self.pin
+
     def collect(self):
         env, S = self.env, self.S
         for t in range(self.T):
-            value, action, logp, self.state = self.policy.act(self.stack(t), self.state, self.mask)
+            if self.fused_input:
+                value, action, logp, self.state = self.policy.act(self.policy_input(t), self.state, self.mask, s2d=True)
+            else:
+                value, action, logp, self.state = self.policy.act(self.stack(t), self.state, self.mask)
             a = action.squeeze(1).to(torch.int32)
             _, reward, done, kill = env.step(a, out_obs=self.frames[t + S].unsqueeze(1))
             self.actions[t] = a; self.rewards[t] = reward; self.dones[t] = done

@@ -473,6 +473,28 @@ def test_single_env_facade_matches_oracle():
     env.close()
 
 
+def test_policy_input_kernel_matches_the_torch_stack():
+    """sf_policy_input (stack + zero the frames from before a reset + 1/255 + space-to-depth, one kernel) against the
+    plain torch formulation, bit for bit; and conv1 on it against conv1 on the NCHW stack."""
+    torch = torch_cuda()
+    from spacefortress_b200.rollout import OnDeviceRollout, SFGRUPolicy
+    n = 300
+    env = make("youturn", n)
+    policy = SFGRUPolicy(env.num_actions).cuda().eval().bfloat16()
+    ro = OnDeviceRollout(env, policy, num_steps=6)
+    ro.collect()
+    ro.valid[::7] = 1; ro.valid[3::7] = 2; ro.valid[5::7] = 3   # resets of different ages
+    for t in (0, 3, 5):
+        stack = ro.stack(t)                                           # [N,4,84,84] u8, masked
+        ref = (stack.to(torch.bfloat16) / 255.0).view(n, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(n, 64, 21, 21)
+        got = ro.policy_input(t)
+        assert got.shape == ref.shape and torch.equal(got.float(), ref.float()), t
+        a = torch.nn.functional.conv2d(got, policy.conv1_s2d_weight(), policy.conv1.bias).float()
+        b = policy.conv1(stack.to(torch.bfloat16) / 255.0).float()
+        assert (a - b).abs().max().item() <= 0.05 * max(1.0, b.abs().max().item()), t
+    env.close()
+
+
 def test_on_device_rollout_frame_stack_matches_reference_loop():
     """OnDeviceRollout (config 3 plumbing): the 4-frame window over the single-frame buffer equals the
     reference's running `current_obs` (rl/train.py:51-56,92-97: zero the stack on done, shift, append)."""
