@@ -541,38 +541,39 @@ static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const un
 // policy input (consumer side of the on-device rollout): 4-frame stack -> space-to-depth bf16 NHWC
 // ------------------------------------------------------------------------------------------------
 #include <cuda_bf16.h>
-// one thread per 16-byte output chunk: 8 channels = frame f, rows dy0, dy0 + 1, 4 columns of block (Y, X)
-__global__ void __launch_bounds__(256) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
+// One block per (env, Y): the 4 frames x 4 pixel rows it needs (1344 B) are staged in shared memory with coalesced
+// 32-bit loads, then the 21 x 64 bf16 of output row Y go out as coalesced 16-byte stores (8 channels = frame f,
+// rows dy0, dy0 + 1, 4 columns of block X).
+__global__ void __launch_bounds__(128) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
                                                              uint4* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * (21 * 21 * 8);
-  if (gid >= total) return;
-  const int env = (int)(gid / (21 * 21 * 8));
-  const int r = (int)(gid - (long long)env * (21 * 21 * 8));
-  const int c8 = r & 7, yx = r >> 3;
-  const int Y = yx / 21, X = yx - Y * 21;
-  const int f = c8 >> 1, dy0 = (c8 & 1) * 2;
-  const bool keep = f >= 4 - min(max(valid[env], 0), 4);
-  unsigned a = 0u, b = 0u;
-  if (keep) {
-    const unsigned char* src = frames + (long long)f * fstride + (long long)env * (84 * 84) + (4 * Y + dy0) * 84 + 4 * X;
-    a = *reinterpret_cast<const unsigned*>(src);
-    b = *reinterpret_cast<const unsigned*>(src + 84);
+  __shared__ unsigned tile[4 * 4 * 21];  // [frame][dy][X] : 4 pixels each
+  const int env = blockIdx.x / 21, Y = blockIdx.x - env * 21;
+  const int nvalid = min(max(valid[env], 0), 4);
+  for (int k = threadIdx.x; k < 4 * 4 * 21; k += 128) {
+    const int f = k / 84, r = k - f * 84, dy = r / 21, X = r - dy * 21;
+    unsigned v = 0u;
+    if (f >= 4 - nvalid) v = *reinterpret_cast<const unsigned*>(frames + (long long)f * fstride + (long long)env * (84 * 84) + (4 * Y + dy) * 84 + 4 * X);
+    tile[k] = v;
   }
+  __syncthreads();
   auto cvt2 = [](unsigned lo, unsigned hi) {  // bf16(u8 / 255), like torch: u8 -> bf16 (exact), / 255 in fp32, round to bf16
     __nv_bfloat162 v = __floats2bfloat162_rn(__fdiv_rn((float)lo, 255.0f), __fdiv_rn((float)hi, 255.0f));
     return *reinterpret_cast<unsigned*>(&v);
   };
-  uint4 o;
-  o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
-  o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
-  out[gid] = o;
+  uint4* orow = out + ((long long)env * 21 + Y) * (21 * 8);
+  for (int k = threadIdx.x; k < 21 * 8; k += 128) {
+    const int X = k >> 3, c8 = k & 7, f = c8 >> 1, dy0 = (c8 & 1) * 2;
+    const unsigned a = tile[(f * 4 + dy0) * 21 + X], b = tile[(f * 4 + dy0 + 1) * 21 + X];
+    uint4 o;
+    o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
+    o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
+    orow[k] = o;
+  }
 }
 
 extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
   if (!d_frames || !d_valid || !d_out_bf16 || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
-  const long long total = (long long)n * (21 * 21 * 8);
-  sf_policy_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
+  sf_policy_input_kernel<<<(unsigned)n * 21u, 128, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }

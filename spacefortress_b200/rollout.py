@@ -46,11 +46,17 @@ class SFGRUPolicy(nn.Module):
         (already scaled by 1/255 in the policy's dtype)."""
         dt = self.conv1.weight.dtype  # fp32 like the reference, or bf16 via policy.bfloat16()
         if s2d:
-            x = F.relu(F.conv2d(obs_u8, self.conv1_s2d_weight(), self.conv1.bias))
+            # channels_last bf16 all the way: cuDNN's fused conv + bias + relu, and fc1 on the NHWC-flattened
+            # activations (weight columns permuted accordingly) instead of a layout copy
+            x = torch.cudnn_convolution_relu(obs_u8, self.conv1_s2d_weight(), self.conv1.bias, (1, 1), (0, 0), (1, 1), 1)
+            x = torch.cudnn_convolution_relu(x, self.conv2.weight.contiguous(memory_format=torch.channels_last), self.conv2.bias, (2, 2), (0, 0), (1, 1), 1)
+            x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)   # a view for channels_last: [N, 9*9*32]
+            w = self.fc1.weight.view(256, 32, 9, 9).permute(0, 2, 3, 1).reshape(256, 2592)
+            x = F.relu(F.linear(x, w, self.fc1.bias))
         else:
             x = F.relu(self.conv1(obs_u8.to(dt) / 255.0))
-        x = F.relu(self.conv2(x)).flatten(1)
-        x = F.relu(self.fc1(x))
+            x = F.relu(self.conv2(x)).flatten(1)
+            x = F.relu(self.fc1(x))
         if self.feedforward:
             return F.relu(self.core(x)), state
         h = self.core(x, (state * mask).to(x.dtype))

@@ -492,6 +492,12 @@ def test_policy_input_kernel_matches_the_torch_stack():
         a = torch.nn.functional.conv2d(got, policy.conv1_s2d_weight(), policy.conv1.bias).float()
         b = policy.conv1(stack.to(torch.bfloat16) / 255.0).float()
         assert (a - b).abs().max().item() <= 0.05 * max(1.0, b.abs().max().item()), t
+        # the whole feature path (fused conv + bias + relu, NHWC fc1) against the generic one, bf16 tolerance
+        st = torch.zeros(n, 256, device="cuda", dtype=torch.bfloat16); mk = torch.ones(n, 1, device="cuda", dtype=torch.bfloat16)
+        with torch.no_grad():
+            fa, _ = policy.features(got, st, mk, s2d=True)
+            fb, _ = policy.features(stack, st, mk)
+        assert (fa.float() - fb.float()).abs().max().item() <= 0.06 * max(1.0, fb.float().abs().max().item()), t
     env.close()
 
 
