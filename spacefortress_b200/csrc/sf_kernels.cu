@@ -541,39 +541,48 @@ static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const un
 // policy input (consumer side of the on-device rollout): 4-frame stack -> space-to-depth bf16 NHWC
 // ------------------------------------------------------------------------------------------------
 #include <cuda_bf16.h>
-// One block per (env, Y): the 4 frames x 4 pixel rows it needs (1344 B) are staged in shared memory with coalesced
-// 32-bit loads, then the 21 x 64 bf16 of output row Y go out as coalesced 16-byte stores (8 channels = frame f,
-// rows dy0, dy0 + 1, 4 columns of block X).
-__global__ void __launch_bounds__(128) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
-                                                             uint4* __restrict__ out) {
-  __shared__ unsigned tile[4 * 4 * 21];  // [frame][dy][X] : 4 pixels each
-  const int env = blockIdx.x / 21, Y = blockIdx.x - env * 21;
+// One block per env. For each of the 21 output rows Y the 4 frames x 4 pixel rows it needs (1344 B) are staged in
+// shared memory with coalesced 32-bit loads (two tiles: one barrier per row), then the 21 x 64 bf16 of the row go out
+// as coalesced 16-byte stores (8 channels = frame f, rows dy0, dy0 + 1, 4 columns of block X). u8 -> bf16(u8 / 255)
+// through a 256-entry table built with the exact formula (u8 -> fp32, / 255 in fp32, round to bf16, like torch).
+#define SF_PI_THREADS 192
+__global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
+                                                                       uint4* __restrict__ out) {
+  __shared__ unsigned tile[2][4 * 4 * 21];  // [frame][dy][X] : 4 pixels each
+  __shared__ unsigned short lut[256];
+  const int env = blockIdx.x, tid = threadIdx.x;
+  for (int v = tid; v < 256; v += SF_PI_THREADS) { const __nv_bfloat16 h = __float2bfloat16_rn(__fdiv_rn((float)v, 255.0f)); lut[v] = *reinterpret_cast<const unsigned short*>(&h); }
   const int nvalid = min(max(valid[env], 0), 4);
-  for (int k = threadIdx.x; k < 4 * 4 * 21; k += 128) {
-    const int f = k / 84, r = k - f * 84, dy = r / 21, X = r - dy * 21;
-    unsigned v = 0u;
-    if (f >= 4 - nvalid) v = *reinterpret_cast<const unsigned*>(frames + (long long)f * fstride + (long long)env * (84 * 84) + (4 * Y + dy) * 84 + 4 * X);
-    tile[k] = v;
-  }
-  __syncthreads();
-  auto cvt2 = [](unsigned lo, unsigned hi) {  // bf16(u8 / 255), like torch: u8 -> bf16 (exact), / 255 in fp32, round to bf16
-    __nv_bfloat162 v = __floats2bfloat162_rn(__fdiv_rn((float)lo, 255.0f), __fdiv_rn((float)hi, 255.0f));
-    return *reinterpret_cast<unsigned*>(&v);
-  };
-  uint4* orow = out + ((long long)env * 21 + Y) * (21 * 8);
-  for (int k = threadIdx.x; k < 21 * 8; k += 128) {
-    const int X = k >> 3, c8 = k & 7, f = c8 >> 1, dy0 = (c8 & 1) * 2;
-    const unsigned a = tile[(f * 4 + dy0) * 21 + X], b = tile[(f * 4 + dy0 + 1) * 21 + X];
-    uint4 o;
-    o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
-    o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
-    orow[k] = o;
+  // what this thread loads (words k0 = tid and k1 = tid + 192 of the 336-word tile) and stores (chunk tid < 168)
+  const unsigned char* base = frames + (long long)env * (84 * 84);
+  const int k1 = tid + SF_PI_THREADS;
+  const int f0 = tid / 84, r0 = tid - f0 * 84, f1 = k1 / 84, r1 = k1 - f1 * 84;
+  const bool on0 = f0 >= 4 - nvalid, on1 = k1 < 336 && f1 >= 4 - nvalid;
+  const unsigned char* p0 = base + (long long)f0 * fstride + (r0 / 21) * 84 + (r0 % 21) * 4;
+  const unsigned char* p1 = base + (long long)(k1 < 336 ? f1 : 0) * fstride + (r1 / 21) * 84 + (r1 % 21) * 4;
+  const int X = tid >> 3, c8 = tid & 7, f = c8 >> 1, dy0 = (c8 & 1) * 2;
+  const int ta = (f * 4 + dy0) * 21 + X, tb = ta + 21;
+  uint4* orow = out + (long long)env * (21 * 21 * 8);
+  auto cvt2 = [&](unsigned lo, unsigned hi) { return (unsigned)lut[lo] | ((unsigned)lut[hi] << 16); };
+#pragma unroll 1
+  for (int Y = 0; Y < 21; Y++) {
+    unsigned* T = tile[Y & 1];
+    T[tid] = on0 ? *reinterpret_cast<const unsigned*>(p0 + Y * (4 * 84)) : 0u;
+    if (k1 < 336) T[k1] = on1 ? *reinterpret_cast<const unsigned*>(p1 + Y * (4 * 84)) : 0u;
+    __syncthreads();  // (the other tile is free again: every thread passed the previous barrier after reading it)
+    if (tid < 21 * 8) {
+      const unsigned a = T[ta], b = T[tb];
+      uint4 o;
+      o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
+      o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
+      orow[Y * (21 * 8) + tid] = o;
+    }
   }
 }
 
 extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
   if (!d_frames || !d_valid || !d_out_bf16 || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
-  sf_policy_input_kernel<<<(unsigned)n * 21u, 128, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
+  sf_policy_input_kernel<<<(unsigned)n, SF_PI_THREADS, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
