@@ -537,3 +537,24 @@ def test_on_device_rollout_frame_stack_matches_reference_loop():
         ro.valid = torch.where(done, torch.ones_like(ro.valid), torch.clamp(ro.valid + 1, max=ro.S))
     assert sum(int(s.sum() == 0) for s in stacks) == 0
     env.close()
+
+
+def test_ppo_update_on_an_on_device_rollout():
+    """Collect a rollout on the device and update on it without leaving the device (rl/train.py:73-146)."""
+    torch = torch_cuda()
+    from spacefortress_b200.rollout import OnDeviceRollout, SFGRUPolicy
+    from spacefortress_b200.ppo import PPOLearner
+    n, T = 64, 8
+    env = make("youturn", n)
+    policy = SFGRUPolicy(env.num_actions).cuda()
+    ro = OnDeviceRollout(env, policy, num_steps=T)
+    state0, mask0 = ro.state.clone(), ro.mask.clone()
+    ro.collect()
+    with torch.no_grad():
+        next_value, _, _, _ = policy.act(ro.stack(T), ro.state, ro.mask)
+    before = [p.detach().clone() for p in policy.parameters()]
+    stats = PPOLearner(policy, ppo_epoch=2, num_mini_batch=4).update(ro, state0, mask0, next_value.squeeze(1))
+    assert len(stats) == 8 and all(np.isfinite(s).all() for s in stats)
+    assert any(not torch.equal(a, b) for a, b in zip(before, policy.parameters()))
+    env.close()
+
