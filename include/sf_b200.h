@@ -70,6 +70,9 @@ enum {
   SF_FLAG_RAW_REWARD = 16   /* reward = Game.step_one_tick's int (pymodule.cpp:230): no Python-layer shaping, prev_vlner untouched */
 };
 
+/* observation types of SSF_Env (ssf_env.py:51): the image is sf_step's d_obs; the other three are sf_features */
+enum { SF_OBS_IMAGE = 0, SF_OBS_FEATURES = 1, SF_OBS_NORMALIZED_FEATURES = 2, SF_OBS_MONITORS = 3 };
+
 /* Per-env state record for get/set (teacher forcing, checkpointing, getters). Same members as the
  * reference's public Game fields (game.hh:84-107) + prev_vlner (ssf_env.py:92) + rand() position. */
 typedef struct sf_state_record {
@@ -143,8 +146,12 @@ int sf_synthetic_action(uint32_t action_seed, long long global_env, long long t,
 /* Render the current state without stepping (Game.draw + gray + resize). */
 int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
 
-/* Host-buffer convenience path (numpy drop-in for rl/train.py:79-80): H2D actions, step, D2H results,
- * synchronous. Copies go straight from/to the caller's buffers (use sf_host_alloc for them). h_obs may be NULL. */
+/* Host-buffer path (numpy drop-in for rl/train.py:79-80): H2D actions, step, D2H results, synchronous. Copies go
+ * straight from/to the caller's buffers (use sf_host_alloc for them). h_obs may be NULL. Runs on streams the handle
+ * owns: the slab is stepped in slices of consecutive envs so that the kernel of one slice overlaps the device->host
+ * copy of the previous one. Ordered after everything queued with stream == NULL; work queued on any OTHER stream for
+ * this handle must have completed before the call (sf_set_ticks, sf_get_state and sf_set_state synchronise the
+ * device themselves). */
 int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
                  uint8_t* h_fortkill, uint32_t* h_events, int flags);
 
@@ -172,6 +179,17 @@ int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream);
  * of pixel (4*Y + y%4, 4*X + x%4) -- the space-to-depth form in which conv(4->16, k8, s4) is a 2x2 convolution
  * over 64 channels (same sums). value = bf16(u8 / 255). No handle: a pure function of its arguments. */
 int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream);
+
+/* Feature observations of the CURRENT state (SSF_Env._get_features, ssf_env.py:95-157), one row per env:
+ * SF_OBS_FEATURES / SF_OBS_NORMALIZED_FEATURES: 15 + 4 key timers (youturn) or + 2 (autoturn) columns, SF_OBS_MONITORS: 10.
+ * vdir / aim / ndist are Game::computeExtra (game.cpp:282-312, including its fdist bug) evaluated in fp64 on the device;
+ * before the first tick of an episode they are 0 (the reference's mExtra is uninitialised there). len(shells) counts
+ * shells and the vulnerability timer is the real one (the reference's getters for them are broken: pymodule.cpp:44-45,
+ * 131-134). d_out: float32 (sf_features) or float64 (sf_features_f64, what np.array(f) holds in the reference)
+ * [n][sf_num_features]. */
+int sf_num_features(const sf_handle* h, int obs_type);
+int sf_features(sf_handle* h, int obs_type, float* d_out, void* stream);
+int sf_features_f64(sf_handle* h, int obs_type, double* d_out, void* stream);
 
 /* Static tables built at sf_create (host copies, for tests/inspection): background frames. */
 int sf_background(const sf_handle* h, uint8_t* h_native /*[92*90]*/, uint8_t* h_obs /*[84*84]*/);

@@ -151,6 +151,8 @@ def ref_lib():
         L.sfref_get_extra.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sfref_hexagons.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.sfref_wireframe.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.sfref_events.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.sfref_collisions.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.sfref_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
         L.sfref_run.restype = C.c_long
         L.sfref_run_render.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
@@ -299,6 +301,18 @@ class RefEnv:
         b = C.create_string_buffer(8192)
         self.L.sfref_dump(self.h, b, 8192)
         return b.value.decode()
+
+    def events(self):
+        """Game.events of the last tick (pymodule.cpp:136-143)."""
+        b = C.create_string_buffer(4096)
+        self.L.sfref_events(self.h, b, 4096)
+        return tuple(x for x in b.value.decode().split(",") if x)
+
+    def collisions(self):
+        """Game.collisions of the last tick, in pymodule.cpp:182-197's order."""
+        b = C.create_string_buffer(256)
+        self.L.sfref_collisions(self.h, b, 256)
+        return tuple(x for x in b.value.decode().split(",") if x)
 
     def hexagons(self):
         big = (C.c_double * 12)()

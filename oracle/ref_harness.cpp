@@ -281,6 +281,32 @@ void sfref_get_extra(RefEnv* e, double* out4) {
   out4[2] = e->game->mExtra.ndist; out4[3] = e->game->mExtra.aim;
 }
 
+/* Game.events (pymodule.cpp:136-143): the tick's event strings in order, joined with ','; and Game.collisions
+ * (pymodule.cpp:182-197), which fills its tuple from the back: shell, missile, smallhex, bighex */
+int sfref_events(RefEnv* e, char* buf, int cap) {
+  std::string s;
+  for (size_t i = 0; i < e->game->mEvents.size(); i++) { if (i) s += ","; s += e->game->mEvents[i]; }
+  int n = (int)s.size();
+  if (n >= cap) n = cap - 1;
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return n;
+}
+int sfref_collisions(RefEnv* e, char* buf, int cap) {
+  const Collisions& c = e->game->mCollisions;
+  std::string s;
+  if (c.shellShip) s += "shell,";
+  if (c.missileFortress) s += "missile,";
+  if (c.smallHex) s += "smallhex,";
+  if (c.bigHex) s += "bighex,";
+  if (!s.empty()) s.pop_back();
+  int n = (int)s.size();
+  if (n >= cap) n = cap - 1;
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return n;
+}
+
 /* hexagon vertices (hexagon.cpp:13-35): out[12] = big x0,y0..x5,y5 ; small likewise */
 void sfref_hexagons(RefEnv* e, double* big12, double* small12) {
   for (int i = 0; i < 6; i++) {

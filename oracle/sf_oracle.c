@@ -453,6 +453,10 @@ int sfo_action_to_keymask(int gametype, int action_set, int action) {
 void sfo_get_extra(const sfo_env* e, double* out4) {
   const sfr_record* s = &e->s;
   double vdir;
+  if (s->tick == 0) { /* no updateShip yet: mExtra of a fresh Game (zero-filled in oracle/ref_harness.cpp) */
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+    return;
+  }
   if (sqrt(s->ship_vx * s->ship_vx + s->ship_vy * s->ship_vy) == 0.0) vdir = 0.0;
   else {
     double o = atan2(-(FORT_Y - s->ship_y), FORT_X - s->ship_x);

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsf_b200.so")
+# SF_B200_LIB: a variant build of the same library (tools/: -D instrumented builds); never another implementation
+LIB_PATH = os.environ.get("SF_B200_LIB") or os.path.join(HERE, "libsf_b200.so")
 
 SF_OK, SF_ERR_INVALID, SF_ERR_CUDA, SF_ERR_UNSUPPORTED = 0, 1, 2, 3
 MAX_MISSILES = 20
@@ -19,6 +20,8 @@ NATIVE_H, NATIVE_W = 92, 90
 
 KEY_FIRE, KEY_THRUST, KEY_LEFT, KEY_RIGHT = 1, 2, 4, 8
 FLAG_RENDER, FLAG_NO_AUTORESET, FLAG_ACTIONS_ARE_KEYMASKS, FLAG_NATIVE_OBS, FLAG_RAW_REWARD = 1, 2, 4, 8, 16
+
+OBS_TYPES = {"image": 0, "features": 1, "normalized-features": 2, "monitors": 3}  # ssf_env.py:51
 
 EVENT_BITS = {
     "missile-fired": 1 << 0, "fortress-fired": 1 << 1, "hit-fortress": 1 << 2, "vlner-increased": 1 << 3,
@@ -88,6 +91,9 @@ _PROTOTYPES = {
     "sf_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_set_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sf_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sf_num_features": (C.c_int, [C.c_void_p, C.c_int]),
+    "sf_features": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_features_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sf_background": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sf_host_static_frame": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
@@ -103,6 +109,8 @@ def lib():
                           "(there is no fallback implementation)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in _PROTOTYPES.items():
+            if os.environ.get("SF_B200_LIB") and not hasattr(L, name):
+                continue  # an older variant build under test (tools/gpu_ab.py); the product library must export everything
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -116,13 +124,31 @@ def check(rc):
         raise SFError("sf_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
 
 
+class _PinnedBlock(object):
+    """Owns one sf_host_alloc block; freed when the last numpy view of it is garbage collected."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and _LIB is not None:
+                _LIB.sf_host_free(self.ptr)
+            self.ptr = None
+        except Exception:
+            pass
+
+
 def pinned_array(shape, dtype):
-    """numpy array over page-locked host memory (sf_host_alloc): device<->host copies DMA straight into it."""
+    """numpy array over page-locked host memory (sf_host_alloc): device<->host copies DMA straight into it. The
+    memory belongs to the array: it is released (sf_host_free) when the last view of it dies, never while a caller
+    still holds an observation it was handed."""
     import numpy as np
     dt = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dt.itemsize
     p = C.c_void_p()
     check(lib().sf_host_alloc(C.byref(p), max(nbytes, 1)))
     buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    buf._owner = _PinnedBlock(p)  # numpy keeps `buf` alive through .base; `buf` keeps the block alive
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    return arr, p
+    return arr

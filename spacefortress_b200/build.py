@@ -29,11 +29,12 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defs=None):
+    """out / defs: a variant build (tools/: instrumented or experimental -D knobs) beside the product library."""
+    if out is None and not force and not needs_build():
         return LIB
     cmd = [
-        _nvcc(), "-shared", "-o", LIB,
+        _nvcc(), "-shared", "-o", out or LIB,
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17",
         # host side (static tables) and device side must not contract a*b+c: the model is defined
@@ -42,13 +43,13 @@ def build(force=False, verbose=False):
         "--fmad=false",
         "-Xptxas", "-v" if verbose else "-O3",
         "-I", os.path.join(HERE, "..", "include"),
-    ] + os.environ.get("SF_NVCC_DEFS", "").split() + [os.path.join(CSRC, s) for s in SOURCES]
+    ] + (defs.split() if defs is not None else os.environ.get("SF_NVCC_DEFS", "").split()) + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -51,6 +51,7 @@ class Game(object):
                                       "viewport=(130,80,450,460), lw=3, grayscale=True (ssf_env.py:50,164)")
         self.L = _lib.lib()
         self.gametype = config
+        self.device = int(device)
         self._config = config_of(config)
         h = C.c_void_p()
         _lib.check(self.L.sf_create(config.encode(), -1, 1, int(device), C.byref(h)))
@@ -60,7 +61,8 @@ class Game(object):
         _lib.check(self.L.sf_reset(self.h, None, 1, None, 0, None))
         self._pixels = np.zeros((92, 90, 4), np.uint8)  # BGRX like the cairo RGB24 surface (draw.cpp:62-66)
         self._keys = None  # pending key state for the next tick
-        self._touched = set()
+        self._touched = []   # (sym, state) of the press_key / release_key calls since the last tick, in call order
+        self._logged = ()
         self._rec = None
         self._events = 0
         self._last = (0, False, False)
@@ -98,10 +100,10 @@ class Game(object):
             return
         if self._keys is None:
             self._keys = self._current_keymask()
-            self._touched = set()
-        if sym in self._touched:
+            self._touched = []
+        if any(k == sym for k, _ in self._touched):
             raise NotImplementedError("more than one event for the same key inside one tick")
-        self._touched.add(sym)
+        self._touched.append((sym, bool(state)))
         self._keys = (self._keys | _KEY_BIT[sym]) if state else (self._keys & ~_KEY_BIT[sym])
 
     def press_key(self, sym):
@@ -115,6 +117,7 @@ class Game(object):
             raise NotImplementedError("the tick is fixed at 34 ms (ssf_env.py:61)")
         km = self._keys if self._keys is not None else self._current_keymask()
         self._keys = None
+        self._logged, self._touched = tuple(self._touched), []
         a = np.array([km], np.int32)
         rew = np.zeros(1, np.int32)
         done = np.zeros(1, np.uint8)
@@ -134,10 +137,22 @@ class Game(object):
     def _render(self, native):
         import torch
         shape = (1, 92, 90) if native else (1, 84, 84)
-        o = torch.empty(shape, dtype=torch.uint8, device=torch.device("cuda", 0))
-        _lib.check(self.L.sf_render(self.h, C.c_void_p(o.data_ptr()), _lib.FLAG_NATIVE_OBS if native else 0,
-                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return o[0].cpu().numpy()
+        dev = torch.device("cuda", self.device)  # the device the slab lives on (sf_create), not the current one
+        with torch.cuda.device(dev):
+            o = torch.empty(shape, dtype=torch.uint8, device=dev)
+            _lib.check(self.L.sf_render(self.h, C.c_void_p(o.data_ptr()), _lib.FLAG_NATIVE_OBS if native else 0,
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            return o[0].cpu().numpy()
+
+    def features(self, obs_type="features"):
+        """SSF_Env._get_features (ssf_env.py:95-157) as float64, computed on the device (sf_features_f64)."""
+        import torch
+        kind = _lib.OBS_TYPES[obs_type]
+        dev = torch.device("cuda", self.device)
+        with torch.cuda.device(dev):
+            o = torch.empty((1, self.L.sf_num_features(self.h, kind)), dtype=torch.float64, device=dev)
+            _lib.check(self.L.sf_features_f64(self.h, kind, C.c_void_p(o.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            return o[0].cpu().numpy()
 
     def draw(self):
         g = self._render(True)
@@ -210,11 +225,27 @@ class Game(object):
 
     @property
     def events(self):
-        return tuple(name for name, bit in _lib.EVENT_BITS.items() if self._events & bit)
+        """The tick's event strings in the order Game::stepOneTick logs them (game.cpp:124-127 call sites): one
+        press-/release- entry per press_key / release_key call in call order (game.cpp:223) with missile-fired right
+        after the press-fire that caused it (:186), then ship-respawn (:155), explode-* (:342,348), fortress-respawn
+        (:202), fortress-fired (:169), shell-hit-ship (:417) and the missile loop's hit events (:363-393). The device
+        keeps one bit per event kind, so a kind that occurs twice in a tick (two missiles hitting) is listed once."""
+        ev, out = self._events, []
+        names = {FIRE_KEY: "fire", THRUST_KEY: "thrust", LEFT_KEY: "left", RIGHT_KEY: "right"}
+        for sym, state in self._logged:
+            out.append(("press-" if state else "release-") + names[sym])
+            if sym == FIRE_KEY and state and ev & _lib.EVENT_BITS["missile-fired"]:
+                out.append("missile-fired")
+        for name in ("ship-respawn", "explode-bighex", "explode-smallhex", "fortress-respawn", "fortress-fired", "shell-hit-ship",
+                     "hit-fortress", "vlner-increased", "fortress-destroyed", "vlner-reset", "hit-dead-fortress"):
+            if ev & _lib.EVENT_BITS[name]:
+                out.append(name)
+        return tuple(out)
 
     @property
     def collisions(self):
-        return tuple(name for name, bit in _lib.COLLISION_BITS.items() if self._events & bit)
+        """pymodule.cpp:182-197 fills its tuple from the back: the order is shell, missile, smallhex, bighex."""
+        return tuple(name for name in ("shell", "missile", "smallhex", "bighex") if self._events & _lib.COLLISION_BITS[name])
 
     @property
     def stats(self):
@@ -226,27 +257,10 @@ class Game(object):
         r = self.record
         return (r.fire_timer, r.thrust_timer, r.left_timer, r.right_timer)
 
-    # computeExtra (game.cpp:282-312), evaluated from the (frozen-while-dead) ship state
+    # computeExtra (game.cpp:282-312): evaluated on the device (sf_features_f64, columns 6..8 of 'features')
     def _extra(self):
-        r = self.record
-        fx, fy = 355.0, 315.0
-        if np.sqrt(r.ship_vx * r.ship_vx + r.ship_vy * r.ship_vy) == 0.0:
-            vdir = 0.0
-        else:
-            o = np.arctan2(-(fy - r.ship_y), fx - r.ship_x)
-            v = np.arctan2(r.ship_vy, r.ship_vx)
-            d = v - o
-            if d > np.pi:
-                d -= np.pi * 2
-            if d < -np.pi:
-                d += np.pi * 2
-            vdir = d / np.pi * 180
-        aim = np.arctan2(r.ship_y - fy, r.ship_x - fx) / np.pi * 180 - r.ship_angle + 180
-        if aim < -180:
-            aim += 360
-        fdist = np.sqrt((r.ship_x - fx) ** 2 + (r.ship_y - r.ship_y) ** 2)  # sic: game.cpp:310 (quirk Q11)
-        ndist = -1 + (fdist - 40.0) / ((200.0 - 40.0) / 2.0)
-        return float(vdir), float(aim), float(ndist)
+        f = self.features("features")
+        return float(f[7]), float(f[6]), float(f[8])
 
     vdir = property(lambda s: s._extra()[0])
     aim = property(lambda s: s._extra()[1])

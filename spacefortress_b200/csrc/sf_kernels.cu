@@ -78,7 +78,7 @@ __device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, const SfEn
 }
 
 // the renderer's view of one stepped env (written by the env's lane into the block's record array)
-__device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, int env, SfEnvRec& r) {
+__device__ __forceinline__ void sf_make_env_rec(const SfEnv& e, int env, unsigned shell_vis, SfEnvRec& r) {
   r.px = e.pos.x; r.py = e.pos.y;
   r.core = (unsigned)e.q0.x; r.pmask = (unsigned)e.q0.y;
   r.points_i = __float2int_rz(__int_as_float(e.q3.x));
@@ -92,9 +92,8 @@ __device__ __forceinline__ void sf_make_env_rec(const SfDev& D, const SfEnv& e, 
   }
   r.life = (unsigned)e.st3.z + 1u;
   r.building = 0;  // decided by sf_publish_recs
-  int vis;
-  r.ns = sf_count_strokes(D, env, r.core, r.pmask, &vis);
-  r.shell_vis = vis;
+  r.ns = sf_count_strokes(r.core, r.pmask, shell_vis);
+  r.shell_vis = (int)shell_vis;
 }
 
 struct SfRollArgs {
@@ -107,6 +106,8 @@ struct SfRollArgs {
   unsigned char* done;
   unsigned char* fortkill;
   unsigned* events;
+  int* group_ctr;      // {groups handed out beyond the first gridDim.x, blocks that have finished}: zero between launches
+  int env0, envn;      // the envs this launch steps: [env0, env0 + envn) (sf_step_host steps the slab in slices)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -116,14 +117,14 @@ struct SfRollArgs {
 // warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
 // warps run the block-cooperative frame pipeline (sf_render.cuh).
 // one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
-__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfEnvRec* recs) {
+__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, const SfHot* H, int group, int t, SfEnvRec* recs) {
   const int lane = threadIdx.x & 31;
-  const SfHot* H = &sf_block_smem().hot;  // the step's tables from shared memory
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
-  const int env = group * A.EB + lane;
-  const bool mine = lane < A.EB && env < D.n;
+  const int env = A.env0 + group * A.EB + lane;
+  const bool mine = lane < A.EB && env < A.env0 + A.envn;
   SfEnv e;
   bool finished = false;
+  unsigned shell_vis = 0;
   if (mine) {
     sf_load_env(D, env, e);
     int a = A.actions ? A.actions[(size_t)t * D.n + env]
@@ -137,42 +138,68 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
     if (A.fortkill) A.fortkill[oi] = o.fort_kill;
     if (A.events) A.events[oi] = o.events;
     finished = o.done && autoreset;
+    shell_vis = o.shell_vis;
   }
   if (__any_sync(0xffffffffu, finished)) {
     sf_accumulate_episode(D, e, finished, lane);
-    if (finished) sf_new_game(D, H, env, e);  // gym_vecenv: the returned obs is the first frame of the new episode
+    if (finished) { sf_new_game(D, H, env, e); shell_vis = 0; }  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
     sf_store_env(D, env, e);
-    sf_make_env_rec(D, e, env, recs[lane]);
+    sf_make_env_rec(e, env, shell_vis, recs[lane]);
   } else recs[lane].env = -1;
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31;
+  const bool stepper = threadIdx.x < 32;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
+  SfStageState st;
+  st.stage = 0; st.prev_used = 0;
+  st.hot = &D.tab->hot;
+  // warp 0 starts stepping at once (tables from global memory); the drawing warps load the block's tables meanwhile
+#ifdef SF_INIT_BEFORE_STEP  // experiment knob: the round-1 order (every warp loads the tables, then the first step)
   sf_block_smem_init(D.tab);
+  st.hot = &B.hot;
+#else
+  if (stepper) sf_stage_ctrl_init(lane); else sf_block_smem_init_t<true>(D.tab);
+#endif
   sf_warp_smem_init(W, lane);
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = A.obs;
   out.tick_bytes = (size_t)D.n * out.obs_bytes;
-  SfStageState st;
-  st.stage = 0; st.prev_used = 0;
-  // the block is persistent over its groups; the step of tick t + 1 (warp 0) runs while the other warps draw tick t
+  // The block is persistent: its first group is blockIdx.x, further ones are handed out first come first served (the
+  // groups differ in cost, and so do the SMs' speeds). Warp 0 fetches the id of the NEXT group when it starts a group; the
+  // other warps read it when they are done with the current one, many barriers later. The step of tick t + 1 (warp 0)
+  // runs while the other warps draw tick t, across groups too.
+  int group = blockIdx.x, k = 0;
 #pragma unroll 1
-  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x)
-    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, group, t, &Tm.env[32 * h]); });
+  while (group < A.ngroups) {
+    if (threadIdx.x == 0) B.next_group[(k + 1) & 1] = (int)gridDim.x + atomicAdd(&A.group_ctr[0], 1);
+    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, st.hot, group, t, &Tm.env[32 * h]); });
+    k++;
+#ifdef SF_STATIC_GROUPS  // experiment knob: the round-1 static striding over the groups
+    group += (int)gridDim.x;
+#else
+    group = B.next_group[k & 1];
+#endif
+  }
+  // the last block to leave re-arms the counters for the next launch (every block has made its last fetch by then)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&A.group_ctr[1], 1) == (int)gridDim.x - 1) { A.group_ctr[0] = 0; A.group_ctr[1] = 0; __threadfence(); }
+  }
 }
 
 // state-only: one env per thread
 __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A) {
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = A.env0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool mine = env < D.n;
+  const bool mine = env < A.env0 + A.envn;
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   SfEnv e;
   if (mine) sf_load_env(D, env, e);
@@ -221,7 +248,7 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
       if (mine) {
         SfEnv e;
         sf_load_env(D, env, e);
-        sf_make_env_rec(D, e, env, Tm.env[lane]);
+        sf_make_env_rec(e, env, sf_visible_shells(D, env, (unsigned)e.q0.y), Tm.env[lane]);
       } else Tm.env[lane].env = -1;
       __syncwarp();
     });
@@ -255,6 +282,86 @@ __global__ void sf_reset_kernel(SfDev D, const unsigned char* mask, int clear_pr
   if (clear_prev_vlner) e.q1.w = 0;
   sf_new_game(D, &D.tab->hot, env, e);
   sf_store_env(D, env, e);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// feature observations (ssf_env.py:95-157) from the state, one thread per env
+// ------------------------------------------------------------------------------------------------
+// computeExtra (game.cpp:282-312). The reference evaluates it inside updateShip while the ship is alive and keeps the
+// values while it is dead; position, velocity and heading are frozen while dead, so evaluating it from the current
+// state gives the same numbers. Before the first tick of a Game the reference's mExtra is uninitialised memory; the
+// test harness zero-fills the Game, and so does this (tick 0 -> 0, 0, 0). fdist keeps the bug of the reference (Q11:
+// the y term is ship.y - ship.y).
+struct SfExtra { double vdir, aim, ndist; };
+__device__ inline SfExtra sf_compute_extra(const SfEnv& e) {
+  SfExtra x;
+  x.vdir = 0.0; x.aim = 0.0; x.ndist = 0.0;
+  if (e.q3.z == 0) return x;
+  const double ang = (double)((unsigned)e.q0.x & SF_CORE_ANGLE_MASK);
+  if (SF_DSQRT(SF_DADD(SF_DMUL(e.vel.x, e.vel.x), SF_DMUL(e.vel.y, e.vel.y))) != 0.0) {   // Vector::norm (vector.cpp:30-32)
+    const double o = atan2(-SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x));
+    const double v = atan2(e.vel.y, e.vel.x);
+    double d = SF_DSUB(v, o);
+    if (d > SF_PI) d = SF_DSUB(d, SF_PI * 2);
+    if (d < -SF_PI) d = SF_DADD(d, SF_PI * 2);
+    x.vdir = sf_rad2deg(d);
+  }
+  double o = atan2(SF_DSUB(e.pos.y, SF_FORT_Y), SF_DSUB(e.pos.x, SF_FORT_X));
+  o = SF_DADD(SF_DSUB(sf_rad2deg(o), ang), 180.0);
+  if (o < -180.0) o = SF_DADD(o, 360.0);
+  x.aim = o;
+  const double dx = SF_DSUB(e.pos.x, SF_FORT_X), dy0 = SF_DSUB(e.pos.y, e.pos.y);
+  const double fdist = SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy0, dy0)));
+  x.ndist = SF_DADD(-1.0, SF_DDIV(SF_DSUB(fdist, 40.0), SF_DDIV(SF_DSUB(200.0, 40.0), 2.0)));   // normDist (game.cpp:282-284)
+  return x;
+}
+__device__ __forceinline__ double sf_clip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }
+__device__ __forceinline__ double sf_pymod360(double v) {  // Python's float `v % 360`
+  double m = fmod(v, 360.0);
+  if (m != 0.0) { if (m < 0.0) m = SF_DADD(m, 360.0); } else m = 0.0;
+  return m;
+}
+
+template <class OutT>
+__global__ void sf_features_kernel(SfDev D, int kind, OutT* out) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n) return;
+  SfEnv e;
+  sf_load_env(D, env, e);
+  const SfExtra x = sf_compute_extra(e);
+  const unsigned core = (unsigned)e.q0.x;
+  const double alive = (core & SF_CORE_SHIP_ALIVE) ? 1.0 : 0.0, falive = (core & SF_CORE_FORT_ALIVE) ? 1.0 : 0.0;
+  const int vuln = e.q1.z;
+  const double kill_window = (vuln > 10 && e.q1.y < 250) ? 1.0 : 0.0;   // vulnerability_timer < fortressVulnerabilityTime
+  const int nm = __popc((unsigned)e.q0.y & SF_PMASK_MISSILES), ns = __popc(((unsigned)e.q0.y >> SF_PMASK_SHELL_SHIFT) & 0xFu);
+  const double fang = 10.0 * (double)((core >> SF_CORE_FANG_SHIFT) & 63u), sang = (double)(core & SF_CORE_ANGLE_MASK);
+  const int nt = D.autoturn ? 2 : 4;
+  double f[19];
+  int nf;
+  if (kind == SF_OBS_MONITORS) {          // ssf_env.py:96-108
+    nf = 10;
+    f[0] = nm > 0 ? 0.5 : -0.5; f[1] = falive != 0.0 ? 0.5 : -0.5; f[2] = vuln > 10 ? 0.5 : -0.5; f[3] = kill_window != 0.0 ? 0.5 : -0.5;
+    f[4] = x.aim < 3 ? 0.5 : -0.5; f[5] = x.aim > 3 ? 0.5 : -0.5;
+    f[6] = x.ndist > .75 ? 0.5 : -0.5; f[7] = x.ndist > .25 ? 0.5 : -0.5; f[8] = x.ndist < -.25 ? 0.5 : -0.5; f[9] = x.ndist < -.75 ? 0.5 : -0.5;
+  } else if (kind == SF_OBS_NORMALIZED_FEATURES) {  // ssf_env.py:109-133 (sic: max(vulnerability, 10)); np.clip(f, -1, 1)
+    nf = 15 + nt;
+    f[0] = alive; f[1] = SF_DDIV(e.pos.x, 90.0); f[2] = SF_DDIV(e.pos.y, 92.0); f[3] = SF_DDIV(e.vel.x, 10.0); f[4] = SF_DDIV(e.vel.y, 10.0);
+    f[5] = SF_DDIV(sang, 360.0); f[6] = SF_DDIV(x.aim, 180.0); f[7] = SF_DDIV(sf_pymod360(x.vdir), 360.0); f[8] = x.ndist;
+    f[9] = falive; f[10] = SF_DDIV(fang, 360.0); f[11] = SF_DDIV((double)max(vuln, 10), 10.0); f[12] = kill_window;
+    f[13] = SF_DDIV((double)nm, 20.0); f[14] = SF_DDIV((double)ns, 20.0);
+    const double max_ticks = 5294.0;  // np.floor(180000 / 34), ssf_env.py:166
+    f[15] = SF_DDIV((double)e.q2.x, max_ticks); f[16] = SF_DDIV((double)e.q2.y, max_ticks);
+    f[17] = SF_DDIV((double)e.q2.z, max_ticks); f[18] = SF_DDIV((double)e.q2.w, max_ticks);
+    for (int k = 0; k < 19; k++) f[k] = sf_clip1(f[k]);
+  } else {                               // 'features', ssf_env.py:134-157
+    nf = 15 + nt;
+    f[0] = alive; f[1] = e.pos.x; f[2] = e.pos.y; f[3] = e.vel.x; f[4] = e.vel.y; f[5] = sang; f[6] = x.aim; f[7] = x.vdir; f[8] = x.ndist;
+    f[9] = falive; f[10] = fang; f[11] = (double)vuln; f[12] = kill_window; f[13] = (double)nm; f[14] = (double)ns;
+    f[15] = (double)e.q2.x; f[16] = (double)e.q2.y; f[17] = (double)e.q2.z; f[18] = (double)e.q2.w;
+  }
+  OutT* o = out + (size_t)env * nf;
+  for (int k = 0; k < nf; k++) o[k] = (OutT)f[k];
 }
 
 // ---- state records (AoS <-> SoA), one thread per env ----
@@ -352,6 +459,7 @@ static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
+#define SF_HOST_MAX_SLICES 8
 struct sf_handle {
   SfDev dev;
   int device;
@@ -364,6 +472,10 @@ struct sf_handle {
   // pinned staging for sf_step_host
   int* d_actions; unsigned char* d_obs; int* d_reward; unsigned char* d_done; unsigned char* d_kill; unsigned* d_events;
   size_t staging_obs_bytes;
+  int* d_group_ctr;  // sf_rollout_kernel's group hand-out counters (self re-arming)
+  cudaStream_t host_compute, host_copy;  // sf_step_host: kernels of slice k + 1 overlap the device->host copy of slice k
+  cudaEvent_t host_ev[SF_HOST_MAX_SLICES];
+  int host_slices;
 };
 
 extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
@@ -427,6 +539,8 @@ static size_t layout(SfDev& d, char* base) {
   return (size_t)(p - base);
 }
 
+extern "C" int sf_destroy(sf_handle* h);
+
 extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int device, sf_handle** out) {
   if (!out) return fail(SF_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -462,18 +576,22 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   char err[256] = {0};
   if (sf_build_tables(h->h_tab, err, sizeof(err))) { std::string m = err; delete h->h_tab; delete h; return fail(SF_ERR_INVALID, "table build failed: " + m); }
 
+  // every failure below releases what has been allocated (sf_destroy frees whatever is non-NULL)
+  auto bail = [&](const char* what, cudaError_t ce) { std::string m = std::string(what) + ": " + cudaGetErrorString(ce); sf_destroy(h); return fail(SF_ERR_CUDA, m); };
+  cudaError_t ce;
   h->slab_bytes = layout(d, nullptr);
-  cudaError_t ce = cudaMalloc(&h->slab, h->slab_bytes);
-  if (ce != cudaSuccess) { delete h->h_tab; delete h; return fail(SF_ERR_CUDA, std::string("cudaMalloc state slab: ") + cudaGetErrorString(ce)); }
+  if ((ce = cudaMalloc(&h->slab, h->slab_bytes)) != cudaSuccess) return bail("cudaMalloc state slab", ce);
   layout(d, (char*)h->slab);
-  CUDA_TRY(cudaMemset(h->slab, 0, h->slab_bytes));
-  CUDA_TRY(cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
-  CUDA_TRY(cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)));
+  if ((ce = cudaMalloc(&h->d_group_ctr, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc counters", ce);
+  if ((ce = cudaMemset(h->d_group_ctr, 0, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMemset counters", ce);
+  if ((ce = cudaMemset(h->slab, 0, h->slab_bytes)) != cudaSuccess) return bail("cudaMemset state slab", ce);
+  if ((ce = cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload tables", ce);
+  if ((ce = cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout)", ce);
+  if ((ce = cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (render)", ce);
   // default seeding: every env replays srand(1) — the reference never seeds libc (game.cpp:137-148)
   sf_seed_kernel<<<(d.n + 127) / 128, 128>>>(d, nullptr);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaDeviceSynchronize());
+  if ((ce = cudaGetLastError()) != cudaSuccess) return bail("seed kernel launch", ce);
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return bail("seed kernel", ce);
   *out = h;
   return SF_OK;
 }
@@ -481,13 +599,17 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
 extern "C" int sf_destroy(sf_handle* h) {
   if (!h) return SF_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->slab);
+  if (h->slab) cudaFree(h->slab);
   if (h->d_actions) cudaFree(h->d_actions);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
   if (h->d_done) cudaFree(h->d_done);
   if (h->d_kill) cudaFree(h->d_kill);
   if (h->d_events) cudaFree(h->d_events);
+  if (h->d_group_ctr) cudaFree(h->d_group_ctr);
+  if (h->host_compute) cudaStreamDestroy(h->host_compute);
+  if (h->host_copy) cudaStreamDestroy(h->host_copy);
+  for (int k = 0; k < SF_HOST_MAX_SLICES; k++) if (h->host_ev[k]) cudaEventDestroy(h->host_ev[k]);
   delete h->h_tab;
   delete h;
   return SF_OK;
@@ -507,21 +629,29 @@ extern "C" int sf_seed(sf_handle* h, const uint32_t* h_seeds, long long first_gl
   cudaStream_t st = (cudaStream_t)stream;
   h->dev.first_global_env = first_global_env;
   unsigned* d_seeds = nullptr;
+  cudaError_t ce = cudaSuccess;
   if (h_seeds) {
     CUDA_TRY(cudaMalloc(&d_seeds, sizeof(unsigned) * h->dev.n));
-    CUDA_TRY(cudaMemcpyAsync(d_seeds, h_seeds, sizeof(unsigned) * h->dev.n, cudaMemcpyHostToDevice, st));
+    ce = cudaMemcpyAsync(d_seeds, h_seeds, sizeof(unsigned) * h->dev.n, cudaMemcpyHostToDevice, st);
   }
-  sf_seed_kernel<<<(h->dev.n + 127) / 128, 128, 0, st>>>(h->dev, d_seeds);
-  CUDA_TRY(cudaGetLastError());
-  if (d_seeds) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(d_seeds)); }
+  if (ce == cudaSuccess) {
+    sf_seed_kernel<<<(h->dev.n + 127) / 128, 128, 0, st>>>(h->dev, d_seeds);
+    ce = cudaGetLastError();
+  }
+  if (d_seeds) {  // the temporary is released on every path
+    cudaError_t cs = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) ce = cs;
+    cudaFree(d_seeds);
+  }
+  if (ce != cudaSuccess) return fail(SF_ERR_CUDA, std::string("sf_seed: ") + cudaGetErrorString(ce));
   return SF_OK;
 }
 
 // Envs per group (= per block and tick). While every group can have its own SM the envs are spread evenly over
 // the SMs (4096 envs -> 28 per block, 147 blocks); beyond that a group is a full warp of 32 stepping lanes and
 // the blocks are persistent over their groups.
-static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) {
-  const int n = h->dev.n, sms = h->num_sms * SF_BLOCKS_PER_SM, teams = sms;
+static void group_shape(const sf_handle* h, int n, int* EB, int* ngroups, int* blocks) {
+  const int sms = h->num_sms * SF_BLOCKS_PER_SM, teams = sms;
   int eb = n <= teams * SF_GROUP_ENVS ? (n + teams - 1) / teams : SF_GROUP_ENVS;
   if (const char* ov = getenv("SF_ENVS_PER_BLOCK")) { int e = atoi(ov); if (e >= 1 && e <= SF_GROUP_ENVS) eb = e; }  // tuning knob
   *EB = eb;
@@ -531,7 +661,7 @@ static void group_shape(const sf_handle* h, int* EB, int* ngroups, int* blocks) 
 
 static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const unsigned char* d_mask, cudaStream_t st) {
   int EB, ngroups, blocks;
-  group_shape(h, &EB, &ngroups, &blocks);
+  group_shape(h, h->dev.n, &EB, &ngroups, &blocks);
   sf_render_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(h->dev, d_obs, flags, d_mask, EB, ngroups);
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
@@ -582,17 +712,41 @@ __global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const un
 
 extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
   if (!d_frames || !d_valid || !d_out_bf16 || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
+  cudaPointerAttributes pa;  // no handle: launch on the device that owns the frames, whatever the caller's current device is
+  CUDA_TRY(cudaPointerGetAttributes(&pa, d_frames));
+  if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) return fail(SF_ERR_INVALID, "sf_policy_input: d_frames is not device memory");
+  CUDA_TRY(cudaSetDevice(pa.device));
   sf_policy_input_kernel<<<(unsigned)n, SF_PI_THREADS, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
+
+
+extern "C" int sf_num_features(const sf_handle* h, int obs_type) {
+  if (!h) return -1;
+  if (obs_type == SF_OBS_MONITORS) return 10;
+  if (obs_type == SF_OBS_FEATURES || obs_type == SF_OBS_NORMALIZED_FEATURES) return 15 + (h->dev.autoturn ? 2 : 4);
+  return -1;
+}
+static int features_common(sf_handle* h, int obs_type, void* d_out, bool f64, void* stream) {
+  if (!h || !d_out) return fail(SF_ERR_INVALID, "handle or out is NULL");
+  if (sf_num_features(h, obs_type) < 0) return fail(SF_ERR_INVALID, "obs_type must be SF_OBS_FEATURES, SF_OBS_NORMALIZED_FEATURES or SF_OBS_MONITORS");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (f64) sf_features_kernel<double><<<(h->dev.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->dev, obs_type, (double*)d_out);
+  else sf_features_kernel<float><<<(h->dev.n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->dev, obs_type, (float*)d_out);
+  CUDA_TRY(cudaGetLastError());
+  return SF_OK;
+}
+extern "C" int sf_features(sf_handle* h, int obs_type, float* d_out, void* stream) { return features_common(h, obs_type, d_out, false, stream); }
+extern "C" int sf_features_f64(sf_handle* h, int obs_type, double* d_out, void* stream) { return features_common(h, obs_type, d_out, true, stream); }
 
 extern "C" int sf_set_ticks(sf_handle* h, const int32_t* h_ticks) {
   if (!h || !h_ticks) return fail(SF_ERR_INVALID, "handle or ticks is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   int* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(int) * (size_t)h->dev.n));
-  cudaError_t ce = cudaMemcpy(d, h_ticks, sizeof(int) * (size_t)h->dev.n, cudaMemcpyHostToDevice);
+  cudaError_t ce = cudaDeviceSynchronize();  // synchronous call: ordered after whatever any stream has queued for this slab
+  if (ce == cudaSuccess) ce = cudaMemcpy(d, h_ticks, sizeof(int) * (size_t)h->dev.n, cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) {
     sf_set_ticks_kernel<<<(h->dev.n + 127) / 128, 128>>>(h->dev, d);
     ce = cudaDeviceSynchronize();
@@ -624,10 +778,11 @@ static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
   if (render) {
     SfRollArgs b = a;
     int blocks;
-    group_shape(h, &b.EB, &b.ngroups, &blocks);
+    group_shape(h, b.envn, &b.EB, &b.ngroups, &blocks);
+    b.group_ctr = h->d_group_ctr;
     sf_rollout_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
   } else {
-    sf_step_only_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d, a);
+    sf_step_only_kernel<<<(a.envn + 127) / 128, 128, 0, st>>>(d, a);
   }
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
@@ -639,7 +794,7 @@ extern "C" int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, i
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
   a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
-  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events; a.group_ctr = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -649,7 +804,7 @@ extern "C" int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
   a.T = T; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
-  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr; a.group_ctr = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -659,6 +814,13 @@ extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, l
 
 static int ensure_staging(sf_handle* h, size_t obs_bytes) {
   size_t n = (size_t)h->dev.n;
+  if (!h->host_compute) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->host_compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->host_copy, cudaStreamNonBlocking));
+    for (int k = 0; k < SF_HOST_MAX_SLICES; k++) CUDA_TRY(cudaEventCreateWithFlags(&h->host_ev[k], cudaEventDisableTiming));
+    h->host_slices = 4;
+    if (const char* ov = getenv("SF_HOST_SLICES")) { int v = atoi(ov); if (v >= 1 && v <= SF_HOST_MAX_SLICES) h->host_slices = v; }  // tuning knob
+  }
   if (!h->d_actions) {
     CUDA_TRY(cudaMalloc(&h->d_actions, n * 4)); CUDA_TRY(cudaMalloc(&h->d_reward, n * 4));
     CUDA_TRY(cudaMalloc(&h->d_done, n)); CUDA_TRY(cudaMalloc(&h->d_kill, n)); CUDA_TRY(cudaMalloc(&h->d_events, n * 4));
@@ -690,19 +852,34 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   bool render = (flags & SF_FLAG_RENDER) && h_obs;
   int rc = ensure_staging(h, render ? n * per : 0);
   if (rc) return rc;
-  cudaStream_t st = 0;  // legacy default stream: ordered with every other call made with stream == NULL
-  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, st));
-  SfRollArgs a;
-  a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
-  a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events;
-  rc = launch_rollout(h, a, st);
-  if (rc) return rc;
-  if (render) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * per, cudaMemcpyDeviceToHost, st));
-  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, st));
-  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-  if (h_fortkill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, st));
-  if (h_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  // Synchronous, on the handle's own streams. The slab is stepped in slices of consecutive envs: the kernel of slice
+  // k + 1 runs while the frames of slice k cross PCIe (one cudaMemcpyAsync per buffer and slice), so only the first
+  // slice's kernel is exposed. Work the caller has queued on OTHER streams for this handle must be complete (the Python
+  // wrapper synchronises its stream first); everything queued here is complete on return.
+  cudaStream_t sc = h->host_compute, sx = h->host_copy;
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, sc));
+  const int slices = (render && n >= 2048) ? h->host_slices : 1;
+  for (int k = 0; k < slices; k++) {
+    const size_t e0 = n * k / slices, e1 = n * (k + 1) / slices;
+    SfRollArgs a;
+    a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
+    a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events; a.group_ctr = nullptr;
+    a.env0 = (int)e0; a.envn = (int)(e1 - e0);
+    rc = launch_rollout(h, a, sc);
+    if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
+    if (render) {
+      CUDA_TRY(cudaEventRecord(h->host_ev[k], sc));
+      CUDA_TRY(cudaStreamWaitEvent(sx, h->host_ev[k], 0));
+      CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * per, h->d_obs + e0 * per, (e1 - e0) * per, cudaMemcpyDeviceToHost, sx));
+    }
+  }
+  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, sc));
+  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, sc));
+  if (h_fortkill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, sc));
+  if (h_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, sc));
+  cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sx);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(SF_ERR_CUDA, std::string("sf_step_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   return SF_OK;
 }
 
@@ -712,9 +889,11 @@ extern "C" int sf_get_state(sf_handle* h, int first, int count, sf_state_record*
   CUDA_TRY(cudaSetDevice(h->device));
   sf_state_record* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(sf_state_record) * (size_t)count));
-  CUDA_TRY(cudaDeviceSynchronize());
-  sf_get_state_kernel<<<(count + 63) / 64, 64>>>(h->dev, first, count, d);
-  cudaError_t ce = cudaMemcpy(h_out, d, sizeof(sf_state_record) * (size_t)count, cudaMemcpyDeviceToHost);
+  cudaError_t ce = cudaDeviceSynchronize();  // every stream: the state may be in flight on the caller's stream
+  if (ce == cudaSuccess) {
+    sf_get_state_kernel<<<(count + 63) / 64, 64>>>(h->dev, first, count, d);
+    ce = cudaMemcpy(h_out, d, sizeof(sf_state_record) * (size_t)count, cudaMemcpyDeviceToHost);
+  }
   cudaFree(d);
   if (ce != cudaSuccess) return fail(SF_ERR_CUDA, std::string("get_state: ") + cudaGetErrorString(ce));
   return SF_OK;
@@ -741,8 +920,8 @@ extern "C" int sf_set_state(sf_handle* h, int first, int count, const sf_state_r
   sf_state_record* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(sf_state_record) * (size_t)count));
   cudaError_t ce = cudaMemcpy(d, h_in, sizeof(sf_state_record) * (size_t)count, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
   if (ce == cudaSuccess) {
-    CUDA_TRY(cudaDeviceSynchronize());
     sf_set_state_kernel<<<(count + 63) / 64, 64>>>(h->dev, first, count, d);
     ce = cudaDeviceSynchronize();
   }
@@ -773,6 +952,15 @@ extern "C" int sf_barrier_cycles(unsigned long long* h_out, int reset) {
   cudaMemcpyFromSymbol(h_out, sf_bar_cycles, sizeof(unsigned long long) * 8);
   if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf_bar_cycles, z, sizeof(z)); }
   return SF_OK;
+}
+#endif
+#ifdef SF_TIMELINE
+extern "C" int sf_timeline(unsigned long long* h_out) {  // [160][2][SF_TL_MAX]: (globaltimer ns << 8) | tag; zeroed after the read
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h_out, sf_tl, sizeof(unsigned long long) * 160 * 2 * SF_TL_MAX);
+  static unsigned long long z[160 * 2 * SF_TL_MAX];
+  cudaMemcpyToSymbol(sf_tl, z, sizeof(z));
+  return SF_TL_MAX;
 }
 #endif
 #ifdef SF_PHASE_TIMING

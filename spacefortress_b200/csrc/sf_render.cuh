@@ -146,6 +146,10 @@ struct __align__(16) SfBlockSmem {
   int wf_nlines[4];
   unsigned colour_white, padc[3];
   unsigned char exp_colour[SF_EXP_STROKES + 3];
+#ifdef SF_TIMELINE
+  int tl_n[4];
+#endif
+  int next_group[2], padg[2];  // rollout kernel: the block's next groups (written by warp 0 one group ahead)
   SfTeamSmem team[2];
 };
 
@@ -176,6 +180,25 @@ __device__ __forceinline__ void sf_render_sync() {  // the warps that draw: all 
   sf_bar_add(1, t0);
 #endif
 }
+#ifdef SF_TIMELINE  // tools/gpu_timeline.py: wall-clock marks (globaltimer, ns) of warps 0 and 1 of every block
+#define SF_TL_MAX 96
+__device__ unsigned long long sf_tl[160 * 2 * SF_TL_MAX];
+__device__ __forceinline__ void sf_tl_mark(int tag) {
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && warp < 2 && blockIdx.x < 160) {
+    SfBlockSmem& B = sf_block_smem();
+    const int k = B.tl_n[warp]++;
+    if (k < SF_TL_MAX) {
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      sf_tl[(blockIdx.x * 2 + warp) * SF_TL_MAX + k] = (g << 8) | (unsigned long long)tag;
+    }
+  }
+}
+#define SF_TL(tag) sf_tl_mark(tag)
+#else
+#define SF_TL(tag) ((void)0)
+#endif
 __device__ __forceinline__ SfWarpSmem& sf_warp_smem(int warp) { return reinterpret_cast<SfWarpSmem*>(sf_smem_raw + sizeof(SfBlockSmem))[warp]; }
 __device__ __forceinline__ SfWarpSmem& sf_my_smem() { return sf_warp_smem(threadIdx.x >> 5); }
 #define SF_RENDER_SMEM_BYTES(warps) (sizeof(SfBlockSmem) + sizeof(SfWarpSmem) * (warps))
@@ -217,9 +240,23 @@ __device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a /
 }
 __device__ __forceinline__ int sf_div15(int d) { return (d * 2185) >> 15; }  // exact for 0 <= d < 4694
 
-// once per block at kernel start (every thread of the block calls it, before any early exit)
-__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
+// Once per block at kernel start. DRAWERS_ONLY = false: every thread of the block calls it (before any early exit)
+// and it ends with a block barrier. DRAWERS_ONLY = true (the rollout kernel): only the drawing warps call it — warp 0
+// is already stepping the first tick with the tables in global memory — and it ends with the drawing warps' barrier;
+// the first stage barrier then publishes the tables to warp 0. The control words of the two stage copies are warp 0's
+// (sf_stage_ctrl_init).
+template <bool DRAWERS_ONLY>
+__device__ __forceinline__ void sf_block_smem_init_t(const SfTables* T) {
   SfBlockSmem& B = sf_block_smem();
+  const int tid = DRAWERS_ONLY ? (int)threadIdx.x - 32 : (int)threadIdx.x;
+  const int nth = DRAWERS_ONLY ? (int)blockDim.x - 32 : (int)blockDim.x;
+  struct { int x; } threadIdx_{tid}, blockDim_{nth};
+#define threadIdx threadIdx_
+#define blockDim blockDim_
+#ifdef SF_TIMELINE
+  if (tid == 0) B.tl_n[DRAWERS_ONLY ? 1 : 0] = 0;
+  if (!DRAWERS_ONLY && tid == 32) B.tl_n[1] = 0;
+#endif
   for (int k = threadIdx.x; k < 168; k += blockDim.x) {
     const SfTap t = k < 84 ? T->xtap[k] : T->ytap[k - 84];
     int4 v = make_int4(t.si | (t.cnt << 8), __float_as_int(t.a[0]), __float_as_int(t.a[1]), __float_as_int(t.a[2]));
@@ -243,16 +280,33 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int c = 0; c < 2; c++) {
     for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[c].cells)[k] = 0u;
     for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[c].arc_mask[0][0])[k] = 0u;
-    if (threadIdx.x == 0) {
-      SfTeamSmem& Tm = B.team[c];
-      Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
-    }
   }
   if (threadIdx.x == 0) B.colour_white = T->colour_white;
   for (int k = threadIdx.x; k < SF_EXP_STROKES; k += blockDim.x) B.exp_colour[k] = T->exp_colour[k];
+#undef threadIdx
+#undef blockDim
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
+  if (DRAWERS_ONLY) sf_render_sync(); else __syncthreads();
+  SF_TL(2);
+}
+// warp 0, before it prepares the first stage: the control words of both stage copies
+__device__ __forceinline__ void sf_stage_ctrl_init(int lane) {
+  SfBlockSmem& B = sf_block_smem();
+#ifdef SF_TIMELINE
+  if (lane == 0) B.tl_n[0] = 0;
+  __syncwarp();
+  SF_TL(1); SF_TL(2);
+#endif
+  if (lane < 2) {
+    SfTeamSmem& Tm = B.team[lane];
+    Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
+  if (threadIdx.x < 32) sf_stage_ctrl_init(threadIdx.x);
+  sf_block_smem_init_t<false>(T);
 }
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
@@ -872,16 +926,21 @@ __device__ __forceinline__ unsigned char* sf_frame_ptr(const SfFrameOut& out, in
   return out.obs + (size_t)(e >> 5) * out.tick_bytes + (size_t)env * out.obs_bytes;
 }
 
-// per-env stroke count (written by the env's lane before the scan)
-__device__ __forceinline__ int sf_count_strokes(const SfDev& D, int env, unsigned core, unsigned pmask, int* shell_vis) {
+// shells that are drawn: further than 21 from the fortress (quirk Q9, draw.cpp:249-250; sqrt-free, SfHot::touch2).
+// The step computes the same mask on the fly (sf_env_step); this version is for a state that was not just stepped.
+__device__ __forceinline__ unsigned sf_visible_shells(const SfDev& D, int env, unsigned pmask) {
   unsigned vis = 0;
+  const double thr = D.tab->hot.touch2[2];
   for (unsigned m = (pmask >> SF_PMASK_SHELL_SHIFT) & 0xFu; m; m &= m - 1) {
     const int s = __ffs(m) - 1;
     const double2 p = D.spos[(size_t)s * D.n_pad + env];
     const double dx = SF_DSUB(p.x, SF_FORT_X), dy = SF_DSUB(p.y, SF_FORT_Y);
-    if (SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) > 21.0) vis |= 1u << s;  // quirk Q9, draw.cpp:249-250
+    if (SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy)) > thr) vis |= 1u << s;
   }
-  *shell_vis = (int)vis;
+  return vis;
+}
+// per-env stroke count (written by the env's lane before the scan)
+__device__ __forceinline__ int sf_count_strokes(unsigned core, unsigned pmask, unsigned vis) {
   return ((core & SF_CORE_SHIP_ALIVE) ? 1 : 0) + __popc(pmask & SF_PMASK_MISSILES) + __popc(vis);
 }
 
@@ -1226,6 +1285,7 @@ __device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfTeamSmem& Tm, 
 struct SfStageState {
   int stage;      // copy (0 / 1) the next stage is drawn from
   int prev_used;  // coverage cells the previous stage used in the OTHER copy: zeroed while the next stage is drawn
+  const SfHot* hot;  // the step's tables: the global copy until the block's shared copy is published (first stage barrier)
 };
 
 // warp 0: restart the pools of the copy whose stage it has just prepared
@@ -1351,10 +1411,14 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
   long long t_last_ = clock64(), w_last_ = t_last_;
 #endif
   if (stepper) sf_prepare_first_round(D, B, B.team[st.stage], lane, 0, T, out, prep);
+  SF_TL(3);
   int t = 0;
 #pragma unroll 1
   for (;;) {
+    SF_TL(4);
     sf_team_sync();  // the stage is prepared; every warp is done with the previous one
+    st.hot = &B.hot;
+    SF_TL(5);
     SF_TICK(0); SF_WTICK(8);
     SfTeamSmem& Tm = B.team[st.stage];
     SfTeamSmem& Nx = B.team[st.stage ^ 1];
@@ -1389,4 +1453,5 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
     if (!more) t += nticks;
     if (last) break;
   }
+  SF_TL(7);
 }

@@ -17,6 +17,7 @@ struct SfStepOut {
   int reward;       // shaped (train presets) or raw (test presets) integer reward
   unsigned events;  // SF_EV_*
   bool done, fort_kill;
+  unsigned shell_vis;  // live shells further than 21 from the fortress after the tick (what draw.cpp:249-250 shows), bit per slot
 };
 
 // registers of one env between load and store
@@ -81,9 +82,11 @@ __device__ __forceinline__ bool sf_inside_hex(const SfHot* H, int h, double x, d
   return in;
 }
 
-__device__ __forceinline__ bool sf_touch(double ax, double ay, double bx, double by, double rsum) {  // object.cpp:12-15
+// object.cpp:12-15: sqrt(dx*dx + dy*dy) <= r, evaluated without the square root as d2 <= T(r) (SfHot::touch2: the
+// same decision for every double d2, checked on the host)
+__device__ __forceinline__ double sf_dist2(double ax, double ay, double bx, double by) {
   double dx = SF_DSUB(ax, bx), dy = SF_DSUB(ay, by);
-  return SF_DSQRT(SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy))) <= rsum;
+  return SF_DADD(SF_DMUL(dx, dx), SF_DMUL(dy, dy));
 }
 __device__ __forceinline__ bool sf_outside(double x, double y) {  // game.cpp:129-131
   return x < 0 || x > 710.0 || y > 626.0 || y < 0;
@@ -279,19 +282,22 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
   }
 
   // ---- S13 updateShells (game.cpp:404-423), slot order ----
+  const double thr_ship = T->touch2[0], thr_fort = T->touch2[1], thr_hide = T->touch2[2];
+  unsigned vis = 0;
   for (unsigned m = ((unsigned)e.q0.y >> SF_PMASK_SHELL_SHIFT) & 0xFu; m; m &= m - 1) {
     int s = __ffs(m) - 1;
     double2 p = D.spos[(size_t)s * np + i], v = D.svel[(size_t)s * np + i];
     p.x = SF_DADD(p.x, v.x); p.y = SF_DADD(p.y, v.y);
     D.spos[(size_t)s * np + i] = p;
-    if ((e.q0.x & SF_CORE_SHIP_ALIVE) && sf_touch(p.x, p.y, e.pos.x, e.pos.y, 13.0)) {
+    if ((e.q0.x & SF_CORE_SHIP_ALIVE) && sf_dist2(p.x, p.y, e.pos.x, e.pos.y) <= thr_ship) {
       e.q0.y &= ~(1 << (SF_PMASK_SHELL_SHIFT + s));
       sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); e.st0.z += 1;
       ev |= SF_EV_SHELL_HIT_SHIP | SF_EV_COL_SHELL_SHIP;
     } else if (sf_outside(p.x, p.y)) {
       e.q0.y &= ~(1 << (SF_PMASK_SHELL_SHIFT + s));
-    }
+    } else if (sf_dist2(p.x, p.y, SF_FORT_X, SF_FORT_Y) > thr_hide) vis |= 1u << s;  // quirk Q9: drawn only when further than 21
   }
+  out.shell_vis = vis;
 
   // ---- S14 updateMissiles (game.cpp:353-402), slot order (order dependent) ----
   for (unsigned m = (unsigned)e.q0.y & SF_PMASK_MISSILES; m; m &= m - 1) {
@@ -301,7 +307,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     p.x = SF_DADD(p.x, SF_DMUL(20.0, T->cs[ang][0]));
     p.y = SF_DADD(p.y, SF_DMUL(20.0, T->cs[ang][1]));
     D.mpos[(size_t)s * np + i] = p;
-    if (sf_touch(p.x, p.y, SF_FORT_X, SF_FORT_Y, 23.0)) {
+    if (sf_dist2(p.x, p.y, SF_FORT_X, SF_FORT_Y) <= thr_fort) {
       e.q0.y &= ~(1 << s);
       ev |= SF_EV_COL_MISSILE_FORTRESS;
       if (e.q0.x & SF_CORE_FORT_ALIVE) {

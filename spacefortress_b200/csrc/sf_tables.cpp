@@ -525,6 +525,23 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     for (int k = 0; k < 6; k++) { t->hot.hex[h][k][0] = t->hex_px[h][k]; t->hot.hex[h][k][1] = t->hex_py[h][k]; t->hot.hex[h][k][2] = t->hex_nx[h][k]; t->hot.hex[h][k][3] = t->hex_ny[h][k]; }
   for (int k = 0; k < 8; k++) t->hot.atan2_oct[k] = t->atan2_oct[k];
   t->hot.ship_start_vx = t->ship_start_vx; t->hot.ship_start_vy = t->ship_start_vy;
+  {
+    const double radii[3] = {13.0, 23.0, 21.0};
+    for (int k = 0; k < 3; k++) {
+      const double r = radii[k];
+      double x = r * r;
+      while (sqrt(x) > r) x = nextafter(x, 0.0);                    // (never taken for these radii: r*r is exact)
+      while (sqrt(nextafter(x, INFINITY)) <= r) x = nextafter(x, INFINITY);
+      // exhaustive check of the claim around the threshold: 4096 doubles on each side
+      double lo = x, hi = nextafter(x, INFINITY);
+      for (int i = 0; i < 4096; i++) {
+        if (!(sqrt(lo) <= r) || (sqrt(hi) <= r)) { snprintf(err, errcap, "touch threshold for r=%g is not a cut", r); return 1; }
+        lo = nextafter(lo, 0.0); hi = nextafter(hi, INFINITY);
+      }
+      t->hot.touch2[k] = x;
+    }
+    t->hot.touch2[3] = 0.0;
+  }
   return 0;
 }
 

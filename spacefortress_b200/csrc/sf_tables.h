@@ -64,6 +64,11 @@ struct SfHot {
   double hex[2][6][4];      // per hexagon edge: px, py, nx, ny (== hex_px, hex_py, hex_nx, hex_ny)
   double atan2_oct[8];
   double ship_start_vx, ship_start_vy;
+  // Object::collided (object.cpp:12-15) is sqrt(dx*dx + dy*dy) <= r. sqrt is correctly rounded and monotone, so the test
+  // equals dx*dx + dy*dy <= T(r) with T(r) = the largest double whose rounded square root is <= r (found by stepping
+  // through the doubles around r*r on the host, sf_tables.cpp): [0] r = 13 shell-ship, [1] r = 23 missile-fortress,
+  // [2] r = 21 the shell hide radius of draw.cpp:249-250.
+  double touch2[4];
 };
 
 struct SfTap { int si, cnt; float a[SF_MAX_TAPS]; };  // consecutive source indices si..si+cnt-1 and their weights

@@ -112,22 +112,6 @@ class SSF_Env(object):
     def close(self):
         self.g = None
 
-    # ssf_env.py:95-157
+    # ssf_env.py:95-157: computed on the device (sf_features_f64), float64 like np.array(f) in the reference
     def _get_features(self):
-        g = self.g
-        kill_window = 1 if g.vulnerability > 10 and g.vulnerability_timer < g.vulnerability_time else 0
-        if self.obs_type == "monitors":
-            return np.array([
-                0.5 if len(g.missiles) > 0 else -0.5, 0.5 if g.fortress_alive else -0.5,
-                0.5 if g.vulnerability > 10 else -0.5, 0.5 if kill_window else -0.5,
-                0.5 if g.aim < 3 else -0.5, 0.5 if g.aim > 3 else -0.5, 0.5 if g.ndist > .75 else -0.5,
-                0.5 if g.ndist > .25 else -0.5, 0.5 if g.ndist < -.25 else -0.5, 0.5 if g.ndist < -.75 else -0.5])
-        t = g.timers if self.youturn else g.timers[:2]
-        if self.obs_type == "normalized-features":
-            f = [1 if g.ship_alive else 0, g.ship_x / g.pb_width, g.ship_y / g.pb_height, g.ship_vx / 10, g.ship_vy / 10,
-                 g.ship_angle / 360, g.aim / 180, g.vdir % 360 / 360, g.ndist, 1 if g.fortress_alive else 0,
-                 g.fortress_angle / 360, max(g.vulnerability, 10) / 10, kill_window, len(g.missiles) / 20, len(g.shells) / 20]
-            return np.clip(f + [x / self.max_ticks for x in t], -1, 1)
-        f = [g.ship_alive, g.ship_x, g.ship_y, g.ship_vx, g.ship_vy, g.ship_angle, g.aim, g.vdir, g.ndist, g.fortress_alive,
-             g.fortress_angle, g.vulnerability, kill_window, len(g.missiles), len(g.shells)]
-        return np.array(f + list(t))
+        return self.g.features(self.obs_type)

@@ -58,11 +58,11 @@ def evaluate_actions(policy, obs_u8, state0, masks, actions):
     x = F.relu(policy.conv2(x)).flatten(1)
     x = F.relu(policy.fc1(x)).view(T, N, -1)
     if policy.feedforward:
-        h = F.relu(policy.core(x))
+        h = F.relu(policy.fc2(x))
     else:
         hs, state = [], state0.to(dt)
         for t in range(T):
-            state = policy.core(x[t], state * masks[t].to(dt))
+            state = policy.gru(x[t], state * masks[t].to(dt))
             hs.append(state)
         h = torch.stack(hs, 0)
     logits = policy.action(h).float()
@@ -84,10 +84,19 @@ class PPOLearner(object):
         self.gamma, self.tau, self.ppo_epoch, self.num_mini_batch = gamma, tau, ppo_epoch, num_mini_batch
         self.clip_param, self.value_loss_coeff, self.entropy_coeff, self.max_grad_norm = clip_param, value_loss_coeff, entropy_coeff, max_grad_norm
 
-    def update(self, ro, state0, mask0, next_value):
-        """ro: an OnDeviceRollout after collect(); state0 / mask0: hidden state and mask before its first step;
-        next_value [N]: value of the state after its last step."""
+    def update(self, ro, state0=None, mask0=None, next_value=None, env_chunk=None):
+        """ro: an OnDeviceRollout after collect() (its buffers describe step t until the next collect(): stack(t) is
+        the observation acted on at step t); state0 / mask0: hidden state and mask before its first step (default: the
+        ones the rollout recorded); next_value [N]: value of the state after its last step (default: evaluated here,
+        rl/train.py:100-103). env_chunk: evaluate a minibatch in slices of this many envs with gradient accumulation
+        (same loss: the minibatch means are weighted by slice size) so that 65 536 envs x 128 steps fit in memory."""
         T, N = ro.rewards.shape
+        if state0 is None:
+            state0, mask0 = ro.state0, ro.mask0
+        if next_value is None:
+            with torch.no_grad():
+                x, _ = self.policy.features(ro.stack(T), ro.state, ro.mask)
+                next_value = self.policy.value(x).float().squeeze(1)
         done = ro.dones.float()
         masks = torch.cat([mask0.float().view(1, N), 1.0 - done], 0)           # masks[t+1] = 0 where step t ended an episode
         returns = compute_returns(ro.rewards.float(), ro.values, masks, next_value.float(), True, self.gamma, self.tau)
@@ -98,12 +107,19 @@ class PPOLearner(object):
             perm = torch.randperm(N, device=ro.rewards.device)
             for s in range(0, N, per):                                          # rl/storage.py:95-121: whole env sequences per minibatch
                 idx = perm[s:s + per]
-                obs = torch.stack([ro.stack(t)[idx] for t in range(T)], 0)
-                v, alp, ent = evaluate_actions(self.policy, obs, state0[idx], masks[:-1, idx].unsqueeze(-1), ro.actions[:, idx].long())
-                loss, al, vl = ppo_loss(v, alp, ent, returns[:, idx], ro.logps[:, idx], adv[:, idx], self.clip_param, self.value_loss_coeff, self.entropy_coeff)
                 self.opt.zero_grad()
-                loss.backward()
+                acc = [0.0, 0.0, 0.0, 0.0]
+                ck = len(idx) if not env_chunk else int(env_chunk)
+                for c0 in range(0, len(idx), ck):
+                    sub = idx[c0:c0 + ck]
+                    w = len(sub) / float(len(idx))
+                    obs = torch.stack([ro.stack(t)[sub] for t in range(T)], 0)
+                    v, alp, ent = evaluate_actions(self.policy, obs, state0[sub], masks[:-1, sub].unsqueeze(-1), ro.actions[:, sub].long())
+                    loss, al, vl = ppo_loss(v, alp, ent, returns[:, sub], ro.logps[:, sub], adv[:, sub], self.clip_param, self.value_loss_coeff, self.entropy_coeff)
+                    (loss * w).backward()
+                    for k, x in enumerate((loss, al, vl, ent)):
+                        acc[k] += w * float(x.detach())
                 torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
                 self.opt.step()
-                stats.append(tuple(float(x.detach()) for x in (loss, al, vl, ent)))
+                stats.append(tuple(acc))
         return stats

@@ -42,7 +42,12 @@ def _torch():
 
 class SFVecEnv(object):
     def __init__(self, env_id="SpaceFortress-youturn-image-v0", num_envs=16, device=0, action_set=1, seeds=None,
-                 render=True, native_obs=False, autoreset=True, first_global_env=0, copy_outputs=False):
+                 render=True, native_obs=False, autoreset=True, first_global_env=0, copy_outputs=False, obs_type="image"):
+        """copy_outputs (numpy path): False = step() returns views of the env's page-locked output buffers, which the
+        next step() overwrites, and `infos` as a bool ndarray (the fast path); True = fresh arrays every step and
+        `infos` as a tuple of N bools, exactly what gym_vecenv's np.stack returns (SubprocVecEnv / DummyVecEnv
+        default). obs_type: 'image' (default), or 'features' / 'normalized-features' / 'monitors' (ssf_env.py:95-157):
+        step() / reset() then return the [N, F] float32 feature matrix computed on the device (sf_features)."""
         self.L = _lib.lib()
         self.gametype = _gametype(env_id)
         self.num_envs = int(num_envs)
@@ -51,6 +56,12 @@ class SFVecEnv(object):
         self.native_obs = bool(native_obs)
         self.autoreset = bool(autoreset)
         self.copy_outputs = bool(copy_outputs)
+        if obs_type not in _lib.OBS_TYPES:
+            raise ValueError("obs_type must be one of %r" % (tuple(_lib.OBS_TYPES),))  # ssf_env.py:51
+        self.obs_type = obs_type
+        if obs_type != "image":
+            render = False
+            self.render_on = False
         h = C.c_void_p()
         _lib.check(self.L.sf_create(self.gametype.encode(), int(action_set), self.num_envs, self.device_index, C.byref(h)))
         self.h = h
@@ -58,6 +69,10 @@ class SFVecEnv(object):
         self.action_space = Discrete(self.num_actions)
         self.obs_shape = (1, _lib.NATIVE_H, _lib.NATIVE_W) if native_obs else (1, _lib.OBS_H, _lib.OBS_W)
         self.observation_space = Box(0, 255, self.obs_shape, dtype=np.uint8)  # rl/envs.py:21-25
+        if obs_type != "image":
+            self.num_features = self.L.sf_num_features(self.h, _lib.OBS_TYPES[obs_type])
+            self.obs_shape = (self.num_features,)
+            self.observation_space = Box(-np.inf, np.inf, self.obs_shape, dtype=np.float32)  # ssf_env.py:176
         self.first_global_env = int(first_global_env)
         if seeds is not None or first_global_env:
             self.seed_streams(seeds, first_global_env)
@@ -91,13 +106,10 @@ class SFVecEnv(object):
     def _np_bufs(self):
         if self._np is None:
             n = self.num_envs
-            self._pinned = []
             self._np = {}
-            for k, shape, dt in (("obs", (n,) + self.obs_shape, np.uint8), ("reward", (n,), np.int32), ("done", (n,), np.uint8),
+            for k, shape, dt in (("obs", (n,) + (self.obs_shape if self.obs_type == "image" else (1,)), np.uint8), ("reward", (n,), np.int32), ("done", (n,), np.uint8),
                                  ("kill", (n,), np.uint8), ("events", (n,), np.uint32), ("actions", (n,), np.int32)):
-                arr, ptr = _lib.pinned_array(shape, dt)  # page-locked: D2H lands directly in what step() returns
-                self._np[k] = arr
-                self._pinned.append(ptr)
+                self._np[k] = _lib.pinned_array(shape, dt)  # page-locked: D2H lands directly in what step() returns
         return self._np
 
     @staticmethod
@@ -139,6 +151,8 @@ class SFVecEnv(object):
         obs_ptr = C.c_void_p(b["obs"].data_ptr()) if self.render_on else None
         _lib.check(self.L.sf_reset(self.h, None, int(bool(clear_prev_vlner)), obs_ptr, self._flags, self._stream_ptr()))
         self._t = 0
+        if self.obs_type != "image":
+            return self.features(to_numpy=to_numpy)
         if not self.render_on:
             return None
         if to_numpy:
@@ -162,17 +176,25 @@ class SFVecEnv(object):
         b = self._np_bufs()
         a = b["actions"]
         a[:] = actions.reshape(n)
+        if self._bufs is not None:  # device-path work may be in flight on torch's stream: sf_step_host runs on its own streams
+            _torch().cuda.current_stream(self._device()).synchronize()
         _lib.check(self.L.sf_step_host(
             self.h, a.ctypes.data_as(C.c_void_p), b["obs"].ctypes.data_as(C.c_void_p) if self.render_on else None,
             b["reward"].ctypes.data_as(C.c_void_p), b["done"].ctypes.data_as(C.c_void_p),
             b["kill"].ctypes.data_as(C.c_void_p), b["events"].ctypes.data_as(C.c_void_p), self._flags))
         self._t += 1
-        self.last_events = b["events"].copy()
-        infos = tuple(b["kill"].astype(bool).tolist())  # the reference's info is a bool per env (ssf_env.py:233,250)
-        # obs is the env's page-locked output buffer, overwritten by the next step() (pass copy_outputs=True to
-        # the constructor for fresh arrays like gym_vecenv's np.stack)
-        obs = None if not self.render_on else (b["obs"].copy() if self.copy_outputs else b["obs"])
-        return obs, b["reward"].astype(np.int64), b["done"].astype(bool), infos
+        if self.obs_type != "image":
+            obs = self.features(to_numpy=True)
+        elif not self.render_on:
+            obs = None
+        else:
+            obs = b["obs"].copy() if self.copy_outputs else b["obs"]
+        if self.copy_outputs:  # literal gym_vecenv: fresh arrays, info = tuple of N bools (ssf_env.py:233,250)
+            self.last_events = b["events"].copy()
+            return obs, b["reward"].astype(np.int64), b["done"].astype(bool), tuple(b["kill"].astype(bool).tolist())
+        # fast path: views of the page-locked buffers (valid until the next step()); sum(infos) works like rl/train.py:81
+        self.last_events = b["events"]
+        return obs, b["reward"], b["done"].view(np.bool_), b["kill"].view(np.bool_)
 
     def _step_torch(self, actions, out_obs=None):
         """Device path. out_obs: optional contiguous uint8 CUDA tensor [N,1,84,84] to receive the frames (e.g.
@@ -188,7 +210,19 @@ class SFVecEnv(object):
             C.c_void_p(b["reward"].data_ptr()), C.c_void_p(b["done"].data_ptr()), C.c_void_p(b["kill"].data_ptr()),
             C.c_void_p(b["events"].data_ptr()), self._flags, self._stream_ptr()))
         self._t += 1
-        return (b["obs"] if self.render_on else None), b["reward"], b["done"].bool(), b["kill"].bool()
+        obs = b["obs"] if self.render_on else (self.features() if self.obs_type != "image" else None)
+        return obs, b["reward"], b["done"].bool(), b["kill"].bool()
+
+    def features(self, obs_type=None, to_numpy=False, out=None):
+        """[N, F] float32 feature observations of the current state (ssf_env.py:95-157: 'features' and
+        'normalized-features' have 17 columns for autoturn, 19 for youturn; 'monitors' 10), one thread per env."""
+        torch = _torch()
+        kind = _lib.OBS_TYPES[obs_type or (self.obs_type if self.obs_type != "image" else "features")]
+        nf = self.L.sf_num_features(self.h, kind)
+        if out is None:
+            out = torch.empty((self.num_envs, nf), dtype=torch.float32, device=self._device())
+        _lib.check(self.L.sf_features(self.h, kind, C.c_void_p(out.data_ptr()), self._stream_ptr()))
+        return out.cpu().numpy() if to_numpy else out
 
     def rollout(self, T, actions=None, action_seed=0, out=None, want=("obs", "reward", "done", "kill")):
         """T steps in one launch. actions: int32 CUDA tensor [T,N] or None for the synthetic counter-hash
@@ -264,10 +298,7 @@ class SFVecEnv(object):
 
     def close(self):
         if not self.closed and getattr(self, "h", None):
-            self._np = None
-            for ptr in getattr(self, "_pinned", []):
-                self.L.sf_host_free(ptr)
-            self._pinned = []
+            self._np = None  # the page-locked buffers free themselves when the last array handed out dies
             self.L.sf_destroy(self.h)
             self.h = None
             self.closed = True
@@ -298,6 +329,7 @@ class SubprocVecEnv(SFVecEnv):
     one batched GPU env replaces the N worker processes."""
 
     def __init__(self, env_fns, device=0, **kw):
+        kw.setdefault("copy_outputs", True)  # literal drop-in: fresh arrays and a tuple of bools every step
         env_fns = list(env_fns)
         ids = set(getattr(f, "env_id", None) for f in env_fns)
         if len(ids) != 1 or None in ids:

@@ -483,8 +483,8 @@ def test_policy_input_kernel_matches_the_torch_stack():
     policy = SFGRUPolicy(env.num_actions).cuda().eval().bfloat16()
     ro = OnDeviceRollout(env, policy, num_steps=6)
     ro.collect()
-    ro.valid[::7] = 1; ro.valid[3::7] = 2; ro.valid[5::7] = 3   # resets of different ages
     for t in (0, 3, 5):
+        ro.valid_hist[t][::7] = 1; ro.valid_hist[t][3::7] = 2; ro.valid_hist[t][5::7] = 3   # resets of different ages
         stack = ro.stack(t)                                           # [N,4,84,84] u8, masked
         ref = (stack.to(torch.bfloat16) / 255.0).view(n, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(n, 64, 21, 21)
         got = ro.policy_input(t)
@@ -516,27 +516,65 @@ def test_on_device_rollout_frame_stack_matches_reference_loop():
         recs[i].time = recs[i].tick * 34
     env.set_state(recs)
     torch.manual_seed(0)
-    ro = OnDeviceRollout(env, SFGRUPolicy(env.num_actions).cuda().eval(), num_steps=T)
-    env.set_state(recs)  # OnDeviceRollout reset the envs: restore the staggered clocks (frames stay valid: same ship spawn? no -> re-render)
+
+    class Recording(SFGRUPolicy):  # remembers every input it acted on
+        def act(self, obs, state, mask, **kw):
+            self.seen.append(obs.clone())
+            return SFGRUPolicy.act(self, obs, state, mask, **kw)
+    policy = Recording(env.num_actions).cuda().eval()
+    policy.seen = []
+    ro = OnDeviceRollout(env, policy, num_steps=T)
+    env.set_state(recs)  # OnDeviceRollout reset the envs: restore the staggered clocks and re-render the first frame
     ro.frames[ro.S - 1].copy_(torch.from_numpy(env.render_frames()).cuda())
-    first = ro.frames[ro.S - 1].clone()
     cur = torch.zeros((n, 4, 84, 84), device="cuda")
-    cur[:, -1] = first.float()
-    stacks = []
-    for t in range(T):  # drive collect() step by step through its own pieces to snapshot stack(t)
-        stacks.append(ro.stack(t).clone())
-        assert torch.equal(stacks[-1].float(), cur), t
-        value, action, logp, ro.state = ro.policy.act(stacks[-1], ro.state, ro.mask)
-        a = action.squeeze(1).to(torch.int32)
-        obs, reward, done, kill = env.step(a, out_obs=ro.frames[t + ro.S].unsqueeze(1))
-        mask = (~done).float()
-        cur *= mask.view(-1, 1, 1, 1)
-        cur[:, :-1] = cur[:, 1:].clone()
-        cur[:, -1] = ro.frames[t + ro.S].float()
-        ro.mask = mask.unsqueeze(1)
-        ro.valid = torch.where(done, torch.ones_like(ro.valid), torch.clamp(ro.valid + 1, max=ro.S))
-    assert sum(int(s.sum() == 0) for s in stacks) == 0
+    cur[:, -1] = ro.frames[ro.S - 1].float()
+    for rollout in range(2):  # the second one starts from the carried-over history of the first
+        policy.seen = []
+        ro.collect()
+        assert len(policy.seen) == T
+        for t in range(T):
+            # what the learner replays (PPOLearner.update uses ro.stack(t)) is what the policy acted on ...
+            assert torch.equal(ro.stack(t), policy.seen[t]), (rollout, t)
+            # ... and that is the reference's running current_obs (rl/train.py:51-56,92-97)
+            assert torch.equal(policy.seen[t].float(), cur), (rollout, t)
+            mask = (~ro.dones[t]).float()
+            cur *= mask.view(-1, 1, 1, 1)
+            cur[:, :-1] = cur[:, 1:].clone()
+            cur[:, -1] = ro.frames[t + ro.S].float()
+        assert torch.equal(ro.stack(T).float(), cur)
+        if rollout == 0:
+            assert int(ro.dones.sum()) == n, "every env should have finished its episode inside the first rollout"
+            assert int((ro.valid_hist[:T] < ro.S).sum()) > 0
     env.close()
+
+
+def test_graphed_rollout_equals_the_eager_one():
+    """OnDeviceRollout(graph=True) replays one CUDA graph per step index: with a deterministic policy it produces the
+    same actions, frames, rewards and values as the eager loop, over two consecutive rollouts (history carry-over)."""
+    torch = torch_cuda()
+    from spacefortress_b200 import SFVecEnv
+    from spacefortress_b200.rollout import OnDeviceRollout, SFGRUPolicy
+
+    class Greedy(SFGRUPolicy):
+        def act(self, obs, state, mask, **kw):
+            kw["deterministic"] = True
+            return SFGRUPolicy.act(self, obs, state, mask, **kw)
+    n, T = 96, 6
+    outs = []
+    for graph in (False, True):
+        env = SFVecEnv("youturn", num_envs=n, device=0)
+        torch.manual_seed(3)
+        ro = OnDeviceRollout(env, Greedy(env.num_actions).cuda().eval(), num_steps=T, graph=graph)
+        got = []
+        for _ in range(2):
+            ro.collect()
+            torch.cuda.synchronize()
+            got.append([x.clone() for x in (ro.actions, ro.frames, ro.rewards, ro.dones, ro.values, ro.valid_hist)])
+        outs.append(got)
+        env.close()
+    for r in range(2):
+        for a, b in zip(outs[0][r], outs[1][r]):
+            assert torch.equal(a, b), r
 
 
 def test_ppo_update_on_an_on_device_rollout():
@@ -548,12 +586,9 @@ def test_ppo_update_on_an_on_device_rollout():
     env = make("youturn", n)
     policy = SFGRUPolicy(env.num_actions).cuda()
     ro = OnDeviceRollout(env, policy, num_steps=T)
-    state0, mask0 = ro.state.clone(), ro.mask.clone()
     ro.collect()
-    with torch.no_grad():
-        next_value, _, _, _ = policy.act(ro.stack(T), ro.state, ro.mask)
     before = [p.detach().clone() for p in policy.parameters()]
-    stats = PPOLearner(policy, ppo_epoch=2, num_mini_batch=4).update(ro, state0, mask0, next_value.squeeze(1))
+    stats = PPOLearner(policy, ppo_epoch=2, num_mini_batch=4).update(ro, env_chunk=8)
     assert len(stats) == 8 and all(np.isfinite(s).all() for s in stats)
     assert any(not torch.equal(a, b) for a, b in zip(before, policy.parameters()))
     env.close()
