@@ -186,7 +186,7 @@ def reference_arm(args):
     best = max(vals, key=lambda b: b["value"])
     extra = {}
     try:
-        extra["subproc_pipe_protocol"] = cpu_pipe_arm(ENVS_PER_GPU, 6, cores)       # what north_star names; slower than `value`
+        extra["subproc_pipe_protocol"] = cpu_pipe_arm(ENVS_PER_GPU, 12, cores)       # what north_star names; slower than `value`
         extra["core_only_no_frame"], _ = cpu_arm(40000, cores, render=False)
     except Exception as ex:
         extra["error"] = repr(ex)
@@ -305,6 +305,7 @@ def config_c3(torch, dist, rank, local, world, args, peak):
         class Slice(object):  # the first `sub` envs of the rollout
             rewards, dones, values, logps, actions = ro.rewards[:, :sub], ro.dones[:, :sub], ro.values[:, :sub], ro.logps[:, :sub], ro.actions[:, :sub]
             state0, mask0, state, mask = ro.state0[:sub].float(), ro.mask0[:sub].float(), ro.state[:sub].float(), ro.mask[:sub].float()
+            states_hist = ro.states_hist[:, :sub].float()
             stack = staticmethod(lambda t: ro.stack(t)[:sub])
         learner = PPOLearner(fp32, ppo_epoch=1, num_mini_batch=4)
         torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = True

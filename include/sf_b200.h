@@ -179,6 +179,8 @@ int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream);
  * of pixel (4*Y + y%4, 4*X + x%4) -- the space-to-depth form in which conv(4->16, k8, s4) is a 2x2 convolution
  * over 64 channels (same sums). value = bf16(u8 / 255). No handle: a pure function of its arguments. */
 int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream);
+/* the same with fp32 output (value = fp32(u8) / 255, what obs / 255.0 gives in rl/networks.py:43) for an fp32 / TF32 policy */
+int sf_policy_input_f32(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, float* d_out_f32, void* stream);
 
 /* Feature observations of the CURRENT state (SSF_Env._get_features, ssf_env.py:95-157), one row per env:
  * SF_OBS_FEATURES / SF_OBS_NORMALIZED_FEATURES: 15 + 4 key timers (youturn) or + 2 (autoturn) columns, SF_OBS_MONITORS: 10.

@@ -96,6 +96,16 @@ __device__ __forceinline__ void sf_make_env_rec(const SfEnv& e, int env, unsigne
   r.shell_vis = (int)shell_vis;
 }
 
+// Device-resident scheduling state of sf_rollout_kernel (one per handle; zero at creation, self re-arming): with more
+// groups than blocks, the groups after the first gridDim.x are handed out first come first served (the groups differ
+// in cost and the launch ends with the slowest block: +5..8 % at 65 536 envs over static striding).
+// (Tried and dropped: dealing the envs of a one-group-per-block launch to the blocks by a cost key read from their
+// state, so that every block gets the same mix of dead and live ships — the spread of the block times fell only from
+// 9.8 % to 7.7 % and the sort at the end of every launch cost more than that gained.)
+struct SfSched {
+  int next_group, done;                 // groups handed out beyond the first gridDim.x; blocks that have finished
+};
+
 struct SfRollArgs {
   int T, EB, ngroups, flags;  // EB = envs per group (<= 32), ngroups = ceil(n / EB)
   const int* actions;  // [T][n] or NULL
@@ -106,7 +116,7 @@ struct SfRollArgs {
   unsigned char* done;
   unsigned char* fortkill;
   unsigned* events;
-  int* group_ctr;      // {groups handed out beyond the first gridDim.x, blocks that have finished}: zero between launches
+  SfSched* sched;      // NULL: static assignment (sf_render_kernel-like contiguous groups, no hand-out)
   int env0, envn;      // the envs this launch steps: [env0, env0 + envn) (sf_step_host steps the slab in slices)
 };
 
@@ -117,8 +127,9 @@ struct SfRollArgs {
 // warp 0 steps the group (one env per lane: SoA 128-bit loads/stores) and publishes the env records; then all
 // warps run the block-cooperative frame pipeline (sf_render.cuh).
 // one tick of a group (warp 0, one env per lane): step, outputs, auto-reset, staged env record
-__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, const SfHot* H, int group, int t, SfEnvRec* recs) {
+__device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, int group, int t, SfEnvRec* recs) {
   const int lane = threadIdx.x & 31;
+  const SfHot* H = &sf_block_smem().hot;  // the step's tables from shared memory
   const bool autoreset = !(A.flags & SF_FLAG_NO_AUTORESET);
   const int env = A.env0 + group * A.EB + lane;
   const bool mine = lane < A.EB && env < A.env0 + A.envn;
@@ -151,47 +162,35 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   __syncwarp();
 }
 
+
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   const int lane = threadIdx.x & 31;
-  const bool stepper = threadIdx.x < 32;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
-  SfStageState st;
-  st.stage = 0; st.prev_used = 0;
-  st.hot = &D.tab->hot;
-  // warp 0 starts stepping at once (tables from global memory); the drawing warps load the block's tables meanwhile
-#ifdef SF_INIT_BEFORE_STEP  // experiment knob: the round-1 order (every warp loads the tables, then the first step)
   sf_block_smem_init(D.tab);
-  st.hot = &B.hot;
-#else
-  if (stepper) sf_stage_ctrl_init(lane); else sf_block_smem_init_t<true>(D.tab);
-#endif
   sf_warp_smem_init(W, lane);
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
   out.obs = A.obs;
   out.tick_bytes = (size_t)D.n * out.obs_bytes;
+  SfStageState st;
+  st.stage = 0; st.prev_used = 0;
   // The block is persistent: its first group is blockIdx.x, further ones are handed out first come first served (the
-  // groups differ in cost, and so do the SMs' speeds). Warp 0 fetches the id of the NEXT group when it starts a group; the
-  // other warps read it when they are done with the current one, many barriers later. The step of tick t + 1 (warp 0)
-  // runs while the other warps draw tick t, across groups too.
-  int group = blockIdx.x, k = 0;
+  // groups differ in cost, and so do the SMs' speeds). Warp 0 fetches the id of the NEXT group when it starts a group and
+  // leaves it in shared memory (two slots, alternating); the other warps read it when they are done with the current
+  // group, many barriers later. The step of tick t + 1 (warp 0) runs while the other warps draw tick t, across groups too.
+  int group = blockIdx.x;
 #pragma unroll 1
-  while (group < A.ngroups) {
-    if (threadIdx.x == 0) B.next_group[(k + 1) & 1] = (int)gridDim.x + atomicAdd(&A.group_ctr[0], 1);
-    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, st.hot, group, t, &Tm.env[32 * h]); });
-    k++;
-#ifdef SF_STATIC_GROUPS  // experiment knob: the round-1 static striding over the groups
-    group += (int)gridDim.x;
-#else
-    group = B.next_group[k & 1];
-#endif
+  for (int k = 1; group < A.ngroups; k ^= 1) {
+    if (threadIdx.x == 0) B.next_group[k] = A.sched ? (int)gridDim.x + atomicAdd(&A.sched->next_group, 1) : group + (int)gridDim.x;
+    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, group, t, &Tm.env[32 * h]); });
+    group = B.next_group[k];
   }
   // the last block to leave re-arms the counters for the next launch (every block has made its last fetch by then)
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && A.sched) {
     __threadfence();
-    if (atomicAdd(&A.group_ctr[1], 1) == (int)gridDim.x - 1) { A.group_ctr[0] = 0; A.group_ctr[1] = 0; __threadfence(); }
+    if (atomicAdd(&A.sched->done, 1) == (int)gridDim.x - 1) { A.sched->next_group = 0; A.sched->done = 0; __threadfence(); }
   }
 }
 
@@ -472,7 +471,7 @@ struct sf_handle {
   // pinned staging for sf_step_host
   int* d_actions; unsigned char* d_obs; int* d_reward; unsigned char* d_done; unsigned char* d_kill; unsigned* d_events;
   size_t staging_obs_bytes;
-  int* d_group_ctr;  // sf_rollout_kernel's group hand-out counters (self re-arming)
+  SfSched* d_sched;  // sf_rollout_kernel's scheduling state (group hand-out, cost-dealt envs)
   cudaStream_t host_compute, host_copy;  // sf_step_host: kernels of slice k + 1 overlap the device->host copy of slice k
   cudaEvent_t host_ev[SF_HOST_MAX_SLICES];
   int host_slices;
@@ -582,8 +581,8 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   h->slab_bytes = layout(d, nullptr);
   if ((ce = cudaMalloc(&h->slab, h->slab_bytes)) != cudaSuccess) return bail("cudaMalloc state slab", ce);
   layout(d, (char*)h->slab);
-  if ((ce = cudaMalloc(&h->d_group_ctr, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc counters", ce);
-  if ((ce = cudaMemset(h->d_group_ctr, 0, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMemset counters", ce);
+  if ((ce = cudaMalloc(&h->d_sched, sizeof(SfSched))) != cudaSuccess) return bail("cudaMalloc scheduler state", ce);
+  if ((ce = cudaMemset(h->d_sched, 0, sizeof(SfSched))) != cudaSuccess) return bail("cudaMemset scheduler state", ce);
   if ((ce = cudaMemset(h->slab, 0, h->slab_bytes)) != cudaSuccess) return bail("cudaMemset state slab", ce);
   if ((ce = cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload tables", ce);
   if ((ce = cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout)", ce);
@@ -606,7 +605,7 @@ extern "C" int sf_destroy(sf_handle* h) {
   if (h->d_done) cudaFree(h->d_done);
   if (h->d_kill) cudaFree(h->d_kill);
   if (h->d_events) cudaFree(h->d_events);
-  if (h->d_group_ctr) cudaFree(h->d_group_ctr);
+  if (h->d_sched) cudaFree(h->d_sched);
   if (h->host_compute) cudaStreamDestroy(h->host_compute);
   if (h->host_copy) cudaStreamDestroy(h->host_copy);
   for (int k = 0; k < SF_HOST_MAX_SLICES; k++) if (h->host_ev[k]) cudaEventDestroy(h->host_ev[k]);
@@ -676,12 +675,17 @@ static int launch_render(sf_handle* h, unsigned char* d_obs, int flags, const un
 // as coalesced 16-byte stores (8 channels = frame f, rows dy0, dy0 + 1, 4 columns of block X). u8 -> bf16(u8 / 255)
 // through a 256-entry table built with the exact formula (u8 -> fp32, / 255 in fp32, round to bf16, like torch).
 #define SF_PI_THREADS 192
+template <bool F32>
 __global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const unsigned char* __restrict__ frames, long long fstride, int n, const int* __restrict__ valid,
                                                                        uint4* __restrict__ out) {
   __shared__ unsigned tile[2][4 * 4 * 21];  // [frame][dy][X] : 4 pixels each
-  __shared__ unsigned short lut[256];
+  __shared__ unsigned lut[256];             // bf16 bits of u8 / 255 (F32: the fp32 bits)
   const int env = blockIdx.x, tid = threadIdx.x;
-  for (int v = tid; v < 256; v += SF_PI_THREADS) { const __nv_bfloat16 h = __float2bfloat16_rn(__fdiv_rn((float)v, 255.0f)); lut[v] = *reinterpret_cast<const unsigned short*>(&h); }
+  for (int v = tid; v < 256; v += SF_PI_THREADS) {
+    const float q = __fdiv_rn((float)v, 255.0f);
+    if (F32) lut[v] = __float_as_uint(q);
+    else { const __nv_bfloat16 h = __float2bfloat16_rn(q); lut[v] = *reinterpret_cast<const unsigned short*>(&h); }
+  }
   const int nvalid = min(max(valid[env], 0), 4);
   // what this thread loads (words k0 = tid and k1 = tid + 192 of the 336-word tile) and stores (chunk tid < 168)
   const unsigned char* base = frames + (long long)env * (84 * 84);
@@ -692,8 +696,8 @@ __global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const un
   const unsigned char* p1 = base + (long long)(k1 < 336 ? f1 : 0) * fstride + (r1 / 21) * 84 + (r1 % 21) * 4;
   const int X = tid >> 3, c8 = tid & 7, f = c8 >> 1, dy0 = (c8 & 1) * 2;
   const int ta = (f * 4 + dy0) * 21 + X, tb = ta + 21;
-  uint4* orow = out + (long long)env * (21 * 21 * 8);
-  auto cvt2 = [&](unsigned lo, unsigned hi) { return (unsigned)lut[lo] | ((unsigned)lut[hi] << 16); };
+  uint4* orow = out + (long long)env * (21 * 21 * 8) * (F32 ? 2 : 1);
+  auto cvt2 = [&](unsigned lo, unsigned hi) { return lut[lo] | (lut[hi] << 16); };
 #pragma unroll 1
   for (int Y = 0; Y < 21; Y++) {
     unsigned* T = tile[Y & 1];
@@ -702,25 +706,38 @@ __global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const un
     __syncthreads();  // (the other tile is free again: every thread passed the previous barrier after reading it)
     if (tid < 21 * 8) {
       const unsigned a = T[ta], b = T[tb];
-      uint4 o;
-      o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
-      o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
-      orow[Y * (21 * 8) + tid] = o;
+      if (F32) {
+        uint4 o0, o1;
+        o0.x = lut[a & 255u]; o0.y = lut[(a >> 8) & 255u]; o0.z = lut[(a >> 16) & 255u]; o0.w = lut[a >> 24];
+        o1.x = lut[b & 255u]; o1.y = lut[(b >> 8) & 255u]; o1.z = lut[(b >> 16) & 255u]; o1.w = lut[b >> 24];
+        orow[(Y * (21 * 8) + tid) * 2] = o0; orow[(Y * (21 * 8) + tid) * 2 + 1] = o1;
+      } else {
+        uint4 o;
+        o.x = cvt2(a & 255u, (a >> 8) & 255u); o.y = cvt2((a >> 16) & 255u, a >> 24);
+        o.z = cvt2(b & 255u, (b >> 8) & 255u); o.w = cvt2((b >> 16) & 255u, b >> 24);
+        orow[Y * (21 * 8) + tid] = o;
+      }
     }
   }
 }
 
-extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
-  if (!d_frames || !d_valid || !d_out_bf16 || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
+static int policy_input_common(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out, bool f32, void* stream) {
+  if (!d_frames || !d_valid || !d_out || n <= 0 || (frame_stride_bytes & 3)) return fail(SF_ERR_INVALID, "sf_policy_input: bad arguments");
   cudaPointerAttributes pa;  // no handle: launch on the device that owns the frames, whatever the caller's current device is
   CUDA_TRY(cudaPointerGetAttributes(&pa, d_frames));
   if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) return fail(SF_ERR_INVALID, "sf_policy_input: d_frames is not device memory");
   CUDA_TRY(cudaSetDevice(pa.device));
-  sf_policy_input_kernel<<<(unsigned)n, SF_PI_THREADS, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out_bf16));
+  if (f32) sf_policy_input_kernel<true><<<(unsigned)n, SF_PI_THREADS, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out));
+  else sf_policy_input_kernel<false><<<(unsigned)n, SF_PI_THREADS, 0, (cudaStream_t)stream>>>(d_frames, frame_stride_bytes, n, d_valid, reinterpret_cast<uint4*>(d_out));
   CUDA_TRY(cudaGetLastError());
   return SF_OK;
 }
-
+extern "C" int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream) {
+  return policy_input_common(d_frames, frame_stride_bytes, n, d_valid, d_out_bf16, false, stream);
+}
+extern "C" int sf_policy_input_f32(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, float* d_out_f32, void* stream) {
+  return policy_input_common(d_frames, frame_stride_bytes, n, d_valid, d_out_f32, true, stream);
+}
 
 extern "C" int sf_num_features(const sf_handle* h, int obs_type) {
   if (!h) return -1;
@@ -779,7 +796,7 @@ static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
     SfRollArgs b = a;
     int blocks;
     group_shape(h, b.envn, &b.EB, &b.ngroups, &blocks);
-    b.group_ctr = h->d_group_ctr;
+    b.sched = (a.env0 == 0 && a.envn == d.n) ? h->d_sched : nullptr;  // slices of the slab (sf_step_host): static groups
     sf_rollout_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
   } else {
     sf_step_only_kernel<<<(a.envn + 127) / 128, 128, 0, st>>>(d, a);
@@ -794,7 +811,7 @@ extern "C" int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, i
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
   a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
-  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events; a.group_ctr = nullptr; a.env0 = 0; a.envn = h->dev.n;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events; a.sched = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -804,7 +821,7 @@ extern "C" int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_
   CUDA_TRY(cudaSetDevice(h->device));
   SfRollArgs a;
   a.T = T; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
-  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr; a.group_ctr = nullptr; a.env0 = 0; a.envn = h->dev.n;
+  a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr; a.sched = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -864,7 +881,7 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
     const size_t e0 = n * k / slices, e1 = n * (k + 1) / slices;
     SfRollArgs a;
     a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
-    a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events; a.group_ctr = nullptr;
+    a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events; a.sched = nullptr;
     a.env0 = (int)e0; a.envn = (int)(e1 - e0);
     rc = launch_rollout(h, a, sc);
     if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }

@@ -240,22 +240,14 @@ __device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a /
 }
 __device__ __forceinline__ int sf_div15(int d) { return (d * 2185) >> 15; }  // exact for 0 <= d < 4694
 
-// Once per block at kernel start. DRAWERS_ONLY = false: every thread of the block calls it (before any early exit)
-// and it ends with a block barrier. DRAWERS_ONLY = true (the rollout kernel): only the drawing warps call it — warp 0
-// is already stepping the first tick with the tables in global memory — and it ends with the drawing warps' barrier;
-// the first stage barrier then publishes the tables to warp 0. The control words of the two stage copies are warp 0's
-// (sf_stage_ctrl_init).
-template <bool DRAWERS_ONLY>
-__device__ __forceinline__ void sf_block_smem_init_t(const SfTables* T) {
+// once per block at kernel start (every thread of the block calls it, before any early exit)
+// (Tried and dropped: letting warp 0 step the first tick while the other warps load the tables — its first step ran
+// slower next to the loads and the extra live state cost the drawing code registers: -3 % overall.)
+__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   SfBlockSmem& B = sf_block_smem();
-  const int tid = DRAWERS_ONLY ? (int)threadIdx.x - 32 : (int)threadIdx.x;
-  const int nth = DRAWERS_ONLY ? (int)blockDim.x - 32 : (int)blockDim.x;
-  struct { int x; } threadIdx_{tid}, blockDim_{nth};
-#define threadIdx threadIdx_
-#define blockDim blockDim_
 #ifdef SF_TIMELINE
-  if (tid == 0) B.tl_n[DRAWERS_ONLY ? 1 : 0] = 0;
-  if (!DRAWERS_ONLY && tid == 32) B.tl_n[1] = 0;
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 2) B.tl_n[threadIdx.x >> 5] = 0;
+  SF_TL(1);
 #endif
   for (int k = threadIdx.x; k < 168; k += blockDim.x) {
     const SfTap t = k < 84 ? T->xtap[k] : T->ytap[k - 84];
@@ -274,39 +266,23 @@ __device__ __forceinline__ void sf_block_smem_init_t(const SfTables* T) {
   if (threadIdx.x < 36) B.fort_list_n[threadIdx.x] = (unsigned char)min(T->fort_list_n[threadIdx.x], 255);
   for (int k = threadIdx.x; k < SF_FORT_STATES * 16; k += blockDim.x) B.fort_sparse[k >> 4][k & 15] = T->fort_sparse[k >> 4][k & 15];
   for (int k = threadIdx.x; k < SF_MAGIC_N; k += blockDim.x) B.magic[k] = T->magic[k];
-  for (int k = threadIdx.x; k < (int)(sizeof(SfHot) / sizeof(double)); k += blockDim.x) reinterpret_cast<double*>(&B.hot)[k] = reinterpret_cast<const double*>(&T->hot)[k];
+  for (int k = threadIdx.x; k < (int)(sizeof(SfHot) / 16); k += blockDim.x) reinterpret_cast<int4*>(&B.hot)[k] = __ldg(reinterpret_cast<const int4*>(&T->hot) + k);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
   if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
   for (int c = 0; c < 2; c++) {
     for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[c].cells)[k] = 0u;
     for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[c].arc_mask[0][0])[k] = 0u;
+    if (threadIdx.x == 0) {
+      SfTeamSmem& Tm = B.team[c];
+      Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+    }
   }
   if (threadIdx.x == 0) B.colour_white = T->colour_white;
   for (int k = threadIdx.x; k < SF_EXP_STROKES; k += blockDim.x) B.exp_colour[k] = T->exp_colour[k];
-#undef threadIdx
-#undef blockDim
   // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (DRAWERS_ONLY) sf_render_sync(); else __syncthreads();
+  __syncthreads();
   SF_TL(2);
-}
-// warp 0, before it prepares the first stage: the control words of both stage copies
-__device__ __forceinline__ void sf_stage_ctrl_init(int lane) {
-  SfBlockSmem& B = sf_block_smem();
-#ifdef SF_TIMELINE
-  if (lane == 0) B.tl_n[0] = 0;
-  __syncwarp();
-  SF_TL(1); SF_TL(2);
-#endif
-  if (lane < 2) {
-    SfTeamSmem& Tm = B.team[lane];
-    Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
-  if (threadIdx.x < 32) sf_stage_ctrl_init(threadIdx.x);
-  sf_block_smem_init_t<false>(T);
 }
 // once per warp at kernel start
 __device__ __forceinline__ void sf_warp_smem_init(SfWarpSmem& W, int lane) {
@@ -1285,7 +1261,6 @@ __device__ __forceinline__ void sf_publish_recs(const SfDev& D, SfTeamSmem& Tm, 
 struct SfStageState {
   int stage;      // copy (0 / 1) the next stage is drawn from
   int prev_used;  // coverage cells the previous stage used in the OTHER copy: zeroed while the next stage is drawn
-  const SfHot* hot;  // the step's tables: the global copy until the block's shared copy is published (first stage barrier)
 };
 
 // warp 0: restart the pools of the copy whose stage it has just prepared
@@ -1417,7 +1392,6 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
   for (;;) {
     SF_TL(4);
     sf_team_sync();  // the stage is prepared; every warp is done with the previous one
-    st.hot = &B.hot;
     SF_TL(5);
     SF_TICK(0); SF_WTICK(8);
     SfTeamSmem& Tm = B.team[st.stage];

@@ -48,19 +48,28 @@ def ppo_loss(values, action_log_probs, dist_entropy, returns, old_action_log_pro
     return action_loss + value_loss_coeff * value_loss - entropy_coeff * dist_entropy, action_loss, value_loss
 
 
-def evaluate_actions(policy, obs_u8, state0, masks, actions):
-    """rl/networks.py:41-62,79-86 for a [T,N] sequence: obs_u8 [T,N,4,84,84] u8 stacks, state0 [N,256] the hidden state
-    before the first step, masks [T,N,1] (0 where the PREVIOUS step ended an episode), actions [T,N] int64.
-    Returns values [T,N], action_log_probs [T,N], mean entropy."""
+def evaluate_actions(policy, obs_u8, states, masks, actions, bptt=False):
+    """rl/networks.py:41-62,79-86 on a [T,N] minibatch: obs_u8 [T,N,4,84,84] u8 stacks, masks [T,N,1] (0 where the
+    PREVIOUS step ended an episode), actions [T,N] int64. Returns values [T,N], action_log_probs [T,N], mean entropy.
+
+    bptt=False (the reference): `states` [T,N,256] are the hidden states the policy had BEFORE each step, stored during
+    the rollout. The reference's recurrent_generator (rl/storage.py:89-121) hands ACNet.evaluate_actions one stored state
+    per sample, so ACNet._fwd takes its `obs.size(0) == state.size(0)` branch (rl/networks.py:47-48): ONE GRU step per
+    sample from the stored state, no unrolling through time.
+    bptt=True (extension): `states` [N,256] is the state before the first step and the GRU is unrolled over the T steps
+    (the other branch of ACNet._fwd), which back-propagates through time."""
     T, N = actions.shape
     dt = policy.conv1.weight.dtype
     x = F.relu(policy.conv1(obs_u8.reshape(T * N, *obs_u8.shape[2:]).to(dt) / 255.0))
     x = F.relu(policy.conv2(x)).flatten(1)
-    x = F.relu(policy.fc1(x)).view(T, N, -1)
+    x = F.relu(policy.fc1(x))
     if policy.feedforward:
-        h = F.relu(policy.fc2(x))
+        h = F.relu(policy.fc2(x)).view(T, N, -1)
+    elif not bptt:
+        h = policy.gru(x, states.reshape(T * N, -1).to(dt) * masks.reshape(T * N, 1).to(dt)).view(T, N, -1)
     else:
-        hs, state = [], state0.to(dt)
+        x = x.view(T, N, -1)
+        hs, state = [], states.to(dt)
         for t in range(T):
             state = policy.gru(x[t], state * masks[t].to(dt))
             hs.append(state)
@@ -78,8 +87,9 @@ class PPOLearner(object):
     4 env-chunk minibatches, clip 0.1, value 0.5, entropy 0.05, grad-norm 0.5: rl/arguments.py defaults)."""
 
     def __init__(self, policy, lr=1e-3, gamma=0.99, tau=0.95, ppo_epoch=4, num_mini_batch=4, clip_param=0.1,
-                 value_loss_coeff=0.5, entropy_coeff=0.05, max_grad_norm=0.5):
+                 value_loss_coeff=0.5, entropy_coeff=0.05, max_grad_norm=0.5, bptt=False):
         self.policy = policy
+        self.bptt = bool(bptt)
         self.opt = torch.optim.Adam(policy.parameters(), lr=lr)
         self.gamma, self.tau, self.ppo_epoch, self.num_mini_batch = gamma, tau, ppo_epoch, num_mini_batch
         self.clip_param, self.value_loss_coeff, self.entropy_coeff, self.max_grad_norm = clip_param, value_loss_coeff, entropy_coeff, max_grad_norm
@@ -114,7 +124,8 @@ class PPOLearner(object):
                     sub = idx[c0:c0 + ck]
                     w = len(sub) / float(len(idx))
                     obs = torch.stack([ro.stack(t)[sub] for t in range(T)], 0)
-                    v, alp, ent = evaluate_actions(self.policy, obs, state0[sub], masks[:-1, sub].unsqueeze(-1), ro.actions[:, sub].long())
+                    states = state0[sub] if self.bptt or self.policy.feedforward else ro.states_hist[:T, sub]
+                    v, alp, ent = evaluate_actions(self.policy, obs, states, masks[:-1, sub].unsqueeze(-1), ro.actions[:, sub].long(), bptt=self.bptt)
                     loss, al, vl = ppo_loss(v, alp, ent, returns[:, sub], ro.logps[:, sub], adv[:, sub], self.clip_param, self.value_loss_coeff, self.entropy_coeff)
                     (loss * w).backward()
                     for k, x in enumerate((loss, al, vl, ent)):

@@ -105,6 +105,8 @@ class OnDeviceRollout(object):
         self.mask = torch.ones(n, 1, device=dev, dtype=pdt)
         self.state0 = torch.zeros_like(self.state)
         self.mask0 = torch.ones_like(self.mask)
+        # hidden state BEFORE every step (rl/storage.py:12,38: the learner re-evaluates each sample from its stored state)
+        self.states_hist = torch.zeros((self.T + 1, n, 256), device=dev, dtype=pdt) if not policy.feedforward else None
         self.actions = torch.zeros((self.T, n), dtype=torch.int32, device=dev)
         self.rewards = torch.zeros((self.T, n), dtype=torch.int32, device=dev)
         self.dones = torch.zeros((self.T, n), dtype=torch.bool, device=dev)
@@ -114,10 +116,10 @@ class OnDeviceRollout(object):
         self.final_return = torch.zeros(n, dtype=torch.int64, device=dev)
         self.num_destruction = torch.zeros((), dtype=torch.int64, device=dev)
         self._age_idx = torch.arange(self.S, device=dev, dtype=torch.int32).view(1, self.S, 1, 1)
-        # bf16 policy: its first-layer input comes from the fused stack / mask / scale / space-to-depth kernel
-        self.fused_input = pdt == torch.bfloat16 and self.S == 4
+        # the policy's first-layer input comes from the fused stack / mask / scale / space-to-depth kernel (bf16 or fp32)
+        self.fused_input = pdt in (torch.bfloat16, torch.float32) and self.S == 4 and dev.type == "cuda"
         if self.fused_input:
-            self.pin = torch.empty((n, 64, 21, 21), dtype=torch.bfloat16, device=dev).contiguous(memory_format=torch.channels_last)
+            self.pin = torch.empty((n, 64, 21, 21), dtype=pdt, device=dev).contiguous(memory_format=torch.channels_last)
         self.use_graph = bool(graph)
         self._graphs = None
         self._collected = False
@@ -141,12 +143,15 @@ class OnDeviceRollout(object):
         """The 4-frame stack of step t as the policy's space-to-depth bf16 input (one fused kernel)."""
         from . import _lib
         import ctypes as C
-        _lib.check(self.env.L.sf_policy_input(C.c_void_p(self.frames[t].data_ptr()), int(self.frames.stride(0)), self.env.num_envs,
-                                              C.c_void_p(self.valid_hist[t].data_ptr()), C.c_void_p(self.pin.data_ptr()), self.env._stream_ptr()))
+        fn = self.env.L.sf_policy_input if self.pin.dtype == torch.bfloat16 else self.env.L.sf_policy_input_f32
+        _lib.check(fn(C.c_void_p(self.frames[t].data_ptr()), int(self.frames.stride(0)), self.env.num_envs,
+                      C.c_void_p(self.valid_hist[t].data_ptr()), C.c_void_p(self.pin.data_ptr()), self.env._stream_ptr()))
         return self.pin
 
     def _step(self, t):
         env, S = self.env, self.S
+        if self.states_hist is not None:
+            self.states_hist[t].copy_(self.state)
         if self.fused_input:
             value, action, logp, state = self.policy.act(self.policy_input(t), self.state, self.mask, s2d=True)
         else:
@@ -178,6 +183,8 @@ class OnDeviceRollout(object):
         else:
             for t in range(self.T):
                 self._step(t)
+        if self.states_hist is not None:
+            self.states_hist[self.T].copy_(self.state)
         self._collected = True
         return dict(frames=self.frames, actions=self.actions, rewards=self.rewards, dones=self.dones,
                     values=self.values, logps=self.logps, valid=self.valid_hist)

@@ -473,31 +473,38 @@ def test_single_env_facade_matches_oracle():
     env.close()
 
 
-def test_policy_input_kernel_matches_the_torch_stack():
-    """sf_policy_input (stack + zero the frames from before a reset + 1/255 + space-to-depth, one kernel) against the
-    plain torch formulation, bit for bit; and conv1 on it against conv1 on the NCHW stack."""
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_policy_input_kernel_matches_the_torch_stack(dtype):
+    """sf_policy_input / sf_policy_input_f32 (stack + zero the frames from before a reset + 1/255 + space-to-depth, one
+    kernel) against the plain torch formulation, bit for bit; and conv1 on it against conv1 on the NCHW stack."""
     torch = torch_cuda()
     from spacefortress_b200.rollout import OnDeviceRollout, SFGRUPolicy
     n = 300
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    tol = 0.06 if dtype == "bf16" else 2e-3
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
     env = make("youturn", n)
-    policy = SFGRUPolicy(env.num_actions).cuda().eval().bfloat16()
+    policy = SFGRUPolicy(env.num_actions).cuda().eval().to(dt)
     ro = OnDeviceRollout(env, policy, num_steps=6)
+    assert ro.fused_input
     ro.collect()
     for t in (0, 3, 5):
         ro.valid_hist[t][::7] = 1; ro.valid_hist[t][3::7] = 2; ro.valid_hist[t][5::7] = 3   # resets of different ages
         stack = ro.stack(t)                                           # [N,4,84,84] u8, masked
-        ref = (stack.to(torch.bfloat16) / 255.0).view(n, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(n, 64, 21, 21)
+        ref = (stack.to(dt) / 255.0).view(n, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(n, 64, 21, 21)
         got = ro.policy_input(t)
-        assert got.shape == ref.shape and torch.equal(got.float(), ref.float()), t
+        assert got.shape == ref.shape and got.dtype == dt and torch.equal(got.float(), ref.float()), t
         a = torch.nn.functional.conv2d(got, policy.conv1_s2d_weight(), policy.conv1.bias).float()
-        b = policy.conv1(stack.to(torch.bfloat16) / 255.0).float()
-        assert (a - b).abs().max().item() <= 0.05 * max(1.0, b.abs().max().item()), t
-        # the whole feature path (fused conv + bias + relu, NHWC fc1) against the generic one, bf16 tolerance
-        st = torch.zeros(n, 256, device="cuda", dtype=torch.bfloat16); mk = torch.ones(n, 1, device="cuda", dtype=torch.bfloat16)
+        b = policy.conv1(stack.to(dt) / 255.0).float()
+        assert (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item()), t
+        # the whole feature path (fused conv + bias + relu, NHWC fc1) against the generic one
+        st = torch.zeros(n, 256, device="cuda", dtype=dt); mk = torch.ones(n, 1, device="cuda", dtype=dt)
         with torch.no_grad():
             fa, _ = policy.features(got, st, mk, s2d=True)
             fb, _ = policy.features(stack, st, mk)
-        assert (fa.float() - fb.float()).abs().max().item() <= 0.06 * max(1.0, fb.float().abs().max().item()), t
+        assert (fa.float() - fb.float()).abs().max().item() <= tol * max(1.0, fb.float().abs().max().item()), t
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
     env.close()
 
 

@@ -321,3 +321,17 @@ def test_config5_episode_stats_equal_host_sums():
     # frames of the step after a reset are first frames of a new episode (all envs share seed 1 -> the same spawn order
     # per env index): spot-check one finished env against its oracle
     env.close()
+
+
+def test_one_ppo_minibatch_on_the_gpu_matches_the_reference_code():
+    """The reference's first PPO minibatch (rl/train.py:105-132 evaluated by the reference's own ACNet / RolloutStorage on the
+    CPU, tests/golden/make_ppo_minibatch_golden.py) against ppo.py on the GPU in fp32 (TF32 off): loss terms within 1e-4,
+    every parameter's gradient within 2e-3 of its norm."""
+    torch = torch_cuda()
+    from test_ppo import check_minibatch
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        check_minibatch(torch.device("cuda"), 1e-4, 2e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
