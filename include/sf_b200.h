@@ -179,7 +179,8 @@ int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void* stream);
  * of pixel (4*Y + y%4, 4*X + x%4) -- the space-to-depth form in which conv(4->16, k8, s4) is a 2x2 convolution
  * over 64 channels (same sums). value = bf16(u8 / 255). No handle: a pure function of its arguments. */
 int sf_policy_input(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, void* d_out_bf16, void* stream);
-/* the same with fp32 output (value = fp32(u8) / 255, what obs / 255.0 gives in rl/networks.py:43) for an fp32 / TF32 policy */
+/* the same with fp32 output for an fp32 / TF32 policy: value = fp32(u8) * fp32(1 / 255), bit for bit what torch's CUDA
+ * `obs / 255.0` (rl/networks.py:43) computes (it multiplies by the reciprocal of the scalar) */
 int sf_policy_input_f32(const uint8_t* d_frames, long long frame_stride_bytes, int n, const int32_t* d_valid, float* d_out_f32, void* stream);
 
 /* Feature observations of the CURRENT state (SSF_Env._get_features, ssf_env.py:95-157), one row per env:
@@ -192,6 +193,14 @@ int sf_policy_input_f32(const uint8_t* d_frames, long long frame_stride_bytes, i
 int sf_num_features(const sf_handle* h, int obs_type);
 int sf_features(sf_handle* h, int obs_type, float* d_out, void* stream);
 int sf_features_f64(sf_handle* h, int obs_type, double* d_out, void* stream);
+
+/* Score digits (drawScore, draw.cpp:160-173) are font dependent: the reference asks fontconfig for "monospace" bold and
+ * draws whatever face the machine has. The built-in digits are a 7-segment face on the same metrics. Where a real cairo and
+ * the deployment's font exist, tools/dump_cairo_glyphs.py renders the masks and this call installs them: h_alpha
+ * [10][5 * 27] = coverage of digit d drawn in every one of the 7 slots, over native rows 1..5 x columns 32..58;
+ * h_slot[27] = the slot (0..6) that owns a strip column, 255 for none. Both NULL: back to the built-in face. Rebuilds the
+ * static tables (default observation, pre-resampled chunks) and uploads them; synchronises the device. */
+int sf_set_glyph_masks(sf_handle* h, const uint8_t* h_alpha, const uint8_t* h_slot);
 
 /* Static tables built at sf_create (host copies, for tests/inspection): background frames. */
 int sf_background(const sf_handle* h, uint8_t* h_native /*[92*90]*/, uint8_t* h_obs /*[84*84]*/);

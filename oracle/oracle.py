@@ -124,6 +124,7 @@ def oracle_lib():
         L.sfo_draw_native.argtypes = [C.POINTER(Record), C.c_void_p]
         L.sfo_draw_obs.argtypes = [C.POINTER(Record), C.c_void_p]
         L.sfo_resize_area.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.sfo_set_glyph_masks.argtypes = [C.c_void_p, C.c_void_p]
         _ORACLE = L
     return _ORACLE
 
@@ -233,6 +234,17 @@ class OracleEnv:
         km = np.ascontiguousarray(keymasks, dtype=np.uint8)
         obs = np.zeros((84, 84), np.uint8)
         return self.L.sfo_run(C.byref(self.e), km.ctypes.data, km.size, obs.ctypes.data if render else None)
+
+
+def set_glyph_masks(alpha=None, slot=None):
+    """Digits from a real cairo + font (same format as the product's sf_set_glyph_masks); None restores the 7-segment face."""
+    L = oracle_lib()
+    if alpha is None:
+        L.sfo_set_glyph_masks(None, None)
+        return
+    a = np.ascontiguousarray(alpha, dtype=np.uint8).reshape(10, 5 * 27)
+    s = np.ascontiguousarray(slot, dtype=np.uint8).reshape(27)
+    L.sfo_set_glyph_masks(a.ctypes.data, s.ctypes.data)
 
 
 def resize_area(img, dh=84, dw=84):

@@ -332,8 +332,34 @@ static void fill_box(uint8_t* img, double ux, double uy, double uw, double uh, u
   }
 }
 
+/* Glyph masks from a real cairo + font (tools/dump_cairo_glyphs.py), in the product's format (sf_set_glyph_masks,
+ * include/sf_b200.h): alpha[d][row * 27 + col] = coverage of digit d drawn in EVERY one of the 7 slots, over the strip of
+ * native rows 1..5 x columns 32..58; slot[col] = which slot owns the column (255: none). NULL restores the 7-segment face. */
+#define TXT_X0 32
+#define TXT_Y0 1
+#define TXT_W 27
+#define TXT_H 5
+static uint8_t g_glyph_alpha[10][TXT_H * TXT_W], g_glyph_slot[TXT_W];
+static int g_glyphs_set = 0;
+void sfo_set_glyph_masks(const uint8_t* alpha, const uint8_t* slot) {
+  g_glyphs_set = alpha && slot;
+  if (g_glyphs_set) { memcpy(g_glyph_alpha, alpha, sizeof(g_glyph_alpha)); memcpy(g_glyph_slot, slot, sizeof(g_glyph_slot)); }
+}
+
 /* R7 under model M7: "%07d" of (int)mPoints, centred at user (355, 97), grey .5 */
 static void draw_score(uint8_t* img, int pnts) {
+  if (g_glyphs_set) {
+    int p = pnts < 0 ? 0 : (pnts > 9999999 ? 9999999 : pnts);
+    for (int i = 0; i < TXT_H * TXT_W; i++) {
+      int sl = g_glyph_slot[i % TXT_W];
+      if (sl >= 7) continue;
+      int div = 1;
+      for (int k = sl; k < 6; k++) div *= 10;
+      unsigned a = g_glyph_alpha[(p / div) % 10][i];
+      if (a) blend(&img[(TXT_Y0 + i / TXT_W) * W + TXT_X0 + i % TXT_W], colour8(.5), a);
+    }
+    return;
+  }
   static const unsigned char SEG[10] = {0x3f, 0x06, 0x5b, 0x4f, 0x66, 0x6d, 0x7d, 0x07, 0x7f, 0x6f}; /* gfedcba */
   /* segment boxes inside an 18 x 22 user-unit cell (0.6 em advance, 0.73 em cap height at 30 units) */
   static const double BOX[7][4] = {

@@ -48,6 +48,7 @@ int sfo_num_actions(int gametype, int action_set);
 void sfo_draw_native(const sfr_record* s, uint8_t* gray /* [92*90] */); /* draw.cpp:256-270 + ssf_env.py:205 */
 void sfo_resize_area(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw); /* cv2.resize INTER_AREA, rl/envs.py:29 */
 void sfo_draw_obs(const sfr_record* s, uint8_t* obs84 /* [84*84] */);
+void sfo_set_glyph_masks(const uint8_t* alpha /* [10][5*27] */, const uint8_t* slot /* [27] */); /* real-font digits (NULL: 7-segment face) */
 
 #ifdef __cplusplus
 }

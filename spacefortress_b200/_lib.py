@@ -95,6 +95,7 @@ _PROTOTYPES = {
     "sf_num_features": (C.c_int, [C.c_void_p, C.c_int]),
     "sf_features": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sf_features_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sf_set_glyph_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sf_background": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sf_host_static_frame": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

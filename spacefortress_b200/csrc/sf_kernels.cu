@@ -55,17 +55,19 @@ __device__ __forceinline__ long long sf_warp_sum_ll(long long v) {
   return v;
 }
 
-__device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, const SfEnv& e, bool finished, int lane) {
-  // called by all 32 lanes; `finished` lanes contribute
+__device__ __noinline__ void sf_accumulate_episode(const SfDev& D, int env, SfEnv& e, bool finished, int lane) {
+  // called by all 32 lanes; `finished` lanes contribute (their pending Stats increments go to the arrays first)
   long long f[SF_NUM_EPISODE_STATS];
   long long ret = e.q3.w;
+  int4 st0 = make_int4(0, 0, 0, 0), st1 = st0, st2 = st0;
+  if (finished) { sf_flush_stats(D, env, e); st0 = __ldcg(&D.st0[env]); st1 = __ldcg(&D.st1[env]); st2 = __ldcg(&D.st2[env]); }  // (L2: the flush is a reduction)
   f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = e.q3.z;
-  f[4] = e.st0.x; f[5] = e.st0.y; f[6] = e.st0.z; f[7] = e.st0.w;
-  f[8] = e.st1.x; f[9] = e.st1.y; f[10] = e.st1.z; f[11] = e.st1.w;
-  f[12] = e.st2.x; f[13] = e.st2.y; f[14] = e.st2.z; f[15] = e.st2.w; f[16] = e.st3.x;
+  f[4] = st0.x; f[5] = st0.y; f[6] = st0.z; f[7] = st0.w;
+  f[8] = st1.x; f[9] = st1.y; f[10] = st1.z; f[11] = st1.w;
+  f[12] = st2.x; f[13] = st2.y; f[14] = st2.z; f[15] = st2.w; f[16] = e.st3.x;
   f[17] = (long long)__float2int_rz(__int_as_float(e.q3.x));
   f[18] = __double2ll_rn((double)__int_as_float(e.q3.y) * 1000.0);
-  f[19] = e.st1.y;  // fortress kills of the episode (== destroyedFortresses; rl/train.py:81 sums info)
+  f[19] = st1.y;  // fortress kills of the episode (== destroyedFortresses; rl/train.py:81 sums info)
   f[20] = 0; f[21] = 0; f[22] = 0; f[23] = 0;
 #pragma unroll
   for (int k = 0; k < 20; k++) {
@@ -152,7 +154,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
     shell_vis = o.shell_vis;
   }
   if (__any_sync(0xffffffffu, finished)) {
-    sf_accumulate_episode(D, e, finished, lane);
+    sf_accumulate_episode(D, env, e, finished, lane);
     if (finished) { sf_new_game(D, H, env, e); shell_vis = 0; }  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
@@ -218,9 +220,10 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
       finished = o.done && autoreset;
     }
     if (__any_sync(0xffffffffu, finished)) {
-      sf_accumulate_episode(D, e, finished, lane);
+      sf_accumulate_episode(D, env, e, finished, lane);
       if (finished) sf_new_game(D, &D.tab->hot, env, e);
     }
+    if (mine && (t & 7) == 7) sf_flush_stats(D, env, e);  // the pending increments are 8-bit fields
   }
   if (mine) sf_store_env(D, env, e);
 }
@@ -400,9 +403,10 @@ __global__ void sf_get_state_kernel(SfDev D, int first, int count, sf_state_reco
   r.turn_flag = (r.left_flag && !r.right_flag) ? 1 : (!r.left_flag && r.right_flag) ? 2 : 0;  // game.cpp:265-270
   r.fortress_timer = e.q0.w; r.fortress_death_timer = e.q1.x; r.fortress_vuln_timer = e.q1.y;
   r.vulnerability = e.q1.z; r.tick = e.q3.z; r.time = e.q3.z * SF_TICK_MS;
-  r.stats[0] = e.st0.x; r.stats[1] = e.st0.y; r.stats[2] = e.st0.z; r.stats[3] = e.st0.w;
-  r.stats[4] = e.st1.x; r.stats[5] = e.st1.y; r.stats[6] = e.st1.z; r.stats[7] = e.st1.w;
-  r.stats[8] = e.st2.x; r.stats[9] = e.st2.y; r.stats[10] = e.st2.z; r.stats[11] = e.st2.w;
+  const int4 st0 = D.st0[i], st1 = D.st1[i], st2 = D.st2[i];
+  r.stats[0] = st0.x; r.stats[1] = st0.y; r.stats[2] = st0.z; r.stats[3] = st0.w;
+  r.stats[4] = st1.x; r.stats[5] = st1.y; r.stats[6] = st1.z; r.stats[7] = st1.w;
+  r.stats[8] = st2.x; r.stats[9] = st2.y; r.stats[10] = st2.z; r.stats[11] = st2.w;
   r.stats[12] = e.st3.x;
   r.prev_vlner = e.q1.w;
   r.rng_seed = (unsigned)e.st3.w; r.rng_count = (unsigned)e.st3.z;
@@ -433,9 +437,9 @@ __global__ void sf_set_state_kernel(SfDev D, int first, int count, const sf_stat
   e.q1 = make_int4(r.fortress_death_timer, r.fortress_vuln_timer, r.vulnerability, r.prev_vlner);
   e.q2 = make_int4(r.fire_timer, r.thrust_timer, r.left_timer, r.right_timer);
   e.q3 = make_int4(__float_as_int(r.points), __float_as_int(r.raw_points), r.tick, r.ep_return);
-  e.st0 = make_int4(r.stats[0], r.stats[1], r.stats[2], r.stats[3]);
-  e.st1 = make_int4(r.stats[4], r.stats[5], r.stats[6], r.stats[7]);
-  e.st2 = make_int4(r.stats[8], r.stats[9], r.stats[10], r.stats[11]);
+  D.st0[i] = make_int4(r.stats[0], r.stats[1], r.stats[2], r.stats[3]);
+  D.st1[i] = make_int4(r.stats[4], r.stats[5], r.stats[6], r.stats[7]);
+  D.st2[i] = make_int4(r.stats[8], r.stats[9], r.stats[10], r.stats[11]);
   e.st3.x = r.stats[12];
   for (int s = 0; s < SF_MAX_MISSILES; s++) if ((r.missile_mask >> s) & 1) {
     D.mpos[(size_t)s * D.n_pad + i] = make_double2(r.missile_x[s], r.missile_y[s]);
@@ -682,9 +686,9 @@ __global__ void __launch_bounds__(SF_PI_THREADS) sf_policy_input_kernel(const un
   __shared__ unsigned lut[256];             // bf16 bits of u8 / 255 (F32: the fp32 bits)
   const int env = blockIdx.x, tid = threadIdx.x;
   for (int v = tid; v < 256; v += SF_PI_THREADS) {
-    const float q = __fdiv_rn((float)v, 255.0f);
-    if (F32) lut[v] = __float_as_uint(q);
-    else { const __nv_bfloat16 h = __float2bfloat16_rn(q); lut[v] = *reinterpret_cast<const unsigned short*>(&h); }
+    // fp32: torch's CUDA `x / 255.0` multiplies by the fp32 reciprocal of the scalar; the table reproduces that bit for bit
+    if (F32) lut[v] = __float_as_uint(__fmul_rn((float)v, __fdiv_rn(1.0f, 255.0f)));
+    else { const __nv_bfloat16 h = __float2bfloat16_rn(__fdiv_rn((float)v, 255.0f)); lut[v] = *reinterpret_cast<const unsigned short*>(&h); }
   }
   const int nvalid = min(max(valid[env], 0), 4);
   // what this thread loads (words k0 = tid and k1 = tid + 192 of the 336-word tile) and stores (chunk tid < 168)
@@ -988,6 +992,21 @@ extern "C" int sf_debug_cycles(unsigned long long* h_out, int reset) {
   return SF_OK;
 }
 #endif
+
+extern "C" int sf_set_glyph_masks(sf_handle* h, const uint8_t* h_alpha, const uint8_t* h_slot) {
+  if (!h || (!h_alpha) != (!h_slot)) return fail(SF_ERR_INVALID, "handle is NULL, or only one of alpha / slot given");
+  SfTables* nt = new SfTables();
+  char err[256] = {0};
+  if (sf_build_tables_glyphs(nt, err, sizeof(err), h_alpha, h_slot)) { std::string m = err; delete nt; return fail(SF_ERR_INVALID, "table build failed: " + m); }
+  cudaError_t ce = cudaSetDevice(h->device);
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();  // nothing may be drawing from the old tables
+  if (ce == cudaSuccess) ce = cudaMemcpy((void*)h->dev.tab, nt, sizeof(SfTables), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemset(h->dev.expo_meta, 0, sizeof(uint2) * (size_t)h->dev.n_pad);  // cached resampled boxes may hold old digits
+  if (ce != cudaSuccess) { delete nt; return fail(SF_ERR_CUDA, std::string("sf_set_glyph_masks: ") + cudaGetErrorString(ce)); }
+  delete h->h_tab;
+  h->h_tab = nt;
+  return SF_OK;
+}
 
 extern "C" int sf_background(const sf_handle* h, uint8_t* h_native, uint8_t* h_obs) {
   if (!h) return fail(SF_ERR_INVALID, "handle is NULL");

@@ -20,21 +20,54 @@ struct SfStepOut {
   unsigned shell_vis;  // live shells further than 21 from the fortress after the tick (what draw.cpp:249-250 shows), bit per slot
 };
 
-// registers of one env between load and store
+// Registers of one env between load and store. The twelve Stats counters of st0..st2 (game.hh:29-43) change on a few
+// ticks only, so the step does not carry them: it counts the tick's increments in three words of four 8-bit fields
+// (d0 / d1 / d2 line up with the components of st0 / st1 / st2) and sf_store_env adds them to the arrays only when one is
+// non-zero. That is 96 B less traffic per env-step and 9 registers less for the step.
 struct SfEnv {
   double2 pos, vel;
-  int4 q0, q1, q2, q3, st0, st1, st2, st3;
+  int4 q0, q1, q2, q3, st3;
+  unsigned d0, d1, d2;   // pending increments: st0 (bigHexDeaths smallHexDeaths shellDeaths shipDeaths), st1 (resets destroyedFortresses missedShots totalShots), st2 (totalThrusts totalLefts totalRights vlnerIncs)
 };
+#define SF_ST_INC(word, comp) ((word) += 1u << (8 * (comp)))
 
 __device__ __forceinline__ void sf_load_env(const SfDev& D, int i, SfEnv& e) {
   e.pos = D.pos[i]; e.vel = D.vel[i];
   e.q0 = D.q0[i]; e.q1 = D.q1[i]; e.q2 = D.q2[i]; e.q3 = D.q3[i];
-  e.st0 = D.st0[i]; e.st1 = D.st1[i]; e.st2 = D.st2[i]; e.st3 = D.st3[i];
+  e.st3 = D.st3[i];
+  e.d0 = 0u; e.d1 = 0u; e.d2 = 0u;
 }
-__device__ __forceinline__ void sf_store_env(const SfDev& D, int i, const SfEnv& e) {
+__device__ __forceinline__ int4 sf_add_bytes(int4 v, unsigned d) {
+  v.x += (int)(d & 255u); v.y += (int)((d >> 8) & 255u); v.z += (int)((d >> 16) & 255u); v.w += (int)(d >> 24);
+  return v;
+}
+// the pending Stats increments -> the arrays (a field holds up to 255: flush at least every 12 ticks — 20 missiles could
+// leave the area in one tick)
+// (Reductions, not load-add-store: the stepping warp is bound by latency, and a reduction does not wait for the memory.
+// Only this lane ever touches env i's counters, so the atomicity itself is not needed.)
+__device__ __forceinline__ void sf_red_bytes(int4* p, unsigned d) {
+  int* q = reinterpret_cast<int*>(p);
+  if (d & 0x000000FFu) atomicAdd(q + 0, (int)(d & 255u));
+  if (d & 0x0000FF00u) atomicAdd(q + 1, (int)((d >> 8) & 255u));
+  if (d & 0x00FF0000u) atomicAdd(q + 2, (int)((d >> 16) & 255u));
+  if (d & 0xFF000000u) atomicAdd(q + 3, (int)(d >> 24));
+}
+__device__ __forceinline__ void sf_flush_stats(const SfDev& D, int i, SfEnv& e) {
+#ifdef SF_STATS_RMW
+  if (e.d0) { D.st0[i] = sf_add_bytes(D.st0[i], e.d0); e.d0 = 0u; }
+  if (e.d1) { D.st1[i] = sf_add_bytes(D.st1[i], e.d1); e.d1 = 0u; }
+  if (e.d2) { D.st2[i] = sf_add_bytes(D.st2[i], e.d2); e.d2 = 0u; }
+#else
+  if (e.d0) { sf_red_bytes(&D.st0[i], e.d0); e.d0 = 0u; }
+  if (e.d1) { sf_red_bytes(&D.st1[i], e.d1); e.d1 = 0u; }
+  if (e.d2) { sf_red_bytes(&D.st2[i], e.d2); e.d2 = 0u; }
+#endif
+}
+__device__ __forceinline__ void sf_store_env(const SfDev& D, int i, SfEnv& e) {
   D.pos[i] = e.pos; D.vel[i] = e.vel;
   D.q0[i] = e.q0; D.q1[i] = e.q1; D.q2[i] = e.q2; D.q3[i] = e.q3;
-  D.st0[i] = e.st0; D.st1[i] = e.st1; D.st2[i] = e.st2; D.st3[i] = e.st3;
+  D.st3[i] = e.st3;
+  sf_flush_stats(D, i, e);
 }
 
 // ---- G1: glibc rand() (TYPE_3 lagged sum over a 31-word ring), one stream per env ----
@@ -105,6 +138,42 @@ __device__ __noinline__ double sf_atan2(const SfHot* H, double dy, double dx) {
 __device__ __forceinline__ double sf_rad2deg(double a) { return SF_DMUL(SF_DDIV(a, SF_PI), 180.0); }  // vector.cpp:38-40
 __device__ __forceinline__ double sf_deg2rad(double a) { return SF_DDIV(SF_DMUL(a, SF_PI), 180.0); }  // vector.cpp:34-36
 
+// The reference quantises both of its aiming angles with ceil(): the autoturn heading ceil(angleTo(ship, fortress))
+// (game.cpp:319, vector.cpp:48-52) and the fortress sector ceil(angle_to_ship / 10) * 10 (game.cpp:197,206). Only the
+// smallest multiple k of STEP degrees with k >= theta matters, theta in [0, 360) being the direction of (dx, dy). That
+// is a sign test, not a transcendental: theta <= k  <=>  sin(theta - k) <= 0  <=>  cos(k) * dy - sin(k) * dx <= 0, with
+// cos / sin of integer degrees from the host-libm table. An fp32 atan2f proposes k (within one STEP of the answer), two
+// fp64 cross products confirm or move it. It decides like ceil(rad2deg(atan2())) unless theta lies within ~1e-14
+// degrees of a multiple of STEP — the same measure-zero band in which the 2-ulp device atan2 used before could differ
+// from libm — and the exact octants (the only directions with integer coordinates that ARE multiples of STEP) go through
+// the reference's own libm values (sf_atan2) and its own operation order.
+__device__ __noinline__ int sf_ceil_angle_exact(const SfHot* H, double dy, double dx, int step, bool add_before) {
+  double deg;
+  if (add_before) {  // angleTo (vector.cpp:48-52): a < 0 -> a += 2 pi, then rad2deg
+    double a = sf_atan2(H, dy, dx);
+    if (a < 0) a = SF_DADD(a, SF_PI * 2);
+    deg = sf_rad2deg(a);
+  } else {           // updateFortress (game.cpp:197): stdAngle(rad2deg(a))
+    deg = sf_rad2deg(sf_atan2(H, dy, dx));
+    if (deg < 0) deg = SF_DADD(deg, 360.0);
+  }
+  return step * (int)ceil(SF_DDIV(deg, (double)step));
+}
+template <int STEP>
+__device__ __forceinline__ int sf_ceil_angle(const SfHot* H, double dy, double dx, bool add_before) {  // in [0, 360]
+  if (dy == 0.0 || dx == 0.0 || fabs(dx) == fabs(dy)) return sf_ceil_angle_exact(H, dy, dx, STEP, add_before);
+  float a = atan2f((float)dy, (float)dx) * 57.29577951308232f;
+  if (a < 0.f) a += 360.f;
+  int k = STEP * (int)ceilf(a * (1.0f / STEP));
+  k = min(max(k, STEP), 360);
+  const int ik = k == 360 ? 0 : k, im = k - STEP;
+  const double fk = SF_DSUB(SF_DMUL(H->cs[ik][0], dy), SF_DMUL(H->cs[ik][1], dx));
+  const double fm = SF_DSUB(SF_DMUL(H->cs[im][0], dy), SF_DMUL(H->cs[im][1], dx));
+  if (fk > 0) k += STEP;          // theta > k
+  else if (fm <= 0) k -= STEP;    // theta <= k - STEP
+  return k;
+}
+
 // S12: shell velocity 6*(cos,sin)(deg2rad(angle)) for a real-valued angle (game.cpp:167-168); out of line: rare
 __device__ __noinline__ double2 sf_shell_velocity(double a) {
   double rad = sf_deg2rad(a);
@@ -124,7 +193,7 @@ __device__ __forceinline__ void sf_kill_ship(SfEnv& e) {  // game.cpp:274-280
   if (e.q0.x & SF_CORE_SHIP_ALIVE) {
     e.q0.x &= ~SF_CORE_SHIP_ALIVE;
     e.q0.z = 0;
-    e.st0.w += 1;
+    SF_ST_INC(e.d0, 3);
   }
 }
 
@@ -161,7 +230,8 @@ __device__ inline void sf_new_game(const SfDev& D, const SfHot* H, int i, SfEnv&
   e.q1 = make_int4(0, 250, 0, e.q1.w);                           // mVulnerabilityTimer: 0 + 250 (game.cpp:78)
   e.q2 = make_int4(0, 0, 0, 0);
   e.q3 = make_int4(0, 0, 0, 0);
-  e.st0 = make_int4(0, 0, 0, 0); e.st1 = make_int4(0, 0, 0, 0); e.st2 = make_int4(0, 0, 0, 0);
+  D.st0[i] = make_int4(0, 0, 0, 0); D.st1[i] = make_int4(0, 0, 0, 0); D.st2[i] = make_int4(0, 0, 0, 0);  // the Stats of a fresh Game
+  e.d0 = 0u; e.d1 = 0u; e.d2 = 0u;
   e.st3.x = 0;
 }
 
@@ -194,17 +264,17 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
           sf_reward(e, rew, -D.missile_penalty);
         }
       }
-      core |= SF_CORE_FIRE; e.q2.x = 0; e.st1.w += 1; ev |= SF_EV_PRESS_FIRE;
+      core |= SF_CORE_FIRE; e.q2.x = 0; SF_ST_INC(e.d1, 3); ev |= SF_EV_PRESS_FIRE;
     } else if (!pressed && flag) { core &= ~SF_CORE_FIRE; e.q2.x = 0; }
     pressed = keymask & SF_KEY_THRUST; flag = core & SF_CORE_THRUST;
-    if (pressed && !flag) { core |= SF_CORE_THRUST; e.q2.y = 0; e.st2.x += 1; ev |= SF_EV_PRESS_THRUST; }
+    if (pressed && !flag) { core |= SF_CORE_THRUST; e.q2.y = 0; SF_ST_INC(e.d2, 0); ev |= SF_EV_PRESS_THRUST; }
     else if (!pressed && flag) { core &= ~SF_CORE_THRUST; e.q2.y = 0; }
     if (!D.autoturn) {
       pressed = keymask & SF_KEY_LEFT; flag = core & SF_CORE_LEFT;
-      if (pressed && !flag) { core |= SF_CORE_LEFT; e.q2.z = 0; e.st2.y += 1; ev |= SF_EV_PRESS_LEFT; }
+      if (pressed && !flag) { core |= SF_CORE_LEFT; e.q2.z = 0; SF_ST_INC(e.d2, 1); ev |= SF_EV_PRESS_LEFT; }
       else if (!pressed && flag) { core &= ~SF_CORE_LEFT; e.q2.z = 0; }
       pressed = keymask & SF_KEY_RIGHT; flag = core & SF_CORE_RIGHT;
-      if (pressed && !flag) { core |= SF_CORE_RIGHT; e.q2.w = 0; e.st2.z += 1; ev |= SF_EV_PRESS_RIGHT; }
+      if (pressed && !flag) { core |= SF_CORE_RIGHT; e.q2.w = 0; SF_ST_INC(e.d2, 2); ev |= SF_EV_PRESS_RIGHT; }
       else if (!pressed && flag) { core &= ~SF_CORE_RIGHT; e.q2.w = 0; }
     }
   }
@@ -222,9 +292,11 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
   if (core & SF_CORE_SHIP_ALIVE) {
     int ang = core & SF_CORE_ANGLE_MASK;
     if (D.autoturn) {
-      double a = sf_atan2(T, SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x));  // angleTo, pre-move (Q3)
-      if (a < 0) a = SF_DADD(a, SF_PI * 2);
-      ang = (int)ceil(sf_rad2deg(a));
+#ifdef SF_OLD_ATAN2
+      ang = sf_ceil_angle_exact(T, SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x), 1, true);
+#else
+      ang = sf_ceil_angle<1>(T, SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x), true);  // ceil(angleTo), pre-move (Q3)
+#endif
       if (ang >= 360) ang -= 360;  // stdAngle
     } else {
       bool l = core & SF_CORE_LEFT, r = core & SF_CORE_RIGHT;
@@ -240,10 +312,10 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     e.pos.y = SF_DADD(e.pos.y, e.vel.y);
     e.q0.x = (int)core;
     if (!sf_inside_hex(T, 0, e.pos.x, e.pos.y)) {
-      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); e.st0.x += 1;
+      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); SF_ST_INC(e.d0, 0);
       ev |= SF_EV_EXPLODE_BIGHEX | SF_EV_COL_BIGHEX;
     } else if (sf_inside_hex(T, 1, e.pos.x, e.pos.y)) {
-      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); e.st0.y += 1;
+      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); SF_ST_INC(e.d0, 1);
       ev |= SF_EV_EXPLODE_SMALLHEX | SF_EV_COL_SMALLHEX;
     }
     core = (unsigned)e.q0.x;
@@ -251,13 +323,16 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
 
   // ---- S11 updateFortress (game.cpp:194-216) ----
   {
-    double a = sf_rad2deg(sf_atan2(T, SF_DSUB(e.pos.y, SF_FORT_Y), SF_DSUB(e.pos.x, SF_FORT_X)));
-    if (a < 0) a = SF_DADD(a, 360.0);  // stdAngle on (-180,180]
     if (!(core & SF_CORE_FORT_ALIVE) && e.q1.x > 1000) {
       e.q0.w = 0; core |= SF_CORE_FORT_ALIVE; ev |= SF_EV_FORTRESS_RESPAWN;
     }
     if (core & SF_CORE_SHIP_ALIVE) {  // the fortress only tracks a live ship
-      int sect = (int)ceil(SF_DDIV(a, 10.0));
+      const double fdy = SF_DSUB(e.pos.y, SF_FORT_Y), fdx = SF_DSUB(e.pos.x, SF_FORT_X);
+#ifdef SF_OLD_ATAN2
+      int sect = sf_ceil_angle_exact(T, fdy, fdx, 10, false) / 10;
+#else
+      int sect = sf_ceil_angle<10>(T, fdy, fdx, false) / 10;  // ceil(angle_to_ship / 10)
+#endif
       if (sect >= 36) sect -= 36;
       unsigned last = (core >> SF_CORE_FLAST_SHIFT) & 63u;
       core = (core & ~(63u << SF_CORE_FANG_SHIFT)) | ((unsigned)sect << SF_CORE_FANG_SHIFT);
@@ -266,9 +341,11 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
         e.q0.w = 0;
       }
       if (e.q0.w >= 1000 && (core & SF_CORE_FORT_ALIVE)) {
-        // S12 fireShell with the exact (real) angle
+        // S12 fireShell with the exact (real) angle: stdAngle(rad2deg(atan2(dy, dx))) (game.cpp:197), needed here only
         int slot = sf_first_free(((unsigned)e.q0.y >> SF_PMASK_SHELL_SHIFT) & 0xFu, SF_DEV_SHELLS);
         if (slot >= 0) {
+          double a = sf_rad2deg(sf_atan2(T, fdy, fdx));
+          if (a < 0) a = SF_DADD(a, 360.0);  // stdAngle on (-180,180]
           e.q0.y |= 1 << (SF_PMASK_SHELL_SHIFT + slot);
           D.spos[(size_t)slot * np + i] = make_double2(SF_FORT_X, SF_FORT_Y);
           D.svel[(size_t)slot * np + i] = sf_shell_velocity(a);
@@ -291,7 +368,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     D.spos[(size_t)s * np + i] = p;
     if ((e.q0.x & SF_CORE_SHIP_ALIVE) && sf_dist2(p.x, p.y, e.pos.x, e.pos.y) <= thr_ship) {
       e.q0.y &= ~(1 << (SF_PMASK_SHELL_SHIFT + s));
-      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); e.st0.z += 1;
+      sf_kill_ship(e); sf_reward(e, rew, -(float)D.death_penalty); SF_ST_INC(e.d0, 2);
       ev |= SF_EV_SHELL_HIT_SHIP | SF_EV_COL_SHELL_SHIP;
     } else if (sf_outside(p.x, p.y)) {
       e.q0.y &= ~(1 << (SF_PMASK_SHELL_SHIFT + s));
@@ -313,14 +390,14 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
       if (e.q0.x & SF_CORE_FORT_ALIVE) {
         ev |= SF_EV_HIT_FORTRESS;
         if (e.q1.y >= 250) {
-          e.q1.z += 1; ev |= SF_EV_VLNER_INCREASED; e.st2.w += 1;
+          e.q1.z += 1; ev |= SF_EV_VLNER_INCREASED; SF_ST_INC(e.d2, 3);
           if (e.q1.z > e.st3.x) e.st3.x = e.q1.z;
         } else {
           if (e.q1.z >= 11) {
             e.q0.x &= ~SF_CORE_FORT_ALIVE; e.q1.x = 0;
             sf_reward(e, rew, (float)D.destroy_fortress);
-            ev |= SF_EV_FORTRESS_DESTROYED; e.st1.y += 1;
-          } else { ev |= SF_EV_VLNER_RESET; e.st1.x += 1; }
+            ev |= SF_EV_FORTRESS_DESTROYED; SF_ST_INC(e.d1, 1);
+          } else { ev |= SF_EV_VLNER_RESET; SF_ST_INC(e.d1, 0); }
           e.q1.z = 0;
         }
         e.q1.y = 0;
@@ -328,7 +405,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     } else if (sf_outside(p.x, p.y)) {
       e.q0.y &= ~(1 << s);
       sf_reward(e, rew, -0.0f);  // missPenalty == 0 (configs.cpp:11)
-      e.st1.z += 1; ev |= SF_EV_MISSED_SHOT;
+      SF_ST_INC(e.d1, 2); ev |= SF_EV_MISSED_SHOT;
     }
   }
 

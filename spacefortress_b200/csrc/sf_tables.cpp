@@ -155,7 +155,9 @@ std::vector<Tap> area_tab(int ssize, int dsize) {
 
 static const double WF_FORTRESS[4][4] = {{0, 0, 36, 0}, {0, -18, 18, -18}, {18, -18, 18, 18}, {18, 18, 0, 18}};
 
-int sf_build_tables(SfTables* t, char* err, int errcap) {
+int sf_build_tables(SfTables* t, char* err, int errcap) { return sf_build_tables_glyphs(t, err, errcap, nullptr, nullptr); }
+
+int sf_build_tables_glyphs(SfTables* t, char* err, int errcap, const unsigned char* glyph_alpha, const unsigned char* glyph_slot) {
   memset(t, 0, sizeof(*t));
   for (int a = 0; a < 360; a++) {
     double r = (double)a * M_PI / 180;
@@ -360,8 +362,14 @@ int sf_build_tables(SfTables* t, char* err, int errcap) {
     }
   }
 
-  // ---- score digits: 7-segment face on the metrics of a 30-unit monospace bold font ----
-  {
+  // ---- score digits: masks rendered elsewhere by a real cairo + font, or the 7-segment face on the metrics of a 30-unit
+  // monospace bold font ----
+  if (glyph_alpha && glyph_slot) {
+    memcpy(t->text_alpha, glyph_alpha, sizeof(t->text_alpha));
+    memcpy(t->text_slot, glyph_slot, sizeof(t->text_slot));
+    for (int c = 0; c < SF_TEXT_W; c++)
+      if (t->text_slot[c] >= 7 && t->text_slot[c] != 255) { snprintf(err, errcap, "glyph slot of column %d is %d (0..6 or 255)", c, t->text_slot[c]); return 1; }
+  } else {
     static const unsigned char SEG[10] = {0x3f, 0x06, 0x5b, 0x4f, 0x66, 0x6d, 0x7d, 0x07, 0x7f, 0x6f};
     static const double BOX[7][4] = {{3, 0, 12, 4}, {11, 0, 4, 13}, {11, 9, 4, 13}, {3, 18, 12, 4}, {3, 9, 4, 13}, {3, 0, 4, 13}, {3, 9, 12, 4}};
     const double x0 = 355 - 7 * 18 / 2.0, ytop = 97 - 22 / 2.0;

@@ -132,3 +132,6 @@ struct SfTables {
 
 // builds the tables on the host; returns 0 on success, else a message in err
 int sf_build_tables(SfTables* t, char* err, int errcap);
+// the same with the score digits taken from glyph masks (sf_set_glyph_masks, include/sf_b200.h) instead of the built-in
+// 7-segment face: alpha[10][SF_TEXT_H * SF_TEXT_W], slot[SF_TEXT_W]; both NULL == sf_build_tables
+int sf_build_tables_glyphs(SfTables* t, char* err, int errcap, const unsigned char* alpha, const unsigned char* slot);

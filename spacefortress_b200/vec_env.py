@@ -293,6 +293,16 @@ class SFVecEnv(object):
         vals = out.cpu().tolist()
         return dict(zip(_lib.EPISODE_STAT_NAMES, vals))
 
+    def set_glyph_masks(self, alpha=None, slot=None):
+        """Install score-digit masks rendered by a real cairo + font (tools/dump_cairo_glyphs.py): alpha uint8 [10, 5, 27]
+        (digit d in all 7 slots over native rows 1..5 x columns 32..58), slot uint8 [27]. None: the built-in 7-segment face."""
+        if alpha is None:
+            _lib.check(self.L.sf_set_glyph_masks(self.h, None, None))
+            return
+        a = np.ascontiguousarray(alpha, dtype=np.uint8).reshape(10, 5 * 27)
+        s = np.ascontiguousarray(slot, dtype=np.uint8).reshape(27)
+        _lib.check(self.L.sf_set_glyph_masks(self.h, a.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)))
+
     def state_bytes(self):
         return self.L.sf_state_bytes(self.h)
 

@@ -335,3 +335,57 @@ def test_one_ppo_minibatch_on_the_gpu_matches_the_reference_code():
         check_minibatch(torch.device("cuda"), 1e-4, 2e-3)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+def test_installed_glyph_masks_are_drawn_by_kernels_and_oracle_alike():
+    """sf_set_glyph_masks: score digits from (here: synthetic) font masks in the format tools/dump_cairo_glyphs.py writes.
+    With the same masks installed on both sides the frames stay bit-exact (static default observation with "0000000",
+    the score window of a non-zero score, a dead ship's cached box under the strip); None restores the built-in face."""
+    torch_cuda()
+    from oracle import oracle as O
+    from spacefortress_b200 import SFVecEnv
+    rng = np.random.RandomState(12)
+    slot = np.full(27, 255, np.uint8)
+    for k in range(7):
+        slot[1 + 4 * k:4 + 4 * k] = k      # three columns per digit, one free column between digits
+    alpha = np.zeros((10, 5, 27), np.uint8)
+    for d in range(10):
+        glyph = rng.randint(0, 256, (5, 3)).astype(np.uint8) * (rng.rand(5, 3) < 0.7)
+        for k in range(7):
+            alpha[d, :, 1 + 4 * k:4 + 4 * k] = glyph
+    n = 24
+    env = SFVecEnv("youturn", num_envs=n, device=0)
+    env.reset()
+    recs = env.get_state()
+    for i in range(n):
+        recs[i].points = float([0, 5, 1234567, 9081726][i % 4])
+        if i % 3 == 0:   # dead ship right under the score strip
+            recs[i].ship_alive = 0; recs[i].ship_x = 330.0 + 5 * i; recs[i].ship_y = 120.0
+    env.set_state(recs)
+    try:
+        env.set_glyph_masks(alpha, slot); O.set_glyph_masks(alpha, slot)
+        for native in (True, False):
+            frames = env.render_frames(native=native)
+            frames2 = env.render_frames(native=native)   # second pass: explosion memo path
+            for i in range(n):
+                r = O.Record(); import ctypes as C; C.memmove(C.byref(r), C.byref(recs[i]), C.sizeof(O.Record))
+                exp = O.draw_native(r) if native else O.draw_obs(r)
+                assert np.array_equal(frames[i], exp) and np.array_equal(frames2[i], exp), (native, i)
+        assert env.render_frames(native=True)[1][1:6, 32:59].max() > 0
+        # stepping (cached boxes, score windows) with the installed masks
+        oracles = [O.OracleEnv("youturn", 1) for _ in range(n)]
+        for i in range(n):
+            r = O.Record(); C.memmove(C.byref(r), C.byref(recs[i]), C.sizeof(O.Record)); oracles[i].set_state(r)
+        for t in range(12):
+            a = rng.randint(env.num_actions, size=n)
+            obs, _, _, _ = env.step(a)
+            for i in range(n):
+                oracles[i].step(oracles[i].keymask(int(a[i])))
+                assert np.array_equal(obs[i, 0], oracles[i].obs()), (t, i)
+    finally:
+        O.set_glyph_masks(None)
+    env.set_glyph_masks(None)
+    frames = env.render_frames(native=False)
+    for i in range(n):
+        assert np.array_equal(frames[i], oracles[i].obs()), i
+    env.close()

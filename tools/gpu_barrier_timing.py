@@ -3,7 +3,9 @@ and barrier, nothing else). usage: python tools/gpu_barrier_timing.py [n] [gamet
 import os, subprocess, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS="-DSF_BARRIER_TIMING"), check=True)
+PREBUILT = bool(os.environ.get("SF_B200_LIB"))  # a -DSF_BARRIER_TIMING variant built beforehand (build_variants/)
+if not PREBUILT:
+    subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS="-DSF_BARRIER_TIMING"), check=True)
 import torch
 from spacefortress_b200 import SFVecEnv, _lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -23,9 +25,10 @@ ms = s.elapsed_time(e); v = list(buf)
 blocks = min(148, (n + 31) // 32 if n > 148 * 32 else 147)
 cyc = ms * 1e-3 * 1.965e9
 W = 24
-print("%s n=%d: launch %.3f ms = %.0f cycles; %.3e steps/s" % (gt, n, ms, cyc, n * T / ms * 1e3))
+print(os.path.basename(os.environ.get("SF_B200_LIB", "")), "%s n=%d: launch %.3f ms = %.0f cycles; %.3e steps/s" % (gt, n, ms, cyc, n * T / ms * 1e3))
 print("per drawing warp: stage barrier %.1f %%, drawing-warp barriers %.1f %% of the launch; stepping warp at the stage barrier %.1f %%"
       % (100 * v[0] / (blocks * (W - 1)) / cyc, 100 * v[1] / (blocks * (W - 1)) / cyc, 100 * v[2] / blocks / cyc))
 print("stepping warp, share of the launch: steps %.1f %%, memo state %.1f %%, round scans %.1f %%, stroke gathering %.1f %%, pools + base copies %.1f %%"
       % tuple(100 * v[k] / blocks / cyc for k in (3, 4, 5, 6, 7)))
-subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
+if not PREBUILT:
+    subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
