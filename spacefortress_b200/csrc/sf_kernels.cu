@@ -138,12 +138,30 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   SfEnv e;
   bool finished = false;
   unsigned shell_vis = 0;
+#ifdef SF_BARRIER_TIMING
+  unsigned stmask_ = __ballot_sync(0xffffffffu, mine);
+#endif
+  SF_ST_BEGIN();
+  SfStepSmem& SS = sf_block_smem().step;
+  const bool first_tick = t == 0, last_tick = t == A.T - 1;
   if (mine) {
-    sf_load_env(D, env, e);
+    if (first_tick) sf_load_env(D, env, e);
+    else {  // between the ticks of a launch the group's scalars live in shared memory
+      e.pos = SS.pos[lane]; e.vel = SS.vel[lane];
+      e.q0 = SS.q0[lane]; e.q1 = SS.q1[lane]; e.q2 = SS.q2[lane]; e.q3 = SS.q3[lane]; e.st3 = SS.st3[lane];
+      e.d0 = 0u; e.d1 = 0u; e.d2 = 0u;
+    }
+#ifdef SF_BARRIER_TIMING
+    if (e.q0.x == 0x7fffffff) e.q0.y = 0;  // (a use of the loaded words: the section ends when they have arrived)
+#endif
+    SF_ST(8);
     int a = A.actions ? A.actions[(size_t)t * D.n + env]
                       : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
     int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
     SfStepOut o;
+#ifdef SF_BARRIER_TIMING
+    o.sync_mask = stmask_;
+#endif
     sf_env_step(D, H, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
     size_t oi = (size_t)t * D.n + env;
     if (A.reward) A.reward[oi] = o.reward;
@@ -153,15 +171,24 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
     finished = o.done && autoreset;
     shell_vis = o.shell_vis;
   }
+#ifdef SF_BARRIER_TIMING
+  ts_ = clock64(); stmask_ = 0xffffffffu;
+#endif
   if (__any_sync(0xffffffffu, finished)) {
     sf_accumulate_episode(D, env, e, finished, lane);
     if (finished) { sf_new_game(D, H, env, e); shell_vis = 0; }  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
-    sf_store_env(D, env, e);
+    if (last_tick) sf_store_env(D, env, e);
+    else {
+      SS.pos[lane] = e.pos; SS.vel[lane] = e.vel;
+      SS.q0[lane] = e.q0; SS.q1[lane] = e.q1; SS.q2[lane] = e.q2; SS.q3[lane] = e.q3; SS.st3[lane] = e.st3;
+      sf_flush_stats(D, env, e);
+    }
     sf_make_env_rec(e, env, shell_vis, recs[lane]);
   } else recs[lane].env = -1;
   __syncwarp();
+  SF_ST(15);
 }
 
 
@@ -211,6 +238,9 @@ __global__ void __launch_bounds__(128) sf_step_only_kernel(SfDev D, SfRollArgs A
                         : sf_hash_action(A.action_seed, (unsigned long long)(D.first_global_env + env), (unsigned long long)(A.t0 + t), D.num_actions);
       int km = (A.flags & SF_FLAG_ACTIONS_ARE_KEYMASKS) ? (a & 15) : D.keymask_of_action[min(max(a, 0), D.num_actions - 1)];
       SfStepOut o;
+#ifdef SF_BARRIER_TIMING
+      o.sync_mask = __activemask();
+#endif
       sf_env_step(D, &D.tab->hot, env, e, km, autoreset, (A.flags & SF_FLAG_RAW_REWARD) != 0, o);
       size_t oi = (size_t)t * D.n + env;
       if (A.reward) A.reward[oi] = o.reward;
@@ -970,8 +1000,8 @@ extern "C" int sf_episode_stats(sf_handle* h, long long* d_out, int reset, void*
 #ifdef SF_BARRIER_TIMING
 extern "C" int sf_barrier_cycles(unsigned long long* h_out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h_out, sf_bar_cycles, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(sf_bar_cycles, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(h_out, sf_bar_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sf_bar_cycles, z, sizeof(z)); }
   return SF_OK;
 }
 #endif

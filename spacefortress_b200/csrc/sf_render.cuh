@@ -33,6 +33,7 @@
 #include "sf_state.cuh"
 #include "sf_tables.h"
 
+#define SF_GROUP_ENVS_ 32   // == SF_GROUP_ENVS (defined below)
 #define SF_BATCH_QUADS 32
 #define SF_MAX_GROUPS 256    // (stroke, 8 sub-rows) work groups of one batch: 8 wireframes x <= 30, or 32 one-quad strokes x <= 8
 // A window is the INTER_AREA footprint closure of a box of at most 28x28 native pixels (the explosion sprite):
@@ -128,6 +129,15 @@ struct __align__(16) SfTeamSmem {
   alignas(16) unsigned short cells[SF_POOL_CELLS];  // coverage of every region of the round, zero between rounds
 };
 
+// The scalar state of the block's group between the ticks of one launch (rollout kernel, warp 0 only): loaded from the SoA
+// arrays at the group's first tick, written back at its last one. In between the stepping warp exchanges 112 bytes per env
+// with shared memory instead of issuing 7 global loads and 7 global stores per tick into the memory pipeline that the 23
+// drawing warps keep full (measured: 4.1 k + 7.0 k of its 27 k cycles per tick went there).
+struct __align__(16) SfStepSmem {
+  double2 pos[SF_GROUP_ENVS_], vel[SF_GROUP_ENVS_];
+  int4 q0[SF_GROUP_ENVS_], q1[SF_GROUP_ENVS_], q2[SF_GROUP_ENVS_], q3[SF_GROUP_ENVS_], st3[SF_GROUP_ENVS_];
+};
+
 // per-block shared memory: copies of the static tables that every window touches, and the teams
 struct __align__(16) SfBlockSmem {
   int4 xtap[84];   // INTER_AREA taps {si | cnt<<8, a0, a1, a2} (float bits) for the 84 output columns / rows
@@ -150,6 +160,7 @@ struct __align__(16) SfBlockSmem {
   int tl_n[4];
 #endif
   int next_group[2], padg[2];  // rollout kernel: the block's next groups (written by warp 0 one group ahead)
+  SfStepSmem step;             // rollout kernel: the group's scalar state between ticks
   SfTeamSmem team[2];
 };
 
@@ -159,7 +170,7 @@ extern __shared__ __align__(16) unsigned char sf_smem_raw[];
 __device__ __forceinline__ SfBlockSmem& sf_block_smem() { return *reinterpret_cast<SfBlockSmem*>(sf_smem_raw); }
 __device__ __forceinline__ SfTeamSmem& sf_team(int sg) { return sf_block_smem().team[sg]; }  // sg: the stage copy being drawn (0 / 1), handed down in a register
 #ifdef SF_BARRIER_TIMING  // tools/gpu_barrier_timing.py: cycles the warps spend at the barriers
-__device__ unsigned long long sf_bar_cycles[8];  // [0] stage barrier (drawing warps), [1] drawing-warp barriers, [2] stage barrier (warp 0)
+__device__ unsigned long long sf_bar_cycles[16];  // [8..15]: sections of the step (SF_ST in sf_step.cuh / sf_step_group); [0] stage barrier (drawing warps), [1] drawing-warp barriers, [2] stage barrier (warp 0)
 __device__ __forceinline__ void sf_bar_add(int k, long long t0) { if ((threadIdx.x & 31) == 0) atomicAdd(&sf_bar_cycles[k], (unsigned long long)(clock64() - t0)); }
 #endif
 __device__ __forceinline__ void sf_team_sync() {  // every warp of the block (named barrier 1)

@@ -9,6 +9,13 @@
 #include "sf_state.cuh"
 #include "../../include/sf_b200.h"
 
+#ifdef SF_BARRIER_TIMING  // sections of the step, cycles of warp 0 (tools/gpu_barrier_timing.py); sf_bar_add is in sf_render.cuh
+#define SF_ST_BEGIN() long long ts_ = clock64()
+#define SF_ST(k) do { __syncwarp(stmask_); sf_bar_add(k, ts_); ts_ = clock64(); } while (0)   // stmask_: the lanes that step an env
+#else
+#define SF_ST_BEGIN() ((void)0)
+#define SF_ST(k) ((void)0)
+#endif
 #define SF_TICK_MS 34        // ssf_env.py:61
 #define SF_GAME_TIME 180000  // configs.cpp:55,66,78,86
 #define SF_GAME_TICKS 5295   // first tick with mTime >= gameTime (game.cpp:487-489)
@@ -17,6 +24,9 @@ struct SfStepOut {
   int reward;       // shaped (train presets) or raw (test presets) integer reward
   unsigned events;  // SF_EV_*
   bool done, fort_kill;
+#ifdef SF_BARRIER_TIMING
+  unsigned sync_mask;
+#endif
   unsigned shell_vis;  // live shells further than 21 from the fortress after the tick (what draw.cpp:249-250 shows), bit per slot
 };
 
@@ -244,6 +254,10 @@ __device__ __forceinline__ int sf_first_free(unsigned mask, int n) {
 // One SSF_Env.step: keymask -> key events -> stepOneTick(34) -> shaping -> done -> auto-reset.
 __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv& e, int keymask, bool autoreset, bool raw_reward, SfStepOut& out) {
   const int np = D.n_pad;
+#ifdef SF_BARRIER_TIMING
+  const unsigned stmask_ = out.sync_mask;
+#endif
+  SF_ST_BEGIN();
   float rew = 0.f;
   unsigned ev = 0;
   unsigned core = (unsigned)e.q0.x;
@@ -288,6 +302,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     core = (unsigned)e.q0.x;
   }
 
+  SF_ST(9);
   // ---- S7 updateShip (game.cpp:314-351) ----
   if (core & SF_CORE_SHIP_ALIVE) {
     int ang = core & SF_CORE_ANGLE_MASK;
@@ -321,6 +336,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     core = (unsigned)e.q0.x;
   }
 
+  SF_ST(10);
   // ---- S11 updateFortress (game.cpp:194-216) ----
   {
     if (!(core & SF_CORE_FORT_ALIVE) && e.q1.x > 1000) {
@@ -358,6 +374,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     e.q0.x = (int)core;
   }
 
+  SF_ST(11);
   // ---- S13 updateShells (game.cpp:404-423), slot order ----
   const double thr_ship = T->touch2[0], thr_fort = T->touch2[1], thr_hide = T->touch2[2];
   unsigned vis = 0;
@@ -376,6 +393,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
   }
   out.shell_vis = vis;
 
+  SF_ST(12);
   // ---- S14 updateMissiles (game.cpp:353-402), slot order (order dependent) ----
   for (unsigned m = (unsigned)e.q0.y & SF_PMASK_MISSILES; m; m &= m - 1) {
     int s = __ffs(m) - 1;
@@ -409,6 +427,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     }
   }
 
+  SF_ST(13);
   // ---- S16 stepTimers (game.cpp:425-451) ----
   core = (unsigned)e.q0.x;
   e.q3.z += 1;
@@ -433,4 +452,5 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
   out.reward = reward; out.fort_kill = fort_kill; out.done = done;
   if (done && autoreset) ev |= SF_EV_EPISODE_RESET;
   out.events = ev;
+  SF_ST(14);
 }

@@ -95,7 +95,7 @@ class OnDeviceRollout(object):
     device-side step counter) into a CUDA graph per step index and replays the T graphs: no Python or launch gaps
     inside the loop (rl/train.py:73-98 has a host round trip per step)."""
 
-    def __init__(self, env, policy, num_steps=128, num_stack=4, graph=False):
+    def __init__(self, env, policy, num_steps=128, num_stack=4, graph=False, fused_input=None):
         self.env, self.policy, self.T, self.S = env, policy, int(num_steps), int(num_stack)
         n, dev = env.num_envs, env._device()
         pdt = next(policy.parameters()).dtype
@@ -118,6 +118,8 @@ class OnDeviceRollout(object):
         self._age_idx = torch.arange(self.S, device=dev, dtype=torch.int32).view(1, self.S, 1, 1)
         # the policy's first-layer input comes from the fused stack / mask / scale / space-to-depth kernel (bf16 or fp32)
         self.fused_input = pdt in (torch.bfloat16, torch.float32) and self.S == 4 and dev.type == "cuda"
+        if fused_input is not None:   # False: hand the policy the plain [N,4,84,84] u8 stack (what the reference's ACNet takes)
+            self.fused_input = self.fused_input and bool(fused_input)
         if self.fused_input:
             self.pin = torch.empty((n, 64, 21, 21), dtype=pdt, device=dev).contiguous(memory_format=torch.channels_last)
         self.use_graph = bool(graph)

@@ -530,7 +530,7 @@ def test_on_device_rollout_frame_stack_matches_reference_loop():
             return SFGRUPolicy.act(self, obs, state, mask, **kw)
     policy = Recording(env.num_actions).cuda().eval()
     policy.seen = []
-    ro = OnDeviceRollout(env, policy, num_steps=T)
+    ro = OnDeviceRollout(env, policy, num_steps=T, fused_input=False)   # the policy sees the plain u8 stack here
     env.set_state(recs)  # OnDeviceRollout reset the envs: restore the staggered clocks and re-render the first frame
     ro.frames[ro.S - 1].copy_(torch.from_numpy(env.render_frames()).cuda())
     cur = torch.zeros((n, 4, 84, 84), device="cuda")

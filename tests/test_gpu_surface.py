@@ -347,12 +347,12 @@ def test_installed_glyph_masks_are_drawn_by_kernels_and_oracle_alike():
     rng = np.random.RandomState(12)
     slot = np.full(27, 255, np.uint8)
     for k in range(7):
-        slot[1 + 4 * k:4 + 4 * k] = k      # three columns per digit, one free column between digits
+        slot[4 * k:4 * k + 3] = k          # three columns per digit, one free column between digits
     alpha = np.zeros((10, 5, 27), np.uint8)
     for d in range(10):
         glyph = rng.randint(0, 256, (5, 3)).astype(np.uint8) * (rng.rand(5, 3) < 0.7)
         for k in range(7):
-            alpha[d, :, 1 + 4 * k:4 + 4 * k] = glyph
+            alpha[d, :, 4 * k:4 * k + 3] = glyph
     n = 24
     env = SFVecEnv("youturn", num_envs=n, device=0)
     env.reset()

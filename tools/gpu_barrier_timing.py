@@ -15,7 +15,7 @@ env = SFVecEnv(gt, num_envs=n, device=0); env.reset(to_numpy=False)
 env.rollout(300, want=("reward",))
 out = {"obs": torch.empty((T, n, 1, 84, 84), dtype=torch.uint8, device="cuda")}
 env.rollout(T, out=out); torch.cuda.synchronize()
-L = _lib.lib(); buf = (C.c_ulonglong * 8)()
+L = _lib.lib(); buf = (C.c_ulonglong * 16)()
 L.sf_barrier_cycles.restype = C.c_int; L.sf_barrier_cycles.argtypes = [C.c_void_p, C.c_int]
 L.sf_barrier_cycles(buf, 1)
 s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
@@ -30,5 +30,7 @@ print("per drawing warp: stage barrier %.1f %%, drawing-warp barriers %.1f %% of
       % (100 * v[0] / (blocks * (W - 1)) / cyc, 100 * v[1] / (blocks * (W - 1)) / cyc, 100 * v[2] / blocks / cyc))
 print("stepping warp, share of the launch: steps %.1f %%, memo state %.1f %%, round scans %.1f %%, stroke gathering %.1f %%, pools + base copies %.1f %%"
       % tuple(100 * v[k] / blocks / cyc for k in (3, 4, 5, 6, 7)))
+print("step sections, cycles per tick and block: load %.0f | keys + respawn %.0f | ship %.0f | fortress %.0f | shells %.0f | missiles %.0f | timers + shaping %.0f | outputs + store + record %.0f"
+      % tuple(v[k] / blocks / T for k in (8, 9, 10, 11, 12, 13, 14, 15)))
 if not PREBUILT:
     subprocess.run([sys.executable, os.path.join(ROOT, "spacefortress_b200", "build.py"), "--force"], env=dict(os.environ, SF_NVCC_DEFS=""))
