@@ -55,18 +55,26 @@ __device__ __forceinline__ long long sf_warp_sum_ll(long long v) {
   return v;
 }
 
-__device__ __noinline__ void sf_accumulate_episode(const SfDev& D, int env, SfEnv& e, bool finished, int lane) {
-  // called by all 32 lanes; `finished` lanes contribute (their pending Stats increments go to the arrays first)
-  long long f[SF_NUM_EPISODE_STATS];
-  long long ret = e.q3.w;
+// Out of line and by VALUE: a reference to the env's registers handed to a function that is not inlined would force the
+// whole SfEnv into local memory in the callers (measured: the state-only kernel lost 30 %).
+// Called by all 32 lanes; the `finished` lanes contribute. Their pending Stats increments (d0..d2) go to the arrays first
+// (reductions: read back through L2); the caller zeroes its copies.
+__device__ __noinline__ void sf_accumulate_episode_vals(const SfDev& D, int env, bool finished, int lane, unsigned d0, unsigned d1, unsigned d2, int4 q3, int max_vlner) {
   int4 st0 = make_int4(0, 0, 0, 0), st1 = st0, st2 = st0;
-  if (finished) { sf_flush_stats(D, env, e); st0 = __ldcg(&D.st0[env]); st1 = __ldcg(&D.st1[env]); st2 = __ldcg(&D.st2[env]); }  // (L2: the flush is a reduction)
-  f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = e.q3.z;
+  if (finished) {
+    if (d0) sf_red_bytes(&D.st0[env], d0);
+    if (d1) sf_red_bytes(&D.st1[env], d1);
+    if (d2) sf_red_bytes(&D.st2[env], d2);
+    st0 = __ldcg(&D.st0[env]); st1 = __ldcg(&D.st1[env]); st2 = __ldcg(&D.st2[env]);
+  }
+  long long f[SF_NUM_EPISODE_STATS];
+  long long ret = q3.w;
+  f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = q3.z;
   f[4] = st0.x; f[5] = st0.y; f[6] = st0.z; f[7] = st0.w;
   f[8] = st1.x; f[9] = st1.y; f[10] = st1.z; f[11] = st1.w;
-  f[12] = st2.x; f[13] = st2.y; f[14] = st2.z; f[15] = st2.w; f[16] = e.st3.x;
-  f[17] = (long long)__float2int_rz(__int_as_float(e.q3.x));
-  f[18] = __double2ll_rn((double)__int_as_float(e.q3.y) * 1000.0);
+  f[12] = st2.x; f[13] = st2.y; f[14] = st2.z; f[15] = st2.w; f[16] = max_vlner;
+  f[17] = (long long)__float2int_rz(__int_as_float(q3.x));
+  f[18] = __double2ll_rn((double)__int_as_float(q3.y) * 1000.0);
   f[19] = st1.y;  // fortress kills of the episode (== destroyedFortresses; rl/train.py:81 sums info)
   f[20] = 0; f[21] = 0; f[22] = 0; f[23] = 0;
 #pragma unroll
@@ -74,9 +82,13 @@ __device__ __noinline__ void sf_accumulate_episode(const SfDev& D, int env, SfEn
     long long v = sf_warp_sum_ll(finished ? f[k] : 0);
     if (lane == 0 && v) atomicAdd(&D.epi[k], (unsigned long long)v);
   }
-  int mv = finished ? e.st3.x : 0;
+  int mv = finished ? max_vlner : 0;
   mv = sf_warp_max(mv);
   if (lane == 0 && mv) atomicMax(&D.epi[20], (unsigned long long)mv);
+}
+__device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, int env, SfEnv& e, bool finished, int lane) {
+  sf_accumulate_episode_vals(D, env, finished, lane, e.d0, e.d1, e.d2, e.q3, e.st3.x);
+  if (finished) { e.d0 = 0u; e.d1 = 0u; e.d2 = 0u; }
 }
 
 // the renderer's view of one stepped env (written by the env's lane into the block's record array)

@@ -23,6 +23,22 @@ res = []
 for gt, n, T, reps in (("autoturn", 4096, 20, 9), ("autoturn", 4096, 1, 60), ("autoturn", 4096, 64, 3), ("youturn", 65536, 16, 3)):
     ms = run(gt, n, T, reps)
     res.append("%s/%d/T%d: med %.1f us (min %.1f) = %.1f M/s" % (gt[:4], n, T, 1e3 * np.median(ms), 1e3 * ms.min(), n * T / np.median(ms) / 1e3))
+def run_state(gt, n, T, reps):
+    env = SFVecEnv(gt, num_envs=n, device=0, render=False); env.reset(to_numpy=False)
+    env.rollout(300, want=("reward",), action_seed=7)
+    out = {"reward": torch.empty((T, n), dtype=torch.int32, device="cuda"), "done": torch.empty((T, n), dtype=torch.uint8, device="cuda")}
+    for _ in range(3): env.rollout(T, out=out, action_seed=7)
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps): env.rollout(T, out=out, action_seed=7)
+    e.record(); torch.cuda.synchronize()
+    env.close()
+    return s.elapsed_time(e) / reps
+if os.environ.get("SF_AB_STATE", "1") == "1":
+    for gt, n, T, reps in (("youturn", 65536, 1, 2000), ("autoturn", 65536, 1, 2000), ("youturn", 65536, 64, 50), ("autoturn", 65536, 64, 50)):
+        ms = run_state(gt, n, T, reps)
+        res.append("state %s/%d/T%d: %.1f us = %.2f G/s" % (gt[:4], n, T, 1e3 * ms, n * T / ms / 1e6))
 print(os.path.basename(os.environ.get("SF_B200_LIB", "product")), " | ".join(res), flush=True)
 '''
 libs = sys.argv[1:]
