@@ -3,6 +3,7 @@ DRAM traffic of the rollout kernel, source hot spots. usage: python tools/export
 import csv, io, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 16   # steps per launch of the profiled command
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 for src, dst in (("bench_%s.json" % tag, "%s_bench_n1.json" % tag), ("bench_ref_%s.json" % tag, "%s_bench_reference_arm.json" % tag),
@@ -17,9 +18,9 @@ def val(k):
 keys = [k for k in h if any(t in k for t in ("dram__bytes", "gpu__time_duration", "launch__", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum",
         "sm__warps_active", "issue_stalled", "thread_inst_executed_per_inst", "sm__pipe_tensor", "gpu__dram_throughput", "smsp__issue_active", "l1tex__t_sector_hit_rate", "lts__t_sector_hit_rate"))]
 with open(os.path.join(P, "%s_ncu_key_metrics_rollout_kernel.txt" % tag), "w") as f:
-    f.write("# ncu --set full --clock-control none -k regex:sf_rollout_kernel, launch of `python bench.py --steps 16 --warmup 3` (4096 envs x 16 steps)\n")
+    f.write("# ncu --set full --clock-control none -k regex:sf_rollout_kernel, launch of `python bench.py --steps %d ...` (4096 envs x %d steps)\n" % (K, K))
     for k in sorted(keys): f.write("%-90s %-16s %s\n" % (k, u[h.index(k)], d[h.index(k)]))
-steps = 4096 * 16
+steps = 4096 * K
 traffic = {"source": "profiles/%s_ncu_key_metrics_rollout_kernel.txt" % tag, "env_steps_in_launch": steps,
            "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
            "dram_bytes_per_env_step": (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / steps,
