@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(
   const int lane = threadIdx.x & 31;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
-  sf_block_smem_init(D.tab);
+  sf_block_smem_init(D.static_image);
   sf_warp_smem_init(W, lane);
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
   const int lane = threadIdx.x & 31;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
-  sf_block_smem_init(D.tab);
+  sf_block_smem_init(D.static_image);
   sf_warp_smem_init(W, lane);
   SfFrameOut out;
   out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
@@ -296,6 +296,15 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
       } else Tm.env[lane].env = -1;
       __syncwarp();
     });
+}
+
+// once per handle (and after sf_set_glyph_masks): the static part of SfBlockSmem, built from the tables, as an image in
+// global memory that the rendering kernels fetch with one bulk copy
+__global__ void __launch_bounds__(SF_BLOCK) sf_pack_static_kernel(SfDev D, unsigned char* image) {
+  sf_block_smem_fill(D.tab);
+  __syncthreads();
+  const int4* src = reinterpret_cast<const int4*>(&sf_block_smem());
+  for (int k = threadIdx.x; k < (int)(SF_STATIC_BYTES / 16); k += blockDim.x) reinterpret_cast<int4*>(image)[k] = src[k];
 }
 
 __global__ void sf_seed_kernel(SfDev D, const unsigned* seeds) {
@@ -581,6 +590,7 @@ static size_t layout(SfDev& d, char* base) {
   d.expo_meta = carve<uint2>(p, np);
   d.epi = carve<unsigned long long>(p, SF_NUM_EPISODE_STATS);
   d.tab = carve<SfTables>(p, 1);
+  d.static_image = carve<unsigned char>(p, SF_STATIC_BYTES);
   return (size_t)(p - base);
 }
 
@@ -633,6 +643,9 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   if ((ce = cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload tables", ce);
   if ((ce = cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout)", ce);
   if ((ce = cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (render)", ce);
+  if ((ce = cudaFuncSetAttribute(sf_pack_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (pack)", ce);
+  sf_pack_static_kernel<<<1, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)>>>(d, const_cast<unsigned char*>(d.static_image));
+  if ((ce = cudaGetLastError()) != cudaSuccess) return bail("static image kernel launch", ce);
   // default seeding: every env replays srand(1) — the reference never seeds libc (game.cpp:137-148)
   sf_seed_kernel<<<(d.n + 127) / 128, 128>>>(d, nullptr);
   if ((ce = cudaGetLastError()) != cudaSuccess) return bail("seed kernel launch", ce);
@@ -1044,6 +1057,11 @@ extern "C" int sf_set_glyph_masks(sf_handle* h, const uint8_t* h_alpha, const ui
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();  // nothing may be drawing from the old tables
   if (ce == cudaSuccess) ce = cudaMemcpy((void*)h->dev.tab, nt, sizeof(SfTables), cudaMemcpyHostToDevice);
   if (ce == cudaSuccess) ce = cudaMemset(h->dev.expo_meta, 0, sizeof(uint2) * (size_t)h->dev.n_pad);  // cached resampled boxes may hold old digits
+  if (ce == cudaSuccess) {
+    sf_pack_static_kernel<<<1, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)>>>(h->dev, const_cast<unsigned char*>(h->dev.static_image));
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  }
   if (ce != cudaSuccess) { delete nt; return fail(SF_ERR_CUDA, std::string("sf_set_glyph_masks: ") + cudaGetErrorString(ce)); }
   delete h->h_tab;
   h->h_tab = nt;

@@ -156,6 +156,7 @@ struct __align__(16) SfBlockSmem {
   int wf_nlines[4];
   unsigned colour_white, padc[3];
   unsigned char exp_colour[SF_EXP_STROKES + 3];
+  alignas(16) unsigned long long init_mbar, pad_mbar;  // the bulk copy of the static part above signals this mbarrier
 #ifdef SF_TIMELINE
   int tl_n[4];
 #endif
@@ -163,6 +164,12 @@ struct __align__(16) SfBlockSmem {
   SfStepSmem step;             // rollout kernel: the group's scalar state between ticks
   SfTeamSmem team[2];
 };
+
+// Everything above `init_mbar` is static (a function of the tables only). sf_pack_static_kernel builds it once per
+// handle with sf_block_smem_fill and leaves an image in global memory (SfDev::static_image); every rendering block then
+// fetches the image with ONE bulk copy (cp.async.bulk global -> shared, completion on an mbarrier) instead of ~25 strided
+// loads per thread, while its threads zero the pools (tables ready 1.3 us after block start instead of 5.5 us).
+#define SF_STATIC_BYTES ((offsetof(SfBlockSmem, init_mbar) + 15) & ~(size_t)15)
 
 // all kernels that render use the same dynamic shared array: one SfBlockSmem, then one SfWarpSmem per warp.
 // Helpers that are kept out of line re-derive their slots from it, so the compiler still knows the address space.
@@ -251,15 +258,9 @@ __device__ __forceinline__ int sf_div_small(int a, int b, float inv_b) {  // a /
 }
 __device__ __forceinline__ int sf_div15(int d) { return (d * 2185) >> 15; }  // exact for 0 <= d < 4694
 
-// once per block at kernel start (every thread of the block calls it, before any early exit)
-// (Tried and dropped: letting warp 0 step the first tick while the other warps load the tables — its first step ran
-// slower next to the loads and the extra live state cost the drawing code registers: -3 % overall.)
-__device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
+// The static part of SfBlockSmem from the tables (every thread of the block; no barrier inside).
+__device__ __forceinline__ void sf_block_smem_fill(const SfTables* T) {
   SfBlockSmem& B = sf_block_smem();
-#ifdef SF_TIMELINE
-  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 2) B.tl_n[threadIdx.x >> 5] = 0;
-  SF_TL(1);
-#endif
   for (int k = threadIdx.x; k < 168; k += blockDim.x) {
     const SfTap t = k < 84 ? T->xtap[k] : T->ytap[k - 84];
     int4 v = make_int4(t.si | (t.cnt << 8), __float_as_int(t.a[0]), __float_as_int(t.a[1]), __float_as_int(t.a[2]));
@@ -267,7 +268,7 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   }
   for (int k = threadIdx.x; k < 84 * 84 / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_obs)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_obs) + k);
   for (int k = threadIdx.x; k < SF_NAT_H * SF_NAT_STRIDE / 16; k += blockDim.x) reinterpret_cast<int4*>(B.bg_nat)[k] = __ldg(reinterpret_cast<const int4*>(T->bg_nat) + k);
-  for (int k = threadIdx.x; k < SF_NAT_W; k += blockDim.x) { B.col_out0[k] = (unsigned char)T->col_out0[k]; B.col_out1[k] = (unsigned char)T->col_out1[k]; }
+  for (int k = threadIdx.x; k < SF_NAT_W + 2; k += blockDim.x) { B.col_out0[k] = k < SF_NAT_W ? (unsigned char)T->col_out0[k] : 0; B.col_out1[k] = k < SF_NAT_W ? (unsigned char)T->col_out1[k] : 0; }
   for (int k = threadIdx.x; k < SF_NAT_H; k += blockDim.x) { B.row_out0[k] = (unsigned char)T->row_out0[k]; B.row_out1[k] = (unsigned char)T->row_out1[k]; }
   for (int k = threadIdx.x; k < SF_FORT_STATES * 4; k += blockDim.x) B.fort_rect[k >> 2][k & 3] = T->fort_rect[k >> 2][k & 3];
   for (int k = threadIdx.x; k < 36 * SF_FORT_LIST_SMEM; k += blockDim.x) {
@@ -279,20 +280,44 @@ __device__ __forceinline__ void sf_block_smem_init(const SfTables* T) {
   for (int k = threadIdx.x; k < SF_MAGIC_N; k += blockDim.x) B.magic[k] = T->magic[k];
   for (int k = threadIdx.x; k < (int)(sizeof(SfHot) / 16); k += blockDim.x) reinterpret_cast<int4*>(&B.hot)[k] = __ldg(reinterpret_cast<const int4*>(&T->hot) + k);
   for (int k = threadIdx.x; k < 48; k += blockDim.x) (&B.wf_line[0][0][0])[k] = (&T->wf_line[0][0][0])[k];
-  if (threadIdx.x < 3) B.wf_nlines[threadIdx.x] = T->wf_nlines[threadIdx.x];
+  if (threadIdx.x < 4) B.wf_nlines[threadIdx.x] = threadIdx.x < 3 ? T->wf_nlines[threadIdx.x] : 0;
+  if (threadIdx.x < 4) (&B.colour_white)[threadIdx.x] = threadIdx.x == 0 ? T->colour_white : 0u;
+  for (int k = threadIdx.x; k < SF_EXP_STROKES + 3; k += blockDim.x) B.exp_colour[k] = k < SF_EXP_STROKES ? T->exp_colour[k] : 0;
+}
+
+// once per block at kernel start (every thread of the block calls it, before any early exit): the static part arrives
+// as one bulk copy of the handle's image while the threads zero the pools
+// (Tried and dropped: letting warp 0 step the first tick while the other warps load the tables — its first step ran
+// slower next to the loads and the extra live state cost the drawing code registers: -3 % overall.)
+__device__ __forceinline__ void sf_block_smem_init(const unsigned char* image) {
+  SfBlockSmem& B = sf_block_smem();
+#ifdef SF_TIMELINE
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 2) B.tl_n[threadIdx.x >> 5] = 0;
+  SF_TL(1);
+#endif
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&B.init_mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)SF_STATIC_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(&B)), "l"(image), "r"((unsigned)SF_STATIC_BYTES), "r"(bar) : "memory");
+  }
   for (int c = 0; c < 2; c++) {
     for (int k = threadIdx.x; k < SF_POOL_CELLS / 2; k += blockDim.x) reinterpret_cast<unsigned*>(B.team[c].cells)[k] = 0u;
     for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[c].arc_mask[0][0])[k] = 0u;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 32) {
       SfTeamSmem& Tm = B.team[c];
       Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
     }
   }
-  if (threadIdx.x == 0) B.colour_white = T->colour_white;
-  for (int k = threadIdx.x; k < SF_EXP_STROKES; k += blockDim.x) B.exp_colour[k] = T->exp_colour[k];
-  // the bulk-copy engine (async proxy) reads bg_obs: make the generic-proxy writes above visible to it
+  // the bulk-copy engine (async proxy) reads bg_obs: make generic-proxy writes visible to it
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
+  __syncthreads();   // (also: the mbarrier is initialised before anybody polls it)
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar) : "memory");
+  } while (!ok);
   SF_TL(2);
 }
 // once per warp at kernel start

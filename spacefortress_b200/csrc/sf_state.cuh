@@ -52,6 +52,7 @@ struct SfDev {
   uint2* expo_meta;           // [n] {life, fortress state | bar state<<6 | (points & 0x3FFFF)<<10 | valid quarters<<28}: what expo holds
   unsigned long long* epi;    // [SF_NUM_EPISODE_STATS] finished-episode accumulators
   const SfTables* tab;
+  const unsigned char* static_image;  // the static part of the rendering blocks' shared memory, ready to be bulk-copied (sf_pack_static_kernel)
   // preset (configs.cpp:51-89)
   int autoturn, shaped, destroy_fortress, death_penalty;
   float missile_penalty;
