@@ -55,40 +55,42 @@ __device__ __forceinline__ long long sf_warp_sum_ll(long long v) {
   return v;
 }
 
-// Out of line and by VALUE: a reference to the env's registers handed to a function that is not inlined would force the
-// whole SfEnv into local memory in the callers (measured: the state-only kernel lost 30 %).
-// Called by all 32 lanes; the `finished` lanes contribute. Their pending Stats increments (d0..d2) go to the arrays first
-// (reductions: read back through L2); the caller zeroes its copies.
-__device__ __noinline__ void sf_accumulate_episode_vals(const SfDev& D, int env, bool finished, int lane, unsigned d0, unsigned d1, unsigned d2, int4 q3, int max_vlner) {
-  int4 st0 = make_int4(0, 0, 0, 0), st1 = st0, st2 = st0;
-  if (finished) {
-    if (d0) sf_red_bytes(&D.st0[env], d0);
-    if (d1) sf_red_bytes(&D.st1[env], d1);
-    if (d2) sf_red_bytes(&D.st2[env], d2);
-    st0 = __ldcg(&D.st0[env]); st1 = __ldcg(&D.st1[env]); st2 = __ldcg(&D.st2[env]);
-  }
+// Finished-episode statistics of the `finished` lanes of a warp (called by all 32 lanes). Out of line and by VALUE: a
+// reference to the env's registers handed to a function that is not inlined forces the whole SfEnv into local memory in
+// the caller (measured: the state-only kernel lost 30 %).
+__device__ __noinline__ void sf_accumulate_episode_vals(unsigned long long* epi, bool finished, int lane, int ret_i, int length, int points_bits, int raw_bits,
+                                                        int max_vlner, int4 st0, int4 st1, int4 st2) {
   long long f[SF_NUM_EPISODE_STATS];
-  long long ret = q3.w;
-  f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = q3.z;
+  long long ret = ret_i;
+  f[0] = 1; f[1] = ret; f[2] = ret * ret; f[3] = length;
   f[4] = st0.x; f[5] = st0.y; f[6] = st0.z; f[7] = st0.w;
   f[8] = st1.x; f[9] = st1.y; f[10] = st1.z; f[11] = st1.w;
   f[12] = st2.x; f[13] = st2.y; f[14] = st2.z; f[15] = st2.w; f[16] = max_vlner;
-  f[17] = (long long)__float2int_rz(__int_as_float(q3.x));
-  f[18] = __double2ll_rn((double)__int_as_float(q3.y) * 1000.0);
+  f[17] = (long long)__float2int_rz(__int_as_float(points_bits));
+  f[18] = __double2ll_rn((double)__int_as_float(raw_bits) * 1000.0);
   f[19] = st1.y;  // fortress kills of the episode (== destroyedFortresses; rl/train.py:81 sums info)
   f[20] = 0; f[21] = 0; f[22] = 0; f[23] = 0;
 #pragma unroll
   for (int k = 0; k < 20; k++) {
     long long v = sf_warp_sum_ll(finished ? f[k] : 0);
-    if (lane == 0 && v) atomicAdd(&D.epi[k], (unsigned long long)v);
+    if (lane == 0 && v) atomicAdd(&epi[k], (unsigned long long)v);
   }
   int mv = finished ? max_vlner : 0;
   mv = sf_warp_max(mv);
-  if (lane == 0 && mv) atomicMax(&D.epi[20], (unsigned long long)mv);
+  if (lane == 0 && mv) atomicMax(&epi[20], (unsigned long long)mv);
 }
+// the finished lanes' pending Stats increments go to the arrays first (reductions: read back through L2)
 __device__ __forceinline__ void sf_accumulate_episode(const SfDev& D, int env, SfEnv& e, bool finished, int lane) {
-  sf_accumulate_episode_vals(D, env, finished, lane, e.d0, e.d1, e.d2, e.q3, e.st3.x);
-  if (finished) { e.d0 = 0u; e.d1 = 0u; e.d2 = 0u; }
+  int4 st0 = make_int4(0, 0, 0, 0), st1 = st0, st2 = st0;
+  if (finished) { sf_flush_stats(D, env, e); st0 = __ldcg(&D.st0[env]); st1 = __ldcg(&D.st1[env]); st2 = __ldcg(&D.st2[env]); }
+  sf_accumulate_episode_vals(D.epi, finished, lane, e.q3.w, e.q3.z, e.q3.x, e.q3.y, e.st3.x, st0, st1, st2);
+}
+// The rollout kernel's stepping warp takes the env by REFERENCE instead, out of line: that keeps its SfEnv in local memory
+// (L1) and its register demand low, and with it the register allocation of the whole kernel body — the drawing code
+// inlined next to it then comes out without a single spill (with the by-value call it has ~15 local loads / stores in
+// sf_draw_stage / sf_phase_strokes / sf_env_base_patch and the launch is 5 % slower: tools/gpu_ab.py + nvdisasm -g).
+__device__ __noinline__ void sf_accumulate_episode_ref(const SfDev& D, int env, SfEnv& e, bool finished, int lane) {
+  sf_accumulate_episode(D, env, e, finished, lane);
 }
 
 // the renderer's view of one stepped env (written by the env's lane into the block's record array)
@@ -187,7 +189,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   ts_ = clock64(); stmask_ = 0xffffffffu;
 #endif
   if (__any_sync(0xffffffffu, finished)) {
-    sf_accumulate_episode(D, env, e, finished, lane);
+    sf_accumulate_episode_ref(D, env, e, finished, lane);
     if (finished) { sf_new_game(D, H, env, e); shell_vis = 0; }  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
