@@ -110,6 +110,7 @@ class SFVecEnv(object):
             for k, shape, dt in (("obs", (n,) + (self.obs_shape if self.obs_type == "image" else (1,)), np.uint8), ("reward", (n,), np.int32), ("done", (n,), np.uint8),
                                  ("kill", (n,), np.uint8), ("events", (n,), np.uint32), ("actions", (n,), np.int32)):
                 self._np[k] = _lib.pinned_array(shape, dt)  # page-locked: D2H lands directly in what step() returns
+            self._np_ptr = {k: C.c_void_p(v.ctypes.data) for k, v in self._np.items()}  # (building these per step costs ~10 us)
         return self._np
 
     @staticmethod
@@ -178,10 +179,8 @@ class SFVecEnv(object):
         a[:] = actions.reshape(n)
         if self._bufs is not None:  # device-path work may be in flight on torch's stream: sf_step_host runs on its own streams
             _torch().cuda.current_stream(self._device()).synchronize()
-        _lib.check(self.L.sf_step_host(
-            self.h, a.ctypes.data_as(C.c_void_p), b["obs"].ctypes.data_as(C.c_void_p) if self.render_on else None,
-            b["reward"].ctypes.data_as(C.c_void_p), b["done"].ctypes.data_as(C.c_void_p),
-            b["kill"].ctypes.data_as(C.c_void_p), b["events"].ctypes.data_as(C.c_void_p), self._flags))
+        p = self._np_ptr
+        _lib.check(self.L.sf_step_host(self.h, p["actions"], p["obs"] if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"], self._flags))
         self._t += 1
         if self.obs_type != "image":
             obs = self.features(to_numpy=True)
@@ -309,6 +308,7 @@ class SFVecEnv(object):
     def close(self):
         if not self.closed and getattr(self, "h", None):
             self._np = None  # the page-locked buffers free themselves when the last array handed out dies
+            self._np_ptr = None
             self.L.sf_destroy(self.h)
             self.h = None
             self.closed = True
