@@ -7,8 +7,13 @@
 //                               (SoA, 128-bit loads/stores) up to two ticks ahead and prepares the next stage, the
 //                               other warps run the block-cooperative frame pipeline of sf_render.cuh and stream the
 //                               84x84 frames to HBM.
+//                               Groups beyond the first 148 are handed out first come first served (SfSched); between
+//                               the ticks of a launch the group's scalars stay in shared memory (SfStepSmem); the static
+//                               tables arrive as one bulk copy of a per-handle image (sf_pack_static_kernel).
 //   sf_step_only_kernel         state-only variant (render off), one env per thread.
-//   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel
+//   sf_features_kernel          the feature observation types of ssf_env.py:95-157, one env per thread.
+//   sf_policy_input_kernel      4-frame stack -> the policy's first-layer input (bf16 or fp32, space-to-depth NHWC).
+//   sf_reset_kernel / sf_seed_kernel / sf_render_kernel / sf_get_state_kernel / sf_set_state_kernel / sf_pack_static_kernel
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>

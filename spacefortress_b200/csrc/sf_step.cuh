@@ -47,10 +47,6 @@ __device__ __forceinline__ void sf_load_env(const SfDev& D, int i, SfEnv& e) {
   e.st3 = D.st3[i];
   e.d0 = 0u; e.d1 = 0u; e.d2 = 0u;
 }
-__device__ __forceinline__ int4 sf_add_bytes(int4 v, unsigned d) {
-  v.x += (int)(d & 255u); v.y += (int)((d >> 8) & 255u); v.z += (int)((d >> 16) & 255u); v.w += (int)(d >> 24);
-  return v;
-}
 // the pending Stats increments -> the arrays (a field holds up to 255: flush at least every 12 ticks — 20 missiles could
 // leave the area in one tick)
 // (Reductions, not load-add-store: the stepping warp is bound by latency, and a reduction does not wait for the memory.
@@ -63,15 +59,9 @@ __device__ __forceinline__ void sf_red_bytes(int4* p, unsigned d) {
   if (d & 0xFF000000u) atomicAdd(q + 3, (int)(d >> 24));
 }
 __device__ __forceinline__ void sf_flush_stats(const SfDev& D, int i, SfEnv& e) {
-#ifdef SF_STATS_RMW
-  if (e.d0) { D.st0[i] = sf_add_bytes(D.st0[i], e.d0); e.d0 = 0u; }
-  if (e.d1) { D.st1[i] = sf_add_bytes(D.st1[i], e.d1); e.d1 = 0u; }
-  if (e.d2) { D.st2[i] = sf_add_bytes(D.st2[i], e.d2); e.d2 = 0u; }
-#else
   if (e.d0) { sf_red_bytes(&D.st0[i], e.d0); e.d0 = 0u; }
   if (e.d1) { sf_red_bytes(&D.st1[i], e.d1); e.d1 = 0u; }
   if (e.d2) { sf_red_bytes(&D.st2[i], e.d2); e.d2 = 0u; }
-#endif
 }
 __device__ __forceinline__ void sf_store_env(const SfDev& D, int i, SfEnv& e) {
   D.pos[i] = e.pos; D.vel[i] = e.vel;
@@ -307,11 +297,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
   if (core & SF_CORE_SHIP_ALIVE) {
     int ang = core & SF_CORE_ANGLE_MASK;
     if (D.autoturn) {
-#ifdef SF_OLD_ATAN2
-      ang = sf_ceil_angle_exact(T, SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x), 1, true);
-#else
       ang = sf_ceil_angle<1>(T, SF_DSUB(SF_FORT_Y, e.pos.y), SF_DSUB(SF_FORT_X, e.pos.x), true);  // ceil(angleTo), pre-move (Q3)
-#endif
       if (ang >= 360) ang -= 360;  // stdAngle
     } else {
       bool l = core & SF_CORE_LEFT, r = core & SF_CORE_RIGHT;
@@ -344,11 +330,7 @@ __device__ inline void sf_env_step(const SfDev& D, const SfHot* T, int i, SfEnv&
     }
     if (core & SF_CORE_SHIP_ALIVE) {  // the fortress only tracks a live ship
       const double fdy = SF_DSUB(e.pos.y, SF_FORT_Y), fdx = SF_DSUB(e.pos.x, SF_FORT_X);
-#ifdef SF_OLD_ATAN2
-      int sect = sf_ceil_angle_exact(T, fdy, fdx, 10, false) / 10;
-#else
       int sect = sf_ceil_angle<10>(T, fdy, fdx, false) / 10;  // ceil(angle_to_ship / 10)
-#endif
       if (sect >= 36) sect -= 36;
       unsigned last = (core >> SF_CORE_FLAST_SHIFT) & 63u;
       core = (core & ~(63u << SF_CORE_FANG_SHIFT)) | ((unsigned)sect << SF_CORE_FANG_SHIFT);
