@@ -194,7 +194,11 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
   ts_ = clock64(); stmask_ = 0xffffffffu;
 #endif
   if (__any_sync(0xffffffffu, finished)) {
+#ifdef SF_STEP_ENV_BY_REF
     sf_accumulate_episode_ref(D, env, e, finished, lane);
+#else
+    sf_accumulate_episode(D, env, e, finished, lane);
+#endif
     if (finished) { sf_new_game(D, H, env, e); shell_vis = 0; }  // gym_vecenv: the returned obs is the first frame of the new episode
   }
   if (mine) {
@@ -211,12 +215,32 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
 }
 
 
-__global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
+// The two roles of the rollout kernel, out of line (separate register allocations, see sf_stepper_ticks). Both walk the
+// same sequence of groups: the block's first group is blockIdx.x, further ones are handed out first come first served
+// (the groups differ in cost, and so do the SMs' speeds). Warp 0 fetches the id of the NEXT group when it starts a group
+// and leaves it in shared memory (two slots, alternating); the other warps read it when they are done with the current
+// group, many barriers later. The step of tick t + 1 (warp 0) runs while the other warps draw tick t, across groups too.
+__device__ __noinline__ void sf_rollout_stepper(const SfDev& D, const SfRollArgs& A) {
+  const int lane = threadIdx.x & 31;
+  SfBlockSmem& B = sf_block_smem();
+  const bool native = (A.flags & SF_FLAG_NATIVE_OBS) != 0;
+  int stage = 0, group = blockIdx.x;
+#pragma unroll 1
+  for (int k = 1; group < A.ngroups; k ^= 1) {
+    if (lane == 0) B.next_group[k] = A.sched ? (int)gridDim.x + atomicAdd(&A.sched->next_group, 1) : group + (int)gridDim.x;
+    sf_stepper_ticks(D, B, lane, native, A.T, stage, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, group, t, &Tm.env[32 * h]); });
+    group = B.next_group[k];
+  }
+  // the last block to leave re-arms the counters for the next launch (every block has made its last fetch by then)
+  if (lane == 0 && A.sched) {
+    __threadfence();
+    if (atomicAdd(&A.sched->done, 1) == (int)gridDim.x - 1) { A.sched->next_group = 0; A.sched->done = 0; __threadfence(); }
+  }
+}
+__device__ __forceinline__ void sf_rollout_drawer(const SfDev& D, const SfRollArgs& A) {
   const int lane = threadIdx.x & 31;
   SfBlockSmem& B = sf_block_smem();
   SfWarpSmem& W = sf_my_smem();
-  sf_block_smem_init(D.static_image);
-  sf_warp_smem_init(W, lane);
   SfFrameOut out;
   out.native = (A.flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
   out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
@@ -224,22 +248,18 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(
   out.tick_bytes = (size_t)D.n * out.obs_bytes;
   SfStageState st;
   st.stage = 0; st.prev_used = 0;
-  // The block is persistent: its first group is blockIdx.x, further ones are handed out first come first served (the
-  // groups differ in cost, and so do the SMs' speeds). Warp 0 fetches the id of the NEXT group when it starts a group and
-  // leaves it in shared memory (two slots, alternating); the other warps read it when they are done with the current
-  // group, many barriers later. The step of tick t + 1 (warp 0) runs while the other warps draw tick t, across groups too.
   int group = blockIdx.x;
 #pragma unroll 1
   for (int k = 1; group < A.ngroups; k ^= 1) {
-    if (threadIdx.x == 0) B.next_group[k] = A.sched ? (int)gridDim.x + atomicAdd(&A.sched->next_group, 1) : group + (int)gridDim.x;
-    sf_block_ticks(D, B, W, lane, out, A.T, st, [&](int t, SfTeamSmem& Tm, int h) { sf_step_group(D, A, group, t, &Tm.env[32 * h]); });
+    sf_drawer_ticks(D, B, W, lane, out, A.T, st);
     group = B.next_group[k];
   }
-  // the last block to leave re-arms the counters for the next launch (every block has made its last fetch by then)
-  if (threadIdx.x == 0 && A.sched) {
-    __threadfence();
-    if (atomicAdd(&A.sched->done, 1) == (int)gridDim.x - 1) { A.sched->next_group = 0; A.sched->done = 0; __threadfence(); }
-  }
+}
+
+__global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
+  sf_block_smem_init(D.static_image);
+  sf_warp_smem_init(sf_my_smem(), threadIdx.x & 31);
+  if (threadIdx.x < 32) sf_rollout_stepper(D, A); else sf_rollout_drawer(D, A);
 }
 
 // state-only: one env per thread
@@ -284,25 +304,32 @@ __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_render_kernel(S
   SfWarpSmem& W = sf_my_smem();
   sf_block_smem_init(D.static_image);
   sf_warp_smem_init(W, lane);
-  SfFrameOut out;
-  out.native = (flags & SF_FLAG_NATIVE_OBS) ? 1 : 0;
-  out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
-  out.obs = obs;
-  out.tick_bytes = 0;
-  SfStageState st;
-  st.stage = 0; st.prev_used = 0;
+  const bool native = (flags & SF_FLAG_NATIVE_OBS) != 0;
+  if (threadIdx.x < 32) {
+    int stage = 0;
 #pragma unroll 1
-  for (int group = blockIdx.x; group < ngroups; group += gridDim.x)
-    sf_block_ticks(D, B, W, lane, out, 1, st, [&](int, SfTeamSmem& Tm, int) {
-      const int env = group * EB + lane;
-      const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
-      if (mine) {
-        SfEnv e;
-        sf_load_env(D, env, e);
-        sf_make_env_rec(e, env, sf_visible_shells(D, env, (unsigned)e.q0.y), Tm.env[lane]);
-      } else Tm.env[lane].env = -1;
-      __syncwarp();
-    });
+    for (int group = blockIdx.x; group < ngroups; group += gridDim.x)
+      sf_stepper_ticks(D, B, lane, native, 1, stage, [&](int, SfTeamSmem& Tm, int) {
+        const int env = group * EB + lane;
+        const bool mine = lane < EB && env < D.n && (!mask || mask[env]);
+        if (mine) {
+          SfEnv e;
+          sf_load_env(D, env, e);
+          sf_make_env_rec(e, env, sf_visible_shells(D, env, (unsigned)e.q0.y), Tm.env[lane]);
+        } else Tm.env[lane].env = -1;
+        __syncwarp();
+      });
+  } else {
+    SfFrameOut out;
+    out.native = native ? 1 : 0;
+    out.obs_bytes = out.native ? (size_t)SF_NAT_H * SF_NAT_W : (size_t)84 * 84;
+    out.obs = obs;
+    out.tick_bytes = 0;
+    SfStageState st;
+    st.stage = 0; st.prev_used = 0;
+#pragma unroll 1
+    for (int group = blockIdx.x; group < ngroups; group += gridDim.x) sf_drawer_ticks(D, B, W, lane, out, 1, st);
+  }
 }
 
 // once per handle (and after sf_set_glyph_masks): the static part of SfBlockSmem, built from the tables, as an image in

@@ -1407,21 +1407,22 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
 #endif
 }
 
-// All frames of T consecutive ticks of one group. Every thread of the block calls this. prep(t, Tm, h) is executed by
+// All frames of T consecutive ticks of one group, as two ROLES that run the same stage sequence and meet at one block
+// barrier per stage: sf_stepper_ticks (warp 0) and sf_drawer_ticks (the other warps). prep(t, Tm, h) is executed by
 // warp 0 only and writes the env records of tick t into Tm.env[32h ..] (one env per lane, env = -1: unused); for a
 // rollout it is the step of tick t, which therefore runs while the other warps draw the ticks before it.
 // A STAGE is a round of up to SF_STAGE_TICKS consecutive ticks. Stage s is drawn from copy s & 1 by the drawing warps
 // while warp 0 prepares stage s + 1 in the other copy; ONE block barrier per stage separates them. Nothing of a
 // stage that is being drawn reads the SoA state, so the steps may overwrite it; the strokes of a LATER round of the
 // same stage are gathered (from the state, which still holds the stage's last tick) before the next step.
+// The roles are separate functions on purpose: the rollout kernel calls them out of line, so that each role gets its own
+// register allocation (sharing one loop, the long-lived variables of the drawing warps were spilled around the stepping
+// warp's calls and reloaded inside the drawing code: nvdisasm -g attribution of LDL / STL).
 template <class Prep>
-__device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, SfFrameOut out, int T, SfStageState& st, Prep prep) {
-  const bool stepper = (threadIdx.x >> 5) == 0;
-  unsigned char* const obs0 = out.obs;
-#ifdef SF_PHASE_TIMING
-  long long t_last_ = clock64(), w_last_ = t_last_;
-#endif
-  if (stepper) sf_prepare_first_round(D, B, B.team[st.stage], lane, 0, T, out, prep);
+__device__ __forceinline__ void sf_stepper_ticks(const SfDev& D, SfBlockSmem& B, int lane, bool native, int T, int& stage, Prep prep) {
+  SfFrameOut out;
+  out.obs = nullptr; out.obs_bytes = 0; out.tick_bytes = 0; out.native = native ? 1 : 0;
+  sf_prepare_first_round(D, B, B.team[stage], lane, 0, T, out, prep);
   SF_TL(3);
   int t = 0;
 #pragma unroll 1
@@ -1429,36 +1430,50 @@ __device__ __forceinline__ void sf_block_ticks(const SfDev& D, SfBlockSmem& B, S
     SF_TL(4);
     sf_team_sync();  // the stage is prepared; every warp is done with the previous one
     SF_TL(5);
-    SF_TICK(0); SF_WTICK(8);
-    SfTeamSmem& Tm = B.team[st.stage];
-    SfTeamSmem& Nx = B.team[st.stage ^ 1];
+    SfTeamSmem& Tm = B.team[stage];
+    SfTeamSmem& Nx = B.team[stage ^ 1];
     const bool more = Tm.more != 0;            // more env slots in the stage than this round could take?
     const int nticks = Tm.nticks;
     const bool last = !more && t + nticks >= T;
-    if (stepper) {
-      SF_PROF_RESET();
-      if (more) {
+    if (more) {
 #pragma unroll
-        for (int h = 0; h < SF_STAGE_TICKS; h++) Nx.env[32 * h + lane] = Tm.env[32 * h + lane];
-        if (lane == 0) Nx.nticks = nticks;
-        __syncwarp();
-        sf_round_scan(Nx, lane, Tm.r1, SF_GROUP_ENVS * nticks);
-        sf_gather_strokes(D, Nx, lane, nticks - 1);  // the slots that are left are of the stage's last tick (see above)
-        sf_restart_pools(Nx, lane);
-      } else if (!last) {
-        sf_prepare_first_round(D, B, Nx, lane, t + nticks, T - (t + nticks), out, prep);
-        SF_PROF(70);
-      }
-    } else {
-      // zero the coverage cells of the stage before this one (the other copy)
-      {
-        const int nz = (st.prev_used + 1) >> 1;
-        for (int k = threadIdx.x - 32; k < nz; k += 32 * (SF_RENDER_WARPS - 1)) reinterpret_cast<unsigned*>(Nx.cells)[k] = 0u;
-      }
-      out.obs = obs0 + (size_t)t * out.tick_bytes;
-      sf_draw_stage(D, B, W, lane, out, st.stage);
-      st.prev_used = Tm.cells_used;
+      for (int h = 0; h < SF_STAGE_TICKS; h++) Nx.env[32 * h + lane] = Tm.env[32 * h + lane];
+      if (lane == 0) Nx.nticks = nticks;
+      __syncwarp();
+      sf_round_scan(Nx, lane, Tm.r1, SF_GROUP_ENVS * nticks);
+      sf_gather_strokes(D, Nx, lane, nticks - 1);  // the slots that are left are of the stage's last tick (see above)
+      sf_restart_pools(Nx, lane);
+    } else if (!last) {
+      sf_prepare_first_round(D, B, Nx, lane, t + nticks, T - (t + nticks), out, prep);
     }
+    stage ^= 1;
+    if (!more) t += nticks;
+    if (last) break;
+  }
+  SF_TL(7);
+}
+
+__device__ __forceinline__ void sf_drawer_ticks(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, SfFrameOut out, int T, SfStageState& st) {
+  unsigned char* const obs0 = out.obs;
+  int t = 0;
+#pragma unroll 1
+  for (;;) {
+    SF_TL(4);
+    sf_team_sync();  // the stage is prepared; every warp is done with the previous one
+    SF_TL(5);
+    SfTeamSmem& Tm = B.team[st.stage];
+    SfTeamSmem& Nx = B.team[st.stage ^ 1];
+    const bool more = Tm.more != 0;
+    const int nticks = Tm.nticks;
+    const bool last = !more && t + nticks >= T;
+    // zero the coverage cells of the stage before this one (the other copy)
+    {
+      const int nz = (st.prev_used + 1) >> 1;
+      for (int k = threadIdx.x - 32; k < nz; k += 32 * (SF_RENDER_WARPS - 1)) reinterpret_cast<unsigned*>(Nx.cells)[k] = 0u;
+    }
+    out.obs = obs0 + (size_t)t * out.tick_bytes;
+    sf_draw_stage(D, B, W, lane, out, st.stage);
+    st.prev_used = Tm.cells_used;
     st.stage ^= 1;
     if (!more) t += nticks;
     if (last) break;
