@@ -956,69 +956,87 @@ __device__ __forceinline__ int sf_count_strokes(unsigned core, unsigned pmask, u
   return ((core & SF_CORE_SHIP_ALIVE) ? 1 : 0) + __popc(pmask & SF_PMASK_MISSILES) + __popc(vis);
 }
 
-// warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets
-__device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin, int nslots) {
-  int carry_cnt = 0, carry_need = 0, carry_task = 0;
-  int r1 = nslots, nst = 0, build_env = -1, build_env2 = -1, nbuilders = 0;
-  bool closed = false;   // the round's last slot is known
-  unsigned later_any = 0u;
+// warp 0: choose the envs of the next round (slots r_begin.. while their strokes fit) and their list offsets. The scan
+// is incremental over the ticks of a stage: sf_scan_half(h) continues from the carries the previous tick left in `S`,
+// sf_scan_finish publishes the round's control words; so the second tick of a stage does not scan the first one again.
+struct SfScanState {
+  int carry_cnt, carry_need, carry_task;
+  int r1, nst, build_env, build_env2, nbuilders;
+  bool closed;          // the round's last slot is known
+  unsigned later_any;
+};
+__device__ __forceinline__ void sf_scan_begin(SfScanState& S) {
+  S.carry_cnt = 0; S.carry_need = 0; S.carry_task = 0;
+  S.r1 = 0; S.nst = 0; S.build_env = -1; S.build_env2 = -1; S.nbuilders = 0;
+  S.closed = false; S.later_any = 0u;
+}
+// slots 32h .. 32h + 31 (tick h of the stage); r_begin: first slot that still has to be drawn
+__device__ __forceinline__ void sf_scan_half(SfTeamSmem& Tm, int lane, int h, int r_begin, SfScanState& S) {
+  if (!S.closed) S.r1 = 32 * (h + 1);
+  const int slot = 32 * h + lane;
+  SfEnvRec& rec = Tm.env[slot];
+  const bool cand = slot >= r_begin && rec.env >= 0;
+  const int cnt = cand ? rec.ns : 0;
+  int need = 0;  // worst-case coverage cells of this env's regions
+  if (cand) need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE + __popc(rec.shell_vis) * SF_CELLS_SHELL;
+  // window tasks of the round that do not belong to a stroke: the stale quarters of a dead ship's explosion box,
+  // the strip of a non-zero score (the static base shows "0000000")
+  const bool deadc = cand && !(rec.core & SF_CORE_SHIP_ALIVE), scorec = cand && rec.points_i > 0;
+  const int qvalidc = deadc ? (rec.building >> 4) & 15 : 0;
+  const int cnttc = (deadc ? 4 - __popc(qvalidc) : 0) + (scorec ? 1 : 0);
+  // one scan for the three counters: strokes (8 bits per env are not enough for the sum: 10 bits), cells (15 bits), tasks (9 bits)
+  unsigned long long packed = (unsigned long long)cnt | ((unsigned long long)need << 12) | ((unsigned long long)cnttc << 32);
 #pragma unroll
-  for (int h = 0; h < SF_STAGE_TICKS; h++) {
-    const int slot = 32 * h + lane;
-    SfEnvRec& rec = Tm.env[slot];
-    const bool cand = slot >= r_begin && slot < nslots && rec.env >= 0;
-    const int cnt = cand ? rec.ns : 0;
-    int need = 0;  // worst-case coverage cells of this env's regions
-    if (cand) need = ((rec.core & SF_CORE_SHIP_ALIVE) ? SF_CELLS_SHIP : 0) + __popc(rec.pmask & SF_PMASK_MISSILES) * SF_CELLS_MISSILE + __popc(rec.shell_vis) * SF_CELLS_SHELL;
-    int incl = cnt, incl_need = need;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, incl_need, o);
-      if (lane >= o) { incl += t; incl_need += u; }
-    }
-    incl += carry_cnt; incl_need += carry_need;
-    const unsigned builders = __ballot_sync(0xffffffffu, cand && (rec.building & 1));
-    // a round builds the explosions of at most two envs: the round ends before the third builder
-    unsigned third = builders;
-    for (int k = nbuilders; k < 2 && third; k++) third &= third - 1;
-    const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (third ? ~((third & (0u - third)) - 1u) : 0u);
-    if (!closed && over) { r1 = 32 * h + __ffs(over) - 1; closed = true; }
-    for (unsigned bm = builders; bm && build_env2 < 0; bm &= bm - 1) {
-      const int sl = 32 * h + __ffs(bm) - 1;
-      if (build_env < 0) build_env = sl; else build_env2 = sl;
-    }
-    nbuilders += __popc(builders);
-    const bool in_round = cand && slot < r1;
-    if (in_round) rec.s0 = incl - cnt;
-    // strokes of the round = inclusive count of its last slot
-    const unsigned inr = __ballot_sync(0xffffffffu, in_round);
-    if (inr) nst = __shfl_sync(0xffffffffu, incl, 31 - __clz((int)inr));
-    later_any |= __ballot_sync(0xffffffffu, cand && slot >= r1);
-    carry_cnt = __shfl_sync(0xffffffffu, incl, 31); carry_need = __shfl_sync(0xffffffffu, incl_need, 31);
-    // window tasks of the round that do not belong to a stroke: the stale quarters of a dead ship's explosion box,
-    // the strip of a non-zero score (the static base shows "0000000")
-    const bool dead = in_round && !(rec.core & SF_CORE_SHIP_ALIVE), score = in_round && rec.points_i > 0;
-    const int qvalid = dead ? (rec.building >> 4) & 15 : 0;
-    const int cntt = (dead ? 4 - __popc(qvalid) : 0) + (score ? 1 : 0);
-    int inclt = cntt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclt, o); if (lane >= o) inclt += t; }
-    inclt += carry_task;
-    int k = inclt - cntt;
-    if (dead) for (int q = 0; q < 4; q++) if (!((qvalid >> q) & 1)) Tm.etask[k++] = (unsigned short)(slot | (q << 6));
-    if (score) Tm.etask[k] = (unsigned short)(slot | (4 << 6));
-    carry_task = __shfl_sync(0xffffffffu, inclt, 31);
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, packed, o); if (lane >= o) packed += t; }
+  const int incl = (int)(packed & 0xFFFu) + S.carry_cnt, incl_need = (int)((packed >> 12) & 0xFFFFFu) + S.carry_need;
+  const int inclt_all = (int)(packed >> 32);
+  const unsigned builders = __ballot_sync(0xffffffffu, cand && (rec.building & 1));
+  // a round builds the explosions of at most two envs: the round ends before the third builder
+  unsigned third = builders;
+  for (int k = S.nbuilders; k < 2 && third; k++) third &= third - 1;
+  const unsigned over = __ballot_sync(0xffffffffu, incl > SF_ROUND_STROKES || incl_need > SF_POOL_CELLS) | (third ? ~((third & (0u - third)) - 1u) : 0u);
+  if (!S.closed && over) { S.r1 = 32 * h + __ffs(over) - 1; S.closed = true; }
+  for (unsigned bm = builders; bm && S.build_env2 < 0; bm &= bm - 1) {
+    const int sl = 32 * h + __ffs(bm) - 1;
+    if (S.build_env < 0) S.build_env = sl; else S.build_env2 = sl;
   }
+  S.nbuilders += __popc(builders);
+  const bool in_round = cand && slot < S.r1;
+  if (in_round) rec.s0 = incl - cnt;
+  // strokes of the round = inclusive count of its last slot
+  const unsigned inr = __ballot_sync(0xffffffffu, in_round);
+  if (inr) S.nst = __shfl_sync(0xffffffffu, incl, 31 - __clz((int)inr));
+  S.later_any |= __ballot_sync(0xffffffffu, cand && slot >= S.r1);
+  // tasks are counted for the slots IN the round only: the slots of a half that are in the round are a prefix of the half,
+  // so the inclusive task count of the round's last slot of this half is what carries over
+  if (in_round) {
+    int k = inclt_all - cnttc + S.carry_task;
+    if (deadc) for (int q = 0; q < 4; q++) if (!((qvalidc >> q) & 1)) Tm.etask[k++] = (unsigned short)(slot | (q << 6));
+    if (scorec) Tm.etask[k] = (unsigned short)(slot | (4 << 6));
+  }
+  if (inr) S.carry_task += __shfl_sync(0xffffffffu, inclt_all, 31 - __clz((int)inr));
+  S.carry_cnt = __shfl_sync(0xffffffffu, incl, 31); S.carry_need = __shfl_sync(0xffffffffu, incl_need, 31);
+}
+__device__ __forceinline__ void sf_scan_finish(SfTeamSmem& Tm, int lane, int r_begin, const SfScanState& S) {
   if (lane == 0) {
-    Tm.more = later_any != 0u;
-    Tm.r0 = r_begin; Tm.r1 = r1; Tm.nstrokes = nst;
-    Tm.build_env = (build_env >= 0 && build_env < r1) ? build_env : -1;
-    Tm.build_env2 = (Tm.build_env >= 0 && build_env2 >= 0 && build_env2 < r1) ? build_env2 : -1;
+    Tm.more = S.later_any != 0u;
+    Tm.r0 = r_begin; Tm.r1 = S.r1; Tm.nstrokes = S.nst;
+    Tm.build_env = (S.build_env >= 0 && S.build_env < S.r1) ? S.build_env : -1;
+    Tm.build_env2 = (Tm.build_env >= 0 && S.build_env2 >= 0 && S.build_env2 < S.r1) ? S.build_env2 : -1;
     // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
-    Tm.chunk = min(max((nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
-    Tm.netask = carry_task;
+    Tm.chunk = min(max((S.nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
+    Tm.netask = S.carry_task;
   }
   __syncwarp();
+}
+// the whole scan at once (a later round of a stage: slots r_begin .. nslots - 1)
+__device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_begin, int nslots) {
+  SfScanState S;
+  sf_scan_begin(S);
+#pragma unroll
+  for (int h = 0; h < SF_STAGE_TICKS; h++)
+    if (32 * h < nslots && 32 * (h + 1) > r_begin) sf_scan_half(Tm, lane, h, r_begin, S);
+  sf_scan_finish(Tm, lane, r_begin, S);
 }
 
 // Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
@@ -1121,10 +1139,17 @@ __device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm
     const unsigned core = rec.core;
     SfStrokeRec* S = &Tm.stroke[rec.s0];
     if (core & SF_CORE_SHIP_ALIVE) { S->x = rec.px; S->y = rec.py; S->desc = 0 | ((int)(core & SF_CORE_ANGLE_MASK) << 2) | (slot << 12); S->region = -1; S++; }
-    for (unsigned m = rec.pmask & SF_PMASK_MISSILES; m; m &= m - 1) {
-      const int k = __ffs(m) - 1;
-      const double2 p = D.mpos[(size_t)k * np + env];
-      S->x = p.x; S->y = p.y; S->desc = 1 | ((int)D.mang[(size_t)k * np + env] << 2) | (slot << 12); S->region = -1; S++;
+    // (up to three missiles per trip: the loads of a trip are in flight together — each is an L2 round trip for this one
+    // warp. Plain scalars: indexed arrays end up in local memory here)
+    for (unsigned m = rec.pmask & SF_PMASK_MISSILES; m;) {
+      const int k0 = __ffs(m) - 1; m &= m - 1;
+      const int k1 = m ? __ffs(m) - 1 : k0; m &= m - 1;
+      const int k2 = m ? __ffs(m) - 1 : k0; m &= m - 1;
+      const double2 p0 = D.mpos[(size_t)k0 * np + env], p1 = D.mpos[(size_t)k1 * np + env], p2 = D.mpos[(size_t)k2 * np + env];
+      const int a0 = D.mang[(size_t)k0 * np + env], a1 = D.mang[(size_t)k1 * np + env], a2 = D.mang[(size_t)k2 * np + env];
+      S->x = p0.x; S->y = p0.y; S->desc = 1 | (a0 << 2) | (slot << 12); S->region = -1; S++;
+      if (k1 != k0) { S->x = p1.x; S->y = p1.y; S->desc = 1 | (a1 << 2) | (slot << 12); S->region = -1; S++; }
+      if (k2 != k0) { S->x = p2.x; S->y = p2.y; S->desc = 1 | (a2 << 2) | (slot << 12); S->region = -1; S++; }
     }
     for (unsigned m = (unsigned)rec.shell_vis; m; m &= m - 1) {
       const int k = __ffs(m) - 1;
@@ -1322,7 +1347,10 @@ __device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, const SfB
   SF_BT(3);
   sf_publish_recs(D, Tm, lane, 0, native);
   SF_BT(4);
-  sf_round_scan(Tm, lane, 0, SF_GROUP_ENVS);
+  SfScanState S;
+  sf_scan_begin(S);
+  sf_scan_half(Tm, lane, 0, 0, S);
+  sf_scan_finish(Tm, lane, 0, S);
   SF_BT(5);
   sf_gather_strokes(D, Tm, lane, 0);
   SF_BT(6);
@@ -1333,7 +1361,8 @@ __device__ __forceinline__ void sf_prepare_first_round(const SfDev& D, const SfB
     SF_BT(3);
     sf_publish_recs(D, Tm, lane, 1, native);
     SF_BT(4);
-    sf_round_scan(Tm, lane, 0, 2 * SF_GROUP_ENVS);
+    sf_scan_half(Tm, lane, 1, 0, S);   // continues the first tick's scan (the round was not closed: !Tm.more)
+    sf_scan_finish(Tm, lane, 0, S);
     SF_BT(5);
     sf_gather_strokes(D, Tm, lane, 1);
     SF_BT(6);
