@@ -513,20 +513,33 @@ def ours(args):
     # ---- e2e through the numpy drop-in API (host actions -> host observations) ------------------------
     rng = np.random.RandomState(1 + rank)
     acts = rng.randint(0, env.num_actions, size=(args.e2e_steps + 3, n)).astype(np.int32)
-    for t in range(3):
-        env.step(acts[t])
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(args.e2e_steps):
-        o, r, d, info = env.step(acts[3 + t])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = n * world * args.e2e_steps / e2e_s
-    d2h_bytes = n * (7056 + 4 + 1 + 1 + 4)
+
+    def e2e_run(delta):
+        """steps of SFVecEnv.step(np.ndarray); delta: frames reach the host buffer as SF_FLAG_HOST_DELTA updates (the
+        default of SFVecEnv) or as whole-frame copies. Returns (env-steps/s over all ranks, s, observation bytes per step)."""
+        env.host_delta = delta
+        for t in range(3):
+            env.step(acts[t])
+        b0 = env.host_delta_stats()
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(args.e2e_steps):
+            o, r, d, info = env.step(acts[3 + t])
+        torch.cuda.synchronize()
+        s_ = time.perf_counter() - t0
+        b1 = env.host_delta_stats()
+        assert (b1[1] - b0[1] == args.e2e_steps) if delta else (b1[2] - b0[2] == args.e2e_steps), (delta, b0, b1)
+        if world > 1:
+            t = torch.tensor([s_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ = float(t.item())
+        obs_b = (b1[0] - b0[0]) / args.e2e_steps if delta else n * 7056
+        return n * world * args.e2e_steps / s_, s_, obs_b
+
+    full_value, full_s, full_obs_b = e2e_run(False)
+    e2e_value, e2e_s, obs_b = e2e_run(True)
+    d2h_bytes = obs_b + n * (4 + 1 + 1 + 4)
+    full_d2h = full_obs_b + n * (4 + 1 + 1 + 4)
     # what bounds it: a plain device->host copy of one step's frames into pinned memory, all ranks at the same time,
     # and the T = 1 kernel alone
     pin = torch.empty(n * 7056, dtype=torch.uint8, pin_memory=True)
@@ -575,9 +588,16 @@ def ours(args):
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
                 "api": "SFVecEnv.step(np.ndarray) -> sf_step_host, actions from and results into page-locked numpy buffers, %d steps" % args.e2e_steps,
+                "transfer": "SF_FLAG_HOST_DELTA (SFVecEnv's default): every frame is rendered on the device every step; the GPU writes the 32-byte granules "
+                            "that differ from the previous step's frame straight into the page-locked host buffer, which then holds exactly the full frames "
+                            "(tests/test_gpu_surface.py::test_host_delta_*). d2h_bytes_per_step is what was written, counted on the device",
                 "ms_per_step": step_ms,
+                "full_copy": {"value": full_value, "ms_per_step": 1e3 * full_s / args.e2e_steps, "d2h_bytes_per_step": full_d2h,
+                              "note": "the same loop with SFVecEnv(host_delta=False): whole frames copied device -> host every step (4 slices, copy of slice k under the kernel of slice k + 1)"},
                 "bound": {"pinned_d2h_probe_ms": probe_ms, "pinned_d2h_probe_gbs_per_rank": n * 7056 / (probe_ms * 1e-3) / 1e9, "kernel_T1_ms": kern1_ms,
-                          "e2e_gbs_per_rank": d2h_bytes / (step_ms * 1e-3) / 1e9, "frac_of_pcie_probe": (n * 7056 / (probe_ms * 1e-3)) and (d2h_bytes / (step_ms * 1e-3)) / (n * 7056 / (probe_ms * 1e-3)),
+                          "full_copy_gbs_per_rank": full_d2h / (full_s / args.e2e_steps) / 1e9,
+                          "full_copy_frac_of_pcie_probe": (full_d2h / (full_s / args.e2e_steps)) / (n * 7056 / (probe_ms * 1e-3)),
+                          "delta_frac_of_kernel_T1": kern1_ms / step_ms,
                           "note": "probe = 20 back-to-back copies of one step's frames (%.1f MB) device -> pinned host, every rank at once, max over ranks" % (n * 7056 / 1e6)}},
         "gpu_launches": 1,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -67,7 +67,8 @@ enum {
   SF_FLAG_NO_AUTORESET = 2, /* leave finished envs finished (single-env facade: SSF_Env has no auto-reset) */
   SF_FLAG_ACTIONS_ARE_KEYMASKS = 4, /* actions[] already hold key masks instead of action ids */
   SF_FLAG_NATIVE_OBS = 8,   /* obs is the native 92x90 frame (SSF_Env.step) instead of 84x84 */
-  SF_FLAG_RAW_REWARD = 16   /* reward = Game.step_one_tick's int (pymodule.cpp:230): no Python-layer shaping, prev_vlner untouched */
+  SF_FLAG_RAW_REWARD = 16,  /* reward = Game.step_one_tick's int (pymodule.cpp:230): no Python-layer shaping, prev_vlner untouched */
+  SF_FLAG_HOST_DELTA = 32   /* sf_step_host only: h_obs is page-locked and unchanged since the previous call (see sf_step_host) */
 };
 
 /* observation types of SSF_Env (ssf_env.py:51): the image is sf_step's d_obs; the other three are sf_features */
@@ -151,9 +152,19 @@ int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
  * owns: the slab is stepped in slices of consecutive envs so that the kernel of one slice overlaps the device->host
  * copy of the previous one. Ordered after everything queued with stream == NULL; work queued on any OTHER stream for
  * this handle must have completed before the call (sf_set_ticks, sf_get_state and sf_set_state synchronise the
- * device themselves). */
+ * device themselves).
+ * SF_FLAG_HOST_DELTA: the caller promises that h_obs is page-locked (sf_host_alloc / cudaHostAlloc / cudaHostRegister, 16-byte
+ * aligned) and that nothing but sf_step_host has written to it since the previous call that passed the same pointer with
+ * this flag. The frames of consecutive steps differ in a few dozen bytes per env, so the library keeps a device copy of
+ * the buffer's contents and writes only the 32-byte granules that changed, straight into h_obs from the GPU; the buffer
+ * holds exactly what the full copy would have produced (resets, auto-resets and device-path steps in between included:
+ * the comparison is against the buffer's contents, not the env's history). The first call for a buffer sends whole
+ * frames. Fails with SF_ERR_INVALID if h_obs is not page-locked. */
 int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
                  uint8_t* h_fortkill, uint32_t* h_events, int flags);
+/* out3[0] = observation bytes the SF_FLAG_HOST_DELTA calls have written to host buffers, out3[1] = number of such calls,
+ * out3[2] = number of rendering sf_step_host calls that sent whole frames. */
+int sf_host_delta_stats(sf_handle* h, unsigned long long* out3);
 
 /* Page-locked host memory for the buffers handed to sf_step_host: the device<->host copies then run as
  * direct DMA into the caller's arrays (pageable memory also works, but is staged by the driver). */

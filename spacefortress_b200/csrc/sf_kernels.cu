@@ -564,6 +564,10 @@ struct sf_handle {
   cudaStream_t host_compute, host_copy;  // sf_step_host: kernels of slice k + 1 overlap the device->host copy of slice k
   cudaEvent_t host_ev[SF_HOST_MAX_SLICES];
   int host_slices;
+  // SF_FLAG_HOST_DELTA: device copy of what the caller's page-locked h_obs holds, so that only changed bytes cross PCIe
+  unsigned char* d_mirror; size_t mirror_cap, mirror_bytes; const void* mirror_host;
+  unsigned long long* d_delta_stats;  // [0] observation bytes written to the host by delta calls, [1] delta calls
+  unsigned long long full_calls;      // calls that sent whole frames (first call, new buffer, flag absent)
 };
 
 extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
@@ -699,6 +703,8 @@ extern "C" int sf_destroy(sf_handle* h) {
   if (h->d_kill) cudaFree(h->d_kill);
   if (h->d_events) cudaFree(h->d_events);
   if (h->d_sched) cudaFree(h->d_sched);
+  if (h->d_mirror) cudaFree(h->d_mirror);
+  if (h->d_delta_stats) cudaFree(h->d_delta_stats);
   if (h->host_compute) cudaStreamDestroy(h->host_compute);
   if (h->host_copy) cudaStreamDestroy(h->host_copy);
   for (int k = 0; k < SF_HOST_MAX_SLICES; k++) if (h->host_ev[k]) cudaEventDestroy(h->host_ev[k]);
@@ -922,6 +928,44 @@ extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, l
   return sf_hash_action(action_seed, (unsigned long long)global_env, (unsigned long long)t, num_actions);
 }
 
+// SF_FLAG_HOST_DELTA. Between two steps of an env only a few dozen bytes of its frame change (the moving objects and
+// now and then a score digit), so the frames are not copied: `mirror` is the device's copy of what the caller's
+// page-locked buffer holds, and this kernel compares the new frames with it 16 bytes per thread and stores, straight
+// into the host buffer (its device alias: posted writes across PCIe), the 32-byte granules that differ. The host buffer
+// ends up identical to a full copy; the traffic is ~300-500 B per env-step instead of 7056.
+__global__ void __launch_bounds__(256) sf_host_delta_kernel(const uint4* __restrict__ cur, uint4* __restrict__ mirror, uint4* __restrict__ host,
+                                                             size_t n16, int tail, unsigned long long* stats) {
+  __shared__ unsigned block_sent;
+  if (threadIdx.x == 0) block_sent = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n16_warp = (n16 + 31) & ~(size_t)31;  // whole warps stay in the loop for the ballot
+  unsigned sent = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16_warp; i += stride) {
+    const bool in = i < n16;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (in) { a = __ldcg(cur + i); b = __ldcg(mirror + i); }
+    const bool diff = (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
+    const unsigned m = __ballot_sync(0xffffffffu, diff);
+    if (m == 0) continue;
+    if (in && ((m >> (lane & ~1u)) & 3u)) { host[i] = a; sent++; }  // both halves of a 32-byte granule: one full sector
+    if (diff) mirror[i] = a;
+  }
+  if (tail && blockIdx.x == 0 && threadIdx.x < (unsigned)tail) {  // the last (bytes % 16) bytes go every time
+    const size_t o = n16 * 16 + threadIdx.x;
+    const unsigned char v = reinterpret_cast<const unsigned char*>(cur)[o];
+    reinterpret_cast<unsigned char*>(host)[o] = v; reinterpret_cast<unsigned char*>(mirror)[o] = v;
+  }
+  for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
+  if (lane == 0 && sent) atomicAdd(&block_sent, sent);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (block_sent) atomicAdd(&stats[0], (unsigned long long)block_sent * 16u);
+    if (blockIdx.x == 0) atomicAdd(&stats[1], 1ull);
+  }
+}
+
 static int ensure_staging(sf_handle* h, size_t obs_bytes) {
   size_t n = (size_t)h->dev.n;
   if (!h->host_compute) {
@@ -945,7 +989,7 @@ static int ensure_staging(sf_handle* h, size_t obs_bytes) {
 
 extern "C" int sf_host_alloc(void** out, long long bytes) {
   if (!out || bytes <= 0) return fail(SF_ERR_INVALID, "sf_host_alloc: bad arguments");
-  CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+  CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped));
   return SF_OK;
 }
 extern "C" int sf_host_free(void* p) {
@@ -967,9 +1011,33 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   // slice's kernel is exposed. Work the caller has queued on OTHER streams for this handle must be complete (the Python
   // wrapper synchronises its stream first); everything queued here is complete on return.
   cudaStream_t sc = h->host_compute, sx = h->host_copy;
+  // SF_FLAG_HOST_DELTA: h_obs is page-locked and still holds what the previous call with this flag wrote there
+  uint4* host_alias = nullptr;
+  const size_t obs_bytes = n * per;
+  const bool want_delta = render && (flags & SF_FLAG_HOST_DELTA);
+  if (want_delta) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h_obs) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+      cudaGetLastError();
+      return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a page-locked h_obs (sf_host_alloc, cudaHostAlloc, cudaHostRegister)");
+    }
+    if (((uintptr_t)h_obs | (uintptr_t)at.devicePointer) & 15) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a 16-byte aligned h_obs");
+    host_alias = reinterpret_cast<uint4*>(at.devicePointer);
+    if (obs_bytes > h->mirror_cap) {
+      if (h->d_mirror) { cudaFree(h->d_mirror); h->d_mirror = nullptr; h->mirror_cap = 0; }
+      CUDA_TRY(cudaMalloc(&h->d_mirror, obs_bytes));
+      h->mirror_cap = obs_bytes; h->mirror_host = nullptr;
+    }
+    if (!h->d_delta_stats) {
+      CUDA_TRY(cudaMalloc(&h->d_delta_stats, 16));
+      CUDA_TRY(cudaMemset(h->d_delta_stats, 0, 16));
+    }
+  }
+  const bool delta = want_delta && h->mirror_host == h_obs && h->mirror_bytes == obs_bytes;
+  flags &= ~SF_FLAG_HOST_DELTA;
   CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
   CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, sc));
-  const int slices = (render && n >= 2048) ? h->host_slices : 1;
+  const int slices = (render && !delta && n >= 2048) ? h->host_slices : 1;
   for (int k = 0; k < slices; k++) {
     const size_t e0 = n * k / slices, e1 = n * (k + 1) / slices;
     SfRollArgs a;
@@ -978,18 +1046,43 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
     a.env0 = (int)e0; a.envn = (int)(e1 - e0);
     rc = launch_rollout(h, a, sc);
     if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
-    if (render) {
+    if (render && !delta) {
       CUDA_TRY(cudaEventRecord(h->host_ev[k], sc));
       CUDA_TRY(cudaStreamWaitEvent(sx, h->host_ev[k], 0));
       CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * per, h->d_obs + e0 * per, (e1 - e0) * per, cudaMemcpyDeviceToHost, sx));
     }
   }
+  if (delta) {
+    const size_t n16 = obs_bytes / 16;
+    const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)h->num_sms * 8);
+    sf_host_delta_kernel<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(h->d_mirror), host_alias,
+                                                              n16, (int)(obs_bytes & 15), h->d_delta_stats);
+    CUDA_TRY(cudaGetLastError());
+  } else if (want_delta) {  // whole frames went out: from here on the mirror describes this buffer
+    CUDA_TRY(cudaMemcpyAsync(h->d_mirror, h->d_obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
+    h->mirror_host = h_obs; h->mirror_bytes = obs_bytes;
+  }
+  if (render && !delta) h->full_calls++;
   if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, sc));
   if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, sc));
   if (h_fortkill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, sc));
   if (h_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, sc));
   cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sx);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(SF_ERR_CUDA, std::string("sf_step_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    h->mirror_host = nullptr;
+    return fail(SF_ERR_CUDA, std::string("sf_step_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  return SF_OK;
+}
+
+extern "C" int sf_host_delta_stats(sf_handle* h, unsigned long long* out3) {
+  if (!h || !out3) return fail(SF_ERR_INVALID, "handle or out is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  out3[0] = out3[1] = 0; out3[2] = h->full_calls;
+  if (h->d_delta_stats) {
+    CUDA_TRY(cudaStreamSynchronize(h->host_compute));
+    CUDA_TRY(cudaMemcpy(out3, h->d_delta_stats, 16, cudaMemcpyDeviceToHost));
+  }
   return SF_OK;
 }
 

@@ -42,12 +42,16 @@ def _torch():
 
 class SFVecEnv(object):
     def __init__(self, env_id="SpaceFortress-youturn-image-v0", num_envs=16, device=0, action_set=1, seeds=None,
-                 render=True, native_obs=False, autoreset=True, first_global_env=0, copy_outputs=False, obs_type="image"):
+                 render=True, native_obs=False, autoreset=True, first_global_env=0, copy_outputs=False, obs_type="image",
+                 host_delta=True):
         """copy_outputs (numpy path): False = step() returns views of the env's page-locked output buffers, which the
         next step() overwrites, and `infos` as a bool ndarray (the fast path); True = fresh arrays every step and
         `infos` as a tuple of N bools, exactly what gym_vecenv's np.stack returns (SubprocVecEnv / DummyVecEnv
         default). obs_type: 'image' (default), or 'features' / 'normalized-features' / 'monitors' (ssf_env.py:95-157):
-        step() / reset() then return the [N, F] float32 feature matrix computed on the device (sf_features)."""
+        step() / reset() then return the [N, F] float32 feature matrix computed on the device (sf_features).
+        host_delta (numpy path): the frames reach the page-locked observation buffer as SF_FLAG_HOST_DELTA updates (only
+        the bytes that changed since the previous step cross PCIe; the buffer's contents are those of a full copy). The
+        views step() returns are then read-only, because the next update builds on them. False: whole frames every step."""
         self.L = _lib.lib()
         self.gametype = _gametype(env_id)
         self.num_envs = int(num_envs)
@@ -56,6 +60,7 @@ class SFVecEnv(object):
         self.native_obs = bool(native_obs)
         self.autoreset = bool(autoreset)
         self.copy_outputs = bool(copy_outputs)
+        self.host_delta = bool(host_delta)
         if obs_type not in _lib.OBS_TYPES:
             raise ValueError("obs_type must be one of %r" % (tuple(_lib.OBS_TYPES),))  # ssf_env.py:51
         self.obs_type = obs_type
@@ -111,6 +116,8 @@ class SFVecEnv(object):
                                  ("kill", (n,), np.uint8), ("events", (n,), np.uint32), ("actions", (n,), np.int32)):
                 self._np[k] = _lib.pinned_array(shape, dt)  # page-locked: D2H lands directly in what step() returns
             self._np_ptr = {k: C.c_void_p(v.ctypes.data) for k, v in self._np.items()}  # (building these per step costs ~10 us)
+            self._obs_ro = self._np["obs"].view()  # what step() hands out under host_delta: the next update builds on its contents
+            self._obs_ro.flags.writeable = False
         return self._np
 
     @staticmethod
@@ -180,14 +187,15 @@ class SFVecEnv(object):
         if self._bufs is not None:  # device-path work may be in flight on torch's stream: sf_step_host runs on its own streams
             _torch().cuda.current_stream(self._device()).synchronize()
         p = self._np_ptr
-        _lib.check(self.L.sf_step_host(self.h, p["actions"], p["obs"] if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"], self._flags))
+        _lib.check(self.L.sf_step_host(self.h, p["actions"], p["obs"] if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"],
+                                       self._flags | (_lib.FLAG_HOST_DELTA if self.host_delta and self.render_on else 0)))
         self._t += 1
         if self.obs_type != "image":
             obs = self.features(to_numpy=True)
         elif not self.render_on:
             obs = None
         else:
-            obs = b["obs"].copy() if self.copy_outputs else b["obs"]
+            obs = b["obs"].copy() if self.copy_outputs else (self._obs_ro if self.host_delta else b["obs"])
         if self.copy_outputs:  # literal gym_vecenv: fresh arrays, info = tuple of N bools (ssf_env.py:233,250)
             self.last_events = b["events"].copy()
             return obs, b["reward"].astype(np.int64), b["done"].astype(bool), tuple(b["kill"].astype(bool).tolist())
@@ -211,6 +219,12 @@ class SFVecEnv(object):
         self._t += 1
         obs = b["obs"] if self.render_on else (self.features() if self.obs_type != "image" else None)
         return obs, b["reward"], b["done"].bool(), b["kill"].bool()
+
+    def host_delta_stats(self):
+        """(observation bytes written to host buffers by delta updates, number of delta updates, number of whole-frame steps)."""
+        out = (C.c_ulonglong * 3)()
+        _lib.check(self.L.sf_host_delta_stats(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def features(self, obs_type=None, to_numpy=False, out=None):
         """[N, F] float32 feature observations of the current state (ssf_env.py:95-157: 'features' and

@@ -237,6 +237,58 @@ def test_drop_in_vec_env_returns_fresh_arrays_and_fast_path_aliases():
     assert np.array_equal(ob, snap)  # the pinned block lives as long as the array that was handed out
 
 
+@pytest.mark.parametrize("gametype,native,n", [("youturn", False, 2500), ("autoturn", True, 301)])
+def test_host_delta_updates_equal_whole_frame_copies(gametype, native, n):
+    """SF_FLAG_HOST_DELTA (SFVecEnv's default numpy path): the page-locked observation buffer, updated with only the
+    32-byte granules that changed, equals the whole-frame copy at every step — across auto-resets (staggered clocks),
+    an explicit reset(), device-path steps taken in between, and for a frame size that is not a multiple of 16 bytes."""
+    torch = torch_cuda()
+    from spacefortress_b200 import SFVecEnv
+    a = SFVecEnv(gametype, num_envs=n, device=0, native_obs=native)                      # delta
+    b = SFVecEnv(gametype, num_envs=n, device=0, native_obs=native, host_delta=False)    # whole frames
+    ticks = (5295 - 1 - (np.arange(n) % 37)).astype(np.int32)
+    rng = np.random.RandomState(3)
+    for e in (a, b):
+        e.reset()
+        e.set_ticks(ticks)
+    per = a.obs_shape[1] * a.obs_shape[2]
+    resets = 0
+    for t in range(60):
+        act = rng.randint(0, a.num_actions, size=n)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert np.array_equal(oa, ob), (t, int((oa != ob).sum()))
+        assert np.array_equal(ra, rb) and np.array_equal(da, db) and np.array_equal(ia, ib)
+        resets += int(da.sum())
+        if t == 20:   # the env's history changes under the buffer: the update is against the buffer's contents
+            for e in (a, b):
+                e.reset()
+        if t == 30:
+            dact = torch.from_numpy(act.astype(np.int32)).cuda()
+            for e in (a, b):
+                e.step(dact); e.step(dact)
+    assert resets > n // 2  # the envs whose clocks ran out before the reset() at t = 20 crossed their episode end
+    assert not oa.flags.writeable and ob.flags.writeable
+    sent, calls, full = a.host_delta_stats()
+    assert calls == 59 and full == 1 and b.host_delta_stats() == (0, 0, 60)
+    assert sent / calls < 0.25 * n * per, sent / calls / n  # a few hundred bytes per env-step, not 7056 (resets included)
+    a.close(); b.close()
+
+
+def test_host_delta_needs_page_locked_memory():
+    torch_cuda()
+    import ctypes as C
+    from spacefortress_b200 import SFVecEnv, _lib
+    env = SFVecEnv("autoturn", num_envs=64, device=0)
+    env.reset()
+    act = np.zeros(64, np.int32); obs = np.zeros((64, 1, 84, 84), np.uint8); rew = np.zeros(64, np.int32); done = np.zeros(64, np.uint8)
+    rc = env.L.sf_step_host(env.h, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, None, None, _lib.FLAG_RENDER | _lib.FLAG_HOST_DELTA)
+    assert rc != 0 and b"page-locked" in env.L.sf_last_error()
+    rc = env.L.sf_step_host(env.h, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, None, None, _lib.FLAG_RENDER)
+    assert rc == 0 and obs.any()   # pageable memory is fine for whole-frame copies
+    env.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE.json configs at their own sizes
 # ---------------------------------------------------------------------------------------------------------------------
