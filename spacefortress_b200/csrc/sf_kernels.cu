@@ -139,6 +139,11 @@ struct SfRollArgs {
   unsigned* events;
   SfSched* sched;      // NULL: static assignment (sf_render_kernel-like contiguous groups, no hand-out)
   int env0, envn;      // the envs this launch steps: [env0, env0 + envn) (sf_step_host steps the slab in slices)
+  // SF_FLAG_HOST_DELTA (sf_step_host, T == 1): every block ends by sending the changed granules of its own frames
+  uint4* host_obs;     // device alias of the caller's page-locked observation buffer, or NULL
+  uint4* mirror;       // device copy of what that buffer holds
+  unsigned long long* delta_stats;
+  int delta_lanes;     // granule in 16-byte lanes
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -256,10 +261,58 @@ __device__ __forceinline__ void sf_rollout_drawer(const SfDev& D, const SfRollAr
   }
 }
 
+// SF_FLAG_HOST_DELTA inside the kernel: the block compares the frames of its own groups (just written: L2) with the
+// mirror, 16 bytes per thread and four in flight, and stores the granules that differ straight into the host buffer
+// (posted writes across PCIe) and into the mirror. Blocks finish at different times (at T = 1 the median block is done
+// after ~70 % of the launch), so most of this and most of the PCIe traffic hides under the slower blocks; a separate
+// kernel (sf_host_delta_kernel, the fallback for frames that are not a multiple of 16 bytes) would start after the
+// slowest block.
+__device__ __noinline__ void sf_block_host_delta(const SfDev& D, const SfRollArgs& A) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = (1u << A.delta_lanes) - 1u, gsh = lane & ~(unsigned)(A.delta_lanes - 1);
+  const uint4* cur = reinterpret_cast<const uint4*>(A.obs);
+  const size_t per16 = (size_t)(84 * 84) / 16;
+  unsigned sent = 0;
+#pragma unroll 1
+  for (int group = blockIdx.x; group < A.ngroups; group += gridDim.x) {
+    const int env_lo = A.env0 + group * A.EB, env_hi = min(env_lo + A.EB, A.env0 + A.envn);
+    const size_t c1 = (size_t)env_hi * per16;
+#pragma unroll 1
+    for (size_t base = (size_t)env_lo * per16; base < c1; base += 4 * SF_BLOCK) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const size_t i = base + u * SF_BLOCK + threadIdx.x;
+        a[u] = b[u] = make_uint4(0, 0, 0, 0);
+        if (i < c1) { a[u] = __ldcg(cur + i); b[u] = __ldcg(A.mirror + i); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const size_t i = base + u * SF_BLOCK + threadIdx.x;
+        const bool diff = (a[u].x != b[u].x) | (a[u].y != b[u].y) | (a[u].z != b[u].z) | (a[u].w != b[u].w);
+        const unsigned m = __ballot_sync(0xffffffffu, diff);
+        if (m == 0) continue;
+        if (i < c1 && ((m >> gsh) & gmask)) { A.host_obs[i] = a[u]; sent++; }
+        if (diff) A.mirror[i] = a[u];
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
+  if (lane == 0 && sent) atomicAdd(&A.delta_stats[0], (unsigned long long)sent * 16u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&A.delta_stats[1], 1ull);
+}
+
+// (HOST_DELTA is a second instantiation, used by sf_step_host only: the register allocation of the plain kernel is
+// sensitive to anything that is added to its body)
+template <bool HOST_DELTA>
 __global__ void __launch_bounds__(SF_BLOCK, SF_BLOCKS_PER_SM) sf_rollout_kernel(const __grid_constant__ SfDev D, const __grid_constant__ SfRollArgs A) {
   sf_block_smem_init(D.static_image);
   sf_warp_smem_init(sf_my_smem(), threadIdx.x & 31);
   if (threadIdx.x < 32) sf_rollout_stepper(D, A); else sf_rollout_drawer(D, A);
+  if (HOST_DELTA) {
+    __syncthreads();  // every frame of this block's groups is written (the bulk copies were waited for before the patches)
+    sf_block_host_delta(D, A);
+  }
 }
 
 // state-only: one env per thread
@@ -568,6 +621,7 @@ struct sf_handle {
   unsigned char* d_mirror; size_t mirror_cap, mirror_bytes; const void* mirror_host;
   unsigned long long* d_delta_stats;  // [0] observation bytes written to the host by delta calls, [1] delta calls
   unsigned long long full_calls;      // calls that sent whole frames (first call, new buffer, flag absent)
+  int delta_lanes;                    // granule of the delta updates in 16-byte lanes (2; SF_DELTA_GRANULE = 16 | 32 | 64 bytes overrides)
 };
 
 extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
@@ -679,7 +733,8 @@ extern "C" int sf_create(const char* gametype, int action_set, int n_envs, int d
   if ((ce = cudaMemset(h->d_sched, 0, sizeof(SfSched))) != cudaSuccess) return bail("cudaMemset scheduler state", ce);
   if ((ce = cudaMemset(h->slab, 0, h->slab_bytes)) != cudaSuccess) return bail("cudaMemset state slab", ce);
   if ((ce = cudaMemcpy((void*)d.tab, h->h_tab, sizeof(SfTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload tables", ce);
-  if ((ce = cudaFuncSetAttribute(sf_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout)", ce);
+  if ((ce = cudaFuncSetAttribute(sf_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout)", ce);
+  if ((ce = cudaFuncSetAttribute(sf_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (rollout, host delta)", ce);
   if ((ce = cudaFuncSetAttribute(sf_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (render)", ce);
   if ((ce = cudaFuncSetAttribute(sf_pack_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK))) != cudaSuccess) return bail("shared memory opt-in (pack)", ce);
   sf_pack_static_kernel<<<1, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK)>>>(d, const_cast<unsigned char*>(d.static_image));
@@ -895,8 +950,9 @@ static int launch_rollout(sf_handle* h, const SfRollArgs& a, cudaStream_t st) {
     SfRollArgs b = a;
     int blocks;
     group_shape(h, b.envn, &b.EB, &b.ngroups, &blocks);
-    b.sched = (a.env0 == 0 && a.envn == d.n) ? h->d_sched : nullptr;  // slices of the slab (sf_step_host): static groups
-    sf_rollout_kernel<<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
+    b.sched = (a.env0 == 0 && a.envn == d.n && !a.host_obs) ? h->d_sched : nullptr;  // slices of the slab (sf_step_host), in-kernel delta: static groups
+    if (b.host_obs) sf_rollout_kernel<true><<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
+    else sf_rollout_kernel<false><<<blocks, SF_BLOCK, SF_RENDER_SMEM_BYTES(SF_WARPS_PER_BLOCK), st>>>(d, b);
   } else {
     sf_step_only_kernel<<<(a.envn + 127) / 128, 128, 0, st>>>(d, a);
   }
@@ -908,7 +964,7 @@ extern "C" int sf_step(sf_handle* h, const int32_t* d_actions, uint8_t* d_obs, i
                        uint8_t* d_fortkill, uint32_t* d_events, int flags, void* stream) {
   if (!h || !d_actions) return fail(SF_ERR_INVALID, "handle or actions is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
-  SfRollArgs a;
+  SfRollArgs a = {};
   a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = 0; a.t0 = 0;
   a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = d_events; a.sched = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
@@ -918,7 +974,7 @@ extern "C" int sf_rollout(sf_handle* h, int T, const int32_t* d_actions, uint32_
                           int32_t* d_reward, uint8_t* d_done, uint8_t* d_fortkill, int flags, void* stream) {
   if (!h || T <= 0) return fail(SF_ERR_INVALID, "handle is NULL or T <= 0");
   CUDA_TRY(cudaSetDevice(h->device));
-  SfRollArgs a;
+  SfRollArgs a = {};
   a.T = T; a.EB = 1; a.ngroups = 0; a.flags = flags; a.actions = d_actions; a.action_seed = action_seed; a.t0 = t0;
   a.obs = d_obs; a.reward = d_reward; a.done = d_done; a.fortkill = d_fortkill; a.events = nullptr; a.sched = nullptr; a.env0 = 0; a.envn = h->dev.n;
   return launch_rollout(h, a, (cudaStream_t)stream);
@@ -933,6 +989,7 @@ extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, l
 // page-locked buffer holds, and this kernel compares the new frames with it 16 bytes per thread and stores, straight
 // into the host buffer (its device alias: posted writes across PCIe), the 32-byte granules that differ. The host buffer
 // ends up identical to a full copy; the traffic is ~300-500 B per env-step instead of 7056.
+template <int LANES>  // lanes (of 16 bytes) per granule
 __global__ void __launch_bounds__(256) sf_host_delta_kernel(const uint4* __restrict__ cur, uint4* __restrict__ mirror, uint4* __restrict__ host,
                                                              size_t n16, int tail, unsigned long long* stats) {
   __shared__ unsigned block_sent;
@@ -949,7 +1006,7 @@ __global__ void __launch_bounds__(256) sf_host_delta_kernel(const uint4* __restr
     const bool diff = (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
     const unsigned m = __ballot_sync(0xffffffffu, diff);
     if (m == 0) continue;
-    if (in && ((m >> (lane & ~1u)) & 3u)) { host[i] = a; sent++; }  // both halves of a 32-byte granule: one full sector
+    if (in && ((m >> (lane & ~(unsigned)(LANES - 1))) & ((1u << LANES) - 1u))) { host[i] = a; sent++; }  // whole granules (32 bytes: one full sector)
     if (diff) mirror[i] = a;
   }
   if (tail && blockIdx.x == 0 && threadIdx.x < (unsigned)tail) {  // the last (bytes % 16) bytes go every time
@@ -974,6 +1031,8 @@ static int ensure_staging(sf_handle* h, size_t obs_bytes) {
     for (int k = 0; k < SF_HOST_MAX_SLICES; k++) CUDA_TRY(cudaEventCreateWithFlags(&h->host_ev[k], cudaEventDisableTiming));
     h->host_slices = 4;
     if (const char* ov = getenv("SF_HOST_SLICES")) { int v = atoi(ov); if (v >= 1 && v <= SF_HOST_MAX_SLICES) h->host_slices = v; }  // tuning knob
+    h->delta_lanes = 2;
+    if (const char* ov = getenv("SF_DELTA_GRANULE")) { int v = atoi(ov); if (v == 16 || v == 32 || v == 64) h->delta_lanes = v / 16; }  // tuning knob
   }
   if (!h->d_actions) {
     CUDA_TRY(cudaMalloc(&h->d_actions, n * 4)); CUDA_TRY(cudaMalloc(&h->d_reward, n * 4));
@@ -997,8 +1056,28 @@ extern "C" int sf_host_free(void* p) {
   return SF_OK;
 }
 
+// The device's address for a page-locked host buffer (NULL for pageable memory): kernels read / write such buffers in
+// place across PCIe, which for the small per-env arrays of a step replaces a DMA copy (several microseconds each).
+static void* device_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (!host || cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+#ifdef SF_HOST_PROFILE  // tools/: host-side phases of sf_step_host (ns, averaged, printed every 512 calls)
+#include <time.h>
+static double g_hp[8]; static long g_hp_calls; static double g_hp_last;
+static double hp_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e9 + ts.tv_nsec; }
+#define SF_HP(k) do { double t_ = hp_now(); if (k == 0) { g_hp_calls++; } else g_hp[k] += t_ - g_hp_last; g_hp_last = t_; \
+  if (k == 5 && g_hp_calls % 512 == 0) { fprintf(stderr, "sf_step_host phases (us): entry %.1f legacy-sync %.1f aliases %.1f launches %.1f wait %.1f\n", \
+    g_hp[1] / 512e3, g_hp[2] / 512e3, g_hp[3] / 512e3, g_hp[4] / 512e3, g_hp[5] / 512e3); for (double& v : g_hp) v = 0; } } while (0)
+#else
+#define SF_HP(k) do {} while (0)
+#endif
+
 extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
                             uint8_t* h_fortkill, uint32_t* h_events, int flags) {
+  SF_HP(0);
   if (!h || !h_actions) return fail(SF_ERR_INVALID, "handle or actions is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   size_t n = (size_t)h->dev.n;
@@ -1016,13 +1095,9 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   const size_t obs_bytes = n * per;
   const bool want_delta = render && (flags & SF_FLAG_HOST_DELTA);
   if (want_delta) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, h_obs) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-      cudaGetLastError();
-      return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a page-locked h_obs (sf_host_alloc, cudaHostAlloc, cudaHostRegister)");
-    }
-    if (((uintptr_t)h_obs | (uintptr_t)at.devicePointer) & 15) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a 16-byte aligned h_obs");
-    host_alias = reinterpret_cast<uint4*>(at.devicePointer);
+    host_alias = reinterpret_cast<uint4*>(device_alias(h_obs));
+    if (!host_alias) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a page-locked h_obs (sf_host_alloc, cudaHostAlloc, cudaHostRegister)");
+    if (((uintptr_t)h_obs | (uintptr_t)host_alias) & 15) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a 16-byte aligned h_obs");
     if (obs_bytes > h->mirror_cap) {
       if (h->d_mirror) { cudaFree(h->d_mirror); h->d_mirror = nullptr; h->mirror_cap = 0; }
       CUDA_TRY(cudaMalloc(&h->d_mirror, obs_bytes));
@@ -1035,15 +1110,28 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   }
   const bool delta = want_delta && h->mirror_host == h_obs && h->mirror_bytes == obs_bytes;
   flags &= ~SF_FLAG_HOST_DELTA;
-  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
-  CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, sc));
+  SF_HP(1);
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+  SF_HP(2);  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
+  // page-locked actions / rewards / dones / kills / events are read and written in place by the kernel
+  const int* k_actions = (const int*)device_alias(h_actions);
+  int* k_reward = (int*)device_alias(h_reward);
+  unsigned char* k_done = (unsigned char*)device_alias(h_done);
+  unsigned char* k_kill = (unsigned char*)device_alias(h_fortkill);
+  unsigned* k_events = (unsigned*)device_alias(h_events);
+  SF_HP(3);
+  if (!k_actions) CUDA_TRY(cudaMemcpyAsync(h->d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, sc));
   const int slices = (render && !delta && n >= 2048) ? h->host_slices : 1;
+  const bool fused_delta = delta && per % 16 == 0;  // the blocks of the step kernel send their own frames' changes
   for (int k = 0; k < slices; k++) {
     const size_t e0 = n * k / slices, e1 = n * (k + 1) / slices;
-    SfRollArgs a;
-    a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.actions = h->d_actions; a.action_seed = 0; a.t0 = 0;
-    a.obs = render ? h->d_obs : nullptr; a.reward = h->d_reward; a.done = h->d_done; a.fortkill = h->d_kill; a.events = h->d_events; a.sched = nullptr;
+    SfRollArgs a = {};
+    a.T = 1; a.EB = 1; a.ngroups = 0; a.flags = render ? flags : (flags & ~SF_FLAG_RENDER); a.action_seed = 0; a.t0 = 0;
+    a.actions = k_actions ? k_actions : h->d_actions;
+    a.obs = render ? h->d_obs : nullptr; a.reward = k_reward ? k_reward : h->d_reward; a.done = k_done ? k_done : h->d_done;
+    a.fortkill = k_kill ? k_kill : h->d_kill; a.events = k_events ? k_events : h->d_events; a.sched = nullptr;
     a.env0 = (int)e0; a.envn = (int)(e1 - e0);
+    if (fused_delta) { a.host_obs = host_alias; a.mirror = reinterpret_cast<uint4*>(h->d_mirror); a.delta_stats = h->d_delta_stats; a.delta_lanes = h->delta_lanes; }
     rc = launch_rollout(h, a, sc);
     if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
     if (render && !delta) {
@@ -1052,22 +1140,25 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
       CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * per, h->d_obs + e0 * per, (e1 - e0) * per, cudaMemcpyDeviceToHost, sx));
     }
   }
-  if (delta) {
+  if (delta && !fused_delta) {
     const size_t n16 = obs_bytes / 16;
     const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)h->num_sms * 8);
-    sf_host_delta_kernel<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(h->d_mirror), host_alias,
-                                                              n16, (int)(obs_bytes & 15), h->d_delta_stats);
+    auto kern = h->delta_lanes == 1 ? sf_host_delta_kernel<1> : (h->delta_lanes == 4 ? sf_host_delta_kernel<4> : sf_host_delta_kernel<2>);
+    kern<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(h->d_mirror), host_alias,
+                                              n16, (int)(obs_bytes & 15), h->d_delta_stats);
     CUDA_TRY(cudaGetLastError());
   } else if (want_delta) {  // whole frames went out: from here on the mirror describes this buffer
     CUDA_TRY(cudaMemcpyAsync(h->d_mirror, h->d_obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
     h->mirror_host = h_obs; h->mirror_bytes = obs_bytes;
   }
   if (render && !delta) h->full_calls++;
-  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, sc));
-  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, sc));
-  if (h_fortkill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, sc));
-  if (h_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, sc));
-  cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sx);
+  if (h_reward && !k_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, sc));
+  if (h_done && !k_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, sc));
+  if (h_fortkill && !k_kill) CUDA_TRY(cudaMemcpyAsync(h_fortkill, h->d_kill, n, cudaMemcpyDeviceToHost, sc));
+  if (h_events && !k_events) CUDA_TRY(cudaMemcpyAsync(h_events, h->d_events, n * 4, cudaMemcpyDeviceToHost, sc));
+  SF_HP(4);
+  cudaError_t e1 = cudaStreamSynchronize(sc), e2 = (render && !delta) ? cudaStreamSynchronize(sx) : cudaSuccess;
+  SF_HP(5);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     h->mirror_host = nullptr;
     return fail(SF_ERR_CUDA, std::string("sf_step_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

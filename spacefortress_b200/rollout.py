@@ -188,6 +188,7 @@ class OnDeviceRollout(object):
         if self.states_hist is not None:
             self.states_hist[self.T].copy_(self.state)
         self._collected = True
+        self.env._device_work = True  # graph replays step the env on torch's stream without going through its methods
         return dict(frames=self.frames, actions=self.actions, rewards=self.rewards, dones=self.dones,
                     values=self.values, logps=self.logps, valid=self.valid_hist)
 

@@ -88,6 +88,7 @@ class SFVecEnv(object):
         self._bufs = None
         self._np = None
         self._constructed = False
+        self._device_work = False
         self.closed = False
 
     # ------------------------------------------------------------------ helpers
@@ -120,9 +121,9 @@ class SFVecEnv(object):
             self._obs_ro.flags.writeable = False
         return self._np
 
-    @staticmethod
-    def _stream_ptr():
+    def _stream_ptr(self):
         torch = _torch()
+        self._device_work = True  # something of this env may now be in flight on torch's stream (see _step_numpy)
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ API
@@ -184,8 +185,9 @@ class SFVecEnv(object):
         b = self._np_bufs()
         a = b["actions"]
         a[:] = actions.reshape(n)
-        if self._bufs is not None:  # device-path work may be in flight on torch's stream: sf_step_host runs on its own streams
-            _torch().cuda.current_stream(self._device()).synchronize()
+        if self._device_work:  # device-path work may be in flight on torch's stream: sf_step_host runs on its own streams
+            _torch().cuda.synchronize(self._device())
+            self._device_work = False
         p = self._np_ptr
         _lib.check(self.L.sf_step_host(self.h, p["actions"], p["obs"] if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"],
                                        self._flags | (_lib.FLAG_HOST_DELTA if self.host_delta and self.render_on else 0)))
