@@ -621,7 +621,7 @@ struct sf_handle {
   unsigned char* d_mirror; size_t mirror_cap, mirror_bytes; const void* mirror_host;
   unsigned long long* d_delta_stats;  // [0] observation bytes written to the host by delta calls, [1] delta calls
   unsigned long long full_calls;      // calls that sent whole frames (first call, new buffer, flag absent)
-  int delta_lanes;                    // granule of the delta updates in 16-byte lanes (2; SF_DELTA_GRANULE = 16 | 32 | 64 bytes overrides)
+  int delta_lanes;                    // granule of the delta updates in 16-byte lanes (2; SF_DELTA_GRANULE = 16 ... 256 bytes overrides)
 };
 
 extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
@@ -1032,7 +1032,7 @@ static int ensure_staging(sf_handle* h, size_t obs_bytes) {
     h->host_slices = 4;
     if (const char* ov = getenv("SF_HOST_SLICES")) { int v = atoi(ov); if (v >= 1 && v <= SF_HOST_MAX_SLICES) h->host_slices = v; }  // tuning knob
     h->delta_lanes = 2;
-    if (const char* ov = getenv("SF_DELTA_GRANULE")) { int v = atoi(ov); if (v == 16 || v == 32 || v == 64) h->delta_lanes = v / 16; }  // tuning knob
+    if (const char* ov = getenv("SF_DELTA_GRANULE")) { int v = atoi(ov); if (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) h->delta_lanes = v / 16; }  // tuning knob
   }
   if (!h->d_actions) {
     CUDA_TRY(cudaMalloc(&h->d_actions, n * 4)); CUDA_TRY(cudaMalloc(&h->d_reward, n * 4));
@@ -1143,7 +1143,7 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   if (delta && !fused_delta) {
     const size_t n16 = obs_bytes / 16;
     const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)h->num_sms * 8);
-    auto kern = h->delta_lanes == 1 ? sf_host_delta_kernel<1> : (h->delta_lanes == 4 ? sf_host_delta_kernel<4> : sf_host_delta_kernel<2>);
+    auto kern = h->delta_lanes == 1 ? sf_host_delta_kernel<1> : (h->delta_lanes >= 4 ? sf_host_delta_kernel<4> : sf_host_delta_kernel<2>);
     kern<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(h->d_mirror), host_alias,
                                               n16, (int)(obs_bytes & 15), h->d_delta_stats);
     CUDA_TRY(cudaGetLastError());

@@ -25,18 +25,19 @@ for gt in ("autoturn", "youturn"):
     fl = env._flags | _lib.FLAG_HOST_DELTA
     t0 = time.perf_counter()
     for t in range(steps):
+        env._np["actions"][:] = acts[5 + t]
         env.L.sf_step_host(env.h, p["actions"], p["obs"], p["reward"], p["done"], p["kill"], p["events"], fl)
     t_call = (time.perf_counter() - t0) / steps
     t0 = time.perf_counter()
     for t in range(steps):
         env.L.sf_step_host(env.h, p["actions"], None, p["reward"], p["done"], p["kill"], p["events"], fl & ~1)
     t_state = (time.perf_counter() - t0) / steps
-    a_dev = torch.from_numpy(acts[0]).cuda()
-    env.step(a_dev); torch.cuda.synchronize()
+    a_dev = torch.from_numpy(acts).cuda()
+    env.step(a_dev[0]); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(steps):
-        env.step(a_dev)
+        env.step(a_dev[5 + t])
     e1.record(); torch.cuda.synchronize()
     print("%s n=%d: wrapper %.1f us/step (%.1f M env-steps/s), C call %.1f us, state-only C call %.1f us, device-path kernel %.1f us, obs bytes/env-step %.0f"
           % (gt, n, 1e6 * t_wrap, n / t_wrap / 1e6, 1e6 * t_call, 1e6 * t_state, 1e3 * e0.elapsed_time(e1) / steps, (s1[0] - s0[0]) / steps / n), flush=True)
