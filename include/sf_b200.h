@@ -153,15 +153,19 @@ int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
  * copy of the previous one. Ordered after everything queued with stream == NULL; work queued on any OTHER stream for
  * this handle must have completed before the call (sf_set_ticks, sf_get_state and sf_set_state synchronise the
  * device themselves).
- * SF_FLAG_HOST_DELTA: the caller promises that h_obs is page-locked (sf_host_alloc / cudaHostAlloc / cudaHostRegister, 16-byte
- * aligned) and that nothing but sf_step_host has written to it since the previous call that passed the same pointer with
- * this flag. The frames of consecutive steps differ in a few dozen bytes per env, so the library keeps a device copy of
- * the buffer's contents and writes only the 32-byte granules that changed, straight into h_obs from the GPU; the buffer
- * holds exactly what the full copy would have produced (resets, auto-resets and device-path steps in between included:
+ * SF_FLAG_HOST_DELTA: the caller promises that h_obs is page-locked (sf_host_alloc / cudaHostAlloc / cudaHostRegister,
+ * 16-byte aligned) and that nothing but sf_step_host of this handle has written to it since the previous call that
+ * passed the same pointer with this flag (see sf_host_forget). The frames of consecutive steps differ in a few dozen
+ * bytes per env, so the library keeps a device copy of the buffer's contents and writes only the 32-byte granules that
+ * changed, straight into h_obs from the GPU; the buffer holds exactly what the full copy would have produced (resets, auto-resets and device-path steps in between included:
  * the comparison is against the buffer's contents, not the env's history). The first call for a buffer sends whole
  * frames. Fails with SF_ERR_INVALID if h_obs is not page-locked. */
 int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_obs, int32_t* h_reward, uint8_t* h_done,
                  uint8_t* h_fortkill, uint32_t* h_events, int flags);
+/* The library remembers the contents of up to 4 host buffers per handle (a caller may rotate a few; the least recently
+ * used one is forgotten first). Before a buffer that was passed with SF_FLAG_HOST_DELTA is freed or reused for
+ * something else, tell the library (h_obs == NULL: all of them); sf_destroy forgets everything. */
+int sf_host_forget(sf_handle* h, const void* h_obs);
 /* out3[0] = observation bytes the SF_FLAG_HOST_DELTA calls have written to host buffers, out3[1] = number of such calls,
  * out3[2] = number of rendering sf_step_host calls that sent whole frames. */
 int sf_host_delta_stats(sf_handle* h, unsigned long long* out3);

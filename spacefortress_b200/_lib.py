@@ -19,6 +19,7 @@ OBS_H = OBS_W = 84
 NATIVE_H, NATIVE_W = 92, 90
 
 KEY_FIRE, KEY_THRUST, KEY_LEFT, KEY_RIGHT = 1, 2, 4, 8
+MAX_HOST_MIRRORS = 4  # SF_MAX_MIRRORS: host observation buffers whose contents the library remembers per handle
 FLAG_RENDER, FLAG_NO_AUTORESET, FLAG_ACTIONS_ARE_KEYMASKS, FLAG_NATIVE_OBS, FLAG_RAW_REWARD, FLAG_HOST_DELTA = 1, 2, 4, 8, 16, 32
 
 OBS_TYPES = {"image": 0, "features": 1, "normalized-features": 2, "monitors": 3}  # ssf_env.py:51
@@ -88,6 +89,7 @@ _PROTOTYPES = {
     "sf_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sf_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "sf_host_delta_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sf_host_forget": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sf_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_longlong]),
     "sf_host_free": (C.c_int, [C.c_void_p]),
     "sf_get_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -600,6 +600,7 @@ static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(SF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
+#define SF_MAX_MIRRORS 4
 #define SF_HOST_MAX_SLICES 8
 struct sf_handle {
   SfDev dev;
@@ -618,7 +619,9 @@ struct sf_handle {
   cudaEvent_t host_ev[SF_HOST_MAX_SLICES];
   int host_slices;
   // SF_FLAG_HOST_DELTA: device copy of what the caller's page-locked h_obs holds, so that only changed bytes cross PCIe
-  unsigned char* d_mirror; size_t mirror_cap, mirror_bytes; const void* mirror_host;
+  struct Mirror { const void* host; unsigned char* d; size_t cap, bytes; unsigned long long used; };
+  Mirror mirrors[SF_MAX_MIRRORS];     // one per host buffer (a caller may rotate a few buffers); least recently used goes first
+  unsigned long long mirror_clock;
   unsigned long long* d_delta_stats;  // [0] observation bytes written to the host by delta calls, [1] delta calls
   unsigned long long full_calls;      // calls that sent whole frames (first call, new buffer, flag absent)
   int delta_lanes;                    // granule of the delta updates in 16-byte lanes (2; SF_DELTA_GRANULE = 16 ... 256 bytes overrides)
@@ -758,7 +761,7 @@ extern "C" int sf_destroy(sf_handle* h) {
   if (h->d_kill) cudaFree(h->d_kill);
   if (h->d_events) cudaFree(h->d_events);
   if (h->d_sched) cudaFree(h->d_sched);
-  if (h->d_mirror) cudaFree(h->d_mirror);
+  for (auto& m : h->mirrors) if (m.d) cudaFree(m.d);
   if (h->d_delta_stats) cudaFree(h->d_delta_stats);
   if (h->host_compute) cudaStreamDestroy(h->host_compute);
   if (h->host_copy) cudaStreamDestroy(h->host_copy);
@@ -1092,23 +1095,31 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   cudaStream_t sc = h->host_compute, sx = h->host_copy;
   // SF_FLAG_HOST_DELTA: h_obs is page-locked and still holds what the previous call with this flag wrote there
   uint4* host_alias = nullptr;
+  sf_handle::Mirror* mir = nullptr;
   const size_t obs_bytes = n * per;
   const bool want_delta = render && (flags & SF_FLAG_HOST_DELTA);
   if (want_delta) {
     host_alias = reinterpret_cast<uint4*>(device_alias(h_obs));
     if (!host_alias) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a page-locked h_obs (sf_host_alloc, cudaHostAlloc, cudaHostRegister)");
     if (((uintptr_t)h_obs | (uintptr_t)host_alias) & 15) return fail(SF_ERR_INVALID, "SF_FLAG_HOST_DELTA needs a 16-byte aligned h_obs");
-    if (obs_bytes > h->mirror_cap) {
-      if (h->d_mirror) { cudaFree(h->d_mirror); h->d_mirror = nullptr; h->mirror_cap = 0; }
-      CUDA_TRY(cudaMalloc(&h->d_mirror, obs_bytes));
-      h->mirror_cap = obs_bytes; h->mirror_host = nullptr;
+    for (auto& m : h->mirrors) if (m.host == h_obs) mir = &m;
+    if (!mir) {  // a buffer seen for the first time: a free entry, else the least recently used one
+      for (auto& m : h->mirrors) if (!mir || (mir->host && (!m.host || m.used < mir->used))) mir = &m;
+      mir->host = nullptr;
     }
+    if (obs_bytes > mir->cap) {
+      if (mir->d) { cudaFree(mir->d); mir->d = nullptr; mir->cap = 0; }
+      mir->host = nullptr;
+      CUDA_TRY(cudaMalloc(&mir->d, obs_bytes));
+      mir->cap = obs_bytes;
+    }
+    mir->used = ++h->mirror_clock;
     if (!h->d_delta_stats) {
       CUDA_TRY(cudaMalloc(&h->d_delta_stats, 16));
       CUDA_TRY(cudaMemset(h->d_delta_stats, 0, 16));
     }
   }
-  const bool delta = want_delta && h->mirror_host == h_obs && h->mirror_bytes == obs_bytes;
+  const bool delta = want_delta && mir->host == h_obs && mir->bytes == obs_bytes;
   flags &= ~SF_FLAG_HOST_DELTA;
   SF_HP(1);
   CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
@@ -1131,7 +1142,7 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
     a.obs = render ? h->d_obs : nullptr; a.reward = k_reward ? k_reward : h->d_reward; a.done = k_done ? k_done : h->d_done;
     a.fortkill = k_kill ? k_kill : h->d_kill; a.events = k_events ? k_events : h->d_events; a.sched = nullptr;
     a.env0 = (int)e0; a.envn = (int)(e1 - e0);
-    if (fused_delta) { a.host_obs = host_alias; a.mirror = reinterpret_cast<uint4*>(h->d_mirror); a.delta_stats = h->d_delta_stats; a.delta_lanes = h->delta_lanes; }
+    if (fused_delta) { a.host_obs = host_alias; a.mirror = reinterpret_cast<uint4*>(mir->d); a.delta_stats = h->d_delta_stats; a.delta_lanes = h->delta_lanes; }
     rc = launch_rollout(h, a, sc);
     if (rc) { cudaStreamSynchronize(sc); cudaStreamSynchronize(sx); return rc; }
     if (render && !delta) {
@@ -1144,12 +1155,12 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
     const size_t n16 = obs_bytes / 16;
     const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)h->num_sms * 8);
     auto kern = h->delta_lanes == 1 ? sf_host_delta_kernel<1> : (h->delta_lanes >= 4 ? sf_host_delta_kernel<4> : sf_host_delta_kernel<2>);
-    kern<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(h->d_mirror), host_alias,
+    kern<<<std::max(blocks, 1), 256, 0, sc>>>(reinterpret_cast<const uint4*>(h->d_obs), reinterpret_cast<uint4*>(mir->d), host_alias,
                                               n16, (int)(obs_bytes & 15), h->d_delta_stats);
     CUDA_TRY(cudaGetLastError());
   } else if (want_delta) {  // whole frames went out: from here on the mirror describes this buffer
-    CUDA_TRY(cudaMemcpyAsync(h->d_mirror, h->d_obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
-    h->mirror_host = h_obs; h->mirror_bytes = obs_bytes;
+    CUDA_TRY(cudaMemcpyAsync(mir->d, h->d_obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
+    mir->host = h_obs; mir->bytes = obs_bytes;
   }
   if (render && !delta) h->full_calls++;
   if (h_reward && !k_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * 4, cudaMemcpyDeviceToHost, sc));
@@ -1160,9 +1171,15 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   cudaError_t e1 = cudaStreamSynchronize(sc), e2 = (render && !delta) ? cudaStreamSynchronize(sx) : cudaSuccess;
   SF_HP(5);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    h->mirror_host = nullptr;
+    for (auto& m : h->mirrors) m.host = nullptr;
     return fail(SF_ERR_CUDA, std::string("sf_step_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
+  return SF_OK;
+}
+
+extern "C" int sf_host_forget(sf_handle* h, const void* h_obs) {
+  if (!h) return fail(SF_ERR_INVALID, "handle is NULL");
+  for (auto& m : h->mirrors) if (m.host == h_obs || !h_obs) m.host = nullptr;  // the device memory is kept for the next buffer
   return SF_OK;
 }
 

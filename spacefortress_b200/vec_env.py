@@ -15,6 +15,8 @@ frame of the next episode; reward/done/info belong to the terminal step.
 """
 import ctypes as C
 
+import sys
+
 import numpy as np
 
 from . import _lib
@@ -46,8 +48,11 @@ class SFVecEnv(object):
                  host_delta=True):
         """copy_outputs (numpy path): False = step() returns views of the env's page-locked output buffers, which the
         next step() overwrites, and `infos` as a bool ndarray (the fast path); True = fresh arrays every step and
-        `infos` as a tuple of N bools, exactly what gym_vecenv's np.stack returns (SubprocVecEnv / DummyVecEnv
-        default). obs_type: 'image' (default), or 'features' / 'normalized-features' / 'monitors' (ssf_env.py:95-157):
+        `infos` as a tuple of N bools, exactly what gym_vecenv's np.stack returns; "ring" (SubprocVecEnv / DummyVecEnv
+        default) = the same contract without the host-side copy: the observations come from a rotation of page-locked
+        buffers, each updated in place by the GPU (host_delta), and a buffer is reused only when nobody holds a
+        reference to the array that was handed out (or to a view / torch.from_numpy tensor of it), so an observation
+        a caller keeps is never overwritten; those arrays are read-only (in-place edits would corrupt the next update). obs_type: 'image' (default), or 'features' / 'normalized-features' / 'monitors' (ssf_env.py:95-157):
         step() / reset() then return the [N, F] float32 feature matrix computed on the device (sf_features).
         host_delta (numpy path): the frames reach the page-locked observation buffer as SF_FLAG_HOST_DELTA updates (only
         the bytes that changed since the previous step cross PCIe; the buffer's contents are those of a full copy). The
@@ -59,8 +64,9 @@ class SFVecEnv(object):
         self.render_on = bool(render)
         self.native_obs = bool(native_obs)
         self.autoreset = bool(autoreset)
-        self.copy_outputs = bool(copy_outputs)
+        self.copy_outputs = copy_outputs if copy_outputs == "ring" else bool(copy_outputs)
         self.host_delta = bool(host_delta)
+        self._ring = []
         if obs_type not in _lib.OBS_TYPES:
             raise ValueError("obs_type must be one of %r" % (tuple(_lib.OBS_TYPES),))  # ssf_env.py:51
         self.obs_type = obs_type
@@ -189,13 +195,17 @@ class SFVecEnv(object):
             _torch().cuda.synchronize(self._device())
             self._device_work = False
         p = self._np_ptr
-        _lib.check(self.L.sf_step_host(self.h, p["actions"], p["obs"] if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"],
+        ring = self._ring_buffer() if (self.copy_outputs == "ring" and self.render_on and self.host_delta) else None
+        _lib.check(self.L.sf_step_host(self.h, p["actions"], (ring[3] if ring else p["obs"]) if self.render_on else None, p["reward"], p["done"], p["kill"], p["events"],
                                        self._flags | (_lib.FLAG_HOST_DELTA if self.host_delta and self.render_on else 0)))
         self._t += 1
         if self.obs_type != "image":
             obs = self.features(to_numpy=True)
         elif not self.render_on:
             obs = None
+        elif ring:
+            obs = ring[0].view()
+            obs.flags.writeable = False
         else:
             obs = b["obs"].copy() if self.copy_outputs else (self._obs_ro if self.host_delta else b["obs"])
         if self.copy_outputs:  # literal gym_vecenv: fresh arrays, info = tuple of N bools (ssf_env.py:233,250)
@@ -204,6 +214,25 @@ class SFVecEnv(object):
         # fast path: views of the page-locked buffers (valid until the next step()); sum(infos) works like rl/train.py:81
         self.last_events = b["events"]
         return obs, b["reward"], b["done"].view(np.bool_), b["kill"].view(np.bool_)
+
+    def _ring_buffer(self):
+        """copy_outputs="ring": a page-locked observation buffer that nobody outside holds a view of — the most recently
+        written one first (the smallest update). In a loop like rl/train.py:79-90, where the previous observation is
+        dropped when the next one is bound, two buffers alternate and each update spans two steps."""
+        ring = self._ring
+        for k, e in enumerate(ring):
+            if sys.getrefcount(e[1]) == e[2]:
+                ring.insert(0, ring.pop(k))
+                return e
+        if len(ring) >= _lib.MAX_HOST_MIRRORS:  # every buffer is still held by the caller: let the oldest go (the caller's views keep it alive)
+            old = ring.pop()
+            _lib.check(self.L.sf_host_forget(self.h, old[3]))
+        arr = _lib.pinned_array((self.num_envs,) + self.obs_shape, np.uint8)
+        e = [arr, arr.base if isinstance(arr.base, np.ndarray) else arr, 0, C.c_void_p(arr.ctypes.data)]
+        del arr
+        e[2] = sys.getrefcount(e[1])  # the references this entry itself accounts for
+        ring.insert(0, e)
+        return e
 
     def _step_torch(self, actions, out_obs=None):
         """Device path. out_obs: optional contiguous uint8 CUDA tensor [N,1,84,84] to receive the frames (e.g.
@@ -355,7 +384,7 @@ class SubprocVecEnv(SFVecEnv):
     one batched GPU env replaces the N worker processes."""
 
     def __init__(self, env_fns, device=0, **kw):
-        kw.setdefault("copy_outputs", True)  # literal drop-in: fresh arrays and a tuple of bools every step
+        kw.setdefault("copy_outputs", "ring")  # literal drop-in: fresh (read-only) arrays and a tuple of bools every step
         env_fns = list(env_fns)
         ids = set(getattr(f, "env_id", None) for f in env_fns)
         if len(ids) != 1 or None in ids:

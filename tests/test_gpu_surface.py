@@ -289,6 +289,46 @@ def test_host_delta_needs_page_locked_memory():
     env.close()
 
 
+def test_drop_in_ring_hands_out_fresh_observations_without_a_host_copy():
+    """SubprocVecEnv's default (copy_outputs="ring"): the observations come from a rotation of page-locked buffers that the
+    GPU updates in place; an array the caller still holds is never overwritten, a loop that drops the previous
+    observation (rl/train.py:79-90) alternates between two buffers, and every frame equals the whole-frame copy."""
+    torch_cuda()
+    import gc
+    from spacefortress_b200 import SFVecEnv, SubprocVecEnv, make_env
+    n = 600
+    env = SubprocVecEnv([make_env("SpaceFortress-youturn-image-v0", 0, i) for i in range(n)])
+    ref = SFVecEnv("youturn", num_envs=n, device=0, host_delta=False)
+    env.reset(); ref.reset()
+    rng = np.random.RandomState(5)
+    obs = None
+    for t in range(40):                      # the training-loop pattern: the previous observation dies when the next is bound
+        act = rng.randint(0, env.num_actions, size=n)
+        obs, rew, done, info = env.step(act)
+        want = ref.step(act)[0]
+        assert np.array_equal(obs, want), t
+        assert not obs.flags.writeable and isinstance(info, tuple) and rew.dtype == np.int64
+    assert len(env._ring) == 2
+    sent, calls, full = env.host_delta_stats()
+    assert full == 2 and calls == 38         # one whole-frame copy per buffer, updates from then on
+    held = []
+    for t in range(7):                       # a caller that keeps everything: nothing it holds may change
+        act = rng.randint(0, env.num_actions, size=n)
+        o = env.step(act)[0]
+        want = ref.step(act)[0]
+        held.append((o, want.copy()))
+        for a, b in held:
+            assert np.array_equal(a, b)
+    assert len(set(a.ctypes.data for a, _ in held)) == 7 and len(env._ring) <= 4
+    del held, o, a, b
+    gc.collect()
+    for t in range(12):                      # buffers come back (or new ones land on old addresses): still exact
+        act = rng.randint(0, env.num_actions, size=n)
+        obs = env.step(act)[0]
+        assert np.array_equal(obs, ref.step(act)[0]), t
+    env.close(); ref.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE.json configs at their own sizes
 # ---------------------------------------------------------------------------------------------------------------------

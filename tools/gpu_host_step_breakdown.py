@@ -42,3 +42,18 @@ for gt in ("autoturn", "youturn"):
     print("%s n=%d: wrapper %.1f us/step (%.1f M env-steps/s), C call %.1f us, state-only C call %.1f us, device-path kernel %.1f us, obs bytes/env-step %.0f"
           % (gt, n, 1e6 * t_wrap, n / t_wrap / 1e6, 1e6 * t_call, 1e6 * t_state, 1e3 * e0.elapsed_time(e1) / steps, (s1[0] - s0[0]) / steps / n), flush=True)
     env.close()
+    for mode, what in (("ring", "SubprocVecEnv look-alike's default: fresh read-only arrays from a rotation of page-locked buffers"),
+                       (True, "private writable copies every step")):
+        lit = SFVecEnv(gt, num_envs=n, device=0, copy_outputs=mode)
+        lit.reset()
+        for t in range(5):
+            o, r, d, i = lit.step(acts[t])   # (bound like in the loop below: the ring's second buffer is allocated here)
+        s0 = lit.host_delta_stats()
+        t0 = time.perf_counter()
+        for t in range(100):
+            o, r, d, i = lit.step(acts[5 + t])
+        dt = time.perf_counter() - t0
+        s1 = lit.host_delta_stats()
+        print("   copy_outputs=%r (%s): %.1f us/step (%.2f M env-steps/s), obs bytes/env-step %.0f"
+              % (mode, what, 1e6 * dt / 100, n * 100 / dt / 1e6, (s1[0] - s0[0]) / 100 / n), flush=True)
+        lit.close()
