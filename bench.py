@@ -12,8 +12,10 @@ launch of the fused multi-step kernel (sf_rollout, T = K steps; actions come fro
 so inputs are resident), bracketed by barrier + synchronize and timed with CUDA events on the launching stream; the
 repetitions go on until >= 0.35 s of launches have been timed and the MEDIAN launch is reported (min / max beside it),
 max over ranks. `e2e` is the same metric through the numpy drop-in API (SFVecEnv.step(np.ndarray) -> sf_step_host):
-host actions in, host observations out, copies inside the timed region, next to a plain pinned device->host copy
-probe run by every rank at the same time. `roofline` is for the dominant (only) kernel. `configs` holds the other
+host actions in, host observations out, transfers inside the timed region: `e2e.value` with the delta updates of the
+page-locked observation buffer (SF_FLAG_HOST_DELTA, the default), `e2e.drop_in_ring` with the fresh-array contract of the
+SubprocVecEnv look-alike, `e2e.full_copy` with whole frames copied every step, next to a plain pinned device->host
+copy probe run by every rank at the same time. `roofline` is for the dominant (only) kernel. `configs` holds the other
 BASELINE.json configs measured in the same run (C3: 65 536-env on-device rollout with the SF-GRU policy, C4: 131 072
 envs/GPU state-only with both game types, C5: 262 144 envs/GPU with staggered episode ends and the episode-stat
 all-reduce inside the timed loop). `cpu_baseline` / `--impl reference` time the reference's own CPU implementation on
@@ -514,12 +516,13 @@ def ours(args):
     rng = np.random.RandomState(1 + rank)
     acts = rng.randint(0, env.num_actions, size=(args.e2e_steps + 3, n)).astype(np.int32)
 
-    def e2e_run(delta):
+    def e2e_run(delta, copy_outputs=False):
         """steps of SFVecEnv.step(np.ndarray); delta: frames reach the host buffer as SF_FLAG_HOST_DELTA updates (the
         default of SFVecEnv) or as whole-frame copies. Returns (env-steps/s over all ranks, s, observation bytes per step)."""
         env.host_delta = delta
+        env.copy_outputs = copy_outputs
         for t in range(3):
-            env.step(acts[t])
+            o, r, d, info = env.step(acts[t])
         b0 = env.host_delta_stats()
         barrier()
         t0 = time.perf_counter()
@@ -537,6 +540,7 @@ def ours(args):
         return n * world * args.e2e_steps / s_, s_, obs_b
 
     full_value, full_s, full_obs_b = e2e_run(False)
+    ring_value, ring_s, ring_obs_b = e2e_run(True, "ring")
     e2e_value, e2e_s, obs_b = e2e_run(True)
     d2h_bytes = obs_b + n * (4 + 1 + 1 + 4)
     full_d2h = full_obs_b + n * (4 + 1 + 1 + 4)
@@ -592,6 +596,9 @@ def ours(args):
                             "that differ from the previous step's frame straight into the page-locked host buffer, which then holds exactly the full frames "
                             "(tests/test_gpu_surface.py::test_host_delta_*). d2h_bytes_per_step is what was written, counted on the device",
                 "ms_per_step": step_ms,
+                "drop_in_ring": {"value": ring_value, "ms_per_step": 1e3 * ring_s / args.e2e_steps, "d2h_bytes_per_step": ring_obs_b + n * (4 + 1 + 1 + 4),
+                                 "note": "the same loop with copy_outputs='ring', which is what the SubprocVecEnv / DummyVecEnv look-alikes do: every step returns a fresh read-only observation array "
+                                         "(a rotation of page-locked buffers, each updated in place; never one the caller still holds), int64 rewards, bool dones and a tuple of N bools"},
                 "full_copy": {"value": full_value, "ms_per_step": 1e3 * full_s / args.e2e_steps, "d2h_bytes_per_step": full_d2h,
                               "note": "the same loop with SFVecEnv(host_delta=False): whole frames copied device -> host every step (4 slices, copy of slice k under the kernel of slice k + 1)"},
                 "bound": {"pinned_d2h_probe_ms": probe_ms, "pinned_d2h_probe_gbs_per_rank": n * 7056 / (probe_ms * 1e-3) / 1e9, "kernel_T1_ms": kern1_ms,
