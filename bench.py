@@ -592,7 +592,7 @@ def ours(args):
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": d2h_bytes,
                 "api": "SFVecEnv.step(np.ndarray) -> sf_step_host, actions from and results into page-locked numpy buffers, %d steps" % args.e2e_steps,
-                "transfer": "SF_FLAG_HOST_DELTA (SFVecEnv's default): every frame is rendered on the device every step; the GPU writes the 32-byte granules "
+                "transfer": "SF_FLAG_HOST_DELTA (SFVecEnv's default): every frame is rendered on the device every step; the GPU writes the 64-byte granules "
                             "that differ from the previous step's frame straight into the page-locked host buffer, which then holds exactly the full frames "
                             "(tests/test_gpu_surface.py::test_host_delta_*). d2h_bytes_per_step is what was written, counted on the device",
                 "ms_per_step": step_ms,

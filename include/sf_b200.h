@@ -156,7 +156,7 @@ int sf_render(sf_handle* h, uint8_t* d_obs, int flags, void* stream);
  * SF_FLAG_HOST_DELTA: the caller promises that h_obs is page-locked (sf_host_alloc / cudaHostAlloc / cudaHostRegister,
  * 16-byte aligned) and that nothing but sf_step_host of this handle has written to it since the previous call that
  * passed the same pointer with this flag (see sf_host_forget). The frames of consecutive steps differ in a few dozen
- * bytes per env, so the library keeps a device copy of the buffer's contents and writes only the 32-byte granules that
+ * bytes per env, so the library keeps a device copy of the buffer's contents and writes only the 64-byte granules (host cache lines) that
  * changed, straight into h_obs from the GPU; the buffer holds exactly what the full copy would have produced (resets, auto-resets and device-path steps in between included:
  * the comparison is against the buffer's contents, not the env's history). The first call for a buffer sends whole
  * frames. Fails with SF_ERR_INVALID if h_obs is not page-locked. */

@@ -624,7 +624,7 @@ struct sf_handle {
   unsigned long long mirror_clock;
   unsigned long long* d_delta_stats;  // [0] observation bytes written to the host by delta calls, [1] delta calls
   unsigned long long full_calls;      // calls that sent whole frames (first call, new buffer, flag absent)
-  int delta_lanes;                    // granule of the delta updates in 16-byte lanes (2; SF_DELTA_GRANULE = 16 ... 256 bytes overrides)
+  int delta_lanes;                    // granule of the delta updates in 16-byte lanes (4; SF_DELTA_GRANULE = 16 ... 256 bytes overrides)
 };
 
 extern "C" const char* sf_last_error(void) { return g_err.c_str(); }
@@ -990,8 +990,8 @@ extern "C" int sf_synthetic_action(uint32_t action_seed, long long global_env, l
 // SF_FLAG_HOST_DELTA. Between two steps of an env only a few dozen bytes of its frame change (the moving objects and
 // now and then a score digit), so the frames are not copied: `mirror` is the device's copy of what the caller's
 // page-locked buffer holds, and this kernel compares the new frames with it 16 bytes per thread and stores, straight
-// into the host buffer (its device alias: posted writes across PCIe), the 32-byte granules that differ. The host buffer
-// ends up identical to a full copy; the traffic is ~300-500 B per env-step instead of 7056.
+// into the host buffer (its device alias: posted writes across PCIe), the granules (64 bytes: a host cache line) that differ. The host buffer
+// ends up identical to a full copy; the traffic is ~600-1100 B per env-step instead of 7056.
 template <int LANES>  // lanes (of 16 bytes) per granule
 __global__ void __launch_bounds__(256) sf_host_delta_kernel(const uint4* __restrict__ cur, uint4* __restrict__ mirror, uint4* __restrict__ host,
                                                              size_t n16, int tail, unsigned long long* stats) {
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(256) sf_host_delta_kernel(const uint4* __restr
     const bool diff = (a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w);
     const unsigned m = __ballot_sync(0xffffffffu, diff);
     if (m == 0) continue;
-    if (in && ((m >> (lane & ~(unsigned)(LANES - 1))) & ((1u << LANES) - 1u))) { host[i] = a; sent++; }  // whole granules (32 bytes: one full sector)
+    if (in && ((m >> (lane & ~(unsigned)(LANES - 1))) & ((1u << LANES) - 1u))) { host[i] = a; sent++; }  // whole granules
     if (diff) mirror[i] = a;
   }
   if (tail && blockIdx.x == 0 && threadIdx.x < (unsigned)tail) {  // the last (bytes % 16) bytes go every time
@@ -1034,7 +1034,7 @@ static int ensure_staging(sf_handle* h, size_t obs_bytes) {
     for (int k = 0; k < SF_HOST_MAX_SLICES; k++) CUDA_TRY(cudaEventCreateWithFlags(&h->host_ev[k], cudaEventDisableTiming));
     h->host_slices = 4;
     if (const char* ov = getenv("SF_HOST_SLICES")) { int v = atoi(ov); if (v >= 1 && v <= SF_HOST_MAX_SLICES) h->host_slices = v; }  // tuning knob
-    h->delta_lanes = 2;
+    h->delta_lanes = 4;  // 64 bytes: whole host cache lines (no partial-line writes in the host's memory system)
     if (const char* ov = getenv("SF_DELTA_GRANULE")) { int v = atoi(ov); if (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) h->delta_lanes = v / 16; }  // tuning knob
   }
   if (!h->d_actions) {

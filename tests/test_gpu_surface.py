@@ -240,7 +240,7 @@ def test_drop_in_vec_env_returns_fresh_arrays_and_fast_path_aliases():
 @pytest.mark.parametrize("gametype,native,n", [("youturn", False, 2500), ("autoturn", True, 301)])
 def test_host_delta_updates_equal_whole_frame_copies(gametype, native, n):
     """SF_FLAG_HOST_DELTA (SFVecEnv's default numpy path): the page-locked observation buffer, updated with only the
-    32-byte granules that changed, equals the whole-frame copy at every step — across auto-resets (staggered clocks),
+    64-byte granules that changed, equals the whole-frame copy at every step — across auto-resets (staggered clocks),
     an explicit reset(), device-path steps taken in between, and for a frame size that is not a multiple of 16 bytes."""
     torch = torch_cuda()
     from spacefortress_b200 import SFVecEnv
@@ -271,7 +271,7 @@ def test_host_delta_updates_equal_whole_frame_copies(gametype, native, n):
     assert not oa.flags.writeable and ob.flags.writeable
     sent, calls, full = a.host_delta_stats()
     assert calls == 59 and full == 1 and b.host_delta_stats() == (0, 0, 60)
-    assert sent / calls < 0.25 * n * per, sent / calls / n  # a few hundred bytes per env-step, not 7056 (resets included)
+    assert sent / calls < 0.35 * n * per, sent / calls / n  # around a thousand bytes per env-step, not 7056 (resets included)
     a.close(); b.close()
 
 
