@@ -237,11 +237,12 @@ def test_drop_in_vec_env_returns_fresh_arrays_and_fast_path_aliases():
     assert np.array_equal(ob, snap)  # the pinned block lives as long as the array that was handed out
 
 
-@pytest.mark.parametrize("gametype,native,n", [("youturn", False, 2500), ("autoturn", True, 301)])
+@pytest.mark.parametrize("gametype,native,n", [("youturn", False, 2500), ("autoturn", False, 6001), ("autoturn", True, 301)])
 def test_host_delta_updates_equal_whole_frame_copies(gametype, native, n):
     """SF_FLAG_HOST_DELTA (SFVecEnv's default numpy path): the page-locked observation buffer, updated with only the
     64-byte granules that changed, equals the whole-frame copy at every step — across auto-resets (staggered clocks),
-    an explicit reset(), device-path steps taken in between, and for a frame size that is not a multiple of 16 bytes."""
+    an explicit reset(), device-path steps taken in between, with more groups than blocks (6001 envs: the blocks of the step
+    kernel send the changes of several groups each) and for a frame size that is not a multiple of 16 bytes."""
     torch = torch_cuda()
     from spacefortress_b200 import SFVecEnv
     a = SFVecEnv(gametype, num_envs=n, device=0, native_obs=native)                      # delta
