@@ -1088,9 +1088,9 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   bool render = (flags & SF_FLAG_RENDER) && h_obs;
   int rc = ensure_staging(h, render ? n * per : 0);
   if (rc) return rc;
-  // Synchronous, on the handle's own streams. The slab is stepped in slices of consecutive envs: the kernel of slice
-  // k + 1 runs while the frames of slice k cross PCIe (one cudaMemcpyAsync per buffer and slice), so only the first
-  // slice's kernel is exposed. Work the caller has queued on OTHER streams for this handle must be complete (the Python
+  // Synchronous, on the handle's own streams. Whole-frame mode: the slab is stepped in slices of consecutive envs, the
+  // kernel of slice k + 1 runs while the frames of slice k cross PCIe (one cudaMemcpyAsync per buffer and slice), so only
+  // the first slice's kernel is exposed. Delta mode: one launch, no copies (see sf_block_host_delta). Work the caller has queued on OTHER streams for this handle must be complete (the Python
   // wrapper synchronises its stream first); everything queued here is complete on return.
   cudaStream_t sc = h->host_compute, sx = h->host_copy;
   // SF_FLAG_HOST_DELTA: h_obs is page-locked and still holds what the previous call with this flag wrote there
@@ -1122,8 +1122,8 @@ extern "C" int sf_step_host(sf_handle* h, const int32_t* h_actions, uint8_t* h_o
   const bool delta = want_delta && mir->host == h_obs && mir->bytes == obs_bytes;
   flags &= ~SF_FLAG_HOST_DELTA;
   SF_HP(1);
-  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
-  SF_HP(2);  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
+  CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // calls made with stream == NULL (sf_reset, sf_seed ...) come first
+  SF_HP(2);
   // page-locked actions / rewards / dones / kills / events are read and written in place by the kernel
   const int* k_actions = (const int*)device_alias(h_actions);
   int* k_reward = (int*)device_alias(h_reward);
