@@ -1024,7 +1024,8 @@ __device__ __forceinline__ void sf_scan_finish(SfTeamSmem& Tm, int lane, int r_b
     Tm.build_env = (S.build_env >= 0 && S.build_env < S.r1) ? S.build_env : -1;
     Tm.build_env2 = (Tm.build_env >= 0 && S.build_env2 >= 0 && S.build_env2 < S.r1) ? S.build_env2 : -1;
     // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
-    Tm.chunk = min(max((S.nst + (SF_RENDER_WARPS - 1) - 1) / (SF_RENDER_WARPS - 1), 1), 8);
+    // (the last drawing warp issues the round's bulk copies instead, see sf_draw_stage: no batch for it unless the list is full)
+    Tm.chunk = min(max((S.nst + (SF_RENDER_WARPS - 2) - 1) / (SF_RENDER_WARPS - 2), 1), 8);
     Tm.netask = S.carry_task;
   }
   __syncwarp();
@@ -1040,16 +1041,17 @@ __device__ __forceinline__ void sf_round_scan(SfTeamSmem& Tm, int lane, int r_be
 }
 
 // Static base of the observation of env slot e: the whole default observation (hexagons, "0000000", empty bar) goes
-// out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes)...
-__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int lane, int e, const SfFrameOut& out, int sg) {
+// out as ONE asynchronous bulk copy from the block's shared-memory copy (TMA engine, 7056 bytes; one copy per lane of
+// the issuing warp, see sf_draw_stage)...
+__device__ __forceinline__ void sf_env_base_issue(const SfBlockSmem& B, int e, const SfFrameOut& out, int sg) {
   const int env = sf_team(sg).env[e].env;
-  if (env < 0 || lane != 0) return;
+  if (env < 0) return;
   const unsigned src = (unsigned)__cvta_generic_to_shared(B.bg_obs);
   unsigned char* gb = sf_frame_ptr(out, e, env);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gb), "r"(src), "r"(84 * 84) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-// ... and, once the bulk copies of this warp have landed, the few 16-byte chunks that the fortress state (about 12
+// ... and, once the bulk copies have landed, the few 16-byte chunks that the fortress state (about 12
 // for a live fortress, 53 for its explosion) and a non-empty vulnerability bar change are patched from the
 // pre-resampled state tables.
 __device__ __forceinline__ void sf_env_base_patch(const SfDev& D, const SfBlockSmem& B, int lane, int e, const SfFrameOut& out, int sg) {
@@ -1166,7 +1168,7 @@ __device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm
 // list: at most one batch per warp) and publishes its records; after a barrier of the drawing warps, B3: the
 // passes of ALL batches are dealt round-robin over ALL drawing warps, so the scan conversion is balanced whatever
 // the size of the individual strokes.
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst, int sg) {
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst, int sg, bool base_issuer = false) {
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team(sg);
   const int chunk = Tm.chunk;
@@ -1192,6 +1194,7 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   } else {
     if (lane == 0) W.ngroups = 0;
   }
+  if (base_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the round's bulk copies have landed: every warp knows after the barrier
   sf_render_sync();  // every batch is published, the explosion items are done
   SF_PROF(64);
   // B2, second half: the sprite (its stamp is visible to the stepping warp long before it looks at the next stage). A
@@ -1386,16 +1389,19 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
 #endif
   const int r0 = Tm.r0, r1 = Tm.r1, nst = Tm.nstrokes;
   // ---- B: stroke tasks ----
-  if (!out.native) {  // (issuing a bulk copy costs a few hundred cycles: spread over the drawing warps, not on the stepping warp)
+  // The default observations of the round go out as bulk copies issued by ONE warp, the last drawing warp, one copy per
+  // lane: it has no geometry batch (Tm.chunk), so the time the copy engine's queue makes an issuer wait (when all 23 warps
+  // issued their two or three copies at the same moment that was 7 % of all stall samples) is spent by a warp that would
+  // idle; it waits for the copies before the barrier that ends B1, after which every warp may patch.
+  const bool base_issuer = !out.native && wi == nw - 1;
+  if (base_issuer) {
 #pragma unroll 1
-    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_issue(B, lane, e, out, sg);
+    for (int e = r0 + lane; e < r1; e += 32) sf_env_base_issue(B, e, out, sg);
   }
   SF_PROF_RESET();
-  sf_phase_strokes(D, B, W, lane, wi, nw, nst, sg);
+  sf_phase_strokes(D, B, W, lane, wi, nw, nst, sg, base_issuer);
   SF_PROF(69);
   if (!out.native) {
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's bulk copies have landed
-    __syncwarp();
     SF_PROF(65);
 #pragma unroll 1
     for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out, sg);
