@@ -118,7 +118,8 @@ struct __align__(16) SfTeamSmem {
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
   int next_task, netask, pad_q, chunk;  // phase C work queue; env tasks of the round; strokes per batch of phase B1
-  int more, nticks, build_env2, padm2;    // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS)
+  int more, nticks, build_env2, base_ready;  // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS);
+                                             // the round's bulk copies have landed (set by the warp that issued them)
   int nregions, cells_used, dbg_max_b, dbg_max_c;
   unsigned short etask[SF_STAGE_SLOTS * 5];  // env slot | kind<<6: kind 0..3 = quarter of a dead ship's explosion box, 4 = score strip
   unsigned short exp_item0[SF_EXP_QUADS];   // build: copies of the y phase's per-quad table entries (SfExpPhase) for the sprite pass
@@ -1023,6 +1024,7 @@ __device__ __forceinline__ void sf_scan_finish(SfTeamSmem& Tm, int lane, int r_b
     Tm.r0 = r_begin; Tm.r1 = S.r1; Tm.nstrokes = S.nst;
     Tm.build_env = (S.build_env >= 0 && S.build_env < S.r1) ? S.build_env : -1;
     Tm.build_env2 = (Tm.build_env >= 0 && S.build_env2 >= 0 && S.build_env2 < S.r1) ? S.build_env2 : -1;
+    Tm.base_ready = 0;
     // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
     // (the last drawing warp issues the round's bulk copies instead, see sf_draw_stage: no batch for it unless the list is full)
     Tm.chunk = min(max((S.nst + (SF_RENDER_WARPS - 2) - 1) / (SF_RENDER_WARPS - 2), 1), 8);
@@ -1168,7 +1170,7 @@ __device__ __forceinline__ void sf_gather_strokes(const SfDev& D, SfTeamSmem& Tm
 // list: at most one batch per warp) and publishes its records; after a barrier of the drawing warps, B3: the
 // passes of ALL batches are dealt round-robin over ALL drawing warps, so the scan conversion is balanced whatever
 // the size of the individual strokes.
-__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst, int sg, bool base_issuer = false) {
+__device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B, SfWarpSmem& W, int lane, int wi, int nw, int nst, int sg) {
   const SfTables* T = D.tab;
   SfTeamSmem& Tm = sf_team(sg);
   const int chunk = Tm.chunk;
@@ -1194,7 +1196,6 @@ __device__ __forceinline__ void sf_phase_strokes(const SfDev& D, SfBlockSmem& B,
   } else {
     if (lane == 0) W.ngroups = 0;
   }
-  if (base_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the round's bulk copies have landed: every warp knows after the barrier
   sf_render_sync();  // every batch is published, the explosion items are done
   SF_PROF(64);
   // B2, second half: the sprite (its stamp is visible to the stepping warp long before it looks at the next stage). A
@@ -1392,16 +1393,26 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
   // The default observations of the round go out as bulk copies issued by ONE warp, the last drawing warp, one copy per
   // lane: it has no geometry batch (Tm.chunk), so the time the copy engine's queue makes an issuer wait (when all 23 warps
   // issued their two or three copies at the same moment that was 7 % of all stall samples) is spent by a warp that would
-  // idle; it waits for the copies before the barrier that ends B1, after which every warp may patch.
+  // idle; after its share of the passes it waits for the copies (long done) and raises Tm.base_ready, which the other warps
+  // look at before they patch.
   const bool base_issuer = !out.native && wi == nw - 1;
   if (base_issuer) {
 #pragma unroll 1
     for (int e = r0 + lane; e < r1; e += 32) sf_env_base_issue(B, e, out, sg);
   }
   SF_PROF_RESET();
-  sf_phase_strokes(D, B, W, lane, wi, nw, nst, sg, base_issuer);
+  sf_phase_strokes(D, B, W, lane, wi, nw, nst, sg);
   SF_PROF(69);
   if (!out.native) {
+    // the copies were issued a whole phase ago: the issuer's wait returns at once, and so does everybody's look at the flag
+    if (base_issuer) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); *(volatile int*)&Tm.base_ready = 1; }
+    } else {
+      while (*(volatile int*)&Tm.base_ready == 0) {}
+    }
+    __syncwarp();
     SF_PROF(65);
 #pragma unroll 1
     for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out, sg);
