@@ -173,7 +173,7 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
     else {  // between the ticks of a launch the group's scalars live in shared memory
       e.pos = SS.pos[lane]; e.vel = SS.vel[lane];
       e.q0 = SS.q0[lane]; e.q1 = SS.q1[lane]; e.q2 = SS.q2[lane]; e.q3 = SS.q3[lane]; e.st3 = SS.st3[lane];
-      e.d0 = 0u; e.d1 = 0u; e.d2 = 0u;
+      e.d0 = SS.d0[lane]; e.d1 = SS.d1[lane]; e.d2 = SS.d2[lane];
     }
 #ifdef SF_BARRIER_TIMING
     if (e.q0.x == 0x7fffffff) e.q0.y = 0;  // (a use of the loaded words: the section ends when they have arrived)
@@ -211,7 +211,8 @@ __device__ __noinline__ void sf_step_group(const SfDev& D, const SfRollArgs& A, 
     else {
       SS.pos[lane] = e.pos; SS.vel[lane] = e.vel;
       SS.q0[lane] = e.q0; SS.q1[lane] = e.q1; SS.q2[lane] = e.q2; SS.q3[lane] = e.q3; SS.st3[lane] = e.st3;
-      sf_flush_stats(D, env, e);
+      if ((t & 7) == 7) sf_flush_stats(D, env, e);  // the pending Stats increments are 8-bit fields: every 8 ticks is often enough (as in sf_step_only_kernel)
+      SS.d0[lane] = e.d0; SS.d1[lane] = e.d1; SS.d2[lane] = e.d2;
     }
     sf_make_env_rec(e, env, shell_vis, recs[lane]);
   } else recs[lane].env = -1;

@@ -137,6 +137,7 @@ struct __align__(16) SfTeamSmem {
 struct __align__(16) SfStepSmem {
   double2 pos[SF_GROUP_ENVS_], vel[SF_GROUP_ENVS_];
   int4 q0[SF_GROUP_ENVS_], q1[SF_GROUP_ENVS_], q2[SF_GROUP_ENVS_], q3[SF_GROUP_ENVS_], st3[SF_GROUP_ENVS_];
+  unsigned d0[SF_GROUP_ENVS_], d1[SF_GROUP_ENVS_], d2[SF_GROUP_ENVS_];  // pending Stats increments (8-bit fields, flushed every 8 ticks)
 };
 
 // per-block shared memory: copies of the static tables that every window touches, and the teams
