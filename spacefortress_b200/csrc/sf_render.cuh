@@ -117,7 +117,7 @@ struct __align__(16) SfTeamSmem {
   SfStrokeRec stroke[SF_ROUND_STROKES];
   int4 region[SF_POOL_REGIONS];      // {x0, y0, w | h<<16, first cell | tag<<15 | colour<<16}
   int r0, r1, nstrokes, build_env;   // the current round: env slots [r0, r1), strokes in the list, the env slot whose explosion is built (-1)
-  int next_task, netask, pad_q, chunk;  // phase C work queue; env tasks of the round; strokes per batch of phase B1
+  int next_task, netask, next_patch, chunk;  // phase C work queue; env tasks of the round; base patches handed out; strokes per batch of phase B1
   int more, nticks, build_env2, base_ready;  // env slots of the stage are left for another round; ticks the stage covers (1 .. SF_STAGE_TICKS);
                                              // the round's bulk copies have landed (set by the warp that issued them)
   int nregions, cells_used, dbg_max_b, dbg_max_c;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void sf_block_smem_init(const unsigned char* image) {
     for (int k = threadIdx.x; k < SF_EXP_W * SF_EXP_W * 4; k += blockDim.x) (&B.team[c].arc_mask[0][0])[k] = 0u;
     if (threadIdx.x == 32) {
       SfTeamSmem& Tm = B.team[c];
-      Tm.next_task = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
+      Tm.next_task = 0; Tm.next_patch = 0; Tm.netask = 0; Tm.chunk = 8; Tm.nregions = 0; Tm.cells_used = 0;
     }
   }
   // the bulk-copy engine (async proxy) reads bg_obs: make generic-proxy writes visible to it
@@ -1331,7 +1331,7 @@ struct SfStageState {
 
 // warp 0: restart the pools of the copy whose stage it has just prepared
 __device__ __forceinline__ void sf_restart_pools(SfTeamSmem& Tm, int lane) {
-  if (lane == 0) { Tm.next_task = 0; Tm.nregions = 0; Tm.cells_used = 0; }
+  if (lane == 0) { Tm.next_task = 0; Tm.next_patch = 0; Tm.nregions = 0; Tm.cells_used = 0; }
   __syncwarp();
 }
 
@@ -1415,8 +1415,15 @@ __device__ __forceinline__ void sf_draw_stage(const SfDev& D, SfBlockSmem& B, Sf
     }
     __syncwarp();
     SF_PROF(65);
+    // first come first served: the warps leave the passes one pass apart, and a patch is as long as a pass
 #pragma unroll 1
-    for (int e = r0 + wi; e < r1; e += nw) sf_env_base_patch(D, B, lane, e, out, sg);
+    for (;;) {
+      int e = 0;
+      if (lane == 0) e = atomicAdd(&Tm.next_patch, 1);
+      e = r0 + __shfl_sync(0xffffffffu, e, 0);
+      if (e >= r1) break;
+      sf_env_base_patch(D, B, lane, e, out, sg);
+    }
     SF_PROF(66);
   }
 #ifdef SF_PHASE_TIMING
