@@ -1027,8 +1027,11 @@ __device__ __forceinline__ void sf_scan_finish(SfTeamSmem& Tm, int lane, int r_b
     Tm.build_env2 = (Tm.build_env >= 0 && S.build_env2 >= 0 && S.build_env2 < S.r1) ? S.build_env2 : -1;
     Tm.base_ready = 0;
     // phase B1 hands the strokes out in equal batches of <= 8, one per drawing warp
-    // (the last drawing warp issues the round's bulk copies instead, see sf_draw_stage: no batch for it unless the list is full)
-    Tm.chunk = min(max((S.nst + (SF_RENDER_WARPS - 2) - 1) / (SF_RENDER_WARPS - 2), 1), 8);
+    // (the last drawing warps get no batch: one of them issues the round's bulk copies instead, see sf_draw_stage)
+#ifndef SF_CHUNK_WARPS  // B1 is latency bound (a batch of 8 strokes takes as long as one of 4), and every batch rounds its last pass of B3 up:
+#define SF_CHUNK_WARPS 12  // about 12 batches per round measured best (22: +1 % more passes; 8: the same)
+#endif
+    Tm.chunk = min(max((S.nst + SF_CHUNK_WARPS - 1) / SF_CHUNK_WARPS, 1), 8);
     Tm.netask = S.carry_task;
   }
   __syncwarp();
