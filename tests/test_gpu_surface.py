@@ -276,6 +276,26 @@ def test_host_delta_updates_equal_whole_frame_copies(gametype, native, n):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("n", [1, 7, 33, 147, 149, 4737])
+def test_host_delta_at_awkward_batch_sizes(n):
+    """Delta updates at batch sizes around the group / block boundaries (one env, a partial warp, one more env than SMs,
+    one more group than blocks): equal to whole-frame copies, and the device path sees the same frames."""
+    torch = torch_cuda()
+    from spacefortress_b200 import SFVecEnv
+    a = SFVecEnv("youturn", num_envs=n, device=0)
+    b = SFVecEnv("youturn", num_envs=n, device=0, host_delta=False)
+    a.reset(); b.reset()
+    rng = np.random.RandomState(n)
+    for t in range(12):
+        act = rng.randint(0, a.num_actions, size=n)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert np.array_equal(oa, ob), (n, t)
+        assert np.array_equal(ra, rb) and np.array_equal(da, db) and np.array_equal(ia, ib)
+    assert np.array_equal(a.render_frames(to_numpy=True).reshape(oa.shape), oa)
+    a.close(); b.close()
+
+
 def test_host_delta_needs_page_locked_memory():
     torch_cuda()
     import ctypes as C
