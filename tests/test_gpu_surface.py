@@ -343,6 +343,19 @@ def test_drop_in_ring_hands_out_fresh_observations_without_a_host_copy():
     assert len(set(a.ctypes.data for a, _ in held)) == 7 and len(env._ring) <= 4
     del held, o, a, b
     gc.collect()
+    import warnings
+    import torch
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")       # torch warns once that the array is read-only (rl/train.py:86 does exactly this)
+        kept = torch.from_numpy(env.step(act)[0])
+    ref.step(act)
+    snap = kept.clone()
+    for t in range(4):                       # a tensor made from an observation keeps its buffer out of the rotation
+        act = rng.randint(0, env.num_actions, size=n)
+        assert np.array_equal(env.step(act)[0], ref.step(act)[0])
+        assert torch.equal(kept, snap)
+    del kept
+    gc.collect()
     for t in range(12):                      # buffers come back (or new ones land on old addresses): still exact
         act = rng.randint(0, env.num_actions, size=n)
         obs = env.step(act)[0]
